@@ -1,0 +1,94 @@
+"""In-tree build of the native code (no torch, no cmake):
+
+  beom_b200/lib/libbeom_gpu.so    hand-written CUDA kernels + the C ABI (nvcc, sm_100a only)
+  beom_b200/lib/libbeom_host.so   C++ host driver (parameter parser, read_input_data, outputs, time loop)
+  beom_b200/lib/beom_run          executable equivalent of main.f95
+  oracle/libbeom_oracle.so        the CPU checker (tests only), strict IEEE
+  oracle/libbeom_oracle_omp.so    the same source with OpenMP, for the CPU baseline timing
+
+Run as ``python -m beom_b200.build`` or through ``__graft_entry__.build()``.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+LIBDIR = os.path.join(HERE, "lib")
+GPU_SRC = os.path.join(HERE, "csrc", "gpu")
+HOST_SRC = os.path.join(HERE, "csrc", "host")
+ORACLE = os.path.join(ROOT, "oracle")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-fmad=false",  # no FMA contraction: results are bit-identical to a strict IEEE evaluation
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-shared",
+]
+
+
+def _newer(target: str, sources: list[str]) -> bool:
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def _run(cmd: list[str]) -> None:
+    print("+", " ".join(cmd), flush=True)
+    subprocess.run(cmd, check=True)
+
+
+def _sources(d: str, exts: tuple[str, ...]) -> list[str]:
+    return sorted(os.path.join(d, f) for f in os.listdir(d) if f.endswith(exts))
+
+
+def build_gpu(force: bool = False, verbose_ptxas: bool = False) -> str:
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    os.makedirs(LIBDIR, exist_ok=True)
+    out = os.path.join(LIBDIR, "libbeom_gpu.so")
+    cus = _sources(GPU_SRC, (".cu",))
+    deps = cus + _sources(GPU_SRC, (".cuh", ".h")) + [os.path.join(ROOT, "include", "beom_gpu.h")]
+    if force or _newer(out, deps):
+        extra = ["-Xptxas", "-v"] if verbose_ptxas else []
+        _run([nvcc] + NVCC_FLAGS + extra + cus + ["-o", out, "-ldl"])
+    return out
+
+
+def build_host(force: bool = False) -> str:
+    os.makedirs(LIBDIR, exist_ok=True)
+    out = os.path.join(LIBDIR, "libbeom_host.so")
+    ccs = [os.path.join(HOST_SRC, f) for f in ("params.cc", "init.cc", "io.cc", "run.cc")]
+    deps = ccs + _sources(HOST_SRC, (".h",)) + [os.path.join(ROOT, "include", "beom_gpu.h"), os.path.join(LIBDIR, "libbeom_gpu.so")]
+    common = ["-O2", "-std=c++17", "-Wall", "-Wextra", "-fPIC", "-fopenmp", "-ffp-contract=off"]
+    if force or _newer(out, deps):
+        _run(["g++"] + common + ["-shared"] + ccs + ["-o", out, "-L" + LIBDIR, "-lbeom_gpu", "-Wl,-rpath,$ORIGIN"])
+    exe = os.path.join(LIBDIR, "beom_run")
+    if force or _newer(exe, deps + [os.path.join(HOST_SRC, "main.cc"), out]):
+        _run(["g++"] + common + [os.path.join(HOST_SRC, "main.cc"), "-o", exe, "-L" + LIBDIR, "-lbeom_host", "-lbeom_gpu",
+                                 "-Wl,-rpath,$ORIGIN"])
+    return out
+
+
+def build_oracle(force: bool = False) -> str:
+    src = os.path.join(ORACLE, "beom_oracle.c")
+    deps = [src, os.path.join(ORACLE, "beom_oracle.h"), os.path.join(ROOT, "include", "beom_gpu.h")]
+    out = os.path.join(ORACLE, "libbeom_oracle.so")
+    if force or _newer(out, deps):
+        _run(["gcc", "-O2", "-ffp-contract=off", "-Wall", "-Wextra", "-fPIC", "-shared", src, "-o", out, "-lm"])
+    omp = os.path.join(ORACLE, "libbeom_oracle_omp.so")
+    if force or _newer(omp, deps):
+        _run(["gcc", "-O3", "-march=x86-64-v3", "-fopenmp", "-Wall", "-fPIC", "-shared", src, "-o", omp, "-lm"])
+    return out
+
+
+def build_all(force: bool = False) -> None:
+    build_gpu(force)
+    build_host(force)
+    build_oracle(force)
+
+
+if __name__ == "__main__":
+    build_all(force="--force" in sys.argv)

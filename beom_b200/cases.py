@@ -1,0 +1,399 @@
+"""Input generators for the reference's test cases, restated in numpy.
+
+The reference ships Octave scripts (``testcases/*.m``) that write little-endian float32, column-major
+``.bin`` inputs and print a parameter block (``testcases/print_params.m``) to paste into
+``shared_mod.f95``.  Neither Octave nor MATLAB exists in this environment, so each generator below
+follows its script line by line (cited) and writes byte-compatible files; ``print_params`` reproduces
+the *printf rounding* of the script, which changes the numbers the model actually runs with
+(e.g. ``cext`` is printed with ``%0.1f``).
+
+Rounding: MATLAB/Octave ``round`` is half-away-from-zero (``_mround``), unlike Python's.
+"""
+from __future__ import annotations
+
+import math
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+
+
+def _mround(x: float) -> int:
+    return int(math.floor(x + 0.5)) if x >= 0 else -int(math.floor(-x + 0.5))
+
+
+def fwrite_r4(path: str, arr: np.ndarray) -> None:
+    """fwrite(fid, arr, 'real*4', 0, 'ieee-le'): column-major float32 (written plane by plane)."""
+    a = np.asarray(arr)
+    if a.dtype != np.float32:
+        a = a.astype(np.float64).astype("<f4")
+    if a.ndim <= 2:
+        a.flatten(order="F").tofile(path)
+        return
+    tail = a.shape[2:]
+    with open(path, "wb") as f:
+        for flat in range(int(np.prod(tail))):
+            idx = np.unravel_index(flat, tail, order="F")
+            np.ascontiguousarray(a[(slice(None), slice(None)) + tuple(idx)].T).tofile(f)
+
+
+def get_nbr_deg_freedom(h_bo: np.ndarray) -> int:
+    """testcases/get_nbr_deg_freedom.m:11-52."""
+    hdry = 1.0e-3
+    h = np.array(h_bo, dtype=np.float64, copy=True)
+    h[h < 2.0 * hdry] = 0.0
+    h[0, :] = 0.0
+    h[-1, :] = 0.0
+    h[:, 0] = 0.0
+    h[:, -1] = 0.0
+    lm, mm = h.shape[0] - 2, h.shape[1] - 2
+    mask = np.zeros((lm + 4, mm + 4))
+    mask[1:-1, 1:-1] = h > hdry
+    neig = mask[1:-1, 1:-1] + mask[0:-2, 1:-1] + mask[1:-1, 0:-2] + mask[0:-2, 0:-2]
+    return int(np.count_nonzero(neig > 0))
+
+
+def print_params(lm, mm, nlay, ndeg, dl, cext, f0, rhon, topl, dt_s, dt_o, dt_r, dt3d, bvis, dvis, bdrg,
+                 hmin, hsbl, hbbl, g_fb, uadv, qdrg, ocrp, rsta, xper, yper, diag, tauw, idir, odir, desc,
+                 extra: dict | None = None) -> str:
+    """testcases/print_params.m:13-92 -- returns the block of Fortran assignments it displays."""
+    rhon = np.atleast_1d(np.asarray(rhon, dtype=np.float64))
+    topl = np.atleast_1d(np.asarray(topl, dtype=np.float64))
+    out = []
+    out.append("lm         = %d" % lm)
+    out.append("mm         = %d" % mm)
+    out.append("nlay       = %d" % nlay)
+    out.append("ndeg       = %d" % ndeg)
+    if dl < 1.0e3:
+        out.append("dl         = " + "%#0.0f" % dl)
+    elif (dl - math.floor(dl / 1.0e3) * 1.0e3) > 1.0:
+        out.append("dl         = " + "%g" % (dl / 1.0e3) + "e3")
+    else:
+        out.append("dl         = " + "%#0.0f" % (dl / 1.0e3) + "e3")
+    out.append("cext       = " + "%0.1f" % cext)
+    if abs(f0) < 1.0e-4:
+        out.append("f0         = " + "%e" % f0)
+    elif abs(f0) > 1.001e-4:
+        out.append("f0         = " + "%0.3f" % (f0 / 1.0e-4) + "e-4")
+    else:
+        out.append("f0         = " + "%#0.0f" % (f0 / 1.0e-4) + "e-4")
+    if np.all((rhon * 1.0e3 - np.floor(rhon) * 1.0e3) < 1.0):
+        strg = "".join("%#0.0f," % r for r in rhon)
+    else:
+        strg = "".join("%0.3f," % r for r in rhon)
+    out.append("rhon(nlay) = (/" + strg[:-1] + "/)")
+    strg = "".join("%f," % t for t in topl)
+    out.append("topl(nlay) = (/" + strg[:-1] + "/)")
+    out.append("dt_s       = " + "%#f" % dt_s)
+    out.append("dt_o       = " + "%#f" % dt_o)
+    out.append("dt_r       = " + ("%#f" % dt_r if dt_r > 0.0 else "%#0.0f" % dt_r))
+    out.append("dt3d       = " + ("%#f" % dt3d if dt3d > 0.0 else "%#0.0f" % dt3d))
+    out.append("bvis       = " + ("%#f" % bvis if bvis > 0.0 else "%#0.0f" % bvis))
+    out.append("dvis       = " + ("%#0.3f" % dvis if dvis > 0.0 else "%#0.0f" % dvis))
+    out.append("bdrg       = " + ("%e" % bdrg if bdrg > 0.0 else "%#0.0f" % bdrg))
+    out.append("hmin       = " + "%#f" % hmin)
+    for name, val in (("hsbl", hsbl), ("hbbl", hbbl), ("g_fb", g_fb), ("uadv", uadv), ("qdrg", qdrg),
+                      ("ocrp", ocrp), ("rsta", rsta), ("xper", xper), ("yper", yper), ("diag", diag)):
+        out.append("%-10s = " % name + "%#0.0f" % val)
+    strg = "".join("%#0.2f," % t for t in tauw)
+    out.append("tauw       = (" + strg[:-1] + ")")
+    out.append("idir       = '" + idir + "'")
+    out.append("odir       = '" + odir + "'")
+    out.append("desc       = '" + desc + "'")
+    # parameters print_params.m has no slot for (rgld, mcbc, svis, tdrg, topt, plum): appended verbatim
+    for k, v in (extra or {}).items():
+        out.append("%-10s = %s" % (k, v))
+    return "\n".join(out) + "\n"
+
+
+@dataclass
+class Case:
+    name: str
+    lm: int
+    mm: int
+    nlay: int
+    ndeg: int
+    params_text: str
+    files: dict = field(default_factory=dict)  # name -> float array in the script's (i, j, ...) shape
+    info: dict = field(default_factory=dict)
+
+    def write(self, directory: str) -> str:
+        """Write the .bin inputs and the parameter block (``shared_mod_block.f95``); returns its path."""
+        os.makedirs(directory, exist_ok=True)
+        for name, arr in self.files.items():
+            fwrite_r4(os.path.join(directory, name + ".bin"), arr)
+        d = directory if directory.endswith("/") else directory + "/"
+        text = self.params_text.replace("@DIR@", d)
+        path = os.path.join(directory, "shared_mod_block.f95")
+        with open(path, "w") as f:
+            f.write(text)
+        return path
+
+
+def _edge_fill(tmp: np.ndarray) -> np.ndarray:
+    """tmp(1,:)=tmp(2,:); tmp(:,1)=tmp(:,2); tmp(end,:)=tmp(end-1,:); tmp(:,end)=tmp(:,end-1)."""
+    tmp[0, ...] = tmp[1, ...]
+    tmp[:, 0, ...] = tmp[:, 1, ...]
+    tmp[-1, ...] = tmp[-2, ...]
+    tmp[:, -1, ...] = tmp[:, -2, ...]
+    return tmp
+
+
+def stommel1948(dl: float = 100.0e3, dt_s: float = 40.0) -> Case:
+    """testcases/stommel1948.m:17-88.  ``dl`` may be changed to get a smaller/larger grid."""
+    lam = 1.0e7
+    b = 2.0 * math.pi * 1.0e6
+    lm = _mround(lam / dl)
+    mm = _mround(b / dl)
+    rhon = 1027.0
+    hfla = 200.0
+    F = 0.1 / rhon
+    R = 2.0e-4
+    beta = 1.0e-11
+    fmin = 0.0
+    grav = 9.8
+    xs = (np.arange(lm) + 0.5) * dl
+    ys = (np.arange(mm) + 0.5) * dl
+    yy = np.broadcast_to(ys[None, :], (lm, mm))
+    h_bo = np.zeros((lm + 2, mm + 2))
+    h_bo[1:-1, 1:-1] = hfla
+    ndeg = get_nbr_deg_freedom(h_bo)
+    fcor = np.empty((lm, mm))
+    for j in range(1, mm + 1):
+        fcor[:, j - 1] = fmin + (j - 0.5) * dl * beta
+    tausx = -rhon * F * np.cos(math.pi * yy / b)
+    tausy = np.zeros_like(tausx)
+    tmp = np.full((lm + 2, mm + 2), np.nan)
+    tmp[1:-1, 1:-1] = fcor
+    fcor_file = _edge_fill(tmp)
+    tmp = np.full((lm + 2, mm + 2, 2), np.nan)
+    tmp[1:-1, 1:-1, 0] = tausx
+    tmp[1:-1, 1:-1, 1] = tausy
+    taus_file = _edge_fill(tmp)
+    cext = math.sqrt(grav * h_bo.max())
+    text = print_params(lm, mm, 1, ndeg, dl, cext, 0.0, [rhon], [0.0], dt_s, 1.0, 0.0, 0.0, 0.0, 0.0, R, 1.0, 10.0, 10.0,
+                        1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, [0, 0], "@DIR@", "@DIR@", "Test-case for Stommel 1948")
+    # analytical solution, stommel1948.m:31-36, 98-104
+    alpha = hfla * beta / R
+    gamma = F * math.pi / R / b
+    A = -0.5 * alpha + math.sqrt(0.25 * alpha ** 2 + (math.pi / b) ** 2)
+    B = -0.5 * alpha - math.sqrt(0.25 * alpha ** 2 + (math.pi / b) ** 2)
+    p = (1.0 - math.exp(B * lam)) / (math.exp(A * lam) - math.exp(B * lam))
+    q = 1.0 - p
+    xx = np.broadcast_to(xs[:, None], (lm, mm))
+    eta = (-F / grav / hfla * (np.exp(A * xx) * p / A + np.exp(B * xx) * q / B)
+           - (b / math.pi) ** 2 * F / grav / hfla * (p * A * np.exp(A * xx) + q * B * np.exp(B * xx)) * (np.cos(math.pi * yy / b) - 1.0)
+           - (fcor * gamma / grav * (b / math.pi) ** 2 * np.sin(math.pi * yy / b)
+              + beta * gamma / grav * (b / math.pi) ** 3 * (np.cos(math.pi * yy / b) - 1.0))
+           * (p * np.exp(A * xx) + q * np.exp(B * xx) - 1.0))
+    return Case("stommel1948", lm, mm, 1, ndeg, text, {"fcor": fcor_file, "taus": taus_file},
+                {"eta_analytic": eta, "hfla": hfla})
+
+
+def lock_exchange(dt_s: float = 5.0) -> Case:
+    """testcases/lock_exchange.m:11-64."""
+    hmax, nlay = 20.0, 2
+    rhon = [1025.0, 1030.0]
+    topl = [0.0, 0.5]
+    grav, dl, lx, mm = 9.8, 400.0, 64.0e3, 1
+    hmin = 0.005
+    dt_o = 1.0 / 24.0
+    hsal = 10.0 * hmin
+    lm = _mround(lx / dl)
+    h_bo = hmax * np.ones((lm + 2, mm + 2))
+    h_bo[:, 0] = 0.0
+    h_bo[:, -1] = 0.0
+    h_bo[0, :] = 0.0
+    h_bo[-1, :] = 0.0
+    ndeg = get_nbr_deg_freedom(h_bo)
+    cext = math.sqrt(grav * h_bo.max())
+    cint = 0.5 * math.sqrt(grav * hmax * (rhon[1] - rhon[0]) / rhon[1])
+    n = np.zeros((lm + 2, mm + 2, nlay))
+    u = np.zeros_like(n)
+    v = np.zeros_like(n)
+    half = _mround(0.5 * (lm + 2))
+    n[:half, :, 1] = 0.5 * hmax - 4.0 * hsal
+    n[half:, :, 1] = -0.5 * hmax + 4.0 * hsal
+    init = np.stack([n, u, v], axis=3)
+    text = print_params(lm, mm, nlay, ndeg, dl, cext, 0.0, rhon, topl, dt_s, dt_o, 0.0, 0.0, 0.0, 0.03, 0.0, hmin, 10.0,
+                        10.0, 1.0, 1.0, 0.0, 0.0, 0, 0.0, 0.0, 0.0, [0, 0], "@DIR@", "@DIR@", "Test-case for lock-exchange")
+    return Case("lock_exchange", lm, mm, nlay, ndeg, text, {"init": init}, {"cint": cint, "hsal": hsal, "hmax": hmax})
+
+
+def unstable_jet(dl: float = 15.0e3, dt_s: float = 50.0) -> Case:
+    """testcases/unstable_jet.m:8-66 (single layer, doubly periodic)."""
+    hshf = 5.0
+    lx, ly = 3000.0e3, 4000.0e3
+    rhon = 1030.0
+    lm = _mround(lx / dl)
+    lm += (lm % 2 == 0)
+    mm = _mround(ly / dl)
+    mm += (mm % 2 == 0)
+    nlay, grav, fcor = 1, 9.8, 0.5e-4
+    xs = np.arange(1, lm + 3) - 1.5
+    ys = np.arange(1, mm + 3) - 1.5
+    xx = np.broadcast_to(xs[:, None], (lm + 2, mm + 2)).copy()
+    yy = np.broadcast_to(ys[None, :], (lm + 2, mm + 2)).copy()
+    xx = xx - xx.mean()
+    yy = yy - yy.mean()
+    h_bo = hshf + 0.1 * hshf * np.cos(4.0 * math.pi * xx / lm)
+    h_bo[h_bo < 1.0] = 0.0
+    h_bo[0, :] = 0.0
+    h_bo[-1, :] = 0.0
+    h_bo[:, 0] = 0.0
+    h_bo[:, -1] = 0.0
+    cext = math.sqrt(grav * h_bo.max())
+    ndeg = get_nbr_deg_freedom(h_bo)
+    n = np.zeros((lm + 2, mm + 2, nlay))
+    u = np.zeros_like(n)
+    v = np.zeros_like(n)
+    n[:, :, 0] = 1.0 * np.exp(-yy ** 2 / (0.1 * mm) ** 2)
+    for iy in range(2, mm + 2):  # 1-based iy = 2 : mm + 1
+        u[:, iy - 1, :] = (n[:, iy, :] - n[:, iy - 2, :]) / (2.0 * dl) * grav / abs(fcor) * (-1.0)
+    init = np.stack([n, u, v], axis=3)
+    text = print_params(lm, mm, nlay, ndeg, dl, cext, fcor, [rhon], [0.0], dt_s, 2.0, 0.0, 0.0, 0.0, 0.2, 0.0, 0.1, 10.0,
+                        10.0, 1.0, 1.0, 0.0, 0.0, 0.0, 1.0, 1.0, 1.0, [0, 0], "@DIR@", "@DIR@",
+                        "Test-case for barotropic instability")
+    return Case("unstable_jet", lm, mm, nlay, ndeg, text, {"h_bo": h_bo, "init": init}, {})
+
+
+def sill_exchange3D(lx: float = 50.0e3, ly: float = 200.0e3, dt_s: float = 30.0) -> Case:
+    """testcases/sill_exchange3D.m:6-155."""
+    ocrp = 1
+    hmax, dt_r, bdrg, nlay = 700.0, 0.0, 0.0, 2
+    fcor = 0.00014087
+    dl = 400.0
+    lm = _mround(lx / dl)
+    mm = _mround(ly / dl)
+    lm += (lm % 2 == 0)
+    mm += (mm % 2 == 0)
+    npts = 15
+    grav = 9.8
+    rhon = [1027.47, 1027.75]
+    hsill = 400.0
+    topl = [0.0, 0.1428]
+    xs = (np.arange(1, lm + 3) - 1.5) * dl
+    ys = (np.arange(1, mm + 3) - 1.5) * dl
+    yy = np.broadcast_to(ys[None, :], (lm + 2, mm + 2)).copy()
+    xx = np.broadcast_to(xs[:, None], (lm + 2, mm + 2)).copy()
+    xx = xx - xx.mean()
+    yy = yy - yy.mean()
+    h_bo = hsill * np.exp(-(yy / (50.0 * dl)) ** 2)
+    h_bo = hmax - h_bo
+    ndeg = get_nbr_deg_freedom(h_bo)
+    cext = math.sqrt(grav * h_bo.max())
+    n = np.zeros((lm + 2, mm + 2, nlay))
+    u = np.zeros_like(n)
+    v = np.zeros_like(n)
+    hsal = 5.0
+    hmin = hsal / 10.0
+    k = _mround(0.6 * (mm + 2))
+    n[:, :k, 1] = 0.0
+    n[:, k:, 1] = np.minimum(-h_bo[:, k:] + hmax - 100.0 + 4.0 * hsal, 0.0)
+    nort = np.zeros((lm + 2, mm + 2, 3))
+    sout = np.zeros((lm + 2, mm + 2, 3))
+    dt = 0.5 * dl / cext
+    widt = npts * dl
+    for j in range(1, mm + 3):
+        xpos = j - 1.5 + npts - mm
+        xpos = max(xpos, 0.0)
+        xpos = min(xpos, npts - 0.5)
+        nort[:, j - 1, 1:3] = dt * cext / widt * xpos / (npts - xpos)
+        nort[:, j - 1, 0] = dt / (31.0 * 24.0 * 3600.0) * xpos / npts
+    for j in range(1, mm + 3):
+        xpos = npts - (j - 1.5)
+        xpos = max(xpos, 0.0)
+        xpos = min(xpos, npts - 0.5)
+        sout[:, j - 1, 1:3] = dt * cext / widt * xpos / (npts - xpos)
+        sout[:, j - 1, 0] = dt / (31.0 * 24.0 * 3600.0) * xpos / npts
+    nudg = np.maximum(np.maximum(np.zeros_like(nort), nort), sout)
+    nudg[0, :, :] = 0.0
+    nudg[-1, :, :] = 0.0
+    init = np.stack([n, u, v], axis=3)
+    text = print_params(lm, mm, nlay, ndeg, dl, cext, fcor, rhon, topl, dt_s, 0.01, dt_r, 0.0, 0.0, 0.9, bdrg, hmin, 5.0, 5.0,
+                        1.0, 1.0, 1.0, ocrp, 0.0, 0.0, 0.0, 0.0, [0, 0], "@DIR@", "@DIR@", "Test-case: 3D sill exchange")
+    return Case("sill_exchange3D", lm, mm, nlay, ndeg, text, {"init": init, "h_bo": h_bo, "nudg": nudg}, {"hsal": hsal})
+
+
+def conservation(outc: float = 0.0, topo: bool = True, lx: float = 600.0e3, dl: float = 10.0e3, dt_s: float = 50.0) -> Case:
+    """testcases/conservation.m:8-98 (two layers, doubly periodic, no forcing, plain forward-backward)."""
+    xper = yper = 1
+    nlay = 2
+    fcor = 1.0e-4
+    rhon = [1000.0 + 30.0 * k / nlay for k in range(1, nlay + 1)]
+    topl = [(k - 1) / nlay for k in range(1, nlay + 1)]
+    hfla, grav = 200.0, 9.8
+    lm = _mround(lx / dl)
+    lm += (lm % 2 == 0)
+    mm = lm
+    a = np.arange(1, lm + 3) - 1.5
+    xs = (a - a.mean()) * dl
+    ys = xs.copy()
+    xx = np.broadcast_to(xs[:, None], (lm + 2, mm + 2))
+    yy = np.broadcast_to(ys[None, :], (lm + 2, mm + 2))
+    h_bo = hfla * np.ones((lm + 2, mm + 2))
+    if topo:
+        if outc:
+            h_bo = hfla - 0.5 * (2.0 - topl[-1] - topl[-2]) * hfla * np.exp(-(xx ** 2 + yy ** 2) / (0.25 * lx) ** 2)
+        else:
+            h_bo = hfla - 0.5 * (1.0 - topl[-1]) * hfla * np.exp(-(xx ** 2 + yy ** 2) / (0.25 * lx) ** 2)
+    h_bo = np.array(h_bo)
+    h_bo[0, :] = 0.0
+    h_bo[-1, :] = 0.0
+    h_bo[:, 0] = 0.0
+    h_bo[:, -1] = 0.0
+    ndeg = get_nbr_deg_freedom(h_bo)
+    n = np.zeros((lm + 2, mm + 2, nlay))
+    n[:, :, 0] = 1.0 * np.exp(-(xx ** 2 + yy ** 2) / (lx / 12.0) ** 2)
+    init = np.stack([n, np.zeros_like(n), np.zeros_like(n)], axis=3)
+    cext = math.sqrt(grav * h_bo.max())
+    files = {"init": init}
+    if topo:
+        files["h_bo"] = h_bo
+    text = print_params(lm, mm, nlay, ndeg, dl, cext, fcor, rhon, topl, dt_s, 0.5, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0, 10.0, 10.0,
+                        0.0, 1.0, 0.0, outc, 0.0, xper, yper, 1.0, [0, 0], "@DIR@", "@DIR@",
+                        "Test-case for integral conservation of properties")
+    return Case("conservation", lm, mm, nlay, ndeg, text, files, {})
+
+
+def synthetic_basin(n: int = 8192, nlay: int = 4, seed: int = 20261018, dt_s: float = 1.0, wind: bool = True,
+                    mm: int | None = None) -> Case:
+    """The throughput workload of BASELINE.json / SURVEY.md section 8(d): an n x n closed flat basin,
+    1 km mesh, ``nlay`` layers, Leith viscosity every step, generalized forward-backward, wind stress
+    0.1 cos(pi y / L) Pa, initial surface bump + interface noise.  Not a reference script."""
+    lm = n
+    mm = n if mm is None else mm
+    dl = 1000.0
+    rng = np.random.default_rng(seed)
+    rhon = [1025.0 + k for k in range(nlay)]
+    topl = [0.0, 0.1, 0.25, 0.5, 0.6, 0.7, 0.8, 0.9][:nlay]
+    h_bo = np.zeros((lm + 2, mm + 2), dtype=np.float32)
+    h_bo[1:-1, 1:-1] = 1.0
+    ndeg = (lm + 1) * (mm + 1)  # full rectangle: get_nbr_deg_freedom(h_bo) == (lm+1)(mm+1)
+    L = lm * dl
+    xs = ((np.arange(lm + 2) - 0.5) * dl - 0.5 * L).astype(np.float64)
+    ys = ((np.arange(mm + 2) - 0.5) * dl - 0.5 * mm * dl).astype(np.float64)
+    init = np.zeros((lm + 2, mm + 2, nlay, 3), dtype=np.float32)
+    r2 = xs[:, None] ** 2 + ys[None, :] ** 2
+    init[:, :, 0, 0] = (0.5 * np.exp(-r2 / (0.1 * L) ** 2)).astype(np.float32)
+    for k in range(nlay):
+        init[:, :, k, 0] += rng.uniform(-0.01, 0.01, size=(lm + 2, mm + 2)).astype(np.float32)
+    files = {"init": init}
+    if wind:
+        taus = np.zeros((lm + 2, mm + 2, 2), dtype=np.float32)
+        taus[:, :, 0] = (0.1 * np.cos(math.pi * (ys + 0.5 * mm * dl) / (mm * dl)))[None, :].astype(np.float32)
+        files["taus"] = taus
+    text = print_params(lm, mm, nlay, ndeg, dl, 198.0, 1.0e-4, rhon, topl, dt_s, dt_s, 0.0, 0.0, 0.0, 0.2, 0.0, 1.0, 10.0, 10.0,
+                        1.0, 1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, [0, 0], "@DIR@", "@DIR@",
+                        "synthetic %dx%dx%d basin" % (lm, mm, nlay))
+    return Case("synthetic_basin", lm, mm, nlay, ndeg, text, files, {})
+
+
+CASES = {
+    "stommel1948": stommel1948,
+    "lock_exchange": lock_exchange,
+    "unstable_jet": unstable_jet,
+    "sill_exchange3D": sill_exchange3D,
+    "conservation": conservation,
+    "synthetic_basin": synthetic_basin,
+}

@@ -1,0 +1,739 @@
+// beom_gpu.cu -- the C ABI of include/beom_gpu.h: context, HBM layout, upload/download, step
+// sequencing (first_three_timesteps / gener_forward_backward, private_mod.f95:2151-2316).
+// sm_100a only; no CPU path exists in this library.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "comm.h"
+#include "dev.cuh"
+#include "fused.cuh"
+#include "split.cuh"
+
+using namespace beom;
+
+namespace {
+
+std::string g_err;
+int fail(int code, const char *fmt, ...) {
+  char b[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(b, sizeof b, fmt, ap);
+  va_end(ap);
+  g_err = b;
+  return code;
+}
+#define CK(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess) return fail(-100 - (int)e_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+struct Ctx {
+  bool ready = false;
+  beom_params P;
+  beom_gpu_options opt;
+  int lm = 0, mm = 0, nlay = 0, ndeg = 0;
+  int rank = 0, nranks = 1;
+  int j0 = 1, j1 = 1;      // owned grid rows (inclusive)
+  int p_lo = 1, p_hi = 0;  // vector points held on this device (owned + halo rows), inclusive
+  int NX = 0, NY = 0;
+  size_t plane = 0;
+  Dev D;  // template for kernel arguments
+  std::vector<void *> allocs;
+  // host-side maps
+  std::vector<int> cell_of_point;  // [ndeg+1], -1 = not on this device, -2 = orphan (periodic duplicate)
+  int *d_cell = nullptr;
+  std::vector<int> orphans;        // vector indices whose dense cell is a periodic mirror
+  std::vector<double> orphan_val;  // [3][nlay][norph] frozen hlay,u,v
+  int nmir = 0;
+  int *d_mir_dst = nullptr, *d_mir_src = nullptr;
+  SegDev *d_seg = nullptr;
+  int nseg = 0;
+  // buffers
+  uint8_t *flags = nullptr;
+  double *st[5][2] = {{nullptr}};  // hlay,u,v,h_u,h_v x {A,B}
+  int cur = 0;                     // which buffer holds the current state
+  double *rs[3] = {nullptr}, *dx[4] = {nullptr}, *dy[4] = {nullptr};
+  int rs_o = 0, dx_o = 0, dy_o = 0;  // index of the oldest slot
+  double *stage = nullptr;           // (ndeg_local) * nlay * 3 doubles: vector-layout staging
+  size_t stage_elems = 0;
+  bool split_alloc = false;
+  bool use_fused = false;
+  bool any_taus = false;
+  bool visc_valid = false;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  long long launches = 0;
+  int n_3d = 1;
+};
+Ctx g;
+
+template <class T>
+int dalloc(T **p, size_t n, bool zero = true) {
+  void *q = nullptr;
+  CK(cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T)));
+  if (zero) CK(cudaMemsetAsync(q, 0, std::max<size_t>(n, 1) * sizeof(T), g.stream));
+  g.allocs.push_back(q);
+  *p = (T *)q;
+  return 0;
+}
+
+dim3 cell_grid(const Dev &D, int layers, dim3 block, int xpad = 0, int ypad = 0) {
+  const int w = D.x_hi - D.x_lo + 1 + xpad, h = D.y_hi - D.y_lo + 1 + ypad;
+  return dim3((unsigned)((w + block.x - 1) / block.x), (unsigned)((h + block.y - 1) / block.y), (unsigned)layers);
+}
+const dim3 kBlock(128, 2, 1);
+
+// Upload one reference-layout array (vector of ndeg+1 doubles per plane) into dense planes.
+int upload_planes(double *dense, const double *vec, int nplanes) {
+  const int n = g.p_hi - g.p_lo + 1;
+  if (n <= 0) return 0;
+  for (int p = 0; p < nplanes; p++) {
+    CK(cudaMemcpyAsync(g.stage, vec + (size_t)p * (g.ndeg + 1) + g.p_lo, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+    k_scatter<double><<<(n + 255) / 256, 256, 0, g.stream>>>(dense + (size_t)p * g.plane, g.stage, g.d_cell, g.p_lo, n);
+    g.launches++;
+    CK(cudaStreamSynchronize(g.stream));  // staging buffer is reused
+  }
+  return 0;
+}
+
+int mirror(double *field, int nplanes) {
+  if (g.nmir == 0) return 0;
+  k_mirror<<<(g.nmir + 127) / 128, 128, 0, g.stream>>>(field, g.plane, nplanes, g.d_mir_dst, g.d_mir_src, g.nmir);
+  g.launches++;
+  return 0;
+}
+
+void set_state_pointers(Dev &D) {
+  D.hlay = g.st[0][g.cur]; D.u = g.st[1][g.cur]; D.v = g.st[2][g.cur]; D.h_u = g.st[3][g.cur]; D.h_v = g.st[4][g.cur];
+  D.rs1 = g.rs[g.rs_o]; D.rs2 = g.rs[(g.rs_o + 1) % 3]; D.rs_new = g.rs[(g.rs_o + 2) % 3];
+  D.dx1 = g.dx[g.dx_o]; D.dx2 = g.dx[(g.dx_o + 1) % 4]; D.dx3 = g.dx[(g.dx_o + 2) % 4]; D.dx_new = g.dx[(g.dx_o + 3) % 4];
+  D.dy1 = g.dy[g.dy_o]; D.dy2 = g.dy[(g.dy_o + 1) % 4]; D.dy3 = g.dy[(g.dy_o + 2) % 4]; D.dy_new = g.dy[(g.dy_o + 3) % 4];
+}
+
+int alloc_split_buffers() {
+  if (g.split_alloc) return 0;
+  const size_t pl = g.plane, nl = (size_t)g.nlay;
+  Dev &D = g.D;
+  int rc;
+  if ((rc = dalloc(&D.mont, pl * nl)) || (rc = dalloc(&D.rvor, pl * nl)) || (rc = dalloc(&D.pvor, pl * nl)) || (rc = dalloc(&D.dive, pl * nl)) ||
+      (rc = dalloc(&D.d2hx, pl * nl)) || (rc = dalloc(&D.d2hy, pl * nl)) || (rc = dalloc(&D.v_cc, pl * nl)) || (rc = dalloc(&D.v_ll, pl * nl)))
+    return rc;
+  if (g.P.svis > 0.0)
+    if ((rc = dalloc(&D.delu, pl * nl)) || (rc = dalloc(&D.delv, pl * nl)) || (rc = dalloc(&D.UU4, pl * nl)) || (rc = dalloc(&D.VV4, pl * nl))) return rc;
+  g.split_alloc = true;
+  return 0;
+}
+
+// distribute_stress, private_mod.f95:1921-2149
+int run_stress() {
+  Dev D = g.D;
+  set_state_pointers(D);
+  if (!(D.has_wind || D.has_bdrg || D.has_tdrg)) return 0;
+  k_stress_fractions<<<cell_grid(D, 1, kBlock, 1, 1), kBlock, 0, g.stream>>>(D);
+  g.launches++;
+  if (D.has_bdrg) { k_stress_drag<<<cell_grid(D, 1, kBlock), kBlock, 0, g.stream>>>(D, 0); g.launches++; }
+  if (D.has_tdrg) { k_stress_drag<<<cell_grid(D, 1, kBlock), kBlock, 0, g.stream>>>(D, 1); g.launches++; }
+  k_stress_apply<<<cell_grid(D, g.nlay, kBlock), kBlock, 0, g.stream>>>(D);
+  g.launches++;
+  if (D.has_wind) mirror(D.tt3d, 2 * g.nlay);
+  if (D.has_bdrg) mirror(D.tb3d, 2 * g.nlay);
+  if (D.has_tdrg) mirror(D.tu3d, 2 * g.nlay);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+// One step of the split path: the reference's call sequence, one kernel per loop.
+int step_split(int tstp, bool upst, bool first_three) {
+  int rc = alloc_split_buffers();
+  if (rc) return rc;
+  Dev D = g.D;
+  set_state_pointers(D);
+  const int nl = g.nlay;
+  const dim3 grid1 = cell_grid(D, 1, kBlock), gridL = cell_grid(D, nl, kBlock);
+  const bool rgld = g.P.rgld > 0.5;
+  if (first_three) {  // pm:2166-2177
+    k_centred_flux<<<gridL, kBlock, 0, g.stream>>>(D);
+    g.launches++;
+    mirror(D.h_u, nl);
+    mirror(D.h_v, nl);
+  } else if (rgld) {  // pm:2237-2257
+    k_upstream_flux<<<gridL, kBlock, 0, g.stream>>>(D);
+    g.launches++;
+    mirror(D.h_u, nl);
+    mirror(D.h_v, nl);
+  }
+  k_update_h<<<grid1, kBlock, 0, g.stream>>>(D);  // pm:2181 / 2259
+  g.launches++;
+  if (rgld) { k_rgld_correct<<<grid1, kBlock, 0, g.stream>>>(D); g.launches++; }
+  mirror(D.hlay, nl);
+  g.rs_o = (g.rs_o + 1) % 3;
+
+  k_diag<<<gridL, kBlock, 0, g.stream>>>(D);  // pm:2187 / 2266
+  g.launches++;
+  if (g.nmir) { mirror(D.mont, nl); mirror(D.rvor, nl); mirror(D.pvor, nl); mirror(D.dive, nl); mirror(D.d2hx, nl); mirror(D.d2hy, nl); }
+  if (first_three || (g.P.dvis > 1.e-3 && upst) || g.P.svis > 0) {  // pm:2188 / 2268-2270
+    k_visc<<<gridL, kBlock, 0, g.stream>>>(D);
+    g.launches++;
+    if (g.nmir) { mirror(D.v_cc, nl); mirror(D.v_ll, nl); }
+    if (g.P.svis > 0.0) {
+      if (g.nmir) { mirror(D.delu, nl); mirror(D.delv, nl); }
+      k_biharm<<<gridL, kBlock, 0, g.stream>>>(D);
+      g.launches++;
+      if (g.nmir) { mirror(D.UU4, nl); mirror(D.VV4, nl); }
+    }
+  }
+  for (int pass = 0; pass < 2; pass++) {  // pm:2193-2199 / 2276-2282
+    const bool do_u = ((tstp % 2 == 0) == (pass == 0));
+    if (do_u) {
+      k_update_u<<<gridL, kBlock, 0, g.stream>>>(D);
+      g.launches++;
+      mirror(D.u, nl);
+      mirror(D.h_u, nl);
+    } else {
+      k_update_v<<<gridL, kBlock, 0, g.stream>>>(D);
+      g.launches++;
+      mirror(D.v, nl);
+      mirror(D.h_v, nl);
+    }
+  }
+  g.dx_o = (g.dx_o + 1) % 4;
+  g.dy_o = (g.dy_o + 1) % 4;
+  if (g.D.has_nudg && g.P.mcbc < 0.5 && g.nseg > 0 && g.opt.reserved_[0] == 0) {  // pm:2201-2204 / 2285-2288
+    for (int pass = 0; pass < 2; pass++) {
+      k_obc<<<(g.nseg + 63) / 64, 64, 0, g.stream>>>(D, g.d_seg, g.nseg, pass);
+      g.launches++;
+    }
+    if (g.nmir) { mirror(D.u, nl); mirror(D.v, nl); mirror(D.h_u, nl); mirror(D.h_v, nl); }
+  }
+  if (rgld) return fail(-30, "rgld = 1 (surf_pressure) is not implemented on the device yet");
+  CK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *beom_gpu_version(void) { return "beom_b200 0.1 (sm_100a)"; }
+int beom_gpu_abi_version(void) { return BEOM_ABI_VERSION; }
+int beom_gpu_last_error(char *buf, int len) {
+  if (buf && len > 0) snprintf(buf, (size_t)len, "%s", g_err.c_str());
+  return (int)g_err.size();
+}
+void beom_gpu_default_options(beom_gpu_options *opt) {
+  memset(opt, 0, sizeof *opt);
+  opt->device = -1;
+  opt->fused = 1;
+  opt->rank = 0;
+  opt->nranks = 1;
+}
+const char *beom_gpu_path(void) { return g.use_fused ? "fused" : "split"; }
+long long beom_gpu_launch_count(void) { return g.launches; }
+
+int beom_gpu_finalize(void) {
+  if (g.stream) cudaStreamSynchronize(g.stream);
+  for (void *p : g.allocs) cudaFree(p);
+  g.allocs.clear();
+  for (auto &e : g.ev)
+    if (e) { cudaEventDestroy(e); e = nullptr; }
+  if (g.stream) { cudaStreamDestroy(g.stream); g.stream = nullptr; }
+  g = Ctx();
+  return 0;
+}
+
+int beom_gpu_init(const beom_params *par, const beom_fields *fld, const beom_gpu_options *opt_in) {
+  if (g.ready) beom_gpu_finalize();
+  if (!par || !fld) return fail(-1, "beom_gpu_init: null argument");
+  beom_gpu_options opt;
+  if (opt_in) opt = *opt_in;
+  else beom_gpu_default_options(&opt);
+  if (!fld->neig || !fld->subc || !fld->mk_u || !fld->mk_v || !fld->mk_n || !fld->mkpe || !fld->mkpi || !fld->fcor || !fld->h_th)
+    return fail(-2, "beom_gpu_init: a required static field is NULL");
+  if (par->nlay < 1 || par->nlay > BEOM_MAXLAY) return fail(-3, "beom_gpu_init: nlay out of range");
+  if (fld->nudg && !fld->fnud) return fail(-4, "beom_gpu_init: nudg given without fnud");
+
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(-10, "beom_gpu_init: no CUDA device (%s); this library has no CPU fallback", e == cudaSuccess ? "count = 0" : cudaGetErrorString(e));
+  int dev = opt.device;
+  if (dev < 0) {
+    const char *lr = getenv("LOCAL_RANK");
+    dev = lr ? atoi(lr) % ndev : 0;
+  }
+  CK(cudaSetDevice(dev));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10) return fail(-11, "beom_gpu_init: device %d is sm_%d%d; kernels are built for sm_100a only", dev, prop.major, prop.minor);
+
+  g.P = *par;
+  g.opt = opt;
+  g.lm = par->lm; g.mm = par->mm; g.nlay = par->nlay; g.ndeg = par->ndeg;
+  g.rank = opt.nranks > 1 ? opt.rank : 0;
+  g.nranks = opt.nranks > 1 ? opt.nranks : 1;
+  CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&g.ev[0]));
+  CK(cudaEventCreate(&g.ev[1]));
+
+  const int lm = g.lm, mm = g.mm, nlay = g.nlay, ndeg = g.ndeg;
+  const size_t nd1 = (size_t)ndeg + 1;
+  const int32_t *si = fld->subc, *sj = fld->subc + nd1;
+
+  // y-slab owned by this rank: rows 1..mm+1 split evenly
+  {
+    const int rows = mm + 1, base = rows / g.nranks, rem = rows % g.nranks;
+    g.j0 = 1 + g.rank * base + std::min(g.rank, rem);
+    g.j1 = g.j0 + base + (g.rank < rem ? 1 : 0) - 1;
+    if (g.j1 < g.j0) return fail(-5, "beom_gpu_init: more ranks than grid rows");
+  }
+  g.NX = ((lm + 1 + 2 * G) + 15) / 16 * 16;
+  g.NY = (g.j1 - g.j0 + 1) + 2 * G;
+  g.plane = (size_t)g.NX * g.NY;
+  if (g.plane > 0x7fffffffull) return fail(-6, "beom_gpu_init: plane too large for 32-bit cell offsets");
+  const int j_off = G - g.j0;  // Y = j + j_off
+
+  // vector points on this device: rows j0-G .. j1+G (vector order is j outer, i inner: contiguous)
+  g.cell_of_point.assign(nd1, -1);
+  g.p_lo = ndeg + 1; g.p_hi = 0;
+  for (int p = 1; p <= ndeg; p++) {
+    const int j = sj[p], i = si[p];
+    if (j < g.j0 - G || j > g.j1 + G) continue;
+    if (i < 1 - GX0 || i + GX0 >= g.NX) return fail(-7, "beom_gpu_init: subc out of range at point %d", p);
+    g.cell_of_point[p] = (j + j_off) * g.NX + (i + GX0);
+    g.p_lo = std::min(g.p_lo, p);
+    g.p_hi = std::max(g.p_hi, p);
+  }
+  if (g.p_hi < g.p_lo) return fail(-8, "beom_gpu_init: no grid points on rank %d", g.rank);
+
+  // dense flags + point-of-cell map
+  std::vector<uint8_t> hflags(g.plane, 0);
+  std::vector<int> point_of_cell(g.plane, 0);
+  for (int p = g.p_lo; p <= g.p_hi; p++) {
+    const int c = g.cell_of_point[p];
+    if (c < 0) continue;
+    uint8_t f = F_ACT;
+    if (fld->mk_n[p] > 0.5) f |= F_N;
+    if (fld->mk_u[p] > 0.5) f |= F_U;
+    if (fld->mk_v[p] > 0.5) f |= F_V;
+    if (fld->mkpe[p] > 0.5) f |= F_PE;
+    if (fld->mkpi[p] > 0.5) f |= F_PI;
+    hflags[c] = f;
+    point_of_cell[c] = p;
+  }
+  // mirror cells: wherever neig(k,p) is not the point sitting at (i+di, j+dj) (periodic aliases,
+  // private_mod.f95:614-685).  A vector point whose own cell must show another point's values is an
+  // "orphan": nothing ever reads it and its masks are zero, so its state is frozen.
+  {
+    static const int di[8] = {1, 1, 0, -1, -1, -1, 0, 1}, dj[8] = {0, 1, 1, 1, 0, -1, -1, -1};
+    std::vector<int> mdst, msrc;
+    std::vector<int> alias_of_cell(g.plane, -1);
+    for (int p = g.p_lo; p <= g.p_hi; p++) {
+      if (g.cell_of_point[p] < 0) continue;
+      const int j = sj[p], i = si[p];
+      if (j < g.j0 - 1 || j > g.j1 + 1) continue;  // only cells whose neighbours are read
+      for (int k = 0; k < 8; k++) {
+        const int q = fld->neig[(size_t)p * 8 + k];
+        const int c = (j + dj[k] + j_off) * g.NX + (i + di[k] + GX0);
+        if (q == point_of_cell[c] && alias_of_cell[c] < 0) continue;
+        if (q == 0) {
+          if (alias_of_cell[c] == 0 || point_of_cell[c] == 0) continue;
+          return fail(-9, "beom_gpu_init: neig(%d,%d) = 0 but a grid point exists there", k + 1, p);
+        }
+        if (alias_of_cell[c] >= 0) {
+          if (alias_of_cell[c] != q) return fail(-9, "beom_gpu_init: inconsistent connectivity at point %d", p);
+          continue;
+        }
+        if (q < g.p_lo || q > g.p_hi || g.cell_of_point[q] < 0) {
+          if (g.nranks > 1) continue;  // alias source lives on another rank: filled by the halo exchange
+          return fail(-9, "beom_gpu_init: neig(%d,%d) = %d is out of range", k + 1, p, q);
+        }
+        alias_of_cell[c] = q;
+        if (point_of_cell[c] != 0) {  // orphan
+          const int o = point_of_cell[c];
+          if (fld->mk_n[o] > 0.5 || fld->mk_u[o] > 0.5 || fld->mk_v[o] > 0.5 ||
+              (fld->nudg && (fld->nudg[o] != 0.0 || fld->nudg[nd1 + o] != 0.0 || fld->nudg[2 * nd1 + o] != 0.0)))
+            return fail(-9, "beom_gpu_init: unsupported periodic connectivity (aliased point %d is not frozen)", o);
+          g.orphans.push_back(o);
+          g.cell_of_point[o] = -2;
+          point_of_cell[c] = 0;
+        }
+        mdst.push_back(c);
+        msrc.push_back(g.cell_of_point[q]);
+      }
+    }
+    // a mirror's source may itself have been turned into a mirror/orphan: forbid chains
+    for (size_t k = 0; k < msrc.size(); k++)
+      if (msrc[k] < 0) return fail(-9, "beom_gpu_init: chained periodic aliases are not supported");
+    g.nmir = (int)mdst.size();
+    for (int k = 0; k < g.nmir; k++) hflags[mdst[k]] = (uint8_t)(hflags[msrc[k]] & ~F_ACT);
+    if (g.nmir) {
+      int rc;
+      if ((rc = dalloc(&g.d_mir_dst, (size_t)g.nmir, false)) || (rc = dalloc(&g.d_mir_src, (size_t)g.nmir, false))) return rc;
+      CK(cudaMemcpy(g.d_mir_dst, mdst.data(), sizeof(int) * g.nmir, cudaMemcpyHostToDevice));
+      CK(cudaMemcpy(g.d_mir_src, msrc.data(), sizeof(int) * g.nmir, cudaMemcpyHostToDevice));
+    }
+    g.orphan_val.assign((size_t)3 * nlay * g.orphans.size(), 0.0);
+  }
+
+  int rc;
+  if ((rc = dalloc(&g.flags, g.plane, false))) return rc;
+  CK(cudaMemcpy(g.flags, hflags.data(), g.plane, cudaMemcpyHostToDevice));
+  if ((rc = dalloc(&g.d_cell, nd1, false))) return rc;
+  CK(cudaMemcpy(g.d_cell, g.cell_of_point.data(), sizeof(int) * nd1, cudaMemcpyHostToDevice));
+  const int nloc = g.p_hi - g.p_lo + 1;
+  g.stage_elems = (size_t)nloc * nlay * 3;
+  if ((rc = dalloc(&g.stage, g.stage_elems, false))) return rc;
+
+  // ---- Dev template ----
+  Dev &D = g.D;
+  memset(&D, 0, sizeof D);
+  D.NX = g.NX; D.NY = g.NY; D.plane = g.plane;
+  D.x_lo = 1 + GX0; D.x_hi = lm + 1 + GX0;
+  D.y_lo = G; D.y_hi = G + (g.j1 - g.j0);
+  D.i_off = GX0; D.j_off = j_off;
+  D.lm = lm; D.mm = mm; D.nlay = nlay;
+  D.flags = g.flags;
+  const size_t pl = g.plane, nl = (size_t)nlay;
+
+  double *tmp = nullptr;
+  if ((rc = dalloc(&tmp, pl))) return rc;
+  if ((rc = upload_planes(tmp, fld->fcor, 1))) return rc;
+  D.fcor = tmp;
+  if ((rc = dalloc(&tmp, pl))) return rc;
+  if ((rc = upload_planes(tmp, fld->h_th, 1))) return rc;
+  D.h_th = tmp;
+  D.has_nudg = 0;
+  if (fld->nudg) {
+    bool any = false;
+    for (size_t k = 0; k < 3 * nd1 && !any; k++) any = fld->nudg[k] != 0.0;
+    if (any) {
+      if ((rc = dalloc(&tmp, pl * 3))) return rc;
+      if ((rc = upload_planes(tmp, fld->nudg, 3))) return rc;
+      D.nudg = tmp;
+      D.has_nudg = 1;
+    }
+  }
+  D.has_tide = 0;
+  if (fld->tide && fld->w_ti != 0.0 && D.has_nudg) {
+    // tide(2,1,0:ndeg,3): de-interleave amplitude / phase into [3][2] planes
+    std::vector<double> v(nd1);
+    if ((rc = dalloc(&tmp, pl * 6))) return rc;
+    for (int c3 = 0; c3 < 3; c3++)
+      for (int a = 0; a < 2; a++) {
+        for (size_t p = 0; p < nd1; p++) v[p] = fld->tide[((size_t)c3 * nd1 + p) * 2 + a];
+        if ((rc = upload_planes(tmp + ((size_t)c3 * 2 + a) * pl, v.data(), 1))) return rc;
+      }
+    D.tide = tmp;
+    D.has_tide = 1;
+  }
+  if (fld->fnud && (D.has_nudg || g.P.variant != BEOM_VARIANT_STANDARD)) {
+    if ((rc = dalloc(&tmp, pl * nl * 3))) return rc;
+    if ((rc = upload_planes(tmp, fld->fnud, 3 * nlay))) return rc;
+    D.fnud = tmp;
+  }
+  D.has_hdot = 0;
+  if (fld->hdot) {
+    bool any = false;
+    for (size_t k = 0; k < nl * nd1 && !any; k++) any = fld->hdot[k] != 0.0;
+    if (any) {
+      if ((rc = dalloc(&tmp, pl * nl))) return rc;
+      if ((rc = upload_planes(tmp, fld->hdot, nlay))) return rc;
+      D.hdot = tmp;
+      D.has_hdot = 1;
+    }
+  }
+  g.any_taus = false;  // any(abs(taus) > 1.e-7), private_mod.f95:1945
+  if (fld->taus)
+    for (size_t k = 0; k < 2 * nd1 && !g.any_taus; k++) g.any_taus = std::fabs(fld->taus[k]) > 1.e-7;
+  D.has_wind = g.any_taus;
+  D.has_bdrg = par->bdrg > 1.e-7;
+  D.has_tdrg = par->tdrg > 1.e-7;
+  if (D.has_wind) {
+    if ((rc = dalloc(&tmp, pl * 2))) return rc;
+    if ((rc = upload_planes(tmp, fld->taus, 2))) return rc;
+    D.taus = tmp;
+    if ((rc = dalloc(&D.tt3d, pl * nl * 2)) || (rc = dalloc(&D.layt, pl * nl))) return rc;
+  }
+  if (D.has_bdrg)
+    if ((rc = dalloc(&D.tb3d, pl * nl * 2)) || (rc = dalloc(&D.layb, pl * nl)) || (rc = dalloc(&D.taub, pl * 2))) return rc;
+  if (D.has_tdrg)
+    if ((rc = dalloc(&D.tu3d, pl * nl * 2)) || (rc = dalloc(&D.layu, pl * nl)) || (rc = dalloc(&D.taum, pl * 2))) return rc;
+
+  // open-boundary segments as dense cells (private_mod.f95:1060-1240, columns 1,4,5,10,13,16)
+  g.nseg = 0;
+  if (fld->segm && fld->nseg > 0 && fld->flag_nudging) {
+    std::vector<SegDev> segs;
+    for (int s = 0; s < fld->nseg; s++) {
+      auto col = [&](int cidx) { return fld->segm[(size_t)(cidx - 1) * fld->nseg + s]; };
+      const int pw = col(10);
+      if (pw < 1 || sj[pw] < g.j0 || sj[pw] > g.j1) {
+        const int pf = col(1);
+        if (pf < 1 || sj[pf] < g.j0 || sj[pf] > g.j1) continue;
+      }
+      SegDev sd;
+      sd.zonal = col(4); sd.merid = col(5);
+      auto cell = [&](int p) { return (p >= 1 && p <= ndeg) ? g.cell_of_point[p] : -1; };
+      sd.c_face = cell(col(1)); sd.c_wet = cell(col(10)); sd.c_norm = cell(col(13)); sd.c_int = cell(col(16));
+      if (sd.c_face < 0 || sd.c_wet < 0 || sd.c_norm < 0 || sd.c_int < 0) {
+        if (par->mcbc < 0.5) return fail(-12, "beom_gpu_init: open-boundary segment %d touches a cell outside the grid", s + 1);
+        continue;
+      }
+      segs.push_back(sd);
+    }
+    g.nseg = (int)segs.size();
+    if (g.nseg) {
+      if ((rc = dalloc(&g.d_seg, (size_t)g.nseg, false))) return rc;
+      CK(cudaMemcpy(g.d_seg, segs.data(), sizeof(SegDev) * g.nseg, cudaMemcpyHostToDevice));
+    }
+  }
+
+  // state
+  for (int f = 0; f < 5; f++)
+    if ((rc = dalloc(&g.st[f][0], pl * nl))) return rc;
+  for (auto &p : g.rs)
+    if ((rc = dalloc(&p, pl * nl))) return rc;
+  for (auto &p : g.dx)
+    if ((rc = dalloc(&p, pl * nl))) return rc;
+  for (auto &p : g.dy)
+    if ((rc = dalloc(&p, pl * nl))) return rc;
+
+  // scalars and constants, evaluated like the reference does
+  D.invf = fld->invf; D.w_ti = fld->w_ti;
+  D.dl = par->dl; D.dt = par->dt; D.grav = par->grav;
+  D.i_dl = 1.0 / par->dl; D.i_gr = 1.0 / par->grav; D.i_r0 = 1.0 / par->rho0; D.i_r1 = 1.0 / par->rhon[0];
+  D.uadv = par->uadv; D.ocrp = par->ocrp; D.qdrg = par->qdrg; D.rgld = par->rgld;
+  D.hsal = par->hsal; D.hmin = par->hmin; D.hsbl = par->hsbl; D.hbbl = par->hbbl;
+  D.i_ns = 1.0 / (double)(par->nsal - 1);
+  D.two_hs = 2.0 * par->hsal;
+  D.bvis = par->bvis; D.dvis = par->dvis; D.svis = par->svis; D.bdrg = par->bdrg; D.tdrg = par->tdrg;
+  D.beta = par->beta; D.epsi = par->epsi; D.gamm = par->gamm; D.del1 = par->del1; D.del2 = par->del2;
+  D.plum = par->plum; D.pi = par->pi;
+  D.c_ab1 = 1.5 + par->beta;
+  D.c_ab2 = 0.5 + 2.0 * par->beta;
+  for (int l = 0; l < nlay; l++) {
+    D.rhon[l] = par->rhon[l];
+    D.i_rn[l] = 1.0 / par->rhon[l];
+    D.bodf[0][l] = fld->bodf ? fld->bodf[l] : 0.0;
+    D.bodf[1][l] = fld->bodf ? fld->bodf[(size_t)nlay + l] : 0.0;
+  }
+  D.bstress_thr = (par->variant == BEOM_VARIANT_1D ? 0.0 : 2.0) * par->hsal;
+  D.variant = par->variant; D.nsal = par->nsal;
+  D.gene = 0.0; D.ramp = 1.0; D.ctim = 0.0;
+  {
+    const double dtd8 = par->dt / 24.0 / 3600.0;
+    const double q = par->dt3d / dtd8;
+    g.n_3d = std::max((int)std::floor(q + 0.5), 1);
+  }
+
+  g.use_fused = false;
+  if (opt.fused) {
+    rc = fused_configure(g.D, g.P, g.nmir, g.nranks, &g.use_fused);
+    if (rc) return rc;
+    if (g.use_fused)
+      for (int f = 0; f < 5; f++)
+        if ((rc = dalloc(&g.st[f][1], pl * nl))) return rc;
+  }
+  CK(cudaStreamSynchronize(g.stream));
+  g.ready = true;
+  g_err.clear();
+  return 0;
+}
+
+int beom_gpu_upload_state(const double *hlay, const double *u, const double *v) {
+  if (!g.ready) return fail(-20, "beom_gpu_upload_state: not initialised");
+  const size_t pl = g.plane, nl = (size_t)g.nlay, nd1 = (size_t)g.ndeg + 1;
+  const double *src[3] = {hlay, u, v};
+  g.cur = 0;
+  for (int f = 0; f < 5; f++) CK(cudaMemsetAsync(g.st[f][0], 0, pl * nl * sizeof(double), g.stream));
+  for (auto p : g.rs) CK(cudaMemsetAsync(p, 0, pl * nl * sizeof(double), g.stream));
+  for (auto p : g.dx) CK(cudaMemsetAsync(p, 0, pl * nl * sizeof(double), g.stream));
+  for (auto p : g.dy) CK(cudaMemsetAsync(p, 0, pl * nl * sizeof(double), g.stream));
+  g.rs_o = g.dx_o = g.dy_o = 0;
+  // one H2D copy per field (all layers), then scatter into the dense planes
+  const int n = g.p_hi - g.p_lo + 1;
+  for (int f = 0; f < 3; f++) {
+    for (int l = 0; l < g.nlay; l++)
+      CK(cudaMemcpyAsync(g.stage + ((size_t)f * nl + l) * n, src[f] + (size_t)l * nd1 + g.p_lo, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+  }
+  for (int f = 0; f < 3; f++)
+    for (int l = 0; l < g.nlay; l++) {
+      k_scatter<double><<<(n + 255) / 256, 256, 0, g.stream>>>(g.st[f][0] + (size_t)l * pl, g.stage + ((size_t)f * nl + l) * n, g.d_cell, g.p_lo, n);
+      g.launches++;
+    }
+  for (int f = 0; f < 3; f++) mirror(g.st[f][0], g.nlay);
+  const size_t no = g.orphans.size();
+  for (int f = 0; f < 3; f++)
+    for (int l = 0; l < g.nlay; l++)
+      for (size_t k = 0; k < no; k++) g.orphan_val[((size_t)f * nl + l) * no + k] = src[f][(size_t)l * nd1 + g.orphans[k]];
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
+int beom_gpu_stress(void) {
+  if (!g.ready) return fail(-20, "beom_gpu_stress: not initialised");
+  return run_stress();
+}
+
+int beom_gpu_step(int tstp, double ctim, double ramp, double gene, int upst, int first_three) {
+  if (!g.ready) return fail(-20, "beom_gpu_step: not initialised");
+  g.D.ctim = ctim; g.D.ramp = ramp; g.D.gene = gene;
+  if (g.use_fused && fused_supports(first_three != 0, upst != 0)) {
+    Dev D = g.D;
+    set_state_pointers(D);
+    Dev Dout = D;
+    const int nxt = g.cur ^ 1;
+    Dout.hlay = g.st[0][nxt]; Dout.u = g.st[1][nxt]; Dout.v = g.st[2][nxt]; Dout.h_u = g.st[3][nxt]; Dout.h_v = g.st[4][nxt];
+    int nlaunch = 0;
+    int rc = fused_step(D, Dout, tstp, first_three != 0, g.stream, &nlaunch);
+    if (rc) return fail(rc, "fused_step failed: %s", cudaGetErrorString(cudaGetLastError()));
+    g.launches += nlaunch;
+    g.cur = nxt;
+    g.rs_o = (g.rs_o + 1) % 3;
+    g.dx_o = (g.dx_o + 1) % 4;
+    g.dy_o = (g.dy_o + 1) % 4;
+    return 0;
+  }
+  return step_split(tstp, upst != 0, first_three != 0);
+}
+
+int beom_gpu_advance(int tstp0, int tstp1, double tres) {
+  if (!g.ready) return fail(-20, "beom_gpu_advance: not initialised");
+  const beom_params &P = g.P;
+  const double dtd8 = P.dt / 24.0 / 3600.0;
+  static double ramp = 1.0, gene = 0.0;
+  for (int tstp = tstp0; tstp <= tstp1; tstp++) {
+    const double ctim = tres + dtd8 * (double)tstp;
+    int rc;
+    if (tstp <= 3) {
+      if (tstp == 1) {
+        ramp = 1.0; gene = 0.0;
+        if ((rc = run_stress())) return rc;
+        if (P.rsta < 0.5 && ctim < P.dt_r) ramp = ctim / P.dt_r;
+      }
+      if ((rc = beom_gpu_step(tstp, ctim, ramp, gene, 1, 1))) return rc;
+      if (tstp == 3) {
+        gene = P.g_fb;
+        if (gene > 0.5 && P.rgld > 0.5) gene = 0.0;
+      }
+    } else {
+      const bool upst = (tstp % g.n_3d) == 0;
+      if (tstp == tstp0) {
+        gene = P.g_fb;
+        if (gene > 0.5 && P.rgld > 0.5) gene = 0.0;
+      }
+      if (upst && (rc = run_stress())) return rc;
+      ramp = 1.0;
+      if (P.rsta < 0.5 && ctim < P.dt_r) ramp = ctim / P.dt_r;
+      if ((rc = beom_gpu_step(tstp, ctim, ramp, gene, upst ? 1 : 0, 0))) return rc;
+    }
+  }
+  return 0;
+}
+
+static int download_planes(double *dst, const double *dense, int nplanes) {
+  // dst: reference layout [nplanes][ndeg+1]; only this rank's owned+halo points are written
+  const int n = g.p_hi - g.p_lo + 1;
+  const size_t nd1 = (size_t)g.ndeg + 1;
+  for (int p0 = 0; p0 < nplanes; p0 += 3 * g.nlay) {
+    const int np = std::min(3 * g.nlay, nplanes - p0);
+    for (int p = 0; p < np; p++) {
+      k_gather<double><<<(n + 255) / 256, 256, 0, g.stream>>>(g.stage + (size_t)p * n, dense + (size_t)(p0 + p) * g.plane, g.d_cell, g.p_lo, n);
+      g.launches++;
+    }
+    for (int p = 0; p < np; p++)
+      CK(cudaMemcpyAsync(dst + (size_t)(p0 + p) * nd1 + g.p_lo, g.stage + (size_t)p * n, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+  }
+  return 0;
+}
+
+int beom_gpu_download_state(double *hlay, double *u, double *v) {
+  if (!g.ready) return fail(-20, "beom_gpu_download_state: not initialised");
+  double *dst[3] = {hlay, u, v};
+  const size_t nl = (size_t)g.nlay, nd1 = (size_t)g.ndeg + 1, no = g.orphans.size();
+  for (int f = 0; f < 3; f++) {
+    if (!dst[f]) continue;
+    int rc = download_planes(dst[f], g.st[f][g.cur], g.nlay);
+    if (rc) return rc;
+    for (int l = 0; l < g.nlay; l++) {
+      if (g.rank == 0) dst[f][(size_t)l * nd1] = 0.0;  // the discarded cell
+      for (size_t k = 0; k < no; k++) dst[f][(size_t)l * nd1 + g.orphans[k]] = g.orphan_val[((size_t)f * nl + l) * no + k];
+    }
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int beom_gpu_download_aux(double *h_u, double *h_v, double *rs_h, double *dmdx, double *dmdy) {
+  if (!g.ready) return fail(-20, "beom_gpu_download_aux: not initialised");
+  int rc;
+  if (h_u && (rc = download_planes(h_u, g.st[3][g.cur], g.nlay))) return rc;
+  if (h_v && (rc = download_planes(h_v, g.st[4][g.cur], g.nlay))) return rc;
+  const int n = g.p_hi - g.p_lo + 1;
+  const size_t nd1 = (size_t)g.ndeg + 1;
+  auto hist = [&](double *dst, int nh, double *a, double *b, double *c) -> int {
+    for (int l = 0; l < g.nlay; l++) {
+      const size_t L = (size_t)l * g.plane;
+      k_gather_hist<<<(n + 255) / 256, 256, 0, g.stream>>>(g.stage, a + L, b + L, c ? c + L : nullptr, nh, g.d_cell, g.p_lo, n);
+      g.launches++;
+      CK(cudaMemcpyAsync(dst + ((size_t)l * nd1 + g.p_lo) * nh, g.stage, (size_t)n * nh * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+      CK(cudaStreamSynchronize(g.stream));
+    }
+    return 0;
+  };
+  if (rs_h && (rc = hist(rs_h, 2, g.rs[g.rs_o], g.rs[(g.rs_o + 1) % 3], nullptr))) return rc;
+  if (dmdx && (rc = hist(dmdx, 3, g.dx[g.dx_o], g.dx[(g.dx_o + 1) % 4], g.dx[(g.dx_o + 2) % 4]))) return rc;
+  if (dmdy && (rc = hist(dmdy, 3, g.dy[g.dy_o], g.dy[(g.dy_o + 1) % 4], g.dy[(g.dy_o + 2) % 4]))) return rc;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int beom_gpu_download_diag(float *pvor, float *mont, float *v_cc) {
+  (void)pvor; (void)mont; (void)v_cc;
+  return fail(-31, "beom_gpu_download_diag: not implemented yet");
+}
+int beom_gpu_download_pi_s(double *pi_s) {
+  (void)pi_s;
+  return fail(-30, "beom_gpu_download_pi_s: rgld = 1 is not implemented on the device yet");
+}
+int beom_gpu_diagnostics(const double *h_0, double *vol, double *ke, double *pe) {
+  (void)h_0; (void)vol; (void)ke; (void)pe;
+  return fail(-31, "beom_gpu_diagnostics: not implemented yet");
+}
+
+int beom_gpu_sync(void) {
+  if (!g.ready) return fail(-20, "beom_gpu_sync: not initialised");
+  CK(cudaStreamSynchronize(g.stream));
+  CK(cudaGetLastError());
+  return 0;
+}
+int beom_gpu_mark(int which) {
+  if (!g.ready || which < 0 || which > 1) return fail(-20, "beom_gpu_mark: bad call");
+  CK(cudaEventRecord(g.ev[which], g.stream));
+  return 0;
+}
+int beom_gpu_elapsed_ms(double *ms) {
+  if (!g.ready) return fail(-20, "beom_gpu_elapsed_ms: not initialised");
+  CK(cudaEventSynchronize(g.ev[1]));
+  float t = 0;
+  CK(cudaEventElapsedTime(&t, g.ev[0], g.ev[1]));
+  *ms = (double)t;
+  return 0;
+}
+
+int beom_gpu_comm_unique_id(char id[128]) { return comm_unique_id(id, &g_err); }
+int beom_gpu_comm_init(const char id[128], int rank, int nranks, int device) { return comm_init(id, rank, nranks, device, &g_err); }
+int beom_gpu_comm_finalize(void) { return comm_finalize(); }
+
+}  // extern "C"

@@ -1,0 +1,638 @@
+// init.cc -- read_input_data (private_mod.f95:105-250): builds every static field the GPU library is
+// given, in the reference's vector layout.  This part of the reference stays on the host (SURVEY
+// section 2.1 row 4); it is restated in C++ because no Fortran compiler exists here.
+//
+// Layout reminders (private_mod.f95:27-93): point index 0 is the discarded cell; x(0:ndeg,nlay) is
+// stored [nlay][ndeg+1]; neig(8,0:ndeg) is [ndeg+1][8]; fnud(0:ndeg,nlay,3) is [3][nlay][ndeg+1].
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <limits>
+
+#include "host_model.h"
+
+namespace {
+
+struct Fail {
+  std::string msg;
+};
+
+// raw little-endian float32 file of exactly n values; absent file -> empty vector (private_mod.f95:775-776)
+std::vector<float> slurp(const std::string &dir, const char *keyw, size_t n, bool *present) {
+  *present = false;
+  std::vector<float> buf;
+  if (dir.empty()) return buf;
+  std::string path = dir + keyw + ".bin";
+  std::FILE *f = std::fopen(path.c_str(), "rb");
+  if (!f) return buf;
+  buf.resize(n);
+  size_t got = std::fread(buf.data(), sizeof(float), n, f);
+  std::fclose(f);
+  if (got != n) throw Fail{std::string(" could not open/read file ") + keyw + ".bin from directory " + dir};
+  *present = true;
+  return buf;
+}
+
+inline long nint(double x) { return (long)(x >= 0 ? std::floor(x + 0.5) : -std::floor(-x + 0.5)); }
+
+// ------------------------------------------------------------------------------------------------
+// index_grid_points (private_mod.f95:567-764)
+// ------------------------------------------------------------------------------------------------
+void index_grid_points(beom_host *h) {
+  const int lm = h->lm, mm = h->mm;
+  const double hdry = h->p.hdry;
+  const Grid2<double> &H = h->h2d;
+  Grid2<unsigned char> wet;
+  wet.reset(-1, lm + 2, -1, mm + 2, 0);
+  for (int j = -1; j <= mm + 2; j++)
+    for (int i = -1; i <= lm + 2; i++) wet(i, j) = H(i, j) > hdry;
+  // a grid point enters the vector if it carries an eta, u, v or psi point that touches water
+  auto carries = [&](int i, int j) { return wet(i, j) || wet(i - 1, j) || wet(i, j - 1) || wet(i - 1, j - 1); };
+
+  Grid2<int32_t> alias;  // "indc": which vector entry a neighbour reference resolves to
+  alias.reset(-1, lm + 2, -1, mm + 2, 0);
+  int count = 0;
+  for (int j = 0; j <= mm + 1; j++)
+    for (int i = 0; i <= lm + 1; i++)
+      if (carries(i, j)) alias(i, j) = ++count;
+  if (count != h->ndeg) {
+    char b[160];
+    std::snprintf(b, sizeof b, " wrong input parameter! Please set ndeg = %d inside file shared_mod.f95.", count);
+    throw Fail{b};
+  }
+
+  if (h->p.xper > 0.5) {  // pm:614-640
+    for (int j = 1; j <= mm; j++) {
+      const bool both = wet(1, j) && wet(lm, j);
+      if (both) {
+        alias(0, j) = alias(lm, j);
+        alias(lm + 1, j) = alias(1, j);
+        h->mk_u[alias(1, j)] = 1.0;
+      }
+      if (j > 1 && wet(1, j - 1) && wet(1, j) && wet(lm, j - 1) && wet(lm, j)) h->mkpe[alias(1, j)] = 1.0;
+      if (j == mm && both) {
+        alias(0, mm + 1) = alias(lm, mm + 1);
+        alias(lm + 1, mm + 1) = alias(1, mm + 1);
+      }
+    }
+  }
+  if (h->p.yper > 0.5) {  // pm:642-668
+    for (int i = 1; i <= lm; i++) {
+      const bool both = wet(i, 1) && wet(i, mm);
+      if (both) {
+        alias(i, 0) = alias(i, mm);
+        alias(i, mm + 1) = alias(i, 1);
+        h->mk_v[alias(i, 1)] = 1.0;
+      }
+      if (i > 1 && wet(i - 1, 1) && wet(i, 1) && wet(i - 1, mm) && wet(i, mm)) h->mkpe[alias(i, 1)] = 1.0;
+      if (i == lm && both) {
+        alias(lm + 1, 0) = alias(lm + 1, mm);
+        alias(lm + 1, mm + 1) = alias(lm + 1, 1);
+      }
+    }
+  }
+  if (h->p.xper > 0.5 && h->p.yper > 0.5) {  // pm:672-685
+    if (wet(1, 1) && wet(lm, 1) && wet(1, mm)) {
+      alias(0, 0) = alias(lm, mm);
+      h->mkpe[alias(1, 1)] = 1.0;
+      alias(0, mm + 1) = alias(lm, 1);
+    }
+    if (wet(lm, mm) && wet(1, mm) && wet(lm, 1)) {
+      alias(lm + 1, 0) = alias(1, mm);
+      alias(lm + 1, mm + 1) = alias(1, 1);
+    }
+  }
+
+  static const int di[8] = {1, 1, 0, -1, -1, -1, 0, 1}, dj[8] = {0, 1, 1, 1, 0, -1, -1, -1};
+  int p = 0;
+  for (int j = 0; j <= mm + 1; j++)  // pm:692-730
+    for (int i = 0; i <= lm + 1; i++) {
+      if (!carries(i, j)) continue;
+      ++p;
+      if (wet(i, j)) h->mk_n[p] = 1.0;
+      if (wet(i - 1, j) && wet(i, j)) h->mk_u[p] = 1.0;
+      if (wet(i, j - 1) && wet(i, j)) h->mk_v[p] = 1.0;
+      if (wet(i - 1, j - 1) && wet(i, j - 1) && wet(i - 1, j) && wet(i, j)) h->mkpe[p] = 1.0;
+      h->mkpi[p] = 1.0;  // carries() already says one of the four cells is wet (pm:712-714)
+      h->posc[p] = i + 1 + j * (lm + 2);
+      h->subc[p] = i;
+      h->subc[h->nd1 + p] = j;
+      for (int k = 0; k < 8; k++) h->neig[(size_t)p * 8 + k] = alias(i + di[k], j + dj[k]);
+    }
+  for (size_t q = 0; q < h->nd1; q++) h->h_th[q] = H(h->subc[q], h->subc[h->nd1 + q]);  // pm:753-757
+}
+
+// ------------------------------------------------------------------------------------------------
+// get_equilibrium_thickness_h_0 (private_mod.f95:309-502): Newton iteration per water column for
+// the rest thickness with Salmon's outcrop term.
+// ------------------------------------------------------------------------------------------------
+struct RestSolver {
+  int nlay, nsal, itmx;
+  double hsal, thre, sor, dmax;
+  double rho[BEOM_MAXLAY], topl[BEOM_MAXLAY], cons[BEOM_MAXLAY];
+
+  static double cube(double x) { return (x * x) * x; }
+  static double quad(double x) { double y = x * x; return y * y; }
+
+  void prepare() {  // pm:339-355
+    double g[BEOM_MAXLAY];
+    for (int l = 0; l < nlay; l++) {
+      g[l] = dmax * (1.0 - topl[l]);
+      if (l < nlay - 1) g[l] = g[l] - dmax * (1.0 - topl[l + 1]);
+    }
+    double total = 0.0;
+    for (int l = 0; l < nlay; l++) total += g[l];
+    for (int l = 0; l < nlay; l++) {
+      cons[l] = dmax * (-1.0) + total;
+      for (int k = 0; k < l; k++) cons[l] = cons[l] - (rho[l] - rho[k]) * g[k] / rho[l];
+    }
+  }
+
+  // returns false if itmx iterations were not enough (pm:395-401)
+  bool column(double hbot, double *out) const {
+    double g[BEOM_MAXLAY], f[BEOM_MAXLAY], A[BEOM_MAXLAY][BEOM_MAXLAY + 1];
+    for (int l = nlay - 1; l >= 0; l--) {  // pm:370-380
+      double below = 0.0;
+      for (int k = l + 1; k < nlay; k++) below += g[k];
+      g[l] = std::max(hbot - dmax * topl[l] - below, hsal);
+    }
+    for (int iter = 1; iter <= itmx; iter++) {
+      for (int a = 0; a < nlay; a++) {  // pm:383-393
+        double tot = 0.0;
+        for (int k = 0; k < nlay; k++) tot += g[k];
+        f[a] = (hbot - tot) + 1.0 / (double)(nsal - 1) * hsal * cube(hsal / g[a]) + cons[a];
+        f[a] = f[a] * (-1.0);
+        for (int k = 0; k < a; k++) f[a] = f[a] - (rho[a] - rho[k]) * g[k] / rho[a];
+      }
+      if (iter == itmx) return false;
+      bool done = true;
+      for (int a = 0; a < nlay; a++) done = done && (std::fabs(f[a]) < thre);
+      if (done) {
+        for (int a = 0; a < nlay; a++) out[a] = g[a];
+        return true;
+      }
+      for (int a = 0; a < nlay; a++) {  // Jacobian, pm:410-421
+        for (int b = 0; b < nlay; b++) {
+          A[a][b] = std::min(rho[a], rho[b]) / rho[a];
+          if (a == b) A[a][b] = A[a][b] + quad(hsal / g[b]);
+        }
+        A[a][nlay] = f[a] * (-1.0);
+      }
+      for (int k = 0; k < nlay; k++) {  // elimination with partial pivoting, pm:426-455
+        int piv = -1;
+        double best = 0.0;
+        for (int r = k; r < nlay; r++)
+          if (std::fabs(A[r][k]) > best) { best = std::fabs(A[r][k]); piv = r; }
+        if (piv >= 0 && piv != k)
+          for (int c = 0; c <= nlay; c++) std::swap(A[k][c], A[piv][c]);
+        for (int r = k + 1; r < nlay; r++) {
+          for (int c = k; c <= nlay; c++) A[r][c] = A[r][c] - A[k][c] * (A[r][k] / A[k][k]);
+          A[r][k] = 0.0;
+        }
+      }
+      for (int r = nlay - 1; r >= 0; r--) {  // pm:459-466
+        double acc = 0.0;
+        for (int c = r + 1; c < nlay; c++) acc = acc + A[r][c] * A[c][nlay];
+        A[r][nlay] = (A[r][nlay] - acc) / A[r][r];
+      }
+      bool tiny = false;
+      for (int a = 0; a < nlay; a++) {  // pm:468-472
+        g[a] = (1.0 - sor) * g[a] + sor * (A[a][nlay] + g[a]);
+        tiny = tiny || (g[a] <= thre);
+      }
+      if (tiny)
+        for (int a = 0; a < nlay; a++) g[a] = std::max(g[a], thre);
+    }
+    return false;
+  }
+};
+
+// note on the elimination loop: the reference updates maug(ilay,l) for l = k..nlay+1 using
+// maug(ilay,k) *before* it is zeroed; since l = k is processed first and overwrites maug(ilay,k),
+// the factor must be taken per element exactly as written (pm:448-451).  The loop above re-reads
+// A[r][k] each time, like the reference.
+
+void rest_thickness(beom_host *h) {
+  const int nlay = h->nlay;
+  RestSolver s;
+  s.nlay = nlay; s.nsal = h->p.nsal; s.itmx = h->p.itmx;
+  s.hsal = h->p.hsal; s.thre = h->p.tole; s.sor = h->p.sor;
+  s.dmax = *std::max_element(h->h2d.d.begin(), h->h2d.d.end());  // pm:334
+  for (int l = 0; l < nlay; l++) { s.rho[l] = h->p.rhon[l]; s.topl[l] = h->p.topl[l]; }
+  s.prepare();
+  int bad = 0;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(dynamic, 512)
+#endif
+  for (int p = 1; p <= h->ndeg; p++) {
+    if (h->mk_n[p] < 0.5 || bad) continue;
+    double col[BEOM_MAXLAY];
+    const double hbot = h->h2d(h->subc[p], h->subc[h->nd1 + p]);
+    if (!s.column(hbot, col)) { bad = p; continue; }
+    for (int l = 0; l < nlay; l++) h->h_0[(size_t)l * h->nd1 + p] = col[l];
+  }
+  if (bad) {
+    char b[200];
+    std::snprintf(b, sizeof b, " calculation of h_layers did not converge, tolerance (meters) was %g, at point %d", s.thre, bad);
+    throw Fail{b};
+  }
+
+  if (h->p.rgld > 0.5) {  // pm:505-563: start pressure and the Poisson operators
+    const int lm = h->lm, mm = h->mm;
+    const double dl = h->p.dl;
+    const size_t n = h->nd1;
+    std::vector<double> osum(n, 0.0);
+    for (size_t q = 0; q < n; q++) {
+      double tot = 0.0;
+      for (int l = 0; l < nlay; l++) tot += h->h_0[(size_t)l * n + q];
+      h->pi_s[q] = (tot - h->h_th[q]) * h->p.grav;
+      h->Ow[q] = h->Os[q] = h->Osum_[q] = 0.0;
+    }
+    auto W = [&](int q) { return h->neig[(size_t)q * 8 + 4]; };
+    auto S = [&](int q) { return h->neig[(size_t)q * 8 + 6]; };
+    auto E = [&](int q) { return h->neig[(size_t)q * 8 + 0]; };
+    auto N = [&](int q) { return h->neig[(size_t)q * 8 + 2]; };
+    for (int q = 1; q <= h->ndeg; q++) {
+      const int i = h->subc[q], j = h->subc[n + q];
+      const bool xin = 1 < i && i < lm + 1, yin = 1 < j && j < mm + 1;
+      if (xin && yin) {
+        h->Ow[q] = 0.5 * (h->h_th[q] + h->h_th[W(q)]) / (dl * dl);
+        h->Os[q] = 0.5 * (h->h_th[q] + h->h_th[S(q)]) / (dl * dl);
+      } else if (i == 1 && yin) {
+        h->Os[q] = 0.5 * (h->h_th[q] + h->h_th[S(q)]) / (dl * dl);
+      } else if (xin && j == 1) {
+        h->Ow[q] = 0.5 * (h->h_th[q] + h->h_th[W(q)]) / (dl * dl);
+      }
+    }
+    for (int q = 1; q <= h->ndeg; q++) {
+      const int i = h->subc[q], j = h->subc[n + q];
+      if (i < lm && j < mm) osum[q] = h->Ow[q] + h->Ow[E(q)] + h->Os[q] + h->Os[N(q)];
+      else if (i == lm && j < mm) osum[q] = h->Ow[q] + h->Os[q] + h->Os[N(q)];
+      else if (j == mm && i < lm) osum[q] = h->Ow[q] + h->Os[q] + h->Ow[E(q)];
+      else osum[q] = h->Ow[q] + h->Os[q];
+      if (i > 0 && i < lm + 1 && j > 0 && j < mm + 1) h->Osum_[q] = 1 / osum[q];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// index_boundary_points (private_mod.f95:1060-1240): one entry per nudged open-boundary face
+// ------------------------------------------------------------------------------------------------
+void index_boundary_points(beom_host *h, const std::vector<float> &nf) {
+  const int lm = h->lm, mm = h->mm;
+  const double hdry = h->p.hdry;
+  const float tiny4 = std::numeric_limits<float>::min();
+  const Grid2<double> &H = h->h2d;
+  Grid2<int32_t> own;
+  own.reset(-1, lm + 2, -1, mm + 2, 0);
+  {
+    int c = 0;
+    for (int j = 0; j <= mm + 1; j++)
+      for (int i = 0; i <= lm + 1; i++)
+        if (H(i, j) > hdry || H(i - 1, j) > hdry || H(i, j - 1) > hdry || H(i - 1, j - 1) > hdry) own(i, j) = ++c;
+  }
+  auto coef = [&](int i, int j, int comp) -> float {  // comp: 1 eta, 2 u, 3 v
+    if (i < 0 || i > lm + 1 || j < 0 || j > mm + 1) return 0.0f;
+    return nf[((size_t)(comp - 1) * (mm + 2) + j) * (lm + 2) + i];
+  };
+  struct Seg { int32_t c[18]; };
+  std::vector<Seg> segs;
+  auto push = [&](int i, int j, bool zonal, int sign, int di, int dj, int wi, int wj, int ni, int nj, int ci, int cj) {
+    Seg s;
+    std::memset(&s, 0, sizeof s);
+    s.c[0] = own(i, j); s.c[1] = i; s.c[2] = j;
+    s.c[zonal ? 3 : 4] = 1;
+    s.c[5] = sign;
+    s.c[6] = own(di, dj); s.c[7] = di; s.c[8] = dj;      // the dry cell
+    s.c[9] = own(wi, wj); s.c[10] = wi; s.c[11] = wj;    // the wet cell
+    s.c[12] = own(ni, nj); s.c[13] = ni; s.c[14] = nj;   // interior normal-velocity point
+    s.c[15] = own(ci, cj); s.c[16] = ci; s.c[17] = cj;   // interior cell
+    segs.push_back(s);
+  };
+  for (int j = 0; j <= mm + 1; j++)
+    for (int i = 0; i <= lm + 1; i++) {
+      const bool here = H(i, j) > hdry, west = H(i - 1, j) > hdry, south = H(i, j - 1) > hdry;
+      if (here && !west && coef(i, j, 2) > tiny4 && coef(i - 1, j, 2) > tiny4 && h->p.xper < 0.5)
+        push(i, j, true, 1, i - 1, j, i, j, i + 1, j, i + 1, j);
+      if (!here && west && coef(i - 1, j, 2) > tiny4 && coef(i, j, 2) > tiny4 && h->p.xper < 0.5)
+        push(i, j, true, -1, i, j, i - 1, j, i - 1, j, i - 2, j);
+      if (here && !south && coef(i, j, 3) > tiny4 && coef(i, j - 1, 3) > tiny4 && h->p.yper < 0.5)
+        push(i, j, false, 1, i, j - 1, i, j, i, j + 1, i, j + 1);
+      if (!here && south && coef(i, j - 1, 3) > tiny4 && coef(i, j, 3) > tiny4 && h->p.yper < 0.5)
+        push(i, j, false, -1, i, j, i, j - 1, i, j - 1, i, j - 2);
+    }
+  if (segs.empty()) throw Fail{" the nudged open boundary segments could not be identified."};
+  h->nseg = (int)segs.size();
+  h->segm.assign((size_t)h->nseg * 18, 0);
+  for (int s = 0; s < h->nseg; s++)
+    for (int c = 0; c < 18; c++) h->segm[(size_t)c * h->nseg + s] = segs[(size_t)s].c[c];
+}
+
+// ------------------------------------------------------------------------------------------------
+// read_input_file for everything after h_0 (private_mod.f95:840-964)
+// ------------------------------------------------------------------------------------------------
+void read_forcing_files(beom_host *h) {
+  const int lm = h->lm, mm = h->mm, nlay = h->nlay, ndeg = h->ndeg;
+  const size_t n = h->nd1, plane = (size_t)(lm + 2) * (mm + 2);
+  const int32_t *si = h->subc.data(), *sj = h->subc.data() + n;
+  bool present;
+
+  std::vector<float> f = slurp(h->idir, "nudg", plane * 3, &present);  // pm:843-881
+  h->has_nudg = present;
+  if (present) {
+    auto at = [&](int i, int j, int c) { return f[((size_t)c * (mm + 2) + j) * (lm + 2) + i]; };
+    h->nudg.assign(n * 3, 0.0);
+    bool live = false;
+    for (int p = 1; p <= ndeg; p++) {
+      const int i = si[p], j = sj[p];
+      const double ne = (double)at(i, j, 0);
+      double nu = 0.0, nv = 0.0;
+      if (i >= 1 && at(i - 1, j, 1) > 1.e-9f && at(i, j, 1) > 1.e-9f) nu = (double)at(i, j, 1) * 0.5 + (double)at(i - 1, j, 1) * 0.5;
+      if (j >= 1 && at(i, j - 1, 2) > 1.e-9f && at(i, j, 2) > 1.e-9f) nv = (double)at(i, j, 2) * 0.5 + (double)at(i, j - 1, 2) * 0.5;
+      h->nudg[p] = ne;
+      h->nudg[n + p] = nu;
+      h->nudg[2 * n + p] = nv;
+      live = live || ne > 1.e-9 || nu > 1.e-9 || nv > 1.e-9;
+    }
+    if (live) {
+      h->flag_nudging = true;
+      index_boundary_points(h, f);
+    }
+    h->fnud.assign(n * nlay * 3, 0.0);
+    for (int l = 0; l < nlay; l++)
+      for (int p = 1; p <= ndeg; p++) h->fnud[(size_t)l * n + p] = h->hlay[(size_t)l * n + p];
+  }
+
+  f = slurp(h->idir, "init", plane * nlay * 3, &present);  // pm:882-910
+  h->has_init = present;
+  if (present) {
+    if (h->fnud.empty()) h->fnud.assign(n * nlay * 3, 0.0);
+    auto at = [&](int i, int j, int l, int c) { return (double)f[(((size_t)c * nlay + l) * (mm + 2) + j) * (lm + 2) + i]; };
+    double *fn = h->fnud.data(), *fu = fn + n * nlay, *fv = fu + n * nlay;
+    for (int l = 0; l < nlay; l++)
+      for (int p = 1; p <= ndeg; p++) {
+        const int i = si[p], j = sj[p];
+        const size_t k = (size_t)l * n + p;
+        double t = h->hlay[k] + at(i, j, l, 0);
+        if (l < nlay - 1) t = t - at(i, j, l + 1, 0);
+        fn[k] = t * h->mk_n[p];
+        fu[k] = at(i, j, l, 1);
+        fv[k] = at(i, j, l, 2);
+        if (h->p.rsta < 0.5) {
+          h->hlay[k] = fn[k] * h->mk_n[p];
+          h->u[k] = fu[k];
+          h->v[k] = fv[k];
+        }
+      }
+  }
+
+  f = slurp(h->idir, "bodf", (size_t)nlay * 2, &present);  // pm:840-842
+  h->has_bodf = present;
+  h->bodf.assign((size_t)nlay * 2, 0.0);
+  if (present)
+    for (size_t k = 0; k < (size_t)nlay * 2; k++) h->bodf[k] = (double)f[k];
+
+  f = slurp(h->idir, "hdot", plane * nlay, &present);  // pm:911-919
+  h->has_hdot = present;
+  if (present) {
+    h->hdot.assign(n * nlay, 0.0);
+    for (int l = 0; l < nlay; l++)
+      for (int p = 1; p <= ndeg; p++) h->hdot[(size_t)l * n + p] = (double)f[((size_t)l * (mm + 2) + sj[p]) * (lm + 2) + si[p]];
+  }
+
+  // taus defaults to the uniform tauw (pm:302-303); a file replaces it and zeroes the sentinel (pm:921)
+  h->taus.assign(n * 2, 0.0);
+  for (size_t q = 0; q < n; q++) { h->taus[q] = h->p.tauw[0]; h->taus[n + q] = h->p.tauw[1]; }
+  f = slurp(h->idir, "taus", plane * 2, &present);  // pm:920-931
+  h->has_taus = present;
+  if (present) {
+    std::fill(h->taus.begin(), h->taus.end(), 0.0);
+    for (int p = 1; p <= ndeg; p++) {
+      const size_t k = (size_t)sj[p] * (lm + 2) + si[p];
+      h->taus[p] = (double)f[k];
+      h->taus[n + p] = (double)f[plane + k];
+    }
+  }
+
+  f = slurp(h->idir, "tide", plane * 2 * 3, &present);  // pm:951-964; (2,1,0:lm+1,0:mm+1,3)
+  h->has_tide = present;
+  if (present) {
+    if (h->fnud.empty()) h->fnud.assign(n * nlay * 3, 0.0);
+    h->tide.assign(n * 6, 0.0);
+    h->w_ti = (double)f[0];
+    for (int p = 1; p <= ndeg; p++)
+      for (int c = 0; c < 3; c++)
+        for (int a = 0; a < 2; a++)
+          h->tide[((size_t)c * n + p) * 2 + a] = (double)f[(((size_t)c * (mm + 2) + sj[p]) * (lm + 2) + si[p]) * 2 + a];
+  }
+
+  f = slurp(h->idir, "fcor", plane, &present);  // pm:932-950: psi-point average taken in float32
+  h->has_fcor = present;
+  if (present) {
+    float acc = 0.0f;
+    for (size_t k = 0; k < plane; k++) acc = acc + f[k];
+    h->fcor[0] = (double)(acc / (float)plane);
+    auto at = [&](int i, int j) { return f[(size_t)j * (lm + 2) + i]; };
+    for (int p = 1; p <= ndeg; p++) {
+      const int i = si[p], j = sj[p];
+      if (i > 0 && j > 0) {
+        float t = at(i, j) * 0.25f;
+        t = t + at(i - 1, j) * 0.25f;
+        t = t + at(i, j - 1) * 0.25f;
+        t = t + at(i - 1, j - 1) * 0.25f;
+        h->fcor[p] = (double)t;
+      } else
+        h->fcor[p] = (double)at(i, j);
+    }
+  }
+}
+
+void read_input_data(beom_host *h) {
+  const int lm = h->lm, mm = h->mm, nlay = h->nlay;
+  const beom_params &P = h->p;
+  const size_t n = h->nd1;
+
+  // initialize_variables (pm:252-307): only what the host keeps
+  h->neig.assign(n * 8, 0); h->subc.assign(n * 2, 0); h->posc.assign(n, 0);
+  for (auto *v : {&h->mk_u, &h->mk_v, &h->mk_n, &h->mkpe, &h->mkpi, &h->h_th, &h->Ow, &h->Os, &h->Osum_, &h->pi_s}) v->assign(n, 0.0);
+  h->fcor.assign(n, P.f0);
+  for (auto *v : {&h->h_0, &h->hlay, &h->u, &h->v}) v->assign(n * nlay, 0.0);
+
+  // default flat bottom of depth cext**2/grav (pm:119-121), replaced by h_bo.bin if present
+  h->h2d.reset(-1, lm + 2, -1, mm + 2, 0.0);
+  for (int j = 1; j <= mm; j++)
+    for (int i = 1; i <= lm; i++) h->h2d(i, j) = (P.cext * P.cext) / P.grav;
+
+  bool present;
+  std::vector<float> f = slurp(h->idir, "h_bo", (size_t)(lm + 2) * (mm + 2), &present);  // pm:827-839
+  if (present) {
+    std::vector<float> ft;
+    if (P.topt > 0.5) {
+      bool pt;
+      ft = slurp(h->idir, "h_to", (size_t)(lm + 2) * (mm + 2), &pt);
+      if (!pt) throw Fail{" could not open/read file h_to.bin from directory " + h->idir};
+    }
+    std::fill(h->h2d.d.begin(), h->h2d.d.end(), 0.0);
+    for (int j = 0; j <= mm + 1; j++)
+      for (int i = 0; i <= lm + 1; i++) {
+        const size_t k = (size_t)j * (lm + 2) + i;
+        const double d = ft.empty() ? (double)f[k] : (double)(f[k] - ft[k]);
+        h->h2d(i, j) = (d < P.hdry || i == 0 || j == 0 || i == lm + 1 || j == mm + 1) ? 0.0 : d;
+      }
+  }
+
+  index_grid_points(h);
+
+  double dmin = std::numeric_limits<double>::infinity(), dmax = -dmin;  // pm:134-135
+  for (double d : h->h2d.d) {
+    if (d > P.hdry) dmin = std::min(dmin, d);
+    dmax = std::max(dmax, d);
+  }
+  if (P.ocrp < 0.5 && nlay > 1) {  // pm:137-152
+    if (P.topl[nlay - 1] * dmax + 10.0 * P.hmin >= dmin)
+      throw Fail{" Please modify topl so that bathymetry is contained within lower layer."};
+  } else if (P.ocrp < 0.5 && nlay == 1) {
+    if (dmin <= 10.0 * P.hmin) throw Fail{" Please adjust h_bo or hmin so that min(h_bo) > 10. * hmin."};
+  }
+
+  if (P.ocrp < 0.5) {  // pm:154-175: layers stacked from the bottom, no outcrop
+    for (int p = 1; p <= h->ndeg; p++) {
+      if (!(h->mk_n[p] > 0.5)) continue;
+      const double depth = h->h2d(h->subc[p], h->subc[n + p]);
+      for (int l = nlay - 1; l >= 0; l--) {
+        const double above = l > 0 ? dmax * P.topl[l] : 0.0;
+        double below = 0.0;
+        for (int k = l + 1; k < nlay; k++) below += h->h_0[(size_t)k * n + p];
+        h->h_0[(size_t)l * n + p] = depth - above - below;
+      }
+    }
+  } else {
+    rest_thickness(h);  // pm:177-183
+  }
+
+  // h_0.bin holds float32 (pm:185-194); write_array reads it back (pm:2839-2846)
+  h->h_0_r4.resize((size_t)h->ndeg * nlay);
+  for (int l = 0; l < nlay; l++)
+    for (int p = 1; p <= h->ndeg; p++) h->h_0_r4[(size_t)l * h->ndeg + (p - 1)] = (float)h->h_0[(size_t)l * n + p];
+
+  for (int l = 0; l < nlay; l++)  // pm:198-200
+    for (size_t q = 0; q < n; q++) h->hlay[(size_t)l * n + q] = h->h_0[(size_t)l * n + q] * h->mk_n[q];
+
+  read_forcing_files(h);  // pm:204-216
+
+  double acc = 0.0;  // pm:223-229
+  for (size_t q = 0; q < n; q++) acc += h->fcor[q];
+  h->invf = acc / (double)n;
+  h->invf = std::fabs(h->invf) > 1.25e-5 ? 1.0 / h->invf : 0.0;
+
+  const double dtd8 = P.dt / 24.0 / 3600.0;  // pm:1853-1856
+  h->nstp = (int)nint(P.dt_s / dtd8);
+  h->notp = std::max((int)nint(P.dt_o / dtd8), 1);
+  h->n_3d = std::max((int)nint(P.dt3d / dtd8), 1);
+}
+
+void check_consistency_options(const beom_params &P) {  // pm:969-1058 (numerical range checks)
+  std::string m;
+  if (P.lm < 1 || P.mm < 1) m += " grid dimensions (lm,mm) should be >= 1.";
+  if (P.dl < 1.e1) m += " mesh size (dl) should be >= 10 meters.";
+  if (std::fabs(P.f0) > 2.e-4) m += " Coriolis parameter (f0, in s**(-1)) should be within: -2x10**(-4) < f0 < 2x10**(-4).";
+  if (P.dvis < 0.0 || P.dvis > 5.0) m += " Viscosity coefficient should be within: 0 <= dvis < 5.0.";
+  if ((P.bdrg < 0.0 || P.bdrg > 15.e-3) && P.qdrg > 0.5) m += " quadratic bottom drag coefficient bdrg should be within: 0 <= bdrg < 5x10**(-3).";
+  else if (P.bdrg < 0.0 || P.bdrg > 5.e-2) m += " linear bottom drag coefficient bdrg should be within: 0 <= bdrg < 5x10**(-3) x u_max.";
+  if ((P.tdrg < 0.0 || P.tdrg > 15.e-3) && P.qdrg > 0.5) m += " quadratic top drag coefficient tdrg should be within: 0 <= tdrg < 5x10**(-3).";
+  else if (P.tdrg < 0.0 || P.tdrg > 5.e-2) m += " linear top drag coefficient tdrg should be within: 0 <= tdrg < 5x10**(-3) x u_max.";
+  if (!m.empty()) throw Fail{m};
+}
+
+}  // namespace
+
+extern "C" {
+
+beom_host *beom_host_create(const beom_params *par, const char *idir, const char *odir, const char *desc) {
+  beom_host *h = new beom_host();
+  try {
+    h->p = *par;
+    h->lm = par->lm; h->mm = par->mm; h->nlay = par->nlay; h->ndeg = par->ndeg;
+    h->nd1 = (size_t)par->ndeg + 1;
+    auto slash = [](const char *s) {  // pm:1002-1009
+      std::string r = s ? s : "";
+      if (!r.empty() && r.back() != '/') r.push_back('/');
+      return r;
+    };
+    h->idir = slash(idir);
+    h->odir = slash(odir);
+    h->desc = desc ? desc : "";
+    if (par->nlay < 1 || par->nlay > BEOM_MAXLAY) throw Fail{" nlay must be within 1..16."};
+    check_consistency_options(h->p);
+    read_input_data(h);
+    if (!h->odir.empty()) {
+      if (!beom_host_write_grid_files(h)) throw Fail{" could not write grid.bin / h_0.bin into " + h->odir};
+      if (h->p.rsta < 0.5 && !beom_host_save_metadata(h)) throw Fail{" could not write param_basin.txt into " + h->odir};
+    }
+    return h;
+  } catch (const Fail &e) {
+    beom_host_set_error("In main, in subroutine read_input_data," + e.msg);
+  } catch (const std::exception &e) {
+    beom_host_set_error(std::string("In main, in subroutine read_input_data, ") + e.what());
+  }
+  delete h;
+  return nullptr;
+}
+
+void beom_host_destroy(beom_host *h) { delete h; }
+
+double *beom_host_array(beom_host *h, const char *name) {
+  std::string s = name;
+#define F(x) if (s == #x) return h->x.empty() ? nullptr : h->x.data();
+  F(mk_u) F(mk_v) F(mk_n) F(mkpe) F(mkpi) F(fcor) F(h_th) F(nudg) F(fnud) F(hdot) F(taus) F(tide) F(bodf)
+  F(Ow) F(Os) F(Osum_) F(pi_s) F(h_0) F(hlay) F(u) F(v)
+#undef F
+  if (s == "h_2d") return h->h2d.d.data();
+  return nullptr;
+}
+int32_t *beom_host_iarray(beom_host *h, const char *name) {
+  std::string s = name;
+  if (s == "neig") return h->neig.data();
+  if (s == "subc") return h->subc.data();
+  if (s == "posc") return h->posc.data();
+  if (s == "segm") return h->segm.empty() ? nullptr : h->segm.data();
+  return nullptr;
+}
+double beom_host_scalar(const beom_host *h, const char *name) {
+  std::string s = name;
+  if (s == "invf") return h->invf;
+  if (s == "w_ti") return h->w_ti;
+  if (s == "tres") return h->tres;
+  if (s == "ctim") return h->ctim;
+  if (s == "nseg") return (double)h->nseg;
+  if (s == "flag_nudging") return h->flag_nudging ? 1.0 : 0.0;
+  if (s == "irec") return (double)h->irec;
+  return std::nan("");
+}
+const beom_params *beom_host_params(const beom_host *h) { return &h->p; }
+void beom_host_counts(const beom_host *h, int *nstp, int *notp, int *n_3d) {
+  if (nstp) *nstp = h->nstp;
+  if (notp) *notp = h->notp;
+  if (n_3d) *n_3d = h->n_3d;
+}
+
+void beom_host_fields(beom_host *h, beom_fields *f) {
+  std::memset(f, 0, sizeof *f);
+  auto opt = [](std::vector<double> &v) -> const double * { return v.empty() ? nullptr : v.data(); };
+  f->neig = h->neig.data(); f->subc = h->subc.data();
+  f->mk_u = h->mk_u.data(); f->mk_v = h->mk_v.data(); f->mk_n = h->mk_n.data();
+  f->mkpe = h->mkpe.data(); f->mkpi = h->mkpi.data();
+  f->fcor = h->fcor.data(); f->h_th = h->h_th.data();
+  f->nudg = opt(h->nudg); f->fnud = opt(h->fnud); f->hdot = opt(h->hdot);
+  f->taus = opt(h->taus); f->tide = opt(h->tide); f->bodf = opt(h->bodf);
+  f->segm = h->segm.empty() ? nullptr : h->segm.data();
+  f->nseg = h->nseg;
+  if (h->p.rgld > 0.5) { f->Ow = h->Ow.data(); f->Os = h->Os.data(); f->Osum_ = h->Osum_.data(); f->pi_s = h->pi_s.data(); }
+  f->flag_nudging = h->flag_nudging ? 1 : 0;
+  f->invf = h->invf;
+  f->w_ti = h->w_ti;
+}
+
+}  // extern "C"

@@ -1,0 +1,43 @@
+// main.cc -- the executable form of main.f95:26-37: errc/errm initialised, run(), quit().
+// usage: beom_run <shared_mod.f95 | parameter block> [--steps N] [--split] [--variant 0..3]
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "beom_host.h"
+
+int main(int argc, char **argv) {
+  if (argc < 2) {
+    std::fprintf(stderr, "usage: %s <shared_mod.f95> [--steps N] [--split] [--variant k]\n", argv[0]);
+    return 2;
+  }
+  beom_params par;
+  char idir[1024], odir[1024], desc[1024], err[2048];
+  if (beom_params_parse_file(argv[1], &par, idir, odir, desc, sizeof idir)) {
+    beom_host_last_error(err, sizeof err);
+    std::fprintf(stderr, "  *** ERROR CODE = -1 ***\n In main.f95, %s\n", err);
+    return 1;
+  }
+  int steps = 0;
+  beom_gpu_options opt;
+  beom_gpu_default_options(&opt);
+  for (int a = 2; a < argc; a++) {
+    if (!std::strcmp(argv[a], "--steps") && a + 1 < argc) steps = std::atoi(argv[++a]);
+    else if (!std::strcmp(argv[a], "--split")) opt.fused = 0;
+    else if (!std::strcmp(argv[a], "--variant") && a + 1 < argc) par.variant = std::atoi(argv[++a]);
+  }
+  beom_host *h = beom_host_create(&par, idir, odir, desc);
+  if (!h) {
+    beom_host_last_error(err, sizeof err);
+    std::fprintf(stderr, "  *** ERROR CODE = -1 ***\n %s\n", err);
+    return 1;
+  }
+  int rc = beom_host_run(h, &opt, steps);
+  if (rc) {
+    beom_host_last_error(err, sizeof err);
+    std::fprintf(stderr, "  *** ERROR CODE = %d ***\n %s\n", rc, err);
+  }
+  beom_gpu_finalize();
+  beom_host_destroy(h);
+  return rc ? 1 : 0;
+}

@@ -1,0 +1,85 @@
+// run.cc -- run() = read_input_data + integrate_time (private_mod.f95:99-103, 1840-1919) with the
+// per-step routines executed by the GPU library (include/beom_gpu.h).  The time loop is textually
+// the reference's: the same tstp/ctim/ramp/gene/upst bookkeeping, the same output cadence.
+#include <cstdio>
+#include <cstring>
+
+#include "host_model.h"
+
+extern "C" int beom_host_write_diag_record(beom_host *h, const char *var, const float *rec);
+
+namespace {
+int gpu_fail(const char *where, int rc) {
+  char b[512];
+  beom_gpu_last_error(b, sizeof b);
+  beom_host_set_error(std::string("In main, in subroutine integrate_time, ") + where + ": " + b);
+  return rc;
+}
+
+int outputs(beom_host *h, double ctim) {
+  int rc = beom_gpu_download_state(h->hlay.data(), h->u.data(), h->v.data());
+  if (rc) return gpu_fail("beom_gpu_download_state", rc);
+  if (h->p.rgld > 0.5 && (rc = beom_gpu_download_pi_s(h->pi_s.data()))) return gpu_fail("beom_gpu_download_pi_s", rc);
+  rc = beom_host_write_outputs(h, ctim);
+  if (rc) return rc;
+  if (h->p.diag > 0.5) {  // pm:2718-2722
+    const size_t cnt = (size_t)h->ndeg * h->nlay;
+    std::vector<float> pv(cnt), mo(cnt), vc(cnt);
+    if ((rc = beom_gpu_download_diag(pv.data(), mo.data(), vc.data()))) return gpu_fail("beom_gpu_download_diag", rc);
+    if (beom_host_write_diag_record(h, "pvor", pv.data()) || beom_host_write_diag_record(h, "mont", mo.data()) ||
+        beom_host_write_diag_record(h, "v_cc", vc.data())) {
+      beom_host_set_error("write_array: could not write a diag record into " + h->odir);
+      return -1001;
+    }
+  }
+  std::printf(" ctim = %.15g days; dt_s = %.15g days; record = %d\n", ctim, h->p.dt_s, h->irec - 1);
+  return 0;
+}
+}  // namespace
+
+extern "C" int beom_host_run(beom_host *h, const beom_gpu_options *opt, int max_steps) {
+  const beom_params &P = h->p;
+  beom_fields fld;
+  beom_host_fields(h, &fld);
+  int rc = beom_gpu_init(&P, &fld, opt);
+  if (rc) return gpu_fail("beom_gpu_init", rc);
+
+  std::printf(" lm = %d\n mm = %d\n", h->lm, h->mm);  // pm:233-234
+  if (P.rsta > 0.5) {                                  // pm:236-243
+    if ((rc = beom_host_read_restart(h))) return rc;
+    std::printf(" *** Restarting from record number %d at time = %.15g\n", h->irec - 1, h->tres);
+  }
+  if ((rc = beom_gpu_upload_state(h->hlay.data(), h->u.data(), h->v.data()))) return gpu_fail("beom_gpu_upload_state", rc);
+  if (P.rsta < 0.5 && !h->odir.empty() && (rc = outputs(h, 0.0))) return rc;
+
+  // integrate_time, pm:1840-1919
+  std::printf(" dl = %.15g meters.\n dt = %.15g seconds.\n", P.dl, P.dt);
+  const double dtd8 = P.dt / 24.0 / 3600.0;
+  int nstp = h->nstp;
+  if (max_steps > 0 && max_steps < nstp) nstp = max_steps;
+  double ramp = 1.0, gene = 0.0;
+  for (int tstp = 1; tstp <= nstp; tstp++) {
+    const double ctim = h->tres + dtd8 * (double)tstp;
+    if (tstp <= 3) {
+      if (tstp == 1) {  // pm:1861-1866
+        if ((rc = beom_gpu_stress())) return gpu_fail("beom_gpu_stress", rc);
+        if (P.rsta < 0.5 && ctim < P.dt_r) ramp = ctim / P.dt_r;
+      }
+      if ((rc = beom_gpu_step(tstp, ctim, ramp, gene, 1, 1))) return gpu_fail("beom_gpu_step", rc);
+      if (tstp == 3) {  // pm:1877-1884
+        gene = P.g_fb;
+        if (gene > 0.5 && P.rgld > 0.5) gene = 0.0;
+      }
+      continue;  // the reference writes no output during the first three steps
+    }
+    const bool upst = (tstp % h->n_3d) == 0;  // pm:1889-1896
+    if (upst && (rc = beom_gpu_stress())) return gpu_fail("beom_gpu_stress", rc);
+    ramp = 1.0;  // pm:1898-1901
+    if (P.rsta < 0.5 && ctim < P.dt_r) ramp = ctim / P.dt_r;
+    if ((rc = beom_gpu_step(tstp, ctim, ramp, gene, upst ? 1 : 0, 0))) return gpu_fail("beom_gpu_step", rc);
+    if (tstp % h->notp == 0 && !h->odir.empty() && (rc = outputs(h, ctim))) return rc;  // pm:1908-1910
+  }
+  if ((rc = beom_gpu_sync())) return gpu_fail("beom_gpu_sync", rc);
+  if ((rc = beom_gpu_download_state(h->hlay.data(), h->u.data(), h->v.data()))) return gpu_fail("beom_gpu_download_state", rc);
+  return 0;
+}

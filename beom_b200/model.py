@@ -1,0 +1,181 @@
+"""Host-side mirror of the reference's `run` for Python callers: parameter block -> read_input_data
+(C++ host driver) -> GPU library.  Everything numerical happens in the two native libraries; this
+module only moves pointers."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import Fields, Options, Params
+
+
+def parse_params(text: str, variant: int = 0):
+    """shared_mod.f95 text (or a print_params block) -> (Params, idir, odir, desc)."""
+    lib = _lib.host_lib()
+    p = Params()
+    bufs = [C.create_string_buffer(1024) for _ in range(3)]
+    rc = lib.beom_params_parse(text.encode(), C.byref(p), bufs[0], bufs[1], bufs[2], 1024)
+    if rc:
+        raise ValueError(_lib.host_error())
+    p.variant = variant
+    return p, bufs[0].value.decode(), bufs[1].value.decode(), bufs[2].value.decode()
+
+
+class HostModel:
+    """read_input_data (private_mod.f95:105-250) done by the C++ host driver."""
+
+    _PLANES = {"mk_u": 1, "mk_v": 1, "mk_n": 1, "mkpe": 1, "mkpi": 1, "fcor": 1, "h_th": 1, "nudg": 3, "taus": 2,
+               "Ow": 1, "Os": 1, "Osum_": 1, "pi_s": 1}
+
+    def __init__(self, params: Params, idir: str = "", odir: str = "", desc: str = ""):
+        self.lib = _lib.host_lib()
+        self.params = params
+        self.nlay, self.ndeg = params.nlay, params.ndeg
+        self.h = self.lib.beom_host_create(C.byref(params), idir.encode(), odir.encode(), desc.encode())
+        if not self.h:
+            raise RuntimeError(_lib.host_error())
+
+    @classmethod
+    def from_block(cls, path: str, variant: int = 0, write_outputs: bool = False):
+        with open(path) as f:
+            p, idir, odir, desc = parse_params(f.read(), variant)
+        return cls(p, idir, odir if write_outputs else "", desc)
+
+    def close(self):
+        if self.h:
+            self.lib.beom_host_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def array(self, name: str):
+        p = self.lib.beom_host_array(self.h, name.encode())
+        if not p:
+            return None
+        nd1 = self.ndeg + 1
+        if name in ("h_0", "hlay", "u", "v", "hdot"):
+            planes = self.nlay
+        elif name == "fnud":
+            planes = 3 * self.nlay
+        elif name == "tide":
+            return np.ctypeslib.as_array(p, shape=(3, nd1, 2))
+        elif name == "bodf":
+            return np.ctypeslib.as_array(p, shape=(2, self.nlay))
+        else:
+            planes = self._PLANES[name]
+        return np.ctypeslib.as_array(p, shape=(planes, nd1))
+
+    def iarray(self, name: str):
+        p = self.lib.beom_host_iarray(self.h, name.encode())
+        if not p:
+            return None
+        nd1 = self.ndeg + 1
+        if name == "neig":
+            return np.ctypeslib.as_array(p, shape=(nd1, 8))
+        if name == "subc":
+            return np.ctypeslib.as_array(p, shape=(2, nd1))
+        if name == "segm":
+            return np.ctypeslib.as_array(p, shape=(18, int(self.scalar("nseg"))))
+        return np.ctypeslib.as_array(p, shape=(nd1,))
+
+    def scalar(self, name: str) -> float:
+        return self.lib.beom_host_scalar(self.h, name.encode())
+
+    def counts(self):
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        self.lib.beom_host_counts(self.h, C.byref(a), C.byref(b), C.byref(c))
+        return a.value, b.value, c.value
+
+    def fields(self) -> Fields:
+        f = Fields()
+        self.lib.beom_host_fields(self.h, C.byref(f))
+        return f
+
+    def run(self, options: Options | None = None, max_steps: int = 0) -> int:
+        """run() of private_mod.f95:99-103: time loop + outputs, steps executed on the GPU."""
+        opt = options or default_options()
+        rc = self.lib.beom_host_run(self.h, C.byref(opt), max_steps)
+        if rc:
+            raise RuntimeError(_lib.host_error())
+        return rc
+
+
+def default_options(fused: bool = True, rank: int = 0, nranks: int = 1, device: int = -1) -> Options:
+    o = Options()
+    _lib.gpu_lib().beom_gpu_default_options(C.byref(o))
+    o.fused = 1 if fused else 0
+    o.rank, o.nranks, o.device = rank, nranks, device
+    return o
+
+
+def _dp(a: np.ndarray):
+    return a.ctypes.data_as(_lib.c_double_p)
+
+
+class GpuModel:
+    """The C ABI of include/beom_gpu.h for Python callers (tests, bench)."""
+
+    def __init__(self, params: Params, fields: Fields, options: Options | None = None):
+        self.lib = _lib.gpu_lib()
+        self.params = params
+        self.nlay, self.ndeg = params.nlay, params.ndeg
+        self.opt = options or default_options()
+        rc = self.lib.beom_gpu_init(C.byref(params), C.byref(fields), C.byref(self.opt))
+        if rc:
+            raise RuntimeError("beom_gpu_init: %s" % _lib.gpu_error())
+
+    def _ck(self, rc, what):
+        if rc:
+            raise RuntimeError("%s: %s" % (what, _lib.gpu_error()))
+
+    @property
+    def path(self) -> str:
+        return self.lib.beom_gpu_path().decode()
+
+    def upload_state(self, hlay, u, v):
+        for a in (hlay, u, v):
+            assert a.dtype == np.float64 and a.flags.c_contiguous and a.size == self.nlay * (self.ndeg + 1)
+        self._ck(self.lib.beom_gpu_upload_state(_dp(hlay), _dp(u), _dp(v)), "upload_state")
+
+    def stress(self):
+        self._ck(self.lib.beom_gpu_stress(), "stress")
+
+    def step(self, tstp, ctim, ramp, gene, upst, first_three):
+        self._ck(self.lib.beom_gpu_step(tstp, ctim, ramp, gene, int(upst), int(first_three)), "step")
+
+    def advance(self, tstp0, tstp1, tres=0.0):
+        self._ck(self.lib.beom_gpu_advance(tstp0, tstp1, tres), "advance")
+
+    def sync(self):
+        self._ck(self.lib.beom_gpu_sync(), "sync")
+
+    def download_state(self, out=None):
+        shape = (self.nlay, self.ndeg + 1)
+        out = out or tuple(np.zeros(shape) for _ in range(3))
+        self._ck(self.lib.beom_gpu_download_state(_dp(out[0]), _dp(out[1]), _dp(out[2])), "download_state")
+        return out
+
+    def download_aux(self):
+        nd1 = self.ndeg + 1
+        h_u, h_v = np.zeros((self.nlay, nd1)), np.zeros((self.nlay, nd1))
+        rs_h, dmdx, dmdy = np.zeros((self.nlay, nd1, 2)), np.zeros((self.nlay, nd1, 3)), np.zeros((self.nlay, nd1, 3))
+        self._ck(self.lib.beom_gpu_download_aux(_dp(h_u), _dp(h_v), _dp(rs_h), _dp(dmdx), _dp(dmdy)), "download_aux")
+        return h_u, h_v, rs_h, dmdx, dmdy
+
+    def mark(self, which):
+        self._ck(self.lib.beom_gpu_mark(which), "mark")
+
+    def elapsed_ms(self) -> float:
+        ms = C.c_double()
+        self._ck(self.lib.beom_gpu_elapsed_ms(C.byref(ms)), "elapsed_ms")
+        return ms.value
+
+    def launch_count(self) -> int:
+        return int(self.lib.beom_gpu_launch_count())
+
+    def close(self):
+        self.lib.beom_gpu_finalize()

@@ -1,0 +1,177 @@
+/* beom_gpu.h -- C ABI of the B200 (sm_100a) implementation of BEOM's per-timestep
+ * layered shallow-water update.
+ *
+ * This is the drop-in boundary.  The reference (zhazorken/beom) has no FFI of its own: the hot path
+ * is a set of private procedures of `module private_mod' operating on module arrays
+ * (private_mod.f95:27-93) and called from `integrate_time' (private_mod.f95:1840-1919).  Each entry
+ * point below replaces one of those call sites; the citation says which.  The Fortran side binds them
+ * with ISO_C_BINDING (see fortran/beom_gpu_mod.f95 and INTEGRATION.md).
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types; every function returns 0 on success or a negative code,
+ *     the text is available from beom_gpu_last_error().
+ *   - arrays are the reference's own arrays, Fortran column-major, passed by address of their first
+ *     element (index 0 = the "discarded cell" sentinel, private_mod.f95:31-33):
+ *       x(0:ndeg)            -> double[ndeg+1]
+ *       x(0:ndeg,nlay)       -> double[nlay][ndeg+1]
+ *       fnud(0:ndeg,nlay,3)  -> double[3][nlay][ndeg+1]
+ *       nudg(0:ndeg,3)       -> double[3][ndeg+1]
+ *       taus(0:ndeg,2)       -> double[2][ndeg+1]
+ *       tide(2,1,0:ndeg,3)   -> double[3][ndeg+1][1][2]
+ *       bodf(nlay,2)         -> double[2][nlay]
+ *       neig(8,0:ndeg)       -> int32[ndeg+1][8]
+ *       subc(0:ndeg,2)       -> int32[2][ndeg+1]
+ *       segm(nseg,18)        -> int32[18][nseg]
+ *   - the library copies what it needs; host arrays stay owned by the caller.
+ *   - one context per process (the reference is one model per process); one GPU per process;
+ *     several processes (one per GPU, y-slabs) cooperate through beom_gpu_comm_*.
+ */
+#ifndef BEOM_GPU_H
+#define BEOM_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BEOM_MAXLAY 16
+#define BEOM_ABI_VERSION 1
+
+/* Which private_mod*.f95 the update_h epilogue follows (SURVEY section 8, row a1'). */
+enum {
+  BEOM_VARIANT_STANDARD = 0, /* private_mod.f95:1593-1702            */
+  BEOM_VARIANT_1D       = 1, /* private_mod1d.f95:1635-1663, :2046   */
+  BEOM_VARIANT_3D       = 2, /* private_mod3d.f95:1635-1683          */
+  BEOM_VARIANT_PLUME    = 3  /* private_modplumenew.f95:1637-1724    */
+};
+
+/* POD mirror of the public parameters of shared_mod.f95:41-111.  All reals are the *double values the
+ * Fortran parameter holds*, i.e. default-real literals are already rounded through float32
+ * (e.g. grav = (double)9.8f).  beom_params_parse() produces this from a shared_mod.f95-style text. */
+typedef struct beom_params {
+  /* user section, shared_mod.f95:41-77 */
+  int32_t lm, mm, nlay, ndeg;
+  double dl, cext, f0;
+  double rhon[BEOM_MAXLAY], topl[BEOM_MAXLAY];
+  double dt_s, dt_o, dt_r, dt3d, bvis, dvis, bdrg, hmin, hsbl, hbbl;
+  double g_fb, uadv, qdrg, ocrp, rsta, xper, yper, diag, rgld, mcbc;
+  double tauw[2];
+  /* used by private_mod*.f95 but absent from the shipped shared_mod.f95 */
+  double svis, tdrg, topt, plum;
+  /* "other constants", shared_mod.f95:83-111 */
+  double dt, hsal, hdry, tole, pi, grav, rho0, beta, epsi, gamm, del1, del2, sor;
+  int32_t itmx, nsal;
+  /* not in shared_mod.f95: which private_mod file's update_h to follow */
+  int32_t variant;
+  int32_t reserved_;
+} beom_params;
+
+/* Static fields produced by the reference's read_input_data (private_mod.f95:105-250).  Pointers that
+ * are optional may be NULL, meaning "all zero / feature absent". */
+typedef struct beom_fields {
+  const int32_t *neig;   /* required */
+  const int32_t *subc;   /* required */
+  const double  *mk_u, *mk_v, *mk_n, *mkpe, *mkpi; /* required */
+  const double  *fcor;   /* required */
+  const double  *h_th;   /* required */
+  const double  *nudg;   /* optional: NULL = no sponge                   */
+  const double  *fnud;   /* optional: required when nudg or tide present  */
+  const double  *hdot;   /* optional */
+  const double  *taus;   /* optional */
+  const double  *tide;   /* optional */
+  const double  *bodf;   /* optional */
+  const int32_t *segm;   /* optional, with nseg */
+  const double  *Ow, *Os, *Osum_; /* optional (rgld = 1 only)            */
+  const double  *pi_s;   /* optional initial surface pressure (rgld = 1) */
+  int32_t nseg;
+  int32_t flag_nudging;  /* private_mod.f95:93, 868-871 */
+  double  invf;          /* private_mod.f95:223-229 */
+  double  w_ti;          /* private_mod.f95:953 */
+} beom_fields;
+
+/* Behavioural options of this library that have no counterpart in the reference. */
+typedef struct beom_gpu_options {
+  int32_t device;        /* CUDA device ordinal; -1 = current/LOCAL_RANK              */
+  int32_t fused;         /* 1 = fused single-pass step where the case allows, 0 = one  */
+                         /*     kernel per reference loop (always available)           */
+  int32_t rank, nranks;  /* y-slab decomposition; nranks = 1 for a single GPU          */
+  int32_t strict;        /* reserved (kernels are always built -fmad=false)            */
+  int32_t reserved_[3];
+} beom_gpu_options;
+
+const char *beom_gpu_version(void);
+int  beom_gpu_abi_version(void);
+/* Copies the last error text (NUL-terminated, truncated to len) and returns its full length. */
+int  beom_gpu_last_error(char *buf, int len);
+
+/* Replaces nothing in the reference: fills opt with defaults. */
+void beom_gpu_default_options(beom_gpu_options *opt);
+
+/* Called once at the end of read_input_data (after private_mod.f95:243).  Uploads the static fields.
+ * Fails (no CPU fallback) if no sm_100 device is usable. */
+int beom_gpu_init(const beom_params *par, const beom_fields *fld, const beom_gpu_options *opt);
+
+/* After init and after read_restart_record (private_mod.f95:238): hlay,u,v (0:ndeg,nlay).  Zeroes
+ * h_u,h_v,rs_h,dmdx,dmdy like initialize_variables (private_mod.f95:252-307). */
+int beom_gpu_upload_state(const double *hlay, const double *u, const double *v);
+
+/* distribute_stress (private_mod.f95:1921-2149; call sites :1863, :1895). */
+int beom_gpu_stress(void);
+
+/* Body of first_three_timesteps (private_mod.f95:2151-2223; first_three = 1) or
+ * gener_forward_backward (private_mod.f95:2225-2316; first_three = 0).  The scalars are the ones
+ * integrate_time computes (private_mod.f95:1862-1901).  Asynchronous. */
+int beom_gpu_step(int tstp, double ctim, double ramp, double gene, int upst, int first_three);
+
+/* The reference's whole loop body for steps tstp0..tstp1 (private_mod.f95:1861-1906) with ctim,
+ * ramp, upst, gene derived exactly as integrate_time does, tres being the restart time in days.
+ * Convenience for hosts that do not need per-step control; asynchronous. */
+int beom_gpu_advance(int tstp0, int tstp1, double tres);
+
+/* Before write_outputs (private_mod.f95:1909): synchronises and copies hlay,u,v back. */
+int beom_gpu_download_state(double *hlay, double *u, double *v);
+
+/* Optional extra state for bit-level checks: any pointer may be NULL.
+ * h_u,h_v: (0:ndeg,nlay); rs_h: (2,0:ndeg,nlay); dmdx,dmdy: (3,0:ndeg,nlay) in the reference's order
+ * (history index fastest, slot 3 newest). */
+int beom_gpu_download_aux(double *h_u, double *h_v, double *rs_h, double *dmdx, double *dmdy);
+
+/* Diagnostic records of write_array (private_mod.f95:2884-2974) exactly as it would write them:
+ * float32, ndeg x nlay (no sentinel), computed on the device with the reference's mixed
+ * float32/double arithmetic; NULL = skip. */
+int beom_gpu_download_diag(float *pvor, float *mont, float *v_cc);
+
+/* Rigid-lid surface pressure pi_s(0:ndeg) (private_mod.f95:91). */
+int beom_gpu_download_pi_s(double *pi_s);
+
+/* Conservation integrals (testcases/conservation.m:116-211), per layer: sum over wet cells of hlay
+ * (vol), kinetic energy proxy (ke), and, in pe[0], sum of eta_1^2.  Device reduction with
+ * warp shuffles, fixed order; all-reduced over ranks. */
+int beom_gpu_diagnostics(const double *h_0, double *vol, double *ke, double *pe);
+
+/* Blocks until all queued work is done; returns the sticky error if a kernel failed. */
+int beom_gpu_sync(void);
+
+/* Milliseconds of device time between two marks on the library's compute stream (CUDA events).
+ * beom_gpu_mark(0) ... beom_gpu_mark(1); beom_gpu_elapsed_ms() synchronises on mark 1. */
+int beom_gpu_mark(int which);
+int beom_gpu_elapsed_ms(double *ms);
+/* Number of kernel launches issued by this library since init. */
+long long beom_gpu_launch_count(void);
+/* Name of the kernel path in use ("fused" / "split"), for logs. */
+const char *beom_gpu_path(void);
+
+/* Multi-GPU (one process per GPU).  Rank 0 obtains an id (128 bytes), the host broadcasts it by any
+ * means (torch.distributed, MPI, a file), every rank calls comm_init before beom_gpu_init. */
+int beom_gpu_comm_unique_id(char id[128]);
+int beom_gpu_comm_init(const char id[128], int rank, int nranks, int device);
+int beom_gpu_comm_finalize(void);
+
+/* Before quit() (main.f95:35). */
+int beom_gpu_finalize(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BEOM_GPU_H */

@@ -1,0 +1,53 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session", autouse=True)
+def _built():
+    """The native libraries are built in-tree once per session (CPU-only cross compile works)."""
+    from beom_b200 import build
+    build.build_all()
+
+
+# small versions of the named configs: same code paths, sizes the CPU oracle finishes in seconds
+SMALL = {
+    "stommel1948": dict(dl=250.0e3),
+    "lock_exchange": dict(),
+    "unstable_jet": dict(dl=60.0e3),
+    "sill_exchange3D": dict(lx=8.0e3, ly=40.0e3),
+    "conservation": dict(dl=30.0e3),
+}
+
+
+@pytest.fixture(scope="session")
+def case_factory(tmp_path_factory):
+    from beom_b200 import cases, model
+
+    cache = {}
+
+    def make(name, small=True, variant=0, extra=None, **kw):
+        key = (name, small, variant, tuple(sorted((extra or {}).items())), tuple(sorted(kw.items())))
+        if key not in cache:
+            args = dict(SMALL[name]) if (small and name in SMALL) else {}
+            args.update(kw)
+            c = cases.CASES[name](**args)
+            if extra:
+                c.params_text += "".join("%-10s = %s\n" % kv for kv in extra.items())
+            d = str(tmp_path_factory.mktemp(name))
+            blk = c.write(d)
+            cache[key] = (c, d, blk)
+        c, d, blk = cache[key]
+        hm = model.HostModel.from_block(blk, variant=variant)
+        return c, d, hm
+
+    return make
