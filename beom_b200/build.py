@@ -37,7 +37,7 @@ def _newer(target: str, sources: list[str]) -> bool:
 
 
 def _run(cmd: list[str]) -> None:
-    print("+", " ".join(cmd), flush=True)
+    print("+", " ".join(cmd), file=sys.stderr, flush=True)
     subprocess.run(cmd, check=True)
 
 

@@ -712,6 +712,13 @@ int beom_gpu_diagnostics(const double *h_0, double *vol, double *ke, double *pe)
   return fail(-31, "beom_gpu_diagnostics: not implemented yet");
 }
 
+void *beom_gpu_host_alloc(size_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { fail(-50, "cudaHostAlloc(%zu) failed", bytes); return nullptr; }
+  return p;
+}
+void beom_gpu_host_free(void *p) { if (p) cudaFreeHost(p); }
+
 int beom_gpu_sync(void) {
   if (!g.ready) return fail(-20, "beom_gpu_sync: not initialised");
   CK(cudaStreamSynchronize(g.stream));

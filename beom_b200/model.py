@@ -177,5 +177,17 @@ class GpuModel:
     def launch_count(self) -> int:
         return int(self.lib.beom_gpu_launch_count())
 
+    def pinned(self, shape) -> np.ndarray:
+        """A float64 array in page-locked host memory (beom_gpu_host_alloc); freed at close()."""
+        n = int(np.prod(shape))
+        p = self.lib.beom_gpu_host_alloc(n * 8)
+        if not p:
+            raise MemoryError(_lib.gpu_error())
+        self._pinned = getattr(self, "_pinned", []) + [p]
+        return np.ctypeslib.as_array(C.cast(p, _lib.c_double_p), shape=(n,)).reshape(shape)
+
     def close(self):
+        for p in getattr(self, "_pinned", []):
+            self.lib.beom_gpu_host_free(p)
+        self._pinned = []
         self.lib.beom_gpu_finalize()

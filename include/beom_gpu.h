@@ -29,6 +29,7 @@
 #ifndef BEOM_GPU_H
 #define BEOM_GPU_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -149,6 +150,11 @@ int beom_gpu_download_pi_s(double *pi_s);
  * (vol), kinetic energy proxy (ke), and, in pe[0], sum of eta_1^2.  Device reduction with
  * warp shuffles, fixed order; all-reduced over ranks. */
 int beom_gpu_diagnostics(const double *h_0, double *vol, double *ke, double *pe);
+
+/* Page-locked host memory for state arrays that cross the boundary every output interval (the
+ * Fortran side maps it with c_f_pointer); plain malloc'ed arrays work too, only slower. */
+void *beom_gpu_host_alloc(size_t bytes);
+void  beom_gpu_host_free(void *p);
 
 /* Blocks until all queued work is done; returns the sticky error if a kernel failed. */
 int beom_gpu_sync(void);
