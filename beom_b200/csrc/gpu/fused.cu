@@ -26,11 +26,16 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <type_traits>
 
 namespace beom {
 
 namespace {
 
+#ifndef BEOM_FUSED_UNROLL
+#define BEOM_FUSED_UNROLL 1
+#endif
+constexpr int kUnroll = BEOM_FUSED_UNROLL;
 constexpr int kHalo = 2;             // halo lanes on each side of a warp
 constexpr int kUse = 32 - 2 * kHalo;  // 28 result columns per warp
 constexpr int kMaxLay = 8;           // layers per CTA (shared-memory exchange, warps per CTA)
@@ -69,11 +74,12 @@ struct MomIn {  // everything one momentum update needs, gathered by the caller
 };
 
 // update_u (private_mod.f95:1437-1500) when IS_U, update_v (private_mod.f95:1520-1586) otherwise.
-template <bool IS_U, bool VISC>
+template <bool IS_U, bool VISC, bool MASKED>
 __device__ __forceinline__ void momentum(const Dev &D, const MomIn &q, double &vel, double &flux, double &dmd4) {
-  const double hcen = (q.h_a + q.h_b) * (q.mask != 0.0 ? 0.5 : 1.0);
-  const double i__h = 1.0 / (hcen + 1.0 - q.mask);
-  dmd4 = sel(q.mask != 0.0, (q.m_far - q.m_here) * D.i_dl * D.grav);
+  const double hcen = (q.h_a + q.h_b) * (MASKED ? (q.mask != 0.0 ? 0.5 : 1.0) : 0.5);
+  const double i__h = 1.0 / (hcen + 1.0 - (MASKED ? q.mask : 1.0));
+  dmd4 = (q.m_far - q.m_here) * D.i_dl * D.grav;
+  if (MASKED) dmd4 = sel(q.mask != 0.0, dmd4);
   double rhsi;
   if (IS_U) rhsi = dmd4 * (1.0 - D.gene) + 0.25 * q.pv_a * (q.f_a0 + q.f_a1) + 0.25 * q.pv_b * (q.f_b0 + q.f_b1);
   else      rhsi = dmd4 * (1.0 - D.gene) - 0.25 * q.pv_a * (q.f_a0 + q.f_a1) - 0.25 * q.pv_b * (q.f_b0 + q.f_b1);
@@ -85,7 +91,7 @@ __device__ __forceinline__ void momentum(const Dev &D, const MomIn &q, double &v
     if (IS_U) rhsi = rhsi + (q.vcc_here * q.dv_here - q.vcc_far * q.dv_far) * D.i_dl - (q.vll_far * q.rv_far - q.vll_here * q.rv_here) * D.i_dl;
     else      rhsi = rhsi + (q.vcc_here * q.dv_here - q.vcc_far * q.dv_far) * D.i_dl + (q.vll_far * q.rv_far - q.vll_here * q.rv_here) * D.i_dl;
   }
-  double w = q.old + sel(q.mask != 0.0, rhsi) * D.dt;
+  double w = q.old + (MASKED ? sel(q.mask != 0.0, rhsi) : rhsi) * D.dt;
   if (D.has_nudg) {
     double tgt = q.fn;
     if (D.has_wind) {
@@ -138,7 +144,7 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned
                : "memory");
 }
 
-template <bool UFIRST, bool VISC>
+template <bool UFIRST, bool VISC, int NL>
 __global__ void __launch_bounds__(kMaxThreads, 1) k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O,
                                                      const __grid_constant__ StreamTab T, int groups, int rows_per_chunk, int wind_layers) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -147,14 +153,15 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_fused_step(const __grid_cons
   const int nwarps = blockDim.x >> 5;
   const int grp = wid % groups;
   const int l = wid / groups;  // layer of this warp
-  const int nlay = D.nlay;
+  const int nlay = NL > 0 ? NL : D.nlay;
   const int NX = D.NX;
   const int tcols = groups * 32;
   const int tcol = grp * 32 + lane;
   // shared memory: [2][nlay][tcols] new thickness | per-warp mbarriers | per-warp 2-stage raw-input ring
   double *sh_h = reinterpret_cast<double *>(smem_raw);
   unsigned long long *bars = reinterpret_cast<unsigned long long *>(sh_h + (size_t)2 * nlay * tcols);
-  double *ring = reinterpret_cast<double *>(bars + 2 * nwarps) + (size_t)wid * 2 * T.n * kSeg;
+  unsigned long long *gbars = bars + 2 * nwarps;  // [groups][2]: thickness exchange of a column group (split-phase)
+  double *ring = reinterpret_cast<double *>(gbars + 2 * groups) + (size_t)wid * 2 * T.n * kSeg;
 
   const int xw0 = D.x_lo + (blockIdx.x * groups + grp) * kUse - kHalo;  // column of lane 0
   const int xs = min(xw0 - 2, NX - kSeg);                                // first staged column (even)
@@ -188,9 +195,14 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_fused_step(const __grid_cons
     my_src = T.base[my_slot] + (size_t)T.lstride[my_slot] * L + xs;
     my_lag = T.lag[my_slot];
   }
+  const unsigned gbar0 = smem_u32(gbars + 2 * grp);
   if (lane == 0) {
     mbar_init(bar0, 1);
     mbar_init(bar0 + 8, 1);
+    if (l == 0) {
+      mbar_init(gbar0, (unsigned)(nlay * 32));
+      mbar_init(gbar0 + 8, (unsigned)(nlay * 32));
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -230,89 +242,66 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_fused_step(const __grid_cons
   unsigned f_next = D.flags[(size_t)R0 * NX + x];
 
 #define SG(stream, dx) sg[(int)T.slot[stream] * kSeg + (dx)]
-  for (int R = R0; R <= R1; R++) {
+#define SGF(stream, dx) sg[(stream) * kSeg + (dx)]
+#define SELM(p, a) (MASKED ? sel((p), (a)) : (a))
+#define MKN(f) (MASKED ? m_n(f) : 1.0)
+#define MKU(f) (MASKED ? m_u(f) : 1.0)
+#define MKV(f) (MASKED ? m_v(f) : 1.0)
+  // One row of the pipeline.  MASKED = false is the open-water fast path: every mask of the three rows in
+  // flight is 1 on all 32 lanes (and their E/W neighbours), so no select is needed.
+  auto row = [&](auto masked_tag, const int R, const unsigned f_own, const unsigned fw_0) {
+    constexpr bool MASKED = decltype(masked_tag)::value;
     const size_t c = (size_t)R * NX + x;
-    // -------------------------------------------------------------------------------- staged inputs of front row R
     const int st = (R - R0) & 1;
-    mbar_wait(bar0 + 8 * st, (unsigned)(((R - R0) >> 1) & 1));
     const double *sg = ring + (size_t)st * T.n * kSeg + 2 + lane;
-    const unsigned f_own = f_next;
-    f_next = D.flags[c + NX];
-    const double hu_0 = SG(S_HU, 0), huE_0 = SG(S_HU, 1);
-    const double hv_p1 = SG(S_HV, 0);
-    const double hold = SG(S_HL, 0);
-    const double r1 = SG(S_R1, 0), r2 = SG(S_R2, 0);
-    const double u_0 = SG(S_U, 0), uE_0 = SG(S_U, 1);
-    const double v_p1 = SG(S_V, 0), vW_p1 = SG(S_V, -1);
-    const double fcor_0 = SG(S_FCOR, 0), hth_0 = SG(S_HTH, 0);
+    const bool act = f_own & F_ACT;
+    const double hu_0 = SGF(S_HU, 0), huE_0 = SGF(S_HU, 1);
+    const double hv_p1 = SGF(S_HV, 0);
+    const double hold = SGF(S_HL, 0);
+    const double r1 = SGF(S_R1, 0), r2 = SGF(S_R2, 0);
+    const double u_0 = SGF(S_U, 0), uE_0 = SGF(S_U, 1);
+    const double v_p1 = SGF(S_V, 0), vW_p1 = SGF(S_V, -1);
+    const double fcor_0 = SGF(S_FCOR, 0);
     const double hdot_0 = D.has_hdot ? SG(S_HDOT, 0) : 0.0;
     double fnn_0 = 0.0, nudn_0 = 0.0;
     if (D.has_nudg) { fnn_0 = SG(S_FNN, 0); nudn_0 = SG(S_NUDN, 0); }
     MomIn qu, qv;
 
-    const unsigned fw_0 = f_own | (__shfl_up_sync(0xffffffffu, f_own, 1) << 8) | (__shfl_down_sync(0xffffffffu, f_own, 1) << 16);
-    const bool act = f_own & F_ACT;
 
     // -------------------------------------------------------------------------------- update_h, row R (pm:1610-1643)
     double rs_3 = (hu_0 - huE_0) * D.i_dl + (hv_0 - hv_p1) * D.i_dl;
     if (D.has_hdot) rs_3 = rs_3 + hdot_0;
-    rs_3 = sel(f_own & F_N, rs_3);
+    rs_3 = SELM(f_own & F_N, rs_3);
     const double rhs_h = (D.c_ab1 * rs_3 - D.c_ab2 * r2 + D.beta * r1) * D.dt * D.gene + rs_3 * D.dt * (1.0 - D.gene);
     double hn_0 = hold + rhs_h;
     if (D.has_nudg) hn_0 = fnn_0 * nudn_0 + (1.0 - nudn_0) * hn_0;
-    hn_0 = sel(act, hn_0);
+    hn_0 = SELM(act, hn_0);
     const bool row_own = (R >= ya && R <= yb);
-    if (col_ok && row_own && act) {
+    if (col_ok && row_own && (!MASKED || act)) {
       __stcs(o_hlay + c, hn_0);
       __stcs(o_rs + c, rs_3);
     }
     sh_h[((size_t)(R & 1) * nlay + l) * tcols + tcol] = hn_0;
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gbar0 + 8 * st) : "memory");  // split-phase: waited for at the end of the row
 
     // -------------------------------------------------------------------------------- rvor, dive, row R (pm:2388, 2435)
-    const double rv_0 = sel(act && (f_own & F_PE), (v_0 - vW_0 - u_0 + u_m1) * D.i_dl);
-    const double dv_0 = sel(act, (uE_0 - u_0 + v_p1 - v_0) * D.i_dl);
+    const double rv_0 = SELM(act && (f_own & F_PE), (v_0 - vW_0 - u_0 + u_m1) * D.i_dl);
+    const double dv_0 = SELM(act, (uE_0 - u_0 + v_p1 - v_0) * D.i_dl);
 
-    // only the layer-warps of this column group exchange thickness: one named barrier per group
-    asm volatile("bar.sync %0, %1;" ::"r"(grp + 1), "r"(nlay * 32) : "memory");
-
-    // -------------------------------------------------------------------------------- mont, row R (pm:2351-2383)
-    double mpot;
-    if (ocrp) {
-      mpot = hn_0 + D.hmin * (1.0 - m_n((uint8_t)f_own));
-      mpot = cube(D.hsal / mpot);
-      mpot = mpot * (-D.ocrp * D.i_ns * D.hsal * m_n((uint8_t)f_own));
-    } else {
-      mpot = -0.0;
-    }
-    mpot = mpot - 0.0;
-    {
-      const double *col = sh_h + (size_t)(R & 1) * nlay * tcols + tcol;
-      double hcol = 0.0;
-#pragma unroll
-      for (int i = 0; i < kMaxLay; i++) {
-        if (i < nlay) {
-          const double hi = col[(size_t)i * tcols];
-          if (i < l) mpot = mpot - cb[i] * hi;
-          hcol = hcol + hi;
-        }
-      }
-      mpot = hcol - hth_0 + mpot;
-    }
-    const double mo_0 = sel(act, mpot + kin * (uE_0 * uE_0 + u_0 * u_0 + v_p1 * v_p1 + v_0 * v_0));
 
     // -------------------------------------------------------------------------------- d2hx, pvor, row R; d2hy, row R-1
     const double hnE_0 = shdn(hn_0), hnW_0 = shup(hn_0);
-    double d2x_0 = sel((fw_0 & (F_N << 16)) && (fw_0 & (F_N << 8)) && (f_own & F_N), hnE_0 + hnW_0 - hn_0 * 2.0);
+    double d2x_0 = SELM((fw_0 & (F_N << 16)) && (fw_0 & (F_N << 8)) && (f_own & F_N), hnE_0 + hnW_0 - hn_0 * 2.0);
     if (ocrp && (hnE_0 < D.two_hs || hnW_0 < D.two_hs || hn_0 < D.two_hs)) d2x_0 = 0.0;
-    d2x_0 = sel(act, d2x_0);
-    double d2y_m1 = sel((f_own & F_N) && (fw_m2 & F_N) && (fw_m1 & F_N), hn_0 + hn_m2 - hn_m1 * 2.0);
+    d2x_0 = SELM(act, d2x_0);
+    double d2y_m1 = SELM((f_own & F_N) && (fw_m2 & F_N) && (fw_m1 & F_N), hn_0 + hn_m2 - hn_m1 * 2.0);
     if (ocrp && (hn_0 < D.two_hs || hn_m2 < D.two_hs || hn_m1 < D.two_hs)) d2y_m1 = 0.0;
-    d2y_m1 = sel(fw_m1 & F_ACT, d2y_m1);
+    d2y_m1 = SELM(fw_m1 & F_ACT, d2y_m1);
     double pv_0;
     {
       const double have = hn_0 + hnW_0 + hnW_m1 + hn_m1;
-      const double msum = m_n((uint8_t)f_own) + m_n((uint8_t)(fw_0 >> 8)) + m_n((uint8_t)(fw_m1 >> 8)) + m_n((uint8_t)fw_m1);
-      pv_0 = sel(act, sel(f_own & F_PI, fcor_0 + rv_0 * D.uadv) * msum / have);
+      const double msum = MKN((uint8_t)f_own) + MKN((uint8_t)(fw_0 >> 8)) + MKN((uint8_t)(fw_m1 >> 8)) + MKN((uint8_t)fw_m1);
+      pv_0 = SELM(act, SELM(f_own & F_PI, fcor_0 + rv_0 * D.uadv) * msum / have);
     }
 
     // -------------------------------------------------------------------------------- Leith viscosity, row R-1 (pm:2477-2502)
@@ -328,8 +317,8 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_fused_step(const __grid_cons
       const double tcc = a1 + (r_tr - r_tl) * (r_tr - r_tl) + a3 + (r_tr - r_br) * (r_tr - r_br) + (d_ri - d_cc) * (d_ri - d_cc) + b1 +
                          (d_to - d_cc) * (d_to - d_cc) + b3;
       const bool a = fw_m1 & F_ACT;
-      vll_m1 = sel(a, sqrt(tll) * D.dvis * D.dl * D.dl + D.bvis);
-      vcc_m1 = sel(a, sqrt(tcc) * D.dvis * D.dl * D.dl + D.bvis);
+      vll_m1 = SELM(a, sqrt(tll) * D.dvis * D.dl * D.dl + D.bvis);
+      vcc_m1 = SELM(a, sqrt(tcc) * D.dvis * D.dl * D.dl + D.bvis);
     }
 
     // -------------------------------------------------------------------------------- momentum
@@ -339,7 +328,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_fused_step(const __grid_cons
       // ---- u at row R-2 (pm:1422-1503) ----
       const size_t c2 = (size_t)max(R - 2, 0) * NX + x;
       const bool a2 = fw_m2 & F_ACT;
-      qu.h1 = SG(S_DX1, 0); qu.h2 = SG(S_DX2, 0); qu.h3 = SG(S_DX3, 0);
+      qu.h1 = SGF(S_DX1, 0); qu.h2 = SGF(S_DX2, 0); qu.h3 = SGF(S_DX3, 0);
       qu.tw_a = qu.tw_b = qu.te_a = qu.te_b = 0.0;
       if (wind) {
         qu.tw_b = SG(S_TTXU, 0); qu.tw_a = SG(S_TTXU, -1);
@@ -350,7 +339,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_fused_step(const __grid_cons
       qu.fn = qu.nud = 0.0;
       if (D.has_nudg) { qu.fn = SG(S_FNU, 0); qu.nud = SG(S_NUDU, 0); }
       qu.bodf = bodf_u;
-      qu.mask = m_u((uint8_t)fw_m2);
+      qu.mask = MKU((uint8_t)fw_m2);
       qu.h_a = hnW_m2; qu.h_b = hn_m2;
       qu.m_far = shup(mo_m2); qu.m_here = mo_m2;
       qu.pv_a = pv_m2; qu.f_a0 = hv_m2; qu.f_a1 = hvW_m2;
@@ -360,9 +349,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_fused_step(const __grid_cons
       qu.vll_far = vll_m1; qu.rv_far = rv_m1; qu.vll_here = vll_m2; qu.rv_here = rv_m2;
       qu.d2_far = shup(d2x_m2); qu.d2_here = d2x_m2;
       double un, hun, dm;
-      momentum<true, VISC>(D, qu, un, hun, dm);
-      hun = sel(a2, hun);
-      const bool sto = col_ok && a2 && (R - 2 >= ya) && (R - 2 <= yb);
+      momentum<true, VISC, MASKED>(D, qu, un, hun, dm);
+      hun = SELM(a2, hun);
+      const bool sto = col_ok && (!MASKED || a2) && (R - 2 >= ya) && (R - 2 <= yb);
       if (sto) {
         __stcs(o_u + c2, un);
         __stcs(o_hu + c2, hun);
@@ -371,7 +360,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_fused_step(const __grid_cons
       fl2_m2 = hun;
       fl2E_m2 = shdn(hun);
       // ---- v at row R-2 (pm:1505-1591), using the new h_u of rows R-2 and R-3 ----
-      qv.h1 = SG(S_DY1, 0); qv.h2 = SG(S_DY2, 0); qv.h3 = SG(S_DY3, 0);
+      qv.h1 = SGF(S_DY1, 0); qv.h2 = SGF(S_DY2, 0); qv.h3 = SGF(S_DY3, 0);
       qv.tw_a = qv.tw_b = qv.te_a = qv.te_b = 0.0;
       if (wind) {
         qv.tw_b = SG(S_TTYV, 0); qv.tw_a = SG(S_TTYVS, 0);
@@ -382,7 +371,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_fused_step(const __grid_cons
       qv.fn = qv.nud = 0.0;
       if (D.has_nudg) { qv.fn = SG(S_FNV, 0); qv.nud = SG(S_NUDV, 0); }
       qv.bodf = bodf_v;
-      qv.mask = m_v((uint8_t)fw_m2);
+      qv.mask = MKV((uint8_t)fw_m2);
       qv.h_a = hn_m2; qv.h_b = hn_m3;
       qv.m_far = mo_m3; qv.m_here = mo_m2;
       qv.pv_a = pv_m2; qv.f_a0 = fl2_m2; qv.f_a1 = fl2_m3;
@@ -392,10 +381,10 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_fused_step(const __grid_cons
       qv.vll_far = shdn(vll_m2); qv.rv_far = rvE_m2; qv.vll_here = vll_m2; qv.rv_here = rv_m2;
       qv.d2_far = d2y_m3; qv.d2_here = d2y_m2;
       double vn, hvn;
-      momentum<false, VISC>(D, qv, vn, hvn, dm);
+      momentum<false, VISC, MASKED>(D, qv, vn, hvn, dm);
       if (sto) {
         __stcs(o_v + c2, vn);
-        __stcs(o_hv + c2, sel(a2, hvn));
+        __stcs(o_hv + c2, SELM(a2, hvn));
         __stcs(o_dy + c2, dm);
       }
       fl2_m3 = fl2_m2;
@@ -404,7 +393,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_fused_step(const __grid_cons
       // ---- v at row R-1 (pm:1505-1591), old h_u ----
       const size_t c1 = (size_t)max(R - 1, 0) * NX + x, c2 = (size_t)max(R - 2, 0) * NX + x;
       const bool a1 = fw_m1 & F_ACT;
-      qv.h1 = SG(S_DY1, 0); qv.h2 = SG(S_DY2, 0); qv.h3 = SG(S_DY3, 0);
+      qv.h1 = SGF(S_DY1, 0); qv.h2 = SGF(S_DY2, 0); qv.h3 = SGF(S_DY3, 0);
       qv.tw_a = qv.tw_b = qv.te_a = qv.te_b = 0.0;
       if (wind) {
         qv.tw_b = SG(S_TTYV, 0); qv.tw_a = SG(S_TTYVS, 0);
@@ -415,7 +404,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_fused_step(const __grid_cons
       qv.fn = qv.nud = 0.0;
       if (D.has_nudg) { qv.fn = SG(S_FNV, 0); qv.nud = SG(S_NUDV, 0); }
       qv.bodf = bodf_v;
-      qv.mask = m_v((uint8_t)fw_m1);
+      qv.mask = MKV((uint8_t)fw_m1);
       qv.h_a = hn_m1; qv.h_b = hn_m2;
       qv.m_far = mo_m2; qv.m_here = mo_m1;
       qv.pv_a = pv_m1; qv.f_a0 = hu_m1; qv.f_a1 = hu_m2;
@@ -425,9 +414,9 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_fused_step(const __grid_cons
       qv.vll_far = shdn(vll_m1); qv.rv_far = rvE_m1; qv.vll_here = vll_m1; qv.rv_here = rv_m1;
       qv.d2_far = d2y_m2; qv.d2_here = d2y_m1;
       double vn, hvn, dm;
-      momentum<false, VISC>(D, qv, vn, hvn, dm);
-      hvn = sel(a1, hvn);
-      if (col_ok && a1 && (R - 1 >= ya) && (R - 1 <= yb)) {
+      momentum<false, VISC, MASKED>(D, qv, vn, hvn, dm);
+      hvn = SELM(a1, hvn);
+      if (col_ok && (!MASKED || a1) && (R - 1 >= ya) && (R - 1 <= yb)) {
         __stcs(o_v + c1, vn);
         __stcs(o_hv + c1, hvn);
         __stcs(o_dy + c1, dm);
@@ -436,7 +425,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_fused_step(const __grid_cons
       fl2E_m1 = shup(hvn);  // WEST neighbour in this order
       // ---- u at row R-2 (pm:1422-1503), using the new h_v of rows R-2 and R-1 ----
       const bool a2 = fw_m2 & F_ACT;
-      qu.h1 = SG(S_DX1, 0); qu.h2 = SG(S_DX2, 0); qu.h3 = SG(S_DX3, 0);
+      qu.h1 = SGF(S_DX1, 0); qu.h2 = SGF(S_DX2, 0); qu.h3 = SGF(S_DX3, 0);
       qu.tw_a = qu.tw_b = qu.te_a = qu.te_b = 0.0;
       if (wind) {
         qu.tw_b = SG(S_TTXU, 0); qu.tw_a = SG(S_TTXU, -1);
@@ -447,7 +436,7 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_fused_step(const __grid_cons
       qu.fn = qu.nud = 0.0;
       if (D.has_nudg) { qu.fn = SG(S_FNU, 0); qu.nud = SG(S_NUDU, 0); }
       qu.bodf = bodf_u;
-      qu.mask = m_u((uint8_t)fw_m2);
+      qu.mask = MKU((uint8_t)fw_m2);
       qu.h_a = hnW_m2; qu.h_b = hn_m2;
       qu.m_far = shup(mo_m2); qu.m_here = mo_m2;
       qu.pv_a = pv_m2; qu.f_a0 = fl2_m2; qu.f_a1 = fl2E_m2;
@@ -457,15 +446,41 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_fused_step(const __grid_cons
       qu.vll_far = vll_m1; qu.rv_far = rv_m1; qu.vll_here = vll_m2; qu.rv_here = rv_m2;
       qu.d2_far = shup(d2x_m2); qu.d2_here = d2x_m2;
       double un, hun;
-      momentum<true, VISC>(D, qu, un, hun, dm);
-      if (col_ok && a2 && (R - 2 >= ya) && (R - 2 <= yb)) {
+      momentum<true, VISC, MASKED>(D, qu, un, hun, dm);
+      if (col_ok && (!MASKED || a2) && (R - 2 >= ya) && (R - 2 <= yb)) {
         __stcs(o_u + c2, un);
-        __stcs(o_hu + c2, sel(a2, hun));
+        __stcs(o_hu + c2, SELM(a2, hun));
         __stcs(o_dx + c2, dm);
       }
       fl2_m2 = fl2_m1;
       fl2E_m2 = fl2E_m1;
     }
+
+    // -------------------------------------------------------------------------------- mont, row R (pm:2351-2383)
+    mbar_wait(gbar0 + 8 * st, (unsigned)(((R - R0) >> 1) & 1));  // every layer of this column group has published hn(R)
+    double mpot;
+    if (ocrp) {
+      mpot = hn_0 + D.hmin * (1.0 - MKN((uint8_t)f_own));
+      mpot = cube(D.hsal / mpot);
+      mpot = mpot * (-D.ocrp * D.i_ns * D.hsal * MKN((uint8_t)f_own));
+    } else {
+      mpot = -0.0;
+    }
+    mpot = mpot - 0.0;
+    {
+      const double *col = sh_h + (size_t)(R & 1) * nlay * tcols + tcol;
+      double hcol = 0.0;
+#pragma unroll
+      for (int i = 0; i < (NL > 0 ? NL : kMaxLay); i++) {
+        if (i < nlay) {
+          const double hi = col[(size_t)i * tcols];
+          if (i < l) mpot = mpot - cb[i] * hi;
+          hcol = hcol + hi;
+        }
+      }
+      mpot = hcol - SGF(S_HTH, 0) + mpot;
+    }
+    const double mo_0 = SELM(act, mpot + kin * (uE_0 * uE_0 + u_0 * u_0 + v_p1 * v_p1 + v_0 * v_0));
 
     __syncwarp();
     if (R + 2 <= R1) issue(R + 2);  // refill this stage (all lanes have read it)
@@ -492,7 +507,23 @@ __global__ void __launch_bounds__(kMaxThreads, 1) k_fused_step(const __grid_cons
     d2x_m2 = d2x_m1; d2x_m1 = d2x_0;
     d2y_m3 = d2y_m2; d2y_m2 = d2y_m1;
     fw_m2 = fw_m1; fw_m1 = fw_0;
+  };
+  constexpr unsigned kAllMasks = 0x3f | (0x3f << 8) | (0x3f << 16);
+#pragma unroll 1
+  for (int R = R0; R <= R1; R++) {
+    mbar_wait(bar0 + 8 * ((R - R0) & 1), (unsigned)(((R - R0) >> 1) & 1));  // staged inputs of front row R have landed
+    const unsigned f_own = f_next;
+    f_next = D.flags[(size_t)(R + 1) * NX + x];
+    const unsigned fw_0 = f_own | (__shfl_up_sync(0xffffffffu, f_own, 1) << 8) | (__shfl_down_sync(0xffffffffu, f_own, 1) << 16);
+    const bool open_water = __all_sync(0xffffffffu, ((fw_0 & fw_m1 & fw_m2) & kAllMasks) == kAllMasks);
+    if (open_water) row(std::false_type{}, R, f_own, fw_0);
+    else row(std::true_type{}, R, f_own, fw_0);
   }
+#undef SGF
+#undef SELM
+#undef MKN
+#undef MKU
+#undef MKV
 #undef SG
 }
 
@@ -538,16 +569,16 @@ StreamTab make_streams(const Dev &D, bool ufirst) {
 }
 size_t fused_smem_bytes(int nlay, int groups, int nstreams) {
   const size_t nwarps = (size_t)groups * nlay;
-  return (size_t)2 * nlay * groups * 32 * 8 + nwarps * 16 + nwarps * 2 * (size_t)nstreams * kSeg * 8;
+  return (size_t)2 * nlay * groups * 32 * 8 + nwarps * 16 + (size_t)groups * 16 + nwarps * 2 * (size_t)nstreams * kSeg * 8;
 }
-template <bool UF, bool VI>
+template <bool UF, bool VI, int NL>
 int launch(const Dev &in, const Dev &out, const StreamTab &T, dim3 grid, dim3 block, size_t shmem, cudaStream_t s) {
   static size_t configured = 0;
   if (shmem > configured) {
-    if (cudaFuncSetAttribute(k_fused_step<UF, VI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem) != cudaSuccess) return -61;
+    if (cudaFuncSetAttribute(k_fused_step<UF, VI, NL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem) != cudaSuccess) return -61;
     configured = shmem;
   }
-  k_fused_step<UF, VI><<<grid, block, shmem, s>>>(in, out, T, cfg.groups, cfg.rows_per_chunk, cfg.wind_layers);
+  k_fused_step<UF, VI, NL><<<grid, block, shmem, s>>>(in, out, T, cfg.groups, cfg.rows_per_chunk, cfg.wind_layers);
   return 0;
 }
 }  // namespace
@@ -606,8 +637,17 @@ int fused_step(const Dev &in, const Dev &out, int tstp, bool first_three, cudaSt
   const StreamTab T = make_streams(in, ufirst);
   const size_t shmem = fused_smem_bytes(in.nlay, cfg.groups, T.n);
   int rc;
-  if (cfg.visc) rc = ufirst ? launch<true, true>(in, out, T, grid, block, shmem, s) : launch<false, true>(in, out, T, grid, block, shmem, s);
-  else          rc = ufirst ? launch<true, false>(in, out, T, grid, block, shmem, s) : launch<false, false>(in, out, T, grid, block, shmem, s);
+#define BEOM_LAUNCH(NL)                                                                                                          \
+  (cfg.visc ? (ufirst ? launch<true, true, NL>(in, out, T, grid, block, shmem, s) : launch<false, true, NL>(in, out, T, grid, block, shmem, s)) \
+            : (ufirst ? launch<true, false, NL>(in, out, T, grid, block, shmem, s) : launch<false, false, NL>(in, out, T, grid, block, shmem, s)))
+  switch (in.nlay) {
+    case 1: rc = BEOM_LAUNCH(1); break;
+    case 2: rc = BEOM_LAUNCH(2); break;
+    case 3: rc = BEOM_LAUNCH(3); break;
+    case 4: rc = BEOM_LAUNCH(4); break;
+    default: rc = BEOM_LAUNCH(0); break;
+  }
+#undef BEOM_LAUNCH
   if (rc) return rc;
   *nlaunch = 1;
   return cudaGetLastError() == cudaSuccess ? 0 : -60;
