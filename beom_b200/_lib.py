@@ -67,7 +67,7 @@ GPU_SYMBOLS = [
     "beom_gpu_init", "beom_gpu_upload_state", "beom_gpu_stress", "beom_gpu_step", "beom_gpu_advance",
     "beom_gpu_download_state", "beom_gpu_download_aux", "beom_gpu_download_diag", "beom_gpu_download_pi_s",
     "beom_gpu_diagnostics", "beom_gpu_sync", "beom_gpu_mark", "beom_gpu_elapsed_ms", "beom_gpu_launch_count",
-    "beom_gpu_path", "beom_gpu_host_alloc", "beom_gpu_host_free", "beom_gpu_comm_unique_id", "beom_gpu_comm_init", "beom_gpu_comm_finalize", "beom_gpu_finalize",
+    "beom_gpu_path", "beom_gpu_point_range", "beom_gpu_set_window", "beom_gpu_host_alloc", "beom_gpu_host_free", "beom_gpu_comm_unique_id", "beom_gpu_comm_init", "beom_gpu_comm_finalize", "beom_gpu_finalize",
 ]
 
 _gpu = None
@@ -106,6 +106,8 @@ def gpu_lib() -> C.CDLL:
     lib.beom_gpu_mark.argtypes = [C.c_int]
     lib.beom_gpu_elapsed_ms.argtypes = [c_double_p]
     lib.beom_gpu_launch_count.restype = C.c_longlong
+    lib.beom_gpu_point_range.argtypes = [C.POINTER(C.c_int)] * 4
+    lib.beom_gpu_set_window.argtypes = [C.c_int, C.c_int]
     lib.beom_gpu_host_alloc.argtypes = [C.c_size_t]
     lib.beom_gpu_host_alloc.restype = C.c_void_p
     lib.beom_gpu_host_free.argtypes = [C.c_void_p]

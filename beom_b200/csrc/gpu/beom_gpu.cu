@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <initializer_list>
 #include <string>
 #include <vector>
 
@@ -72,8 +73,11 @@ struct Ctx {
   bool visc_valid = false;
   bool stress_const_done = false;  // tt3d = taus*layt does not change when ocrp = 0 and no drag
   cudaStream_t stream = nullptr;
+  double *halo_send[2] = {nullptr, nullptr}, *halo_recv[2] = {nullptr, nullptr};  // [lower, upper] neighbour
+  size_t halo_cap = 0;
   cudaEvent_t ev[2] = {nullptr, nullptr};
   long long launches = 0;
+  size_t win_first = 0, win_stride = 0;  // host state arrays cover points win_first .. win_first+win_stride-1 per layer
   int n_3d = 1;
 };
 Ctx g;
@@ -107,12 +111,49 @@ int upload_planes(double *dense, const double *vec, int nplanes) {
   return 0;
 }
 
-int mirror(double *field, int nplanes) {
-  if (g.nmir == 0) return 0;
-  k_mirror<<<(g.nmir + 127) / 128, 128, 0, g.stream>>>(field, g.plane, nplanes, g.d_mir_dst, g.d_mir_src, g.nmir);
-  g.launches++;
+struct Item {
+  double *p;
+  int planes;
+};
+
+// Make the cells that shadow other cells consistent after `items' were written: periodic aliases on
+// this device (k_mirror) and, with y-slabs, the G halo rows owned by the neighbouring ranks (one packed
+// NCCL send/recv per neighbour).
+int sync_fields(std::initializer_list<Item> items) {
+  if (g.nmir) {
+    for (const Item &it : items) {
+      if (!it.p) continue;
+      k_mirror<<<(g.nmir + 127) / 128, 128, 0, g.stream>>>(it.p, g.plane, it.planes, g.d_mir_dst, g.d_mir_src, g.nmir);
+      g.launches++;
+    }
+  }
+  if (g.nranks > 1) {
+    HaloTab t;
+    memset(&t, 0, sizeof t);
+    for (const Item &it : items) {
+      if (!it.p) continue;
+      if (t.n >= kHaloMaxItems) return fail(-70, "sync_fields: too many fields");
+      t.p[t.n] = it.p;
+      t.planes[t.n] = it.planes;
+      t.off[t.n] = t.total;
+      t.total += it.planes;
+      t.n++;
+    }
+    if (t.n == 0) return 0;
+    const size_t per_plane = (size_t)G * g.NX, count = per_plane * t.total;
+    if (count > g.halo_cap) return fail(-71, "sync_fields: halo buffer too small");
+    const int lo = g.rank > 0 ? g.rank - 1 : -1, hi = g.rank < g.nranks - 1 ? g.rank + 1 : -1;
+    const unsigned blocks = (unsigned)((per_plane + 255) / 256);
+    k_halo_pack<<<dim3(blocks, (unsigned)t.total, 2), 256, 0, g.stream>>>(t, g.plane, g.NX, g.D.y_lo, g.D.y_hi, g.halo_send[0], g.halo_send[1]);
+    g.launches++;
+    int rc = comm_exchange(g.halo_send[0], g.halo_recv[0], lo, g.halo_send[1], g.halo_recv[1], hi, count, g.stream, &g_err);
+    if (rc) return rc;
+    k_halo_unpack<<<dim3(blocks, (unsigned)t.total, 2), 256, 0, g.stream>>>(t, g.plane, g.NX, g.D.y_lo, g.D.y_hi, g.halo_recv[0], g.halo_recv[1], lo >= 0, hi >= 0);
+    g.launches++;
+  }
   return 0;
 }
+int mirror(double *field, int nplanes) { return sync_fields({{field, nplanes}}); }
 
 void set_state_pointers(Dev &D) {
   D.hlay = g.st[0][g.cur]; D.u = g.st[1][g.cur]; D.v = g.st[2][g.cur]; D.h_u = g.st[3][g.cur]; D.h_v = g.st[4][g.cur];
@@ -170,32 +211,30 @@ int step_split(int tstp, bool upst, bool first_three) {
   if (first_three) {  // pm:2166-2177
     k_centred_flux<<<gridL, kBlock, 0, g.stream>>>(D);
     g.launches++;
-    mirror(D.h_u, nl);
-    mirror(D.h_v, nl);
+    sync_fields({{D.h_u, nl}, {D.h_v, nl}});
   } else if (rgld) {  // pm:2237-2257
     k_upstream_flux<<<gridL, kBlock, 0, g.stream>>>(D);
     g.launches++;
-    mirror(D.h_u, nl);
-    mirror(D.h_v, nl);
+    sync_fields({{D.h_u, nl}, {D.h_v, nl}});
   }
   k_update_h<<<grid1, kBlock, 0, g.stream>>>(D);  // pm:2181 / 2259
   g.launches++;
   if (rgld) { k_rgld_correct<<<grid1, kBlock, 0, g.stream>>>(D); g.launches++; }
-  mirror(D.hlay, nl);
+  sync_fields({{D.hlay, nl}, {g.nranks > 1 ? D.rs_new : nullptr, nl}});
   g.rs_o = (g.rs_o + 1) % 3;
 
   k_diag<<<gridL, kBlock, 0, g.stream>>>(D);  // pm:2187 / 2266
   g.launches++;
-  if (g.nmir) { mirror(D.mont, nl); mirror(D.rvor, nl); mirror(D.pvor, nl); mirror(D.dive, nl); mirror(D.d2hx, nl); mirror(D.d2hy, nl); }
+  if (g.nmir || g.nranks > 1) sync_fields({{D.mont, nl}, {D.rvor, nl}, {D.pvor, nl}, {D.dive, nl}, {D.d2hx, nl}, {D.d2hy, nl}});
   if (first_three || (g.P.dvis > 1.e-3 && upst) || g.P.svis > 0) {  // pm:2188 / 2268-2270
     k_visc<<<gridL, kBlock, 0, g.stream>>>(D);
     g.launches++;
-    if (g.nmir) { mirror(D.v_cc, nl); mirror(D.v_ll, nl); }
+    if (g.nmir || g.nranks > 1) sync_fields({{D.v_cc, nl}, {D.v_ll, nl}});
     if (g.P.svis > 0.0) {
-      if (g.nmir) { mirror(D.delu, nl); mirror(D.delv, nl); }
+      if (g.nmir || g.nranks > 1) sync_fields({{D.delu, nl}, {D.delv, nl}});
       k_biharm<<<gridL, kBlock, 0, g.stream>>>(D);
       g.launches++;
-      if (g.nmir) { mirror(D.UU4, nl); mirror(D.VV4, nl); }
+      if (g.nmir || g.nranks > 1) sync_fields({{D.UU4, nl}, {D.VV4, nl}});
     }
   }
   for (int pass = 0; pass < 2; pass++) {  // pm:2193-2199 / 2276-2282
@@ -203,13 +242,11 @@ int step_split(int tstp, bool upst, bool first_three) {
     if (do_u) {
       k_update_u<<<gridL, kBlock, 0, g.stream>>>(D);
       g.launches++;
-      mirror(D.u, nl);
-      mirror(D.h_u, nl);
+      sync_fields({{D.u, nl}, {D.h_u, nl}, {g.nranks > 1 ? D.dx_new : nullptr, nl}});
     } else {
       k_update_v<<<gridL, kBlock, 0, g.stream>>>(D);
       g.launches++;
-      mirror(D.v, nl);
-      mirror(D.h_v, nl);
+      sync_fields({{D.v, nl}, {D.h_v, nl}, {g.nranks > 1 ? D.dy_new : nullptr, nl}});
     }
   }
   g.dx_o = (g.dx_o + 1) % 4;
@@ -219,7 +256,7 @@ int step_split(int tstp, bool upst, bool first_three) {
       k_obc<<<(g.nseg + 63) / 64, 64, 0, g.stream>>>(D, g.d_seg, g.nseg, pass);
       g.launches++;
     }
-    if (g.nmir) { mirror(D.u, nl); mirror(D.v, nl); mirror(D.h_u, nl); mirror(D.h_v, nl); }
+    if (g.nmir || g.nranks > 1) sync_fields({{D.u, nl}, {D.v, nl}, {D.h_u, nl}, {D.h_v, nl}});
   }
   if (rgld) return fail(-30, "rgld = 1 (surf_pressure) is not implemented on the device yet");
   CK(cudaGetLastError());
@@ -513,6 +550,14 @@ int beom_gpu_init(const beom_params *par, const beom_fields *fld, const beom_gpu
   for (auto &p : g.dy)
     if ((rc = dalloc(&p, pl * nl))) return rc;
 
+  if (g.nranks > 1) {
+    if (!comm_ready() || comm_size() != g.nranks || comm_rank() != g.rank)
+      return fail(-13, "beom_gpu_init: nranks = %d but beom_gpu_comm_init was not called with the same rank/size", g.nranks);
+    g.halo_cap = (size_t)G * g.NX * (size_t)nlay * 12;  // up to 12 layered fields per exchange
+    for (int k = 0; k < 2; k++)
+      if ((rc = dalloc(&g.halo_send[k], g.halo_cap)) || (rc = dalloc(&g.halo_recv[k], g.halo_cap))) return rc;
+  }
+
   // scalars and constants, evaluated like the reference does
   D.invf = fld->invf; D.w_ti = fld->w_ti;
   D.dl = par->dl; D.dt = par->dt; D.grav = par->grav;
@@ -550,6 +595,8 @@ int beom_gpu_init(const beom_params *par, const beom_fields *fld, const beom_gpu
         if ((rc = dalloc(&g.st[f][1], pl * nl))) return rc;
   }
   CK(cudaStreamSynchronize(g.stream));
+  g.win_first = 0;
+  g.win_stride = nd1;
   g.ready = true;
   g_err.clear();
   return 0;
@@ -570,7 +617,7 @@ int beom_gpu_upload_state(const double *hlay, const double *u, const double *v) 
   const int n = g.p_hi - g.p_lo + 1;
   for (int f = 0; f < 3; f++) {
     for (int l = 0; l < g.nlay; l++)
-      CK(cudaMemcpyAsync(g.stage + ((size_t)f * nl + l) * n, src[f] + (size_t)l * nd1 + g.p_lo, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, g.stream));
+      CK(cudaMemcpyAsync(g.stage + ((size_t)f * nl + l) * n, src[f] + (size_t)l * g.win_stride + (g.p_lo - g.win_first), (size_t)n * sizeof(double), cudaMemcpyHostToDevice, g.stream));
   }
   for (int f = 0; f < 3; f++)
     for (int l = 0; l < g.nlay; l++) {
@@ -581,7 +628,7 @@ int beom_gpu_upload_state(const double *hlay, const double *u, const double *v) 
   const size_t no = g.orphans.size();
   for (int f = 0; f < 3; f++)
     for (int l = 0; l < g.nlay; l++)
-      for (size_t k = 0; k < no; k++) g.orphan_val[((size_t)f * nl + l) * no + k] = src[f][(size_t)l * nd1 + g.orphans[k]];
+      for (size_t k = 0; k < no; k++) g.orphan_val[((size_t)f * nl + l) * no + k] = src[f][(size_t)l * g.win_stride + (g.orphans[k] - g.win_first)];
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(g.stream));
   return 0;
@@ -605,6 +652,11 @@ int beom_gpu_step(int tstp, double ctim, double ramp, double gene, int upst, int
     int rc = fused_step(D, Dout, tstp, first_three != 0, g.stream, &nlaunch);
     if (rc) return fail(rc, "fused_step failed: %s", cudaGetErrorString(cudaGetLastError()));
     g.launches += nlaunch;
+    if (g.nranks > 1) {
+      rc = sync_fields({{Dout.hlay, g.nlay}, {Dout.u, g.nlay}, {Dout.v, g.nlay}, {Dout.h_u, g.nlay}, {Dout.h_v, g.nlay},
+                        {D.rs_new, g.nlay}, {D.dx_new, g.nlay}, {D.dy_new, g.nlay}});
+      if (rc) return rc;
+    }
     g.cur = nxt;
     g.rs_o = (g.rs_o + 1) % 3;
     g.dx_o = (g.dx_o + 1) % 4;
@@ -659,7 +711,7 @@ static int download_planes(double *dst, const double *dense, int nplanes) {
       g.launches++;
     }
     for (int p = 0; p < np; p++)
-      CK(cudaMemcpyAsync(dst + (size_t)(p0 + p) * nd1 + g.p_lo, g.stage + (size_t)p * n, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+      CK(cudaMemcpyAsync(dst + (size_t)(p0 + p) * g.win_stride + (g.p_lo - g.win_first), g.stage + (size_t)p * n, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
     CK(cudaStreamSynchronize(g.stream));
   }
   return 0;
@@ -674,8 +726,8 @@ int beom_gpu_download_state(double *hlay, double *u, double *v) {
     int rc = download_planes(dst[f], g.st[f][g.cur], g.nlay);
     if (rc) return rc;
     for (int l = 0; l < g.nlay; l++) {
-      if (g.rank == 0) dst[f][(size_t)l * nd1] = 0.0;  // the discarded cell
-      for (size_t k = 0; k < no; k++) dst[f][(size_t)l * nd1 + g.orphans[k]] = g.orphan_val[((size_t)f * nl + l) * no + k];
+      if (g.win_first == 0) dst[f][(size_t)l * g.win_stride] = 0.0;  // the discarded cell
+      for (size_t k = 0; k < no; k++) dst[f][(size_t)l * g.win_stride + (g.orphans[k] - g.win_first)] = g.orphan_val[((size_t)f * nl + l) * no + k];
     }
   }
   CK(cudaGetLastError());
@@ -694,7 +746,7 @@ int beom_gpu_download_aux(double *h_u, double *h_v, double *rs_h, double *dmdx, 
       const size_t L = (size_t)l * g.plane;
       k_gather_hist<<<(n + 255) / 256, 256, 0, g.stream>>>(g.stage, a + L, b + L, c ? c + L : nullptr, nh, g.d_cell, g.p_lo, n);
       g.launches++;
-      CK(cudaMemcpyAsync(dst + ((size_t)l * nd1 + g.p_lo) * nh, g.stage, (size_t)n * nh * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+      CK(cudaMemcpyAsync(dst + ((size_t)l * g.win_stride + (g.p_lo - g.win_first)) * nh, g.stage, (size_t)n * nh * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
       CK(cudaStreamSynchronize(g.stream));
     }
     return 0;
@@ -717,6 +769,30 @@ int beom_gpu_download_pi_s(double *pi_s) {
 int beom_gpu_diagnostics(const double *h_0, double *vol, double *ke, double *pe) {
   (void)h_0; (void)vol; (void)ke; (void)pe;
   return fail(-31, "beom_gpu_diagnostics: not implemented yet");
+}
+
+int beom_gpu_point_range(int *first, int *count, int *own_first, int *own_count) {
+  if (!g.ready) return fail(-20, "beom_gpu_point_range: not initialised");
+  if (first) *first = g.p_lo;
+  if (count) *count = g.p_hi - g.p_lo + 1;
+  int of = 0, ol = -1;  // owned = rows j0..j1
+  for (int p = g.p_lo; p <= g.p_hi; p++) {
+    const int c = g.cell_of_point[p];
+    if (c < 0) continue;
+    const int y = c / g.NX;
+    if (y >= g.D.y_lo && y <= g.D.y_hi) { if (!of) of = p; ol = p; }
+  }
+  if (own_first) *own_first = of;
+  if (own_count) *own_count = ol - of + 1;
+  return 0;
+}
+int beom_gpu_set_window(int first, int count) {
+  if (!g.ready) return fail(-20, "beom_gpu_set_window: not initialised");
+  if (count <= 0) { g.win_first = 0; g.win_stride = (size_t)g.ndeg + 1; return 0; }
+  if (first > g.p_lo || first + count - 1 < g.p_hi) return fail(-21, "beom_gpu_set_window: window [%d,%d] does not cover this rank's points [%d,%d]", first, first + count - 1, g.p_lo, g.p_hi);
+  g.win_first = (size_t)first;
+  g.win_stride = (size_t)count;
+  return 0;
 }
 
 void *beom_gpu_host_alloc(size_t bytes) {

@@ -32,10 +32,6 @@ namespace beom {
 
 namespace {
 
-#ifndef BEOM_FUSED_UNROLL
-#define BEOM_FUSED_UNROLL 1
-#endif
-constexpr int kUnroll = BEOM_FUSED_UNROLL;
 constexpr int kHalo = 2;             // halo lanes on each side of a warp
 constexpr int kUse = 32 - 2 * kHalo;  // 28 result columns per warp
 constexpr int kMaxLay = 8;           // layers per CTA (shared-memory exchange, warps per CTA)
@@ -586,7 +582,8 @@ int launch(const Dev &in, const Dev &out, const StreamTab &T, dim3 grid, dim3 bl
 int fused_configure(const Dev &D, const beom_params &P, int nmir, int nranks, bool *enabled) {
   *enabled = false;
   cfg = FusedCfg();
-  if (nmir != 0 || nranks != 1) return 0;                    // periodic aliases / slabs: split path (for now)
+  (void)nranks;
+  if (nmir != 0) return 0;  // periodic aliases: split path (for now)
   if (P.rgld > 0.5 || P.svis > 0.0 || P.variant != BEOM_VARIANT_STANDARD) return 0;
   if (D.has_tide) return 0;
   if (D.nlay > kMaxLay) return 0;

@@ -136,9 +136,20 @@ class GpuModel:
     def path(self) -> str:
         return self.lib.beom_gpu_path().decode()
 
+    def point_range(self):
+        """(first, count, own_first, own_count) of the vector points on this rank."""
+        v = [C.c_int() for _ in range(4)]
+        self._ck(self.lib.beom_gpu_point_range(*[C.byref(x) for x in v]), "point_range")
+        return tuple(x.value for x in v)
+
+    def set_window(self, first, count):
+        self._ck(self.lib.beom_gpu_set_window(first, count), "set_window")
+        self._win = count
+
     def upload_state(self, hlay, u, v):
+        npts = getattr(self, "_win", 0) or (self.ndeg + 1)
         for a in (hlay, u, v):
-            assert a.dtype == np.float64 and a.flags.c_contiguous and a.size == self.nlay * (self.ndeg + 1)
+            assert a.dtype == np.float64 and a.flags.c_contiguous and a.size == self.nlay * npts
         self._ck(self.lib.beom_gpu_upload_state(_dp(hlay), _dp(u), _dp(v)), "upload_state")
 
     def stress(self):
@@ -154,7 +165,7 @@ class GpuModel:
         self._ck(self.lib.beom_gpu_sync(), "sync")
 
     def download_state(self, out=None):
-        shape = (self.nlay, self.ndeg + 1)
+        shape = (self.nlay, getattr(self, "_win", 0) or (self.ndeg + 1))
         out = out or tuple(np.zeros(shape) for _ in range(3))
         self._ck(self.lib.beom_gpu_download_state(_dp(out[0]), _dp(out[1]), _dp(out[2])), "download_state")
         return out

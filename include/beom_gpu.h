@@ -151,6 +151,13 @@ int beom_gpu_download_pi_s(double *pi_s);
  * warp shuffles, fixed order; all-reduced over ranks. */
 int beom_gpu_diagnostics(const double *h_0, double *vol, double *ke, double *pe);
 
+/* y-slab runs: the vector points this rank holds (owned rows + halo rows: first,count) and owns
+ * (own_first, own_count).  beom_gpu_set_window(first, count) declares that the state arrays passed to
+ * upload_state / download_state / download_aux from now on hold only points first..first+count-1 of
+ * each layer ([nlay][count], must cover the rank's points); count <= 0 restores whole arrays. */
+int beom_gpu_point_range(int *first, int *count, int *own_first, int *own_count);
+int beom_gpu_set_window(int first, int count);
+
 /* Page-locked host memory for state arrays that cross the boundary every output interval (the
  * Fortran side maps it with c_f_pointer); plain malloc'ed arrays work too, only slower. */
 void *beom_gpu_host_alloc(size_t bytes);

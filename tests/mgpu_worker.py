@@ -1,0 +1,60 @@
+"""Worker of tests/test_multigpu.py: one rank per GPU under torchrun; compares this rank's slab with
+the CPU oracle bit for bit."""
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    import torch
+    import torch.distributed as dist
+    from beom_b200 import cases, dist as bdist, model
+    from oracle.pyoracle import Oracle
+
+    rank, world, local = bdist.env_rank()
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    bdist.init_comm(rank, world, local)
+    name, nsteps, fused = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+    if name == "synthetic_basin":
+        c = cases.synthetic_basin(n=300, mm=170, nlay=4)
+    else:
+        c = cases.sill_exchange3D(lx=8.0e3, ly=40.0e3)
+    d = tempfile.mkdtemp(prefix="beom_mg%d_" % rank)
+    blk = c.write(d)
+    hm = model.HostModel.from_block(blk)
+    orc = Oracle(hm.params, d)
+    orc.advance(1, nsteps)
+    gm = model.GpuModel(hm.params, hm.fields(), model.default_options(fused=bool(fused), rank=rank, nranks=world, device=local))
+    first, count, own_first, own_count = gm.point_range()
+    gm.upload_state(hm.array("hlay"), hm.array("u"), hm.array("v"))
+    gm.advance(1, nsteps)
+    hl, u, v = gm.download_state()
+    aux = gm.download_aux()
+    sl = slice(own_first, own_first + own_count)
+    bad = []
+    for nm, got in (("hlay", hl), ("u", u), ("v", v), ("h_u", aux[0]), ("h_v", aux[1])):
+        want = orc.array(nm)
+        if not np.array_equal(got[:, sl], want[:, sl]):
+            bad.append("%s (max abs %.3e)" % (nm, float(np.max(np.abs(got[:, sl] - want[:, sl])))))
+    for nm, got in (("rs_h", aux[2]), ("dmdx", aux[3]), ("dmdy", aux[4])):
+        want = orc.array(nm)
+        if not np.array_equal(got[:, sl], want[:, sl]):
+            bad.append(nm)
+    path = gm.path
+    gm.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    if bad:
+        print("rank %d/%d %s path: MISMATCH %s" % (rank, world, path, bad), flush=True)
+        sys.exit(1)
+    print("rank %d/%d %s path: points %d..%d bit-identical to the oracle after %d steps" % (rank, world, path, own_first, own_first + own_count - 1, nsteps), flush=True)
+
+
+if __name__ == "__main__":
+    main()
