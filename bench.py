@@ -176,33 +176,48 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     steps, warm = args.steps, max(args.warmup, 3)
 
-    tmp = tempfile.mkdtemp(prefix="beom_bench_r%d_" % rank)
+    from beom_b200 import dist as bdist
+    bdist.init_comm(rank, world, local_rank)
+    # inputs are written once (rank 0) into a directory every rank of this node can read
+    shared = [tempfile.mkdtemp(prefix="beom_bench_") if rank == 0 else None]
+    if world > 1:
+        dist.broadcast_object_list(shared, src=0)
+    tmp = shared[0]
     try:
         t0 = time.perf_counter()
-        c, blk = make_case(n, nlay, tmp)
-        hm = model.HostModel.from_block(blk)
-        log("[rank %d] inputs + read_input_data: %.1f s" % (rank, time.perf_counter() - t0))
-        for f in os.listdir(tmp):
-            if f.endswith(".bin"):
-                os.remove(os.path.join(tmp, f))
-        opt = model.default_options(fused=not args.split, rank=rank, nranks=world, device=local_rank)
+        c = None
+        if rank == 0:
+            c, blk = make_case(n, nlay, tmp)
+            log("[rank 0] inputs written: %.1f s" % (time.perf_counter() - t0))
         if world > 1:
-            lib = _lib.gpu_lib()
-            uid = torch.zeros(128, dtype=torch.uint8)
-            if rank == 0:
-                buf = C.create_string_buffer(128)
-                if lib.beom_gpu_comm_unique_id(buf):
-                    raise RuntimeError(_lib.gpu_error())
-                uid = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).clone()
-            uid = uid.cuda()
-            dist.broadcast(uid, 0)
-            if lib.beom_gpu_comm_init(bytes(uid.cpu().numpy().tobytes()), rank, world, local_rank):
-                raise RuntimeError(_lib.gpu_error())
-        gm = model.GpuModel(hm.params, hm.fields(), opt)
-        nd1 = c.ndeg + 1
-        hl = gm.pinned((nlay, nd1)); uu = gm.pinned((nlay, nd1)); vv = gm.pinned((nlay, nd1))
-        hl[:] = hm.array("hlay"); uu[:] = hm.array("u"); vv[:] = hm.array("v")
-        hm.close()
+            dist.barrier()
+        blk = os.path.join(tmp, "shared_mod_block.f95")
+        nd1 = (n + 1) * (n + 1) + 1
+        opt = model.default_options(fused=not args.split, rank=rank, nranks=world, device=local_rank)
+        gm = hl = uu = vv = None
+        # read_input_data holds ~25 GB of host arrays for this grid: at most two ranks do it at a time
+        for turn in range(0, world, 2):
+            if turn <= rank < turn + 2:
+                t0 = time.perf_counter()
+                hm = model.HostModel.from_block(blk)
+                gm = model.GpuModel(hm.params, hm.fields(), opt)
+                first, count, own_first, own_count = gm.point_range()
+                if world > 1:
+                    gm.set_window(first, count)
+                else:
+                    first, count = 0, nd1
+                hl = gm.pinned((nlay, count)); uu = gm.pinned((nlay, count)); vv = gm.pinned((nlay, count))
+                hl[:] = hm.array("hlay")[:, first:first + count]
+                uu[:] = hm.array("u")[:, first:first + count]
+                vv[:] = hm.array("v")[:, first:first + count]
+                hm.close()
+                log("[rank %d] read_input_data + beom_gpu_init: %.1f s" % (rank, time.perf_counter() - t0))
+            if world > 1:
+                dist.barrier()
+        if rank == 0:
+            for f in os.listdir(tmp):
+                if f.endswith(".bin"):
+                    os.remove(os.path.join(tmp, f))
 
         def barrier():
             gm.sync()
@@ -218,7 +233,8 @@ def main():
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
-            time.sleep(0.3)
+        time.sleep(0.3)  # let nvidia-smi start sampling; every rank waits the same, then they line up again
+        barrier()
         l0 = gm.launch_count()
         gm.mark(0)
         gm.advance(warm + 1, warm + steps)
@@ -248,14 +264,15 @@ def main():
                 t = torch.tensor([dt], dtype=torch.float64, device="cuda")
                 dist.all_reduce(t, op=dist.ReduceOp.MAX)
                 dt = float(t.item())
-            nbytes = 3.0 * nlay * nd1 * 8
+            nbytes = 3.0 * nlay * count * 8 * world  # every rank moves its own slab
             e2e = {"value": updates_per_step * steps / dt, "unit": "cell-layer updates/s", "h2d_bytes_per_step": nbytes / steps,
                    "d2h_bytes_per_step": nbytes / steps, "seconds": dt,
                    "what": "beom_gpu_upload_state (pinned host hlay,u,v) + %d steps + beom_gpu_download_state" % steps}
         path = gm.path
         gm.close()
     finally:
-        shutil.rmtree(tmp, ignore_errors=True)
+        if rank == 0:
+            shutil.rmtree(tmp, ignore_errors=True)
 
     if rank != 0:
         if world > 1:

@@ -119,7 +119,7 @@ struct Item {
 // Make the cells that shadow other cells consistent after `items' were written: periodic aliases on
 // this device (k_mirror) and, with y-slabs, the G halo rows owned by the neighbouring ranks (one packed
 // NCCL send/recv per neighbour).
-int sync_fields(std::initializer_list<Item> items) {
+int sync_fields(std::initializer_list<Item> items, bool remote = true) {
   if (g.nmir) {
     for (const Item &it : items) {
       if (!it.p) continue;
@@ -127,7 +127,7 @@ int sync_fields(std::initializer_list<Item> items) {
       g.launches++;
     }
   }
-  if (g.nranks > 1) {
+  if (g.nranks > 1 && remote) {
     HaloTab t;
     memset(&t, 0, sizeof t);
     for (const Item &it : items) {
@@ -624,7 +624,8 @@ int beom_gpu_upload_state(const double *hlay, const double *u, const double *v) 
       k_scatter<double><<<(n + 255) / 256, 256, 0, g.stream>>>(g.st[f][0] + (size_t)l * pl, g.stage + ((size_t)f * nl + l) * n, g.d_cell, g.p_lo, n);
       g.launches++;
     }
-  for (int f = 0; f < 3; f++) mirror(g.st[f][0], g.nlay);
+  // halo rows come straight from the caller's arrays: no exchange here (upload is not a collective)
+  for (int f = 0; f < 3; f++) sync_fields({{g.st[f][0], g.nlay}}, false);
   const size_t no = g.orphans.size();
   for (int f = 0; f < 3; f++)
     for (int l = 0; l < g.nlay; l++)
