@@ -143,8 +143,10 @@ def main():
               "bytes_per_update_algorithmic": ALGO_BYTES_PER_UPDATE}
 
     from beom_b200 import build
+    from oracle import build as obuild
     if rank == 0:
         build.build_all()
+        obuild.build_oracle()
 
     # ---------------------------------------------------------------------------------- reference arm
     if args.impl == "reference":

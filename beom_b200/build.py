@@ -3,8 +3,6 @@
   beom_b200/lib/libbeom_gpu.so    hand-written CUDA kernels + the C ABI (nvcc, sm_100a only)
   beom_b200/lib/libbeom_host.so   C++ host driver (parameter parser, read_input_data, outputs, time loop)
   beom_b200/lib/beom_run          executable equivalent of main.f95
-  oracle/libbeom_oracle.so        the CPU checker (tests only), strict IEEE
-  oracle/libbeom_oracle_omp.so    the same source with OpenMP, for the CPU baseline timing
 
 Run as ``python -m beom_b200.build`` or through ``__graft_entry__.build()``.
 """
@@ -20,7 +18,6 @@ ROOT = os.path.dirname(HERE)
 LIBDIR = os.path.join(HERE, "lib")
 GPU_SRC = os.path.join(HERE, "csrc", "gpu")
 HOST_SRC = os.path.join(HERE, "csrc", "host")
-ORACLE = os.path.join(ROOT, "oracle")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -72,22 +69,9 @@ def build_host(force: bool = False) -> str:
     return out
 
 
-def build_oracle(force: bool = False) -> str:
-    src = os.path.join(ORACLE, "beom_oracle.c")
-    deps = [src, os.path.join(ORACLE, "beom_oracle.h"), os.path.join(ROOT, "include", "beom_gpu.h")]
-    out = os.path.join(ORACLE, "libbeom_oracle.so")
-    if force or _newer(out, deps):
-        _run(["gcc", "-O2", "-ffp-contract=off", "-Wall", "-Wextra", "-fPIC", "-shared", src, "-o", out, "-lm"])
-    omp = os.path.join(ORACLE, "libbeom_oracle_omp.so")
-    if force or _newer(omp, deps):
-        _run(["gcc", "-O3", "-march=x86-64-v3", "-fopenmp", "-Wall", "-fPIC", "-shared", src, "-o", omp, "-lm"])
-    return out
-
-
 def build_all(force: bool = False) -> None:
     build_gpu(force)
     build_host(force)
-    build_oracle(force)
 
 
 if __name__ == "__main__":

@@ -16,7 +16,9 @@ def pytest_configure(config):
 def _built():
     """The native libraries are built in-tree once per session (CPU-only cross compile works)."""
     from beom_b200 import build
+    from oracle import build as obuild
     build.build_all()
+    obuild.build_oracle()
 
 
 # small versions of the named configs: same code paths, sizes the CPU oracle finishes in seconds

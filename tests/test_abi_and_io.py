@@ -1,0 +1,115 @@
+"""The C ABI library loads without a GPU and exports every symbol include/beom_gpu.h declares; without a
+usable device it fails loudly (no CPU fallback).  Host-side output files are byte-compatible with what
+write_array computes (checked against the oracle's records)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from beom_b200 import _lib, model, readers
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared(header):
+    with open(os.path.join(ROOT, header)) as f:
+        text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    return sorted(set(re.findall(r"\b(beom_(?:gpu|host|params)_\w+)\s*\(", text)))
+
+
+def test_gpu_library_exports_every_declared_symbol():
+    lib = _lib.gpu_lib()
+    names = declared("include/beom_gpu.h")
+    assert len(names) >= 25
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert sorted(_lib.GPU_SYMBOLS) == names
+    assert lib.beom_gpu_abi_version() == 1
+    assert b"sm_100a" in lib.beom_gpu_version()
+
+
+def test_host_library_exports_every_declared_symbol():
+    lib = _lib.host_lib()
+    missing = [n for n in declared("beom_b200/csrc/host/beom_host.h") if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_struct_layouts_match_the_header():
+    # sizes computed from the header by hand: a change there must be mirrored in _lib.py
+    assert C.sizeof(_lib.Params) == 4 * 4 + 8 * (3 + 32 + 10 + 10 + 2 + 4 + 13) + 4 * 4
+    assert C.sizeof(_lib.Fields) == 8 * 20 + 4 * 2 + 8 * 2
+    assert C.sizeof(_lib.Options) == 4 * 8
+
+
+def test_no_cpu_fallback(case_factory):
+    """On a machine without a B200 the product path refuses to run instead of computing on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the failure path cannot be exercised")
+    c, d, hm = case_factory("lock_exchange")
+    with pytest.raises(RuntimeError, match="no CUDA device|no CPU fallback|sm_100a"):
+        model.GpuModel(hm.params, hm.fields())
+    lib = _lib.gpu_lib()
+    assert lib.beom_gpu_stress() != 0 and lib.beom_gpu_sync() != 0  # nothing works before a successful init
+    assert "not initialised" in _lib.gpu_error()
+
+
+def test_product_package_never_touches_the_oracle():
+    for base, _, files in os.walk(os.path.join(ROOT, "beom_b200")):
+        for f in files:
+            if f.endswith((".py", ".cc", ".cu", ".cuh", ".h")):
+                with open(os.path.join(base, f), errors="replace") as fh:
+                    text = fh.read()
+                assert "pyoracle" not in text and "beom_oracle" not in text, os.path.join(base, f)
+
+
+@pytest.mark.parametrize("name", ["lock_exchange", "sill_exchange3D", "stommel1948"])
+def test_output_files_are_what_write_array_computes(case_factory, tmp_path, name):
+    from oracle.pyoracle import Oracle
+    from beom_b200 import cases
+    from tests.conftest import SMALL
+    c = cases.CASES[name](**SMALL[name])
+    blk = c.write(str(tmp_path))
+    hm = model.HostModel.from_block(blk, write_outputs=True)  # writes grid.bin, h_0.bin, param_basin.txt
+    orc = Oracle(hm.params, str(tmp_path))
+    assert hm.lib.beom_host_write_outputs(hm.h, 0.0) == 0       # record 1 = initial condition (pm:240-243)
+    assert hm.lib.beom_host_write_outputs(hm.h, 0.5) == 0       # record 2 (same state, later time)
+    n, nlay = c.ndeg, c.nlay
+    for var in ("eta_", "u___", "v___"):
+        raw = np.fromfile(tmp_path / (var + ".bin"), dtype="<f4")
+        assert raw.size == 2 * n * nlay
+        want = orc.record(var)
+        assert np.array_equal(raw[:n * nlay].reshape(nlay, n), want), var
+        assert np.array_equal(raw[n * nlay:].reshape(nlay, n), want), var
+    grid = np.fromfile(tmp_path / "grid.bin", dtype="<i4")
+    assert grid.size == 5 * n
+    sub = orc.iarray("subc")
+    assert np.array_equal(grid[:n], sub[0, 1:] + 1 + sub[1, 1:] * (c.lm + 2))
+    assert np.array_equal(grid[n:2 * n], orc.array("mk_n")[0, 1:].astype(np.int32))
+    h0 = np.fromfile(tmp_path / "h_0.bin", dtype="<f4").reshape(nlay, n)
+    assert np.array_equal(h0, orc.array("h_0")[:, 1:].astype(np.float32))
+    # the reference's own reader logic (get_metadata.m / get_field.m) understands the files
+    meta = readers.get_metadata(str(tmp_path))
+    assert (meta["lm"], meta["mm"], meta["nlay"], meta["ndeg"]) == (c.lm, c.mm, c.nlay, c.ndeg)
+    assert meta["dl"] == hm.params.dl and abs(meta["cext"] - hm.params.cext) < 1e-12
+    assert list(meta["taxi"]) == [0.0, 0.5]
+    eta = readers.get_field("eta_", 0, str(tmp_path), meta)
+    assert eta.shape == (c.lm + 2, c.mm + 2, c.nlay) and np.isnan(eta[0, 0, 0]) and np.isfinite(eta[1, 1, 0])
+
+
+def test_restart_reads_back_the_last_record(tmp_path):
+    """read_restart_record (private_mod.f95:1299-1420): hlay = h_0 + eta_k - eta_k+1 from float32 files."""
+    from beom_b200 import cases
+    c = cases.lock_exchange()
+    blk = c.write(str(tmp_path))
+    hm = model.HostModel.from_block(blk, write_outputs=True)
+    h_before = hm.array("hlay").copy()
+    assert hm.lib.beom_host_write_outputs(hm.h, 0.25) == 0
+    hm.array("hlay")[:] = 0.0
+    hm.array("u")[:] = 7.0
+    assert hm.lib.beom_host_read_restart(hm.h) == 0
+    assert hm.scalar("tres") == 0.25 and hm.scalar("irec") == 2
+    assert np.all(hm.array("u")[:, 1:] == 0.0)
+    assert np.max(np.abs(hm.array("hlay") - h_before)) < 2e-6  # float32 round trip of eta and h_0
