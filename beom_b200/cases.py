@@ -389,6 +389,31 @@ def synthetic_basin(n: int = 8192, nlay: int = 4, seed: int = 20261018, dt_s: fl
     return Case("synthetic_basin", lm, mm, nlay, ndeg, text, files, {})
 
 
+def sponge_basin(nlay: int = 3, lm: int = 40, mm: int = 14, dt_s: float = 0.2, ocrp: float = 0.0) -> Case:
+    """A small closed basin with a thickness sponge everywhere and tilted interfaces.  Not a reference
+    script: it exists to exercise the update_h epilogues of private_mod1d/3d/plumenew.f95, which relax
+    toward fixed thicknesses east of lm/2 and toward the initial state west of it."""
+    dl = 2000.0
+    depth = 900.0
+    h_bo = np.zeros((lm + 2, mm + 2))
+    h_bo[1:-1, 1:-1] = depth
+    ndeg = get_nbr_deg_freedom(h_bo)
+    xs = (np.arange(lm + 2) - 0.5) / lm
+    init = np.zeros((lm + 2, mm + 2, nlay, 3))
+    for k in range(1, nlay):
+        init[:, :, k, 0] = (20.0 * k * (xs - 0.5))[:, None] + 3.0 * np.cos(np.arange(mm + 2) * 0.7)[None, :]
+    init[:, :, 0, 0] = 0.05 * np.sin(6.0 * xs)[:, None]
+    nudg = np.zeros((lm + 2, mm + 2, 3))
+    nudg[1:-1, 1:-1, 0] = 0.02
+    nudg[0:2, 1:-1, 1] = 0.01  # a nudged western face: the reference insists on one open-boundary segment (pm:1226-1231)
+    rhon = [1026.0 + 0.5 * k for k in range(nlay)]
+    topl = [0.0, 0.3, 0.6, 0.8][:nlay]
+    cext = math.sqrt(9.8 * depth)
+    text = print_params(lm, mm, nlay, ndeg, dl, cext, 1.0e-4, rhon, topl, dt_s, dt_s, 0.0, 0.0, 0.0, 0.2, 0.0, 1.0, 10.0, 10.0,
+                        1.0, 1.0, 0.0, ocrp, 0.0, 0.0, 0.0, 0.0, [0, 0], "@DIR@", "@DIR@", "sponge basin (variants)")
+    return Case("sponge_basin", lm, mm, nlay, ndeg, text, {"h_bo": h_bo, "init": init, "nudg": nudg}, {})
+
+
 CASES = {
     "stommel1948": stommel1948,
     "lock_exchange": lock_exchange,
@@ -396,4 +421,5 @@ CASES = {
     "sill_exchange3D": sill_exchange3D,
     "conservation": conservation,
     "synthetic_basin": synthetic_basin,
+    "sponge_basin": sponge_basin,
 }

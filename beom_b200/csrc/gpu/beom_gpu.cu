@@ -251,7 +251,7 @@ int step_split(int tstp, bool upst, bool first_three) {
   }
   g.dx_o = (g.dx_o + 1) % 4;
   g.dy_o = (g.dy_o + 1) % 4;
-  if (g.D.has_nudg && g.P.mcbc < 0.5 && g.nseg > 0 && g.opt.reserved_[0] == 0) {  // pm:2201-2204 / 2285-2288
+  if (g.D.has_nudg && g.P.mcbc < 0.5 && g.nseg > 0) {  // pm:2201-2204 / 2285-2288
     for (int pass = 0; pass < 2; pass++) {
       k_obc<<<(g.nseg + 63) / 64, 64, 0, g.stream>>>(D, g.d_seg, g.nseg, pass);
       g.launches++;
@@ -653,6 +653,14 @@ int beom_gpu_step(int tstp, double ctim, double ramp, double gene, int upst, int
     int rc = fused_step(D, Dout, tstp, first_three != 0, g.stream, &nlaunch);
     if (rc) return fail(rc, "fused_step failed: %s", cudaGetErrorString(cudaGetLastError()));
     g.launches += nlaunch;
+    if (g.D.has_nudg && g.P.mcbc < 0.5 && g.nseg > 0) {  // no_gradient_obc after both components (pm:2285-2288)
+      Dev Dobc = D;
+      Dobc.hlay = Dout.hlay; Dobc.u = Dout.u; Dobc.v = Dout.v; Dobc.h_u = Dout.h_u; Dobc.h_v = Dout.h_v;
+      for (int pass = 0; pass < 2; pass++) {
+        k_obc<<<(g.nseg + 63) / 64, 64, 0, g.stream>>>(Dobc, g.d_seg, g.nseg, pass);
+        g.launches++;
+      }
+    }
     if (g.nranks > 1) {
       rc = sync_fields({{Dout.hlay, g.nlay}, {Dout.u, g.nlay}, {Dout.v, g.nlay}, {Dout.h_u, g.nlay}, {Dout.h_v, g.nlay},
                         {D.rs_new, g.nlay}, {D.dx_new, g.nlay}, {D.dy_new, g.nlay}});

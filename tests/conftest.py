@@ -26,7 +26,7 @@ SMALL = {
     "stommel1948": dict(dl=250.0e3),
     "lock_exchange": dict(),
     "unstable_jet": dict(dl=60.0e3),
-    "sill_exchange3D": dict(lx=8.0e3, ly=40.0e3),
+    "sill_exchange3D": dict(lx=6.0e3, ly=100.0e3),
     "conservation": dict(dl=30.0e3),
 }
 

@@ -24,7 +24,7 @@ GOLDEN = {
     "stommel1948": (dict(dl=250.0e3), 120),
     "lock_exchange": (dict(), 200),
     "unstable_jet": (dict(dl=60.0e3), 80),
-    "sill_exchange3D": (dict(lx=8.0e3, ly=40.0e3), 80),
+    "sill_exchange3D": (dict(lx=6.0e3, ly=100.0e3), 80),
     "conservation": (dict(dl=30.0e3), 100),
 }
 

@@ -24,7 +24,7 @@ def main():
     if name == "synthetic_basin":
         c = cases.synthetic_basin(n=300, mm=170, nlay=4)
     else:
-        c = cases.sill_exchange3D(lx=8.0e3, ly=40.0e3)
+        c = cases.sill_exchange3D(lx=6.0e3, ly=100.0e3)
     d = tempfile.mkdtemp(prefix="beom_mg%d_" % rank)
     blk = c.write(d)
     hm = model.HostModel.from_block(blk)

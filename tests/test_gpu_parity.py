@@ -117,3 +117,44 @@ def test_fused_equals_split_at_scale_and_conserves_volume(case_factory):
     v1 = res[True][0][:, wet].sum(axis=1)
     assert np.all(np.abs(v1 - v0) <= 1e-12 * np.abs(v0))
     assert np.all(np.isfinite(res[True][1])) and np.abs(res[True][1]).max() > 0
+
+
+def _check_state(tag, got, orc, names=("hlay", "u", "v")):
+    for nm, a in zip(names, got):
+        assert_same(tag + ":" + nm, a, orc.array(nm))
+
+
+@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("extra", [
+    dict(mcbc="0."),                                   # a8: no_gradient_obc active on the sponge boundaries
+    dict(bdrg="3.e-3", qdrg="1."),                     # a7: quadratic bottom drag with outcropping (layb)
+    dict(bdrg="1.e-4", qdrg="0.", tdrg="2.e-4"),       # a7: linear bottom + top drag (layu)
+    dict(dt3d="0.001"),                                # stress / viscosity refreshed every n_3d > 1 steps
+], ids=["obc", "quad_drag", "top_drag", "n3d"])
+def test_sill_options_bit_exact(case_factory, fused, extra):
+    c, hm, orc, st, aux, path = run_pair(case_factory, "sill_exchange3D", 40, fused, extra=extra)
+    if "dt3d" in extra:
+        assert orc.counts()[2] > 1 and path == "split"
+    _check_state("sill" + str(extra), st, orc)
+    assert_same("h_u", aux[0], orc.array("h_u"))
+    assert_same("h_v", aux[1], orc.array("h_v"))
+
+
+@pytest.mark.parametrize("variant,nlay,plum", [(1, 2, "0."), (2, 3, "0."), (3, 3, "0."), (3, 3, "1.")],
+                         ids=["1d", "3d", "plume_off", "plume_on"])
+def test_update_h_variants_bit_exact(case_factory, variant, nlay, plum):
+    """a1': the water-mass-transformation epilogues of private_mod1d/3d/plumenew.f95 (split path)."""
+    c, hm, orc, st, aux, path = run_pair(case_factory, "sponge_basin", 60, True, small=False, variant=variant,
+                                         extra=dict(plum=plum), nlay=nlay)
+    assert path == "split" and hm.params.variant == variant
+    _check_state("variant%d" % variant, st, orc)
+    std = run_pair(case_factory, "sponge_basin", 60, False, small=False, variant=0, nlay=nlay)
+    assert not np.array_equal(std[3][0], st[0])  # the epilogue does change the answer
+
+
+@pytest.mark.parametrize("name,extra", [("lock_exchange", dict(svis="50.")), ("sponge_basin", dict(svis="200.", bvis="1.0"))])
+def test_biharmonic_viscosity_bit_exact(case_factory, name, extra):
+    """a3 with svis > 0: masked Laplacians + thickness-weighted biharmonic fluxes (pm:2508-2599, 1471-1473)."""
+    c, hm, orc, st, aux, path = run_pair(case_factory, name, 40, True, small=(name != "sponge_basin"), extra=extra)
+    assert path == "split" and hm.params.svis > 0
+    _check_state("svis", st, orc)
