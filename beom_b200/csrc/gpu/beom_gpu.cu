@@ -258,7 +258,15 @@ int step_split(int tstp, bool upst, bool first_three) {
     }
     if (g.nmir || g.nranks > 1) sync_fields({{D.u, nl}, {D.v, nl}, {D.h_u, nl}, {D.h_v, nl}});
   }
-  if (rgld) return fail(-30, "rgld = 1 (surf_pressure) is not implemented on the device yet");
+  if (rgld) {  // pm:2207-2221 / 2292-2314
+    if (g.nranks > 1 || g.nmir) return fail(-30, "rgld = 1 is supported on one GPU, non-periodic domains only");
+    if (first_three) k_centred_flux<<<gridL, kBlock, 0, g.stream>>>(D);
+    else k_upstream_flux<<<gridL, kBlock, 0, g.stream>>>(D);
+    k_pi_rhs<<<grid1, kBlock, 0, g.stream>>>(D);
+    k_surf_pressure<<<1, 1024, 0, g.stream>>>(D, 1000, 1.e-5, nullptr);
+    k_pi_correct<<<gridL, kBlock, 0, g.stream>>>(D);
+    g.launches += 4;
+  }
   CK(cudaGetLastError());
   return 0;
 }
@@ -511,6 +519,16 @@ int beom_gpu_init(const beom_params *par, const beom_fields *fld, const beom_gpu
     if ((rc = dalloc(&D.tb3d, pl * nl * 2)) || (rc = dalloc(&D.layb, pl * nl)) || (rc = dalloc(&D.taub, pl * 2))) return rc;
   if (D.has_tdrg)
     if ((rc = dalloc(&D.tu3d, pl * nl * 2)) || (rc = dalloc(&D.layu, pl * nl)) || (rc = dalloc(&D.taum, pl * 2))) return rc;
+
+  if (par->rgld > 0.5) {  // rigid lid: Poisson operators and the start pressure (private_mod.f95:505-563)
+    if (!fld->Ow || !fld->Os || !fld->Osum_) return fail(-14, "beom_gpu_init: rgld = 1 needs Ow, Os, Osum_");
+    if (nlay != 2) return fail(-14, "beom_gpu_init: the reference's rigid lid is written for two layers (private_mod.f95:1653-1654)");
+    double *o1 = nullptr, *o2 = nullptr, *o3 = nullptr;
+    if ((rc = dalloc(&o1, pl)) || (rc = dalloc(&o2, pl)) || (rc = dalloc(&o3, pl)) || (rc = dalloc(&D.pi_s, pl)) || (rc = dalloc(&D.pi_rhs, pl))) return rc;
+    if ((rc = upload_planes(o1, fld->Ow, 1)) || (rc = upload_planes(o2, fld->Os, 1)) || (rc = upload_planes(o3, fld->Osum_, 1))) return rc;
+    if (fld->pi_s && (rc = upload_planes(D.pi_s, fld->pi_s, 1))) return rc;
+    D.Ow = o1; D.Os = o2; D.Osum_ = o3;
+  }
 
   // open-boundary segments as dense cells (private_mod.f95:1060-1240, columns 1,4,5,10,13,16)
   g.nseg = 0;
@@ -772,8 +790,14 @@ int beom_gpu_download_diag(float *pvor, float *mont, float *v_cc) {
   return fail(-31, "beom_gpu_download_diag: not implemented yet");
 }
 int beom_gpu_download_pi_s(double *pi_s) {
-  (void)pi_s;
-  return fail(-30, "beom_gpu_download_pi_s: rgld = 1 is not implemented on the device yet");
+  if (!g.ready) return fail(-20, "beom_gpu_download_pi_s: not initialised");
+  if (!g.D.pi_s) return fail(-30, "beom_gpu_download_pi_s: rgld = 0, there is no surface pressure");
+  const size_t keep_first = g.win_first, keep_stride = g.win_stride;
+  g.win_first = 0; g.win_stride = (size_t)g.ndeg + 1;  // pi_s(0:ndeg) is always a whole array
+  int rc = download_planes(pi_s, g.D.pi_s, 1);
+  g.win_first = keep_first; g.win_stride = keep_stride;
+  if (!rc) pi_s[0] = 0.0;
+  return rc;
 }
 int beom_gpu_diagnostics(const double *h_0, double *vol, double *ke, double *pe) {
   (void)h_0; (void)vol; (void)ke; (void)pe;

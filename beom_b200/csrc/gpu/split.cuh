@@ -442,6 +442,92 @@ __global__ void k_obc(const __grid_constant__ Dev D, const SegDev *seg, int nseg
   }
 }
 
+// ---- surf_pressure, private_mod.f95:1705-1838 (rigid lid) ----
+// Right-hand side in gather form.  The reference scatters -h_u/(dl dt) to ipnt and +h_u/(dl dt) to its west
+// neighbour while ipnt ascends (pm:1725-1750); for a given point the order of those updates is: own
+// x-flux, east neighbour's x-flux, own y-flux, north neighbour's y-flux, layer by layer from nlay to 1.
+__global__ void k_pi_rhs(const __grid_constant__ Dev D) {
+  BEOM_CELL(D)
+  const int si = x - D.i_off, sj = y - D.j_off;
+  const double dd = D.dl * D.dt;
+  const bool eE = D.flags[c + 1] & F_ACT, eN = D.flags[c + NX] & F_ACT;
+  double r = 0.0;
+  for (int l = D.nlay - 1; l >= 0; l--) {
+    const size_t L = (size_t)l * D.plane;
+    if (si > 1) r = r - D.h_u[L + c] / dd;
+    if (eE) r = r + D.h_u[L + c + 1] / dd;
+    if (sj > 1) r = r - D.h_v[L + c] / dd;
+    if (eN) r = r + D.h_v[L + c + NX] / dd;
+  }
+  D.pi_rhs[c] = r;
+}
+
+// The reference's sweep is lexicographic Gauss-Seidel (ipnt ascending: row by row, west to east), each
+// point using the already-updated west and south values and the old east and north values
+// (pm:1766-1792).  Updating the anti-diagonals x + y = const one after the other, all points of a diagonal
+// in parallel, has exactly the same data dependencies, hence the same iterates bit for bit.
+// One thread block; max-norm stopping test as in the reference (pm:1756-1803).
+__global__ void __launch_bounds__(1024, 1) k_surf_pressure(const __grid_constant__ Dev D, int maxiters, double pi_tol, int *iters_out) {
+  __shared__ double red[32];
+  __shared__ double s_max;
+  const int NX = D.NX;
+  const int w = D.x_hi - D.x_lo + 1, h = D.y_hi - D.y_lo + 1;
+  const double rp = 1.0;
+  int iters = 0;
+  double maxdiff = pi_tol + 1;
+  while (maxdiff > pi_tol && iters < maxiters) {
+    double local = 0.0;
+    for (int d = 0; d <= w + h - 2; d++) {
+      for (int ry = threadIdx.x; ry < h; ry += blockDim.x) {
+        const int rx = d - ry;
+        if (rx < 0 || rx >= w) continue;
+        const int x = D.x_lo + rx, y = D.y_lo + ry;
+        const size_t c = (size_t)y * NX + x;
+        if (!(D.flags[c] & F_ACT)) continue;
+        const int si = x - D.i_off, sj = y - D.j_off;
+        const double prev = D.pi_s[c], os = D.Osum_[c];
+        double v = (1 - rp) * prev - rp * os * D.pi_rhs[c];
+        if (si < D.lm) v = v + rp * os * D.Ow[c + 1] * D.pi_s[c + 1];
+        if (sj < D.mm) v = v + rp * os * D.Os[c + NX] * D.pi_s[c + NX];
+        if (si > 1) v = v + rp * os * D.Ow[c] * D.pi_s[c - 1];
+        if (sj > 1) v = v + rp * os * D.Os[c] * D.pi_s[c - NX];
+        D.pi_s[c] = v;
+        local = fmax(local, fabs(v - prev));
+      }
+      __syncthreads();
+    }
+    for (int o = 16; o > 0; o >>= 1) local = fmax(local, __shfl_xor_sync(0xffffffffu, local, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      double m = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+      for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+      if (threadIdx.x == 0) s_max = m;
+    }
+    __syncthreads();
+    maxdiff = s_max;
+    iters++;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && iters_out) *iters_out = iters;
+}
+
+// velocity projection, private_mod.f95:1806-1833
+__global__ void k_pi_correct(const __grid_constant__ Dev D) {
+  BEOM_CELL(D)
+  const size_t L = (size_t)blockIdx.z * D.plane;
+  const int si = x - D.i_off, sj = y - D.j_off;
+  const double fac = D.dt / D.dl;
+  if (si > 1 && si < D.lm + 1) {
+    double t = D.u[L + c] - fac * D.pi_s[c];
+    D.u[L + c] = t + fac * D.pi_s[c - 1];
+  }
+  if (sj > 1 && sj < D.mm + 1) {
+    double t = D.v[L + c] - fac * D.pi_s[c];
+    D.v[L + c] = t + fac * D.pi_s[c - NX];
+  }
+}
+
 // ---- mirror cells (periodic aliases, slab halos inside one device): dst <- src for np planes ----
 __global__ void k_mirror(double *field, size_t plane, int nplanes, const int *dst, const int *src, int n) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;

@@ -177,6 +177,11 @@ class GpuModel:
         self._ck(self.lib.beom_gpu_download_aux(_dp(h_u), _dp(h_v), _dp(rs_h), _dp(dmdx), _dp(dmdy)), "download_aux")
         return h_u, h_v, rs_h, dmdx, dmdy
 
+    def download_pi_s(self):
+        out = np.zeros(self.ndeg + 1)
+        self._ck(self.lib.beom_gpu_download_pi_s(_dp(out)), "download_pi_s")
+        return out
+
     def mark(self, which):
         self._ck(self.lib.beom_gpu_mark(which), "mark")
 

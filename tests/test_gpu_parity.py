@@ -158,3 +158,25 @@ def test_biharmonic_viscosity_bit_exact(case_factory, name, extra):
     c, hm, orc, st, aux, path = run_pair(case_factory, name, 40, True, small=(name != "sponge_basin"), extra=extra)
     assert path == "split" and hm.params.svis > 0
     _check_state("svis", st, orc)
+
+
+@pytest.mark.parametrize("name,kw,extra", [("lock_exchange", {}, dict(rgld="1.")),
+                                           ("synthetic_basin", dict(n=48, mm=30, nlay=2), dict(rgld="1.", ocrp="1."))],
+                         ids=["lock_exchange_rgld", "basin_rgld_ocrp"])
+def test_rigid_lid_bit_exact(case_factory, name, kw, extra):
+    """a9/a10: surf_pressure (hyperplane-ordered Gauss-Seidel = the reference's lexicographic sweep), the
+    flux rebuilds and the single-precision column correction of update_h."""
+    c, d, hm = case_factory(name, small=(name == "lock_exchange"), extra=extra, **kw)
+    orc = Oracle(hm.params, d)
+    gm = model.GpuModel(hm.params, hm.fields(), model.default_options(fused=True))
+    assert gm.path == "split"
+    gm.upload_state(hm.array("hlay"), hm.array("u"), hm.array("v"))
+    gm.advance(1, 25)
+    orc.advance(1, 25)
+    st = gm.download_state()
+    pi_s = gm.download_pi_s()
+    gm.close()
+    _check_state("rgld", st, orc)
+    assert_same("pi_s", pi_s, orc.array("pi_s")[0])
+    if "ocrp" in extra:
+        assert np.abs(pi_s).max() > 0
