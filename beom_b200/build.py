@@ -22,7 +22,7 @@ HOST_SRC = os.path.join(HERE, "csrc", "host")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-fmad=false",  # no FMA contraction: results are bit-identical to a strict IEEE evaluation
-    "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall", "-shared",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-Wall",
 ]
 
 
@@ -47,10 +47,30 @@ def build_gpu(force: bool = False, verbose_ptxas: bool = False) -> str:
     os.makedirs(LIBDIR, exist_ok=True)
     out = os.path.join(LIBDIR, "libbeom_gpu.so")
     cus = _sources(GPU_SRC, (".cu",))
-    deps = cus + _sources(GPU_SRC, (".cuh", ".h")) + [os.path.join(ROOT, "include", "beom_gpu.h")]
-    if force or _newer(out, deps):
-        extra = ["-Xptxas", "-v"] if verbose_ptxas else []
-        _run([nvcc] + NVCC_FLAGS + extra + cus + ["-o", out, "-ldl"])
+    hdrs = _sources(GPU_SRC, (".cuh", ".h")) + [os.path.join(ROOT, "include", "beom_gpu.h")]
+    objdir = os.path.join(ROOT, "build", "gpu")
+    os.makedirs(objdir, exist_ok=True)
+    extra = ["-Xptxas", "-v"] if verbose_ptxas else []
+    # one nvcc per translation unit, in parallel (the fused-step instantiations dominate the build time)
+    jobs, objs = [], []
+    for cu in cus:
+        obj = os.path.join(objdir, os.path.basename(cu)[:-3] + ".o")
+        objs.append(obj)
+        if force or _newer(obj, [cu] + hdrs):
+            cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", cu, "-o", obj]
+            print("+", " ".join(cmd), file=sys.stderr, flush=True)
+            log = open(obj + ".log", "w") if verbose_ptxas else None
+            jobs.append((cmd, subprocess.Popen(cmd, stderr=log) if log else subprocess.Popen(cmd), log))
+    failed = []
+    for cmd, pr, log in jobs:
+        if pr.wait() != 0:
+            failed.append(cmd)
+        if log:
+            log.close()
+    if failed:
+        raise subprocess.CalledProcessError(1, failed[0])
+    if force or jobs or _newer(out, objs):
+        _run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a"] + objs + ["-o", out, "-ldl"])
     return out
 
 

@@ -298,6 +298,7 @@ int beom_gpu_finalize(void) {
   for (auto &e : g.ev)
     if (e) { cudaEventDestroy(e); e = nullptr; }
   if (g.stream) { cudaStreamDestroy(g.stream); g.stream = nullptr; }
+  fused_release();
   g = Ctx();
   return 0;
 }

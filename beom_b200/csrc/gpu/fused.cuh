@@ -10,5 +10,23 @@ namespace beom {
 int fused_configure(const Dev &D, const beom_params &P, int nmir, int nranks, bool *enabled);
 bool fused_supports(bool first_three, bool upst);
 int fused_step(const Dev &in, const Dev &out, int tstp, bool first_three, cudaStream_t s, int *nlaunch);
+void fused_release();
+
+// ---- dispatch into the instantiation translation units (fused_inst_*.cu, compiled in parallel) ----
+namespace fusedk { struct StreamTab; }
+struct FusedLaunch {
+  dim3 grid, block;
+  size_t shmem;
+  const Dev *in, *out;
+  const fusedk::StreamTab *tab;
+  const uint8_t *open;
+  int groups, rows_per_chunk, wind_layers;
+  cudaStream_t stream;
+};
+int fused_launch_lean1(const FusedLaunch &a, bool ufirst);
+int fused_launch_lean2(const FusedLaunch &a, bool ufirst);
+int fused_launch_lean3(const FusedLaunch &a, bool ufirst);
+int fused_launch_lean4(const FusedLaunch &a, bool ufirst);
+int fused_launch_general(const FusedLaunch &a, bool ufirst, bool visc, int nlay);
 }  // namespace beom
 #endif

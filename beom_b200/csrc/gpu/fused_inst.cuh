@@ -1,0 +1,20 @@
+// fused_inst.cuh -- launch helper shared by the instantiation units of the fused step kernel.
+#ifndef BEOM_FUSED_INST_CUH
+#define BEOM_FUSED_INST_CUH
+#include "fused.cuh"
+#include "fused_kernel.cuh"
+
+namespace beom {
+template <bool UF, bool VI, int NL, bool LEAN>
+int fused_launch_one(const FusedLaunch &a) {
+  static size_t configured = 0;
+  auto kern = fusedk::k_fused_step<UF, VI, NL, LEAN>;
+  if (a.shmem > configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.shmem) != cudaSuccess) return -61;
+    configured = a.shmem;
+  }
+  kern<<<a.grid, a.block, a.shmem, a.stream>>>(*a.in, *a.out, *a.tab, a.open, a.groups, a.rows_per_chunk, a.wind_layers);
+  return 0;
+}
+}  // namespace beom
+#endif

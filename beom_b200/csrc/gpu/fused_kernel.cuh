@@ -1,0 +1,523 @@
+// fused_kernel.cuh -- the fused single-pass time step (generalized forward-backward regime, tstp >= 4).
+//
+// One kernel per step.  It reads every persistent field once (hlay,u,v,h_u,h_v, 2 rs_h, 3 dmdx,
+// 3 dmdy: 13 doubles per cell-layer) and writes the 8 new ones (hlay,u,v,h_u,h_v + newest rs_h, dmdx,
+// dmdy): the 168 algorithmic bytes of SURVEY.md 8(d).  Everything the reference keeps in 2-D scratch
+// arrays between its loops (mont, rvor, pvor, dive, d2hx, d2hy, v_cc, v_ll; private_mod.f95:48-61)
+// lives in registers here.
+//
+// Mapping.  A warp owns 32 consecutive columns of ONE layer and marches north (row by row) through
+// its y-chunk; lane k is column x0-2+k, lanes 2..29 produce results, lanes 0,1,30,31 are the x halo
+// (recomputed by the neighbouring warp).  Raw inputs are staged by TMA bulk copies into a per-warp
+// shared-memory ring (4 rows deep for h_u,h_v,u,v, which are read at three row lags; 2 rows for the
+// rest); east/west neighbours of COMPUTED values come from warp shuffles, south neighbours from values
+// the thread kept from earlier rows: a 3-row software pipeline
+//     row R   : update_h, rvor, dive, d2hx, pvor, Montgomery/Bernoulli potential          (front)
+//     row R-1 : d2hy, Leith v_cc / v_ll, and the first momentum component if it is v
+//     row R-2 : u (and v when u goes first)
+// The carried state is kept in 4-entry rings indexed by (phase - age) & 3.  In the LEAN instantiation
+// the row loop is unrolled four times with the phase a compile-time constant, so the rings are plain
+// registers that are never moved and every shared-memory address is an immediate offset.
+//
+// What is carried is chosen so that no product or squared difference is evaluated twice (each is the
+// SAME IEEE operation on the SAME operands the reference performs, so results stay bit-identical):
+//   A1,A3,B1,B3  the squared vorticity / divergence differences of the Leith stencils (pm:2477-2502);
+//                their x-shifted copies are shuffled instead of recomputed
+//   P = v_cc*dive, Q = v_ll*rvor   the viscous flux products of update_u / update_v (pm:1474-1477, 1560-1563)
+//   q = 0.25*pvor,  T = q*(h_v + h_v(W))  /  W = q*(h_u + h_u(S))   the Coriolis terms (pm:1461-1462, 1546-1547)
+//   F = 0.16667*d2hx, Gy = 0.16667*d2hy                             (pm:1493-1495, 1579-1581)
+// The upstream flux 0.5(w+|w|)(hc-Ff) + 0.5(w-|w|)(hc-Fh) is evaluated as w*(hc - (w>0 ? Ff : Fh)),
+// which is the same number (one of the two products is an exact zero).
+//
+// A CTA is (column groups) x (layers) warps; the layer-warps of a column group exchange the new layer
+// thickness of the front row through shared memory for the column sums of the Montgomery potential
+// (private_mod.f95:2357-2373) with a split-phase mbarrier.  State is double buffered (in -> out), so
+// halo lanes and neighbouring CTAs always read time level n.
+//
+// Arithmetic: the same expressions in the same order as split.cuh / the reference (-fmad=false), so
+// the two paths agree bit for bit; 0/1 masks are applied as selects (x*1 = x, x*0 = +-0).
+#ifndef BEOM_FUSED_KERNEL_CUH
+#define BEOM_FUSED_KERNEL_CUH
+#include <type_traits>
+
+#include "dev.cuh"
+
+namespace beom {
+namespace fusedk {
+
+constexpr int kHalo = 2;              // halo lanes on each side of a warp
+constexpr int kUse = 32 - 2 * kHalo;  // 28 result columns per warp
+constexpr int kMaxLay = 8;            // layers per CTA (shared-memory exchange, warps per CTA)
+#ifndef BEOM_FUSED_WARPS
+#define BEOM_FUSED_WARPS 12
+#endif
+constexpr int kMaxWarps = BEOM_FUSED_WARPS;  // warps per CTA: 16 -> <= 128 registers per thread, 12 -> <= 168
+constexpr int kSeg = 36;              // doubles per staged row segment: columns xw0-2 .. xw0+33 (16-byte aligned)
+constexpr int kSegB = kSeg * 8;
+
+// ---- raw-input streams: one 36-double row segment per (field, row), staged by TMA bulk copies ----
+enum {
+  S_HU, S_HV, S_U, S_V,  // 4 rows deep
+  S_HL, S_R1, S_R2, S_DX1, S_DX2, S_DX3, S_DY1, S_DY2, S_DY3, S_FCOR, S_HTH,  // 2 rows deep, always present
+  kMandatory,
+  S_HDOT = kMandatory, S_FNN, S_NUDN, S_FNU, S_NUDU, S_FNV, S_NUDV, S_TBX, S_TUX, S_TBY, S_TUY,  // general extras
+  S_TTXU, S_TTYV, S_TTYVS, S_TTYU, S_TTXV, S_TTXVS,  // wind streams come last (..S = south neighbour row)
+  S_COUNT
+};
+static_assert(S_COUNT <= 32, "one lane per stream");
+
+struct StreamTab {
+  int n;                       // enabled streams
+  int n_nowind;                // enabled streams for a layer that receives no wind stress
+  signed char slot[S_COUNT];   // stream -> compact slot (-1 = disabled)
+  const double *base[S_COUNT];  // by slot
+  short lag[S_COUNT];          // row = R - lag
+  unsigned char lstride[S_COUNT];  // layer stride in planes (0 = 2-D field, 1, or 2 for [nlay][2] arrays)
+};
+
+__host__ __device__ constexpr int ring_segments(int nstreams) { return 16 + (nstreams - 4) * 2; }
+
+__device__ __forceinline__ double sel(bool p, double a) { return p ? a : 0.0; }
+__device__ __forceinline__ double shup(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }     // value of lane-1 (west)
+__device__ __forceinline__ double shdn(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }   // value of lane+1 (east)
+__device__ __forceinline__ double sq(double a) { return a * a; }
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+               "r"(bar)
+               : "memory");
+}
+
+// One momentum update: update_u (private_mod.f95:1437-1500) when IS_U, update_v (private_mod.f95:1520-1586)
+// otherwise.  c1, c2 are the two Coriolis products, Ph/Pf and Qf/Qh the viscous flux products (here / far),
+// f_far / f_here the scaled thickness curvatures of the upstream flux.
+struct MomX {  // optional inputs (general instantiation and wind layers)
+  double tw_a = 0.0, tw_b = 0.0;  // wind stress component along the velocity at (W or S), (point)
+  double te_a = 0.0, te_b = 0.0;  // cross component for the Ekman term of the sponge target
+  double tb = 0.0, tu = 0.0;      // bottom / top drag at the point
+  double fn = 0.0, nud = 0.0;     // sponge target and rate
+  double bodf = 0.0;
+};
+template <bool IS_U, bool VISC, bool MASKED, bool LEAN>
+__device__ __forceinline__ void momentum(const Dev &D, const bool wind, const double mask, const double hsum, const double m_far,
+                                         const double m_here, const double c1, const double c2, const double old, const double h1,
+                                         const double h2, const double h3, const double Ph, const double Pf, const double Qf,
+                                         const double Qh, const double f_far, const double f_here, const MomX &q, double &vel,
+                                         double &flux, double &dmd4) {
+  const double hcen = hsum * (MASKED ? (mask != 0.0 ? 0.5 : 1.0) : 0.5);
+  dmd4 = (m_far - m_here) * D.i_dl * D.grav;
+  if (MASKED) dmd4 = sel(mask != 0.0, dmd4);
+  double rhsi;
+  if (LEAN) {  // gene = 1 exactly: dmd4*(1-gene) is an exact zero
+    rhsi = IS_U ? (c1 + c2) : ((-c1) - c2);
+  } else {
+    if (IS_U) rhsi = dmd4 * (1.0 - D.gene) + c1 + c2;
+    else      rhsi = dmd4 * (1.0 - D.gene) - c1 - c2;
+  }
+  double i__h = 0.0;
+  if (wind || (!LEAN && (D.has_bdrg || D.has_tdrg))) i__h = 1.0 / (hcen + 1.0 - (MASKED ? mask : 1.0));
+  if (wind) rhsi = rhsi + 0.5 * (q.tw_a + q.tw_b) * D.ramp * D.i_r0 * i__h;
+  if (!LEAN) {
+    if (D.has_bdrg) rhsi = rhsi - q.tb * D.i_r0 * i__h;
+    if (D.has_tdrg) rhsi = rhsi - q.tu * D.i_r0 * i__h;
+  }
+  const double hist = D.del1 * dmd4 + D.del2 * h3 + D.gamm * h2 + D.epsi * h1;
+  if (LEAN) rhsi = rhsi + hist;  // bodf = 0 and gene = 1 (checked by fused_configure)
+  else      rhsi = rhsi + q.bodf + hist * D.gene;
+  if (VISC) {
+    if (IS_U) rhsi = rhsi + (Ph - Pf) * D.i_dl - (Qf - Qh) * D.i_dl;
+    else      rhsi = rhsi + (Ph - Pf) * D.i_dl + (Qf - Qh) * D.i_dl;
+  }
+  double w = old + (MASKED ? sel(mask != 0.0, rhsi) : rhsi) * D.dt;
+  if (!LEAN) {
+    if (D.has_nudg) {
+      double tgt = q.fn;
+      if (wind) {
+        if (IS_U) tgt = tgt + 0.5 * (q.te_b + q.te_a) * D.i_r1 * D.invf * i__h * D.ramp;
+        else      tgt = tgt - 0.5 * (q.te_b + q.te_a) * D.i_r1 * D.invf * i__h * D.ramp;
+      }
+      w = tgt * q.nud + w * (1.0 - q.nud);
+    }
+  }
+  vel = w;
+  flux = w * (hcen - (w > 0.0 ? f_far : f_here));
+}
+
+template <int V> using ic = std::integral_constant<int, V>;
+
+template <bool UFIRST, bool VISC, int NL, bool LEAN>
+__global__ void __launch_bounds__(kMaxWarps * 32, 1)
+k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const __grid_constant__ StreamTab T,
+             const uint8_t *__restrict__ open, int groups, int rows_per_chunk, int wind_layers) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31;
+  const int wid = threadIdx.x >> 5;
+  const int nwarps = blockDim.x >> 5;
+  const int grp = wid % groups;
+  const int l = wid / groups;  // layer of this warp
+  const int nlay = NL > 0 ? NL : D.nlay;
+  const int NX = D.NX, NY = D.NY;
+  const int tcols = groups * 32;
+  const int tcol = grp * 32 + lane;
+  // shared memory: [2][nlay][tcols] new thickness | per-warp mbarriers [4] | per-group mbarriers [2] | per-warp raw-input ring
+  double *sh_h = reinterpret_cast<double *>(smem_raw);
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(sh_h + (size_t)2 * nlay * tcols);
+  unsigned long long *gbars = bars + 4 * nwarps;  // [groups][2]: thickness exchange of a column group (split-phase)
+  const int nseg = ring_segments(T.n);
+  double *ring = reinterpret_cast<double *>(gbars + 2 * groups) + (size_t)wid * nseg * kSeg;
+
+  const int tile = blockIdx.x * groups + grp;
+  const int xw0 = D.x_lo + tile * kUse - kHalo;   // column of lane 0
+  const int xs = min(xw0 - 2, NX - kSeg);          // first staged column (even)
+  const int x = xs + 2 + lane;
+  const bool col_ok = (xs == xw0 - 2) && lane >= kHalo && lane < 32 - kHalo && x <= D.x_hi;
+  const int ya = D.y_lo + blockIdx.y * rows_per_chunk;
+  const int yb = min(ya + rows_per_chunk - 1, D.y_hi);
+  const size_t L = (size_t)l * D.plane;
+  const bool wind = D.has_wind && ((wind_layers >> l) & 1);
+  const int nstr = wind ? T.n : T.n_nowind;
+
+  // output planes of this layer as byte pointers; off0 / off2 are the running byte offsets of (R, x) / (R-2, x)
+  char *__restrict__ o_hlay = reinterpret_cast<char *>(O.hlay + L), *__restrict__ o_u = reinterpret_cast<char *>(O.u + L);
+  char *__restrict__ o_v = reinterpret_cast<char *>(O.v + L), *__restrict__ o_hu = reinterpret_cast<char *>(O.h_u + L);
+  char *__restrict__ o_hv = reinterpret_cast<char *>(O.h_v + L), *__restrict__ o_rs = reinterpret_cast<char *>(D.rs_new + L);
+  char *__restrict__ o_dx = reinterpret_cast<char *>(D.dx_new + L), *__restrict__ o_dy = reinterpret_cast<char *>(D.dy_new + L);
+
+  double cb[kMaxLay];  // (rhon(l) - rhon(i)) * i_rn(l), private_mod.f95:2359
+#pragma unroll
+  for (int i = 0; i < kMaxLay; i++) cb[i] = (i < l) ? (D.rhon[l] - D.rhon[i]) * D.i_rn[l] : 0.0;
+  const double kin = 0.25 * D.uadv * D.i_gr;  // private_mod.f95:2381
+  const bool ocrp = !LEAN && D.ocrp > 0.5;
+
+  // ---- producer side: every lane owns (at most) one stream of this warp ----
+  const unsigned bar0 = smem_u32(bars + 4 * wid);
+  const unsigned ring0 = smem_u32(ring);
+  const bool my_on = lane < nstr;  // slots are compact and wind-only streams come last
+  const char *my_src = nullptr;
+  int my_lag = 0;
+  if (my_on) {
+    my_src = reinterpret_cast<const char *>(T.base[lane] + (size_t)T.lstride[lane] * L + xs);
+    my_lag = T.lag[lane];
+  }
+  const unsigned my_dst = ring0 + (unsigned)((lane < 4 ? lane * 4 : 16 + (lane - 4) * 2) * kSegB);
+  const int my_mask = lane < 4 ? 3 : 1;
+  const unsigned gbar0 = smem_u32(gbars + 2 * grp);
+  for (int i = lane; i < nseg * kSeg; i += 32) ring[i] = 0.0;  // rows below the chunk read as 0 until staged
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) mbar_init(bar0 + 8 * k, 1);
+    if (l == 0) {
+      mbar_init(gbar0, (unsigned)nlay);
+      mbar_init(gbar0 + 8, (unsigned)nlay);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  const int R0 = ya - 3, R1 = yb + 2;
+  const int Rs = R0 & ~3;  // the row loop starts on a multiple of 4: ring slot = R & 3 = unroll phase
+  const int Rend = LEAN ? (R1 | 3) : R1;  // last row the loop visits (the unrolled loop works in groups of 4)
+  const size_t row_bytes = (size_t)NX * 8;
+  auto issue = [&](int Rt) {  // stage the inputs of front row Rt (every lane has finished reading the slots it refills)
+    const unsigned bar = bar0 + 8 * (Rt & 3);
+    if (lane == 0) mbar_expect_tx(bar, (unsigned)(nstr * kSegB));
+    if (my_on) bulk_g2s(my_dst + (unsigned)((Rt & my_mask) * kSegB), my_src + (size_t)min(max(Rt - my_lag, 0), NY - 1) * row_bytes, kSegB, bar);
+  };
+  issue(Rs);
+  issue(Rs + 1);
+  size_t off0 = ((size_t)Rs * NX + x) * 8;                   // only dereferenced for rows this chunk owns
+  size_t off2 = off0 - 2 * row_bytes;
+
+  // ---- values carried from earlier rows: X[(phase - age) & 3] is X of row R - age ----
+  double hn[4] = {0, 0, 0, 0}, hnW[4] = {0, 0, 0, 0}, rv[4] = {0, 0, 0, 0}, dv[4] = {0, 0, 0, 0};
+  double A1[4] = {0, 0, 0, 0}, A3[4] = {0, 0, 0, 0}, B1[4] = {0, 0, 0, 0}, B3[4] = {0, 0, 0, 0};
+  double Pv[4] = {0, 0, 0, 0}, Qv[4] = {0, 0, 0, 0}, mo[4] = {0, 0, 0, 0}, qp[4] = {0, 0, 0, 0};
+  double Fx[4] = {0, 0, 0, 0}, Gy[4] = {0, 0, 0, 0}, Tc[4] = {0, 0, 0, 0}, fl[4] = {0, 0, 0, 0};
+  double vold = 0.0;              // v(R-2) at time n when u goes first (its ring slot is being refilled)
+  unsigned fw_m1 = 0, fw_m2 = 0;  // flags of (own | W<<8 | E<<16), masked rows only
+
+  const double *sgp = ring + 2 + lane;
+  const int tt_base = LEAN ? kMandatory : (int)T.slot[S_TTXU];  // wind streams keep their order: TTXU, TTYV, TTYVS
+
+#define AT(a, age) a[(PH - (age)) & 3]
+#define LD4(s, age, dx) sgp[(s) * 4 * kSeg + o4_##age + (dx)]
+#define LD2(slot, dx) sgp[(16 + ((slot)-4) * 2) * kSeg + o2 + (dx)]
+#define LDX(stream, dx) LD2((int)T.slot[stream], dx)
+#define SELM(p, a) (MASKED ? sel((p), (a)) : (a))
+#define MKN(f) (MASKED ? m_n(f) : 1.0)
+  // One row of the pipeline.  PH = phase of the carried rings; CT: the ring slot is the compile-time phase.
+  // MASKED = false is the open-water fast path: every mask of the three rows in flight is 1 on all 32 lanes,
+  // so no select is needed.
+  auto row = [&](auto ph_tag, auto ct_tag, auto masked_tag, const int R, const unsigned f_own, const unsigned fw_0, const unsigned bpar) {
+    constexpr int PH = decltype(ph_tag)::value;
+    constexpr bool CT = decltype(ct_tag)::value;
+    constexpr bool MASKED = decltype(masked_tag)::value;
+    const int o4_0 = (CT ? (PH & 3) : (R & 3)) * kSeg, o4_1 = (CT ? ((PH - 1) & 3) : ((R - 1) & 3)) * kSeg;
+    const int o4_2 = (CT ? ((PH - 2) & 3) : ((R - 2) & 3)) * kSeg;
+    const int o2 = (CT ? (PH & 1) : (R & 1)) * kSeg;
+    const int hslot = CT ? (PH & 1) : (R & 1);
+    const unsigned hpar = CT ? ((PH >> 1) & 1) : ((R >> 1) & 1);
+    mbar_wait(bar0 + 8 * (CT ? (PH & 3) : (R & 3)), bpar);  // staged inputs of front row R have landed
+    const bool act = f_own & F_ACT;
+    const bool row_own = (R >= ya && R <= yb);
+    const bool row2_own = (R - 2 >= ya && R - 2 <= yb);
+
+    // -------------------------------------------------------------------------------- update_h, row R (pm:1610-1643)
+    const double hu_0 = LD4(S_HU, 0, 0), huE_0 = LD4(S_HU, 0, 1);
+    const double hv_p1 = LD4(S_HV, 0, 0), hv_0 = LD4(S_HV, 1, 0);
+    double rs_3 = (hu_0 - huE_0) * D.i_dl + (hv_0 - hv_p1) * D.i_dl;
+    if (!LEAN) {
+      if (D.has_hdot) rs_3 = rs_3 + LDX(S_HDOT, 0);
+    }
+    rs_3 = SELM(f_own & F_N, rs_3);
+    const double r1 = LD2(S_R1, 0), r2 = LD2(S_R2, 0);
+    double rhs_h;
+    if (LEAN) rhs_h = (D.c_ab1 * rs_3 - D.c_ab2 * r2 + D.beta * r1) * D.dt;  // gene = 1: the plain term is an exact zero
+    else      rhs_h = (D.c_ab1 * rs_3 - D.c_ab2 * r2 + D.beta * r1) * D.dt * D.gene + rs_3 * D.dt * (1.0 - D.gene);
+    double hn_0 = LD2(S_HL, 0) + rhs_h;
+    if (!LEAN) {
+      if (D.has_nudg) {
+        const double fnn_0 = LDX(S_FNN, 0), nudn_0 = LDX(S_NUDN, 0);
+        hn_0 = fnn_0 * nudn_0 + (1.0 - nudn_0) * hn_0;
+      }
+    }
+    hn_0 = SELM(act, hn_0);
+    if (col_ok && row_own && (!MASKED || act)) {
+      __stcs(reinterpret_cast<double *>(o_hlay + off0), hn_0);
+      __stcs(reinterpret_cast<double *>(o_rs + off0), rs_3);
+    }
+    sh_h[((size_t)hslot * nlay + l) * tcols + tcol] = hn_0;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(gbar0 + 8 * hslot);  // split-phase: waited for at the end of the row
+    AT(hn, 0) = hn_0;
+
+    // -------------------------------------------------------------------------------- rvor, dive, row R (pm:2388, 2435)
+    const double u_0 = LD4(S_U, 0, 0), uE_0 = LD4(S_U, 0, 1), u_m1 = LD4(S_U, 1, 0);
+    const double v_p1 = LD4(S_V, 0, 0), v_0 = LD4(S_V, 1, 0), vW_0 = LD4(S_V, 1, -1);
+    const double rv_0 = SELM(act && (f_own & F_PE), (v_0 - vW_0 - u_0 + u_m1) * D.i_dl);
+    const double dv_0 = SELM(act, (uE_0 - u_0 + v_p1 - v_0) * D.i_dl);
+
+    // -------------------------------------------------------------------------------- d2hx, pvor, row R; d2hy, row R-1
+    const double hnE_0 = shdn(hn_0), hnW_0 = shup(hn_0);
+    AT(hnW, 0) = hnW_0;
+    double d2x_0 = SELM((fw_0 & (F_N << 16)) && (fw_0 & (F_N << 8)) && (f_own & F_N), hnE_0 + hnW_0 - hn_0 * 2.0);
+    if (ocrp && (hnE_0 < D.two_hs || hnW_0 < D.two_hs || hn_0 < D.two_hs)) d2x_0 = 0.0;
+    d2x_0 = SELM(act, d2x_0);
+    AT(Fx, 0) = 0.16667 * d2x_0;
+    double d2y_m1 = SELM((f_own & F_N) && (fw_m2 & F_N) && (fw_m1 & F_N), hn_0 + AT(hn, 2) - AT(hn, 1) * 2.0);
+    if (ocrp && (hn_0 < D.two_hs || AT(hn, 2) < D.two_hs || AT(hn, 1) < D.two_hs)) d2y_m1 = 0.0;
+    d2y_m1 = SELM(fw_m1 & F_ACT, d2y_m1);
+    AT(Gy, 1) = 0.16667 * d2y_m1;
+    {
+      const double have = hn_0 + hnW_0 + AT(hnW, 1) + AT(hn, 1);
+      const double msum = MKN((uint8_t)f_own) + MKN((uint8_t)(fw_0 >> 8)) + MKN((uint8_t)(fw_m1 >> 8)) + MKN((uint8_t)fw_m1);
+      const double pv_0 = SELM(act, SELM(f_own & F_PI, LD2(S_FCOR, 0) + rv_0 * D.uadv) * msum / have);
+      AT(qp, 0) = 0.25 * pv_0;
+    }
+    if (UFIRST) AT(Tc, 0) = AT(qp, 0) * (hv_0 + LD4(S_HV, 1, -1));  // Coriolis term of u with h_v at time n (pm:1461-1462)
+
+    // -------------------------------------------------------------------------------- Leith viscosity, row R-1 (pm:2477-2502)
+    if (VISC) {
+      AT(A1, 0) = sq(shdn(rv_0) - rv_0);
+      AT(A3, 0) = sq(rv_0 - AT(rv, 1));
+      AT(B1, 0) = sq(dv_0 - shup(dv_0));
+      AT(B3, 0) = sq(dv_0 - AT(dv, 1));
+      const double tll = AT(A1, 1) + shup(AT(A1, 1)) + AT(A3, 0) + AT(A3, 1) + AT(B1, 1) + AT(B1, 2) + AT(B3, 1) + shup(AT(B3, 1));
+      const double tcc = AT(A1, 1) + AT(A1, 0) + AT(A3, 0) + shdn(AT(A3, 0)) + shdn(AT(B1, 1)) + AT(B1, 1) + AT(B3, 0) + AT(B3, 1);
+      const bool a = fw_m1 & F_ACT;
+      const double vll_m1 = SELM(a, sqrt(tll) * D.dvis * D.dl * D.dl + D.bvis);
+      const double vcc_m1 = SELM(a, sqrt(tcc) * D.dvis * D.dl * D.dl + D.bvis);
+      AT(Pv, 1) = vcc_m1 * AT(dv, 1);
+      AT(Qv, 1) = vll_m1 * AT(rv, 1);
+    }
+    AT(rv, 0) = rv_0;
+    AT(dv, 0) = dv_0;
+
+    // -------------------------------------------------------------------------------- momentum
+    constexpr int LV = UFIRST ? 2 : 1;  // v is updated at row R - LV
+    const bool a2 = fw_m2 & F_ACT;
+    const bool sto2 = col_ok && (!MASKED || a2) && row2_own;
+    MomX xu, xv;
+    if (wind) {
+      xu.tw_b = LD2(tt_base, 0); xu.tw_a = LD2(tt_base, -1);
+      xv.tw_b = LD2(tt_base + 1, 0); xv.tw_a = LD2(tt_base + 2, 0);
+    }
+    if (!LEAN) {
+      if (wind && D.has_nudg) {
+        xu.te_b = LDX(S_TTYU, 0); xu.te_a = LDX(S_TTYU, -1);
+        xv.te_b = LDX(S_TTXV, 0); xv.te_a = LDX(S_TTXVS, 0);
+      }
+      if (D.has_bdrg) { xu.tb = LDX(S_TBX, 0); xv.tb = LDX(S_TBY, 0); }
+      if (D.has_tdrg) { xu.tu = LDX(S_TUX, 0); xv.tu = LDX(S_TUY, 0); }
+      if (D.has_nudg) { xu.fn = LDX(S_FNU, 0); xu.nud = LDX(S_NUDU, 0); xv.fn = LDX(S_FNV, 0); xv.nud = LDX(S_NUDV, 0); }
+      xu.bodf = D.bodf[0][l]; xv.bodf = D.bodf[1][l];
+    }
+    const double ux1 = LD2(S_DX1, 0), ux2 = LD2(S_DX2, 0), ux3 = LD2(S_DX3, 0);
+    const double vy1 = LD2(S_DY1, 0), vy2 = LD2(S_DY2, 0), vy3 = LD2(S_DY3, 0);
+    if (UFIRST) {
+      // ---- u at row R-2 (pm:1422-1503) ----
+      double un, hun, dm;
+      momentum<true, VISC, MASKED, LEAN>(D, wind, MASKED ? m_u((uint8_t)fw_m2) : 1.0, AT(hnW, 2) + AT(hn, 2), shup(AT(mo, 2)), AT(mo, 2),
+                                         AT(Tc, 2), AT(Tc, 1), LD4(S_U, 2, 0), ux1, ux2, ux3, AT(Pv, 2), shup(AT(Pv, 2)), AT(Qv, 1),
+                                         AT(Qv, 2), shup(AT(Fx, 2)), AT(Fx, 2), xu, un, hun, dm);
+      hun = SELM(a2, hun);
+      if (sto2) {
+        __stcs(reinterpret_cast<double *>(o_u + off2), un);
+        __stcs(reinterpret_cast<double *>(o_hu + off2), hun);
+        __stcs(reinterpret_cast<double *>(o_dx + off2), dm);
+      }
+      AT(fl, 2) = hun;
+      // ---- v at row R-2 (pm:1505-1591), using the new h_u of rows R-2 and R-3 ----
+      const double wc = AT(qp, 2) * (hun + AT(fl, 3));
+      double vn, hvn;
+      momentum<false, VISC, MASKED, LEAN>(D, wind, MASKED ? m_v((uint8_t)fw_m2) : 1.0, AT(hn, 2) + AT(hn, 3), AT(mo, 3), AT(mo, 2), wc,
+                                          shdn(wc), vold, vy1, vy2, vy3, AT(Pv, 2), AT(Pv, 3), shdn(AT(Qv, 2)), AT(Qv, 2), AT(Gy, 3),
+                                          AT(Gy, 2), xv, vn, hvn, dm);
+      if (sto2) {
+        __stcs(reinterpret_cast<double *>(o_v + off2), vn);
+        __stcs(reinterpret_cast<double *>(o_hv + off2), SELM(a2, hvn));
+        __stcs(reinterpret_cast<double *>(o_dy + off2), dm);
+      }
+      vold = LD4(S_V, 2, 0);  // v(R-1): the old v of the next row's update
+    } else {
+      // ---- v at row R-1 (pm:1505-1591), h_u at time n ----
+      const bool a1 = fw_m1 & F_ACT;
+      const double wc = AT(qp, 1) * (LD4(S_HU, 1, 0) + LD4(S_HU, 2, 0));
+      double vn, hvn, dm;
+      momentum<false, VISC, MASKED, LEAN>(D, wind, MASKED ? m_v((uint8_t)fw_m1) : 1.0, AT(hn, 1) + AT(hn, 2), AT(mo, 2), AT(mo, 1), wc,
+                                          shdn(wc), LD4(S_V, 2, 0), vy1, vy2, vy3, AT(Pv, 1), AT(Pv, 2), shdn(AT(Qv, 1)), AT(Qv, 1),
+                                          AT(Gy, 2), AT(Gy, 1), xv, vn, hvn, dm);
+      hvn = SELM(a1, hvn);
+      if (col_ok && (!MASKED || a1) && (R - 1 >= ya) && (R - 1 <= yb)) {
+        __stcs(reinterpret_cast<double *>(o_v + (off2 + row_bytes)), vn);
+        __stcs(reinterpret_cast<double *>(o_hv + (off2 + row_bytes)), hvn);
+        __stcs(reinterpret_cast<double *>(o_dy + (off2 + row_bytes)), dm);
+      }
+      AT(Tc, 1) = AT(qp, 1) * (hvn + shup(hvn));  // Coriolis term of u with the new h_v (pm:1461-1462)
+      // ---- u at row R-2 (pm:1422-1503), using the new h_v of rows R-2 and R-1 ----
+      double un, hun;
+      momentum<true, VISC, MASKED, LEAN>(D, wind, MASKED ? m_u((uint8_t)fw_m2) : 1.0, AT(hnW, 2) + AT(hn, 2), shup(AT(mo, 2)), AT(mo, 2),
+                                         AT(Tc, 2), AT(Tc, 1), LD4(S_U, 2, 0), ux1, ux2, ux3, AT(Pv, 2), shup(AT(Pv, 2)), AT(Qv, 1),
+                                         AT(Qv, 2), shup(AT(Fx, 2)), AT(Fx, 2), xu, un, hun, dm);
+      if (sto2) {
+        __stcs(reinterpret_cast<double *>(o_u + off2), un);
+        __stcs(reinterpret_cast<double *>(o_hu + off2), SELM(a2, hun));
+        __stcs(reinterpret_cast<double *>(o_dx + off2), dm);
+      }
+    }
+
+    // -------------------------------------------------------------------------------- mont, row R (pm:2351-2383)
+    double mpot;
+    if (ocrp) {
+      mpot = hn_0 + D.hmin * (1.0 - MKN((uint8_t)f_own));
+      mpot = cube(D.hsal / mpot);
+      mpot = mpot * (-D.ocrp * D.i_ns * D.hsal * MKN((uint8_t)f_own));
+    } else {
+      mpot = -0.0;
+    }
+    mpot = mpot - 0.0;
+    const double ke = kin * (uE_0 * uE_0 + u_0 * u_0 + v_p1 * v_p1 + v_0 * v_0);
+    const double hth = LD2(S_HTH, 0);
+    mbar_wait(gbar0 + 8 * hslot, hpar);  // every layer of this column group has published hn(R)
+    {
+      const double *col = sh_h + (size_t)hslot * nlay * tcols + tcol;
+      double hcol = 0.0;
+#pragma unroll
+      for (int i = 0; i < (NL > 0 ? NL : kMaxLay); i++) {
+        if (i < nlay) {
+          const double hi = col[(size_t)i * tcols];
+          if (i < l) mpot = mpot - cb[i] * hi;
+          hcol = hcol + hi;
+        }
+      }
+      mpot = hcol - hth + mpot;
+    }
+    AT(mo, 0) = SELM(act, mpot + ke);
+
+    __syncwarp();
+    if (R + 2 <= Rend) issue(R + 2);  // refill the slots this row was the last to read
+    off0 += row_bytes;
+    off2 += row_bytes;
+  };
+#undef LDX
+#undef LD2
+#undef LD4
+#undef AT
+#undef SELM
+#undef MKN
+
+  constexpr unsigned kAllMasks = 0x3f | (0x3f << 8) | (0x3f << 16);
+  const uint8_t *op = open + (size_t)tile * NY;
+  const uint8_t *fl_p = D.flags + x;
+  using Tt = std::true_type;
+  using Ft = std::false_type;
+  auto flags_of = [&](int R) -> unsigned { return (unsigned)fl_p[(size_t)min(R, NY - 1) * NX]; };
+  auto widen = [&](unsigned f) -> unsigned { return f | (__shfl_up_sync(0xffffffffu, f, 1) << 8) | (__shfl_down_sync(0xffffffffu, f, 1) << 16); };
+  if (LEAN) {
+    unsigned bpar = 0;
+    unsigned o_next = op[min(Rs, NY - 1)];
+#pragma unroll 1
+    for (int R = Rs; R <= R1; R += 4) {
+      const unsigned o = o_next;
+      o_next = op[min(R + 4, NY - 1)];
+      if (o & 2) {  // rows R-2 .. R+3 are open water on all 32 columns
+        row(ic<0>{}, Tt{}, Ft{}, R, kAllMasks, kAllMasks, bpar);
+        row(ic<1>{}, Tt{}, Ft{}, R + 1, kAllMasks, kAllMasks, bpar);
+        row(ic<2>{}, Tt{}, Ft{}, R + 2, kAllMasks, kAllMasks, bpar);
+        row(ic<3>{}, Tt{}, Ft{}, R + 3, kAllMasks, kAllMasks, bpar);
+        fw_m1 = fw_m2 = kAllMasks;
+      } else {
+        const unsigned f0 = flags_of(R), f1 = flags_of(R + 1), f2 = flags_of(R + 2), f3 = flags_of(R + 3);
+        const unsigned w0 = widen(f0), w1 = widen(f1), w2 = widen(f2), w3 = widen(f3);
+        row(ic<0>{}, Tt{}, Tt{}, R, f0, w0, bpar);
+        fw_m2 = fw_m1; fw_m1 = w0;
+        row(ic<1>{}, Tt{}, Tt{}, R + 1, f1, w1, bpar);
+        fw_m2 = fw_m1; fw_m1 = w1;
+        row(ic<2>{}, Tt{}, Tt{}, R + 2, f2, w2, bpar);
+        fw_m2 = fw_m1; fw_m1 = w2;
+        row(ic<3>{}, Tt{}, Tt{}, R + 3, f3, w3, bpar);
+        fw_m2 = fw_m1; fw_m1 = w3;
+      }
+      bpar ^= 1;
+    }
+  } else {
+    unsigned f_next = flags_of(Rs);
+    unsigned o_next = op[min(Rs, NY - 1)];
+#pragma unroll 1
+    for (int R = Rs; R <= R1; R++) {
+      const unsigned f_own = f_next, o = o_next;
+      f_next = flags_of(R + 1);
+      o_next = op[min(R + 1, NY - 1)];
+      const unsigned fw_0 = widen(f_own);
+      const unsigned bpar = (unsigned)(((R - Rs) >> 2) & 1);
+      if (o & 1) row(ic<0>{}, Ft{}, Ft{}, R, f_own, fw_0, bpar);
+      else       row(ic<0>{}, Ft{}, Tt{}, R, f_own, fw_0, bpar);
+      fw_m2 = fw_m1; fw_m1 = fw_0;
+#define ROT(a) a[1] = a[2]; a[2] = a[3]; a[3] = a[0];
+      ROT(hn) ROT(hnW) ROT(rv) ROT(dv) ROT(A1) ROT(A3) ROT(B1) ROT(B3) ROT(Pv) ROT(Qv) ROT(mo) ROT(qp) ROT(Fx) ROT(Gy) ROT(Tc) ROT(fl)
+#undef ROT
+    }
+  }
+}
+
+}  // namespace fusedk
+}  // namespace beom
+#endif
