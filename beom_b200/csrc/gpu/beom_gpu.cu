@@ -85,8 +85,9 @@ Ctx g;
 template <class T>
 int dalloc(T **p, size_t n, bool zero = true) {
   void *q = nullptr;
-  CK(cudaMalloc(&q, std::max<size_t>(n, 1) * sizeof(T)));
-  if (zero) CK(cudaMemsetAsync(q, 0, std::max<size_t>(n, 1) * sizeof(T), g.stream));
+  n += 1024;  // slack: the fused step stages whole-CTA row segments that may run past the last row of a plane
+  CK(cudaMalloc(&q, n * sizeof(T)));
+  if (zero) CK(cudaMemsetAsync(q, 0, n * sizeof(T), g.stream));
   g.allocs.push_back(q);
   *p = (T *)q;
   return 0;

@@ -32,8 +32,7 @@ struct FusedCfg {
 __global__ void k_open_rows(const uint8_t *__restrict__ flags, uint8_t *__restrict__ open, int NX, int NY, int x_lo) {
   const int tile = blockIdx.x, R = blockIdx.y * blockDim.y + threadIdx.y, lane = threadIdx.x;
   if (R >= NY) return;
-  const int xw0 = x_lo + tile * kUse - kHalo;
-  const int x = min(xw0 - 2, NX - kSeg) + 2 + lane;
+  const int x = x_lo + tile * kUse - kHalo + lane;  // the warp's 32 columns (fused_kernel.cuh)
   bool ok = true;
   for (int d = 0; d < 3; d++) {
     const int r = R - d;
@@ -87,9 +86,8 @@ StreamTab make_streams(const Dev &D, bool ufirst) {
   }
   return T;
 }
-size_t fused_smem_bytes(int nlay, int groups, int nstreams) {
-  const size_t nwarps = (size_t)groups * nlay;
-  return (size_t)2 * nlay * groups * 32 * 8 + nwarps * 32 + (size_t)groups * 16 + nwarps * (size_t)ring_segments(nstreams) * kSegB;
+size_t fused_smem_bytes(int nlay, int groups, const StreamTab &T, int wind_layers) {
+  return smem_plan(nlay, groups, T.n, T.n_nowind, wind_layers).total;
 }
 }  // namespace
 
@@ -133,12 +131,15 @@ int fused_configure(const Dev &D, const beom_params &P, int nmir, int nranks, bo
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  const int nstreams = make_streams(D, true).n;
-  if (nstreams > 32) return 0;
+  const StreamTab T0 = make_streams(D, true);
+  if (T0.n > 32) return 0;
   const int width = D.x_hi - D.x_lo + 1, rows = D.y_hi - D.y_lo + 1;
-  int groups = std::max(1, std::min(kMaxWarps / D.nlay, (width + kUse - 1) / kUse));
-  while (groups > 1 && fused_smem_bytes(D.nlay, groups, nstreams) > (size_t)max_smem - 1024) groups--;
-  if (fused_smem_bytes(D.nlay, groups, nstreams) > (size_t)max_smem - 1024) return 0;
+  const int wl = D.has_wind ? cfg.wind_layers : 0;
+  // the lean instantiations have their column-group count compiled in (idle groups on a narrow domain are harmless)
+  int groups = cfg.lean ? kMaxWarps / D.nlay : std::max(1, std::min(kMaxWarps / D.nlay, (width + kUse - 1) / kUse));
+  if (cfg.lean && fused_smem_bytes(D.nlay, groups, T0, wl) > (size_t)max_smem - 1024) cfg.lean = false;
+  while (groups > 1 && fused_smem_bytes(D.nlay, groups, T0, wl) > (size_t)max_smem - 1024) groups--;
+  if (fused_smem_bytes(D.nlay, groups, T0, wl) > (size_t)max_smem - 1024) return 0;
   cfg.groups = groups;
   cfg.strips = (width + groups * kUse - 1) / (groups * kUse);
   int chunks = std::max(1, (2 * sms + cfg.strips / 2) / cfg.strips);  // about two CTAs' worth of work per SM
@@ -166,7 +167,7 @@ int fused_step(const Dev &in, const Dev &out, int tstp, bool first_three, cudaSt
   a.block = dim3((unsigned)(cfg.groups * 32 * in.nlay), 1, 1);
   const bool ufirst = (tstp % 2 == 0);
   const StreamTab T = make_streams(in, ufirst);
-  a.shmem = fused_smem_bytes(in.nlay, cfg.groups, T.n);
+  a.shmem = fused_smem_bytes(in.nlay, cfg.groups, T, in.has_wind ? cfg.wind_layers : 0);
   a.in = &in; a.out = &out; a.tab = &T; a.open = cfg.open;
   a.groups = cfg.groups; a.rows_per_chunk = cfg.rows_per_chunk; a.wind_layers = cfg.wind_layers;
   a.stream = s;

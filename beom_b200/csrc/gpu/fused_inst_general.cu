@@ -3,8 +3,8 @@
 namespace beom {
 template <int NL>
 static int pick(const FusedLaunch &a, bool ufirst, bool visc) {
-  return visc ? (ufirst ? fused_launch_one<true, true, NL, false>(a) : fused_launch_one<false, true, NL, false>(a))
-              : (ufirst ? fused_launch_one<true, false, NL, false>(a) : fused_launch_one<false, false, NL, false>(a));
+  return visc ? (ufirst ? fused_launch_one<true, true, NL, false, 0>(a) : fused_launch_one<false, true, NL, false, 0>(a))
+              : (ufirst ? fused_launch_one<true, false, NL, false, 0>(a) : fused_launch_one<false, false, NL, false, 0>(a));
 }
 int fused_launch_general(const FusedLaunch &a, bool ufirst, bool visc, int nlay) {
   switch (nlay) {

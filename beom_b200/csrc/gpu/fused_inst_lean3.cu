@@ -2,6 +2,6 @@
 #include "fused_inst.cuh"
 namespace beom {
 int fused_launch_lean3(const FusedLaunch &a, bool ufirst) {
-  return ufirst ? fused_launch_one<true, true, 3, true>(a) : fused_launch_one<false, true, 3, true>(a);
+  return ufirst ? fused_launch_one<true, true, 3, true, fusedk::kMaxWarps / 3>(a) : fused_launch_one<false, true, 3, true, fusedk::kMaxWarps / 3>(a);
 }
 }  // namespace beom

@@ -8,10 +8,12 @@
 //
 // Mapping.  A warp owns 32 consecutive columns of ONE layer and marches north (row by row) through
 // its y-chunk; lane k is column x0-2+k, lanes 2..29 produce results, lanes 0,1,30,31 are the x halo
-// (recomputed by the neighbouring warp).  Raw inputs are staged by TMA bulk copies into a per-warp
-// shared-memory ring (4 rows deep for h_u,h_v,u,v, which are read at three row lags; 2 rows for the
-// rest); east/west neighbours of COMPUTED values come from warp shuffles, south neighbours from values
-// the thread kept from earlier rows: a 3-row software pipeline
+// (recomputed by the neighbouring warp).  Raw inputs are staged by TMA bulk copies into a shared-memory
+// ring per LAYER, shared by the column-group warps of that layer (one copy per stream and row for the whole
+// CTA width; 4 rows deep for h_u,h_v,u,v, which are read at three row lags, 2 rows for the rest).  The new
+// thickness, the Montgomery potential, P and F (below) live in small shared-memory rings as well, so their
+// east/west and south neighbours are plain shared-memory loads; the other computed values travel by warp
+// shuffles (E/W) and in registers (S): a 3-row software pipeline
 //     row R   : update_h, rvor, dive, d2hx, pvor, Montgomery/Bernoulli potential          (front)
 //     row R-1 : d2hy, Leith v_cc / v_ll, and the first momentum component if it is v
 //     row R-2 : u (and v when u goes first)
@@ -49,11 +51,13 @@ constexpr int kHalo = 2;              // halo lanes on each side of a warp
 constexpr int kUse = 32 - 2 * kHalo;  // 28 result columns per warp
 constexpr int kMaxLay = 8;            // layers per CTA (shared-memory exchange, warps per CTA)
 #ifndef BEOM_FUSED_WARPS
-#define BEOM_FUSED_WARPS 12
+#define BEOM_FUSED_WARPS 16
 #endif
 constexpr int kMaxWarps = BEOM_FUSED_WARPS;  // warps per CTA: 16 -> <= 128 registers per thread, 12 -> <= 168
-constexpr int kSeg = 36;              // doubles per staged row segment: columns xw0-2 .. xw0+33 (16-byte aligned)
-constexpr int kSegB = kSeg * 8;
+constexpr int kPad = 4;               // staged columns on each side of a CTA's result columns (16-byte aligned rows)
+__host__ __device__ constexpr int seg_doubles(int groups) { return groups * kUse + 2 * kPad; }  // one staged row segment
+constexpr int kWRow = 34;             // per-warp state ring: 32 lanes + 1 pad column on each side
+constexpr int kWRings = 3;            // mo, P, F
 
 // ---- raw-input streams: one 36-double row segment per (field, row), staged by TMA bulk copies ----
 enum {
@@ -163,32 +167,63 @@ __device__ __forceinline__ void momentum(const Dev &D, const bool wind, const do
 
 template <int V> using ic = std::integral_constant<int, V>;
 
-template <bool UFIRST, bool VISC, int NL, bool LEAN>
+// shared memory carve-up (host and device agree through these helpers)
+struct SmemPlan {
+  int tpad;        // columns of one thickness row: groups*32 + 2
+  size_t off_bars, off_wring, off_ring, total;
+  size_t seg_bytes;  // one staged row segment
+  int nseg_all, nseg_nowind, wind_layers;
+  // input ring of layer l (layers that receive wind stress stage three more streams)
+  __host__ __device__ size_t ring_bytes(int l) const { return (size_t)(((wind_layers >> l) & 1) ? nseg_all : nseg_nowind) * seg_bytes; }
+  __host__ __device__ size_t ring_off(int l) const {
+    const int nw = __builtin_popcount((unsigned)wind_layers & ((1u << l) - 1u));
+    return off_ring + ((size_t)nw * nseg_all + (size_t)(l - nw) * nseg_nowind) * seg_bytes;
+  }
+};
+__host__ __device__ inline SmemPlan smem_plan(int nlay, int groups, int n_all, int n_nowind, int wind_layers) {
+  SmemPlan p;
+  p.tpad = groups * 32 + 2;
+  size_t o = (size_t)4 * nlay * p.tpad * 8;          // thickness ring [4][nlay][tpad]
+  p.off_bars = o;
+  o += (size_t)(8 * nlay + 2 * groups) * 8;           // full[nlay][4], empty[nlay][4], gbar[groups][2]
+  o = (o + 15) & ~(size_t)15;
+  p.off_wring = o;
+  o += (size_t)nlay * groups * kWRings * 4 * kWRow * 8;  // per-warp state rings
+  o = (o + 127) & ~(size_t)127;
+  p.off_ring = o;
+  p.seg_bytes = (size_t)seg_doubles(groups) * 8;
+  p.nseg_all = ring_segments(n_all);
+  p.nseg_nowind = ring_segments(n_nowind);
+  p.wind_layers = wind_layers & ((1 << nlay) - 1);
+  p.total = p.ring_off(nlay);
+  return p;
+}
+
+template <bool UFIRST, bool VISC, int NL, bool LEAN, int GROUPS>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1)
 k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const __grid_constant__ StreamTab T,
-             const uint8_t *__restrict__ open, int groups, int rows_per_chunk, int wind_layers) {
+             const uint8_t *__restrict__ open, int groups_rt, int rows_per_chunk, int wind_layers) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int wid = threadIdx.x >> 5;
-  const int nwarps = blockDim.x >> 5;
+  const int groups = GROUPS > 0 ? GROUPS : groups_rt;
   const int grp = wid % groups;
   const int l = wid / groups;  // layer of this warp
   const int nlay = NL > 0 ? NL : D.nlay;
   const int NX = D.NX, NY = D.NY;
-  const int tcols = groups * 32;
+  const int wseg = seg_doubles(groups);   // doubles per staged row segment (whole CTA width)
+  const int tpad = groups * 32 + 2;
   const int tcol = grp * 32 + lane;
-  // shared memory: [2][nlay][tcols] new thickness | per-warp mbarriers [4] | per-group mbarriers [2] | per-warp raw-input ring
+  const SmemPlan sp = smem_plan(nlay, groups, T.n, T.n_nowind, D.has_wind ? wind_layers : 0);
   double *sh_h = reinterpret_cast<double *>(smem_raw);
-  unsigned long long *bars = reinterpret_cast<unsigned long long *>(sh_h + (size_t)2 * nlay * tcols);
-  unsigned long long *gbars = bars + 4 * nwarps;  // [groups][2]: thickness exchange of a column group (split-phase)
-  const int nseg = ring_segments(T.n);
-  double *ring = reinterpret_cast<double *>(gbars + 2 * groups) + (size_t)wid * nseg * kSeg;
+  unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem_raw + sp.off_bars);
+  double *wring = reinterpret_cast<double *>(smem_raw + sp.off_wring) + (size_t)wid * kWRings * 4 * kWRow;
+  double *ring = reinterpret_cast<double *>(smem_raw + sp.ring_off(l));  // input ring of this layer
 
   const int tile = blockIdx.x * groups + grp;
-  const int xw0 = D.x_lo + tile * kUse - kHalo;   // column of lane 0
-  const int xs = min(xw0 - 2, NX - kSeg);          // first staged column (even)
-  const int x = xs + 2 + lane;
-  const bool col_ok = (xs == xw0 - 2) && lane >= kHalo && lane < 32 - kHalo && x <= D.x_hi;
+  const int xs = D.x_lo + blockIdx.x * groups * kUse - kPad;  // first staged column of the CTA (even)
+  const int x = xs + 2 + grp * kUse + lane;                    // lane 0 = first result column - 2
+  const bool col_ok = lane >= kHalo && lane < 32 - kHalo && x <= D.x_hi;
   const int ya = D.y_lo + blockIdx.y * rows_per_chunk;
   const int yb = min(ya + rows_per_chunk - 1, D.y_hi);
   const size_t L = (size_t)l * D.plane;
@@ -207,23 +242,37 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
   const double kin = 0.25 * D.uadv * D.i_gr;  // private_mod.f95:2381
   const bool ocrp = !LEAN && D.ocrp > 0.5;
 
-  // ---- producer side: every lane owns (at most) one stream of this warp ----
-  const unsigned bar0 = smem_u32(bars + 4 * wid);
+  // ---- producer side: the warps of a layer share the staging; lane j of warp (l, grp) owns stream grp + j*groups ----
+  const unsigned full0 = smem_u32(bars + 4 * l);               // [4]: inputs of front row R & 3 have landed (tx)
+  const unsigned empty0 = smem_u32(bars + 4 * nlay + 4 * l);   // [4]: every column group has finished row R & 3
+  const unsigned gbar0 = smem_u32(bars + 8 * nlay + 2 * grp);  // [2]: thickness exchange of a column group (split-phase)
   const unsigned ring0 = smem_u32(ring);
-  const bool my_on = lane < nstr;  // slots are compact and wind-only streams come last
+  const int my_s = grp + lane * groups;  // slots are compact and wind-only streams come last
+  const bool my_on = my_s < nstr;
   const char *my_src = nullptr;
   int my_lag = 0;
   if (my_on) {
-    my_src = reinterpret_cast<const char *>(T.base[lane] + (size_t)T.lstride[lane] * L + xs);
-    my_lag = T.lag[lane];
+    my_src = reinterpret_cast<const char *>(T.base[my_s] + (size_t)T.lstride[my_s] * L + xs);
+    my_lag = T.lag[my_s];
   }
-  const unsigned my_dst = ring0 + (unsigned)((lane < 4 ? lane * 4 : 16 + (lane - 4) * 2) * kSegB);
-  const int my_mask = lane < 4 ? 3 : 1;
-  const unsigned gbar0 = smem_u32(gbars + 2 * grp);
-  for (int i = lane; i < nseg * kSeg; i += 32) ring[i] = 0.0;  // rows below the chunk read as 0 until staged
+  const unsigned segb = (unsigned)(wseg * 8);
+  const unsigned my_dst = ring0 + (unsigned)(my_s < 4 ? my_s * 4 : 16 + (my_s - 4) * 2) * segb;
+  const int my_mask = my_s < 4 ? 3 : 1;
+  const unsigned my_bytes = (grp < nstr ? (unsigned)((nstr - grp + groups - 1) / groups) : 0u) * segb;  // this warp's share of a row
+  {  // rows below the chunk read as 0 until staged; so do the state rings
+    const int n = (int)(sp.ring_bytes(l) / 8);
+    for (int i = grp * 32 + lane; i < n; i += groups * 32) ring[i] = 0.0;
+    for (int i = lane; i < kWRings * 4 * kWRow; i += 32) wring[i] = 0.0;
+    for (int i = threadIdx.x; i < 4 * nlay * tpad; i += blockDim.x) sh_h[i] = 0.0;
+  }
   if (lane == 0) {
+    if (grp == 0) {
 #pragma unroll
-    for (int k = 0; k < 4; k++) mbar_init(bar0 + 8 * k, 1);
+      for (int k = 0; k < 4; k++) {
+        mbar_init(full0 + 8 * k, (unsigned)groups);
+        mbar_init(empty0 + 8 * k, (unsigned)groups);
+      }
+    }
     if (l == 0) {
       mbar_init(gbar0, (unsigned)nlay);
       mbar_init(gbar0 + 8, (unsigned)nlay);
@@ -236,10 +285,10 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
   const int Rs = R0 & ~3;  // the row loop starts on a multiple of 4: ring slot = R & 3 = unroll phase
   const int Rend = LEAN ? (R1 | 3) : R1;  // last row the loop visits (the unrolled loop works in groups of 4)
   const size_t row_bytes = (size_t)NX * 8;
-  auto issue = [&](int Rt) {  // stage the inputs of front row Rt (every lane has finished reading the slots it refills)
-    const unsigned bar = bar0 + 8 * (Rt & 3);
-    if (lane == 0) mbar_expect_tx(bar, (unsigned)(nstr * kSegB));
-    if (my_on) bulk_g2s(my_dst + (unsigned)((Rt & my_mask) * kSegB), my_src + (size_t)min(max(Rt - my_lag, 0), NY - 1) * row_bytes, kSegB, bar);
+  auto issue = [&](int Rt) {  // stage this warp's share of the inputs of front row Rt
+    const unsigned bar = full0 + 8 * (Rt & 3);
+    if (lane == 0) mbar_expect_tx(bar, my_bytes);
+    if (my_on) bulk_g2s(my_dst + (unsigned)(Rt & my_mask) * segb, my_src + (size_t)min(max(Rt - my_lag, 0), NY - 1) * row_bytes, segb, bar);
   };
   issue(Rs);
   issue(Rs + 1);
@@ -247,22 +296,28 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
   size_t off2 = off0 - 2 * row_bytes;
 
   // ---- values carried from earlier rows: X[(phase - age) & 3] is X of row R - age ----
-  double hn[4] = {0, 0, 0, 0}, hnW[4] = {0, 0, 0, 0}, rv[4] = {0, 0, 0, 0}, dv[4] = {0, 0, 0, 0};
+  double rv[4] = {0, 0, 0, 0}, dv[4] = {0, 0, 0, 0};
   double A1[4] = {0, 0, 0, 0}, A3[4] = {0, 0, 0, 0}, B1[4] = {0, 0, 0, 0}, B3[4] = {0, 0, 0, 0};
-  double Pv[4] = {0, 0, 0, 0}, Qv[4] = {0, 0, 0, 0}, mo[4] = {0, 0, 0, 0}, qp[4] = {0, 0, 0, 0};
-  double Fx[4] = {0, 0, 0, 0}, Gy[4] = {0, 0, 0, 0}, Tc[4] = {0, 0, 0, 0}, fl[4] = {0, 0, 0, 0};
+  double Qv[4] = {0, 0, 0, 0}, qp[4] = {0, 0, 0, 0};
+  double Gy[4] = {0, 0, 0, 0}, Tc[4] = {0, 0, 0, 0}, fl[4] = {0, 0, 0, 0};
   double vold = 0.0;              // v(R-2) at time n when u goes first (its ring slot is being refilled)
   unsigned fw_m1 = 0, fw_m2 = 0;  // flags of (own | W<<8 | E<<16), masked rows only
 
-  const double *sgp = ring + 2 + lane;
+  const double *sgp = ring + 2 + grp * kUse + lane;
+  double *shp = sh_h + (size_t)l * tpad + 1 + tcol;  // + slot*nlay*tpad: this thread's thickness of row slot
+  double *wrp = wring + 1 + lane;                     // + (ring*4 + slot)*kWRow
   const int tt_base = LEAN ? kMandatory : (int)T.slot[S_TTXU];  // wind streams keep their order: TTXU, TTYV, TTYVS
 
 #define AT(a, age) a[(PH - (age)) & 3]
-#define LD4(s, age, dx) sgp[(s) * 4 * kSeg + o4_##age + (dx)]
-#define LD2(slot, dx) sgp[(16 + ((slot)-4) * 2) * kSeg + o2 + (dx)]
+#define SLOT(age) (CT ? ((PH - (age)) & 3) : ((R - (age)) & 3))
+#define LD4(s, age, dx) sgp[((s) * 4 + SLOT(age)) * wseg + (dx)]
+#define LD2(slot, dx) sgp[(16 + ((slot)-4) * 2 + (SLOT(0) & 1)) * wseg + (dx)]
 #define LDX(stream, dx) LD2((int)T.slot[stream], dx)
+#define HN(age, dx) shp[SLOT(age) * nlay * tpad + (dx)]
+#define WR(ring_id, age, dx) wrp[((ring_id)*4 + SLOT(age)) * kWRow + (dx)]
 #define SELM(p, a) (MASKED ? sel((p), (a)) : (a))
 #define MKN(f) (MASKED ? m_n(f) : 1.0)
+  enum { W_MO = 0, W_PV = 1, W_FX = 2 };
   // One row of the pipeline.  PH = phase of the carried rings; CT: the ring slot is the compile-time phase.
   // MASKED = false is the open-water fast path: every mask of the three rows in flight is 1 on all 32 lanes,
   // so no select is needed.
@@ -270,12 +325,9 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
     constexpr int PH = decltype(ph_tag)::value;
     constexpr bool CT = decltype(ct_tag)::value;
     constexpr bool MASKED = decltype(masked_tag)::value;
-    const int o4_0 = (CT ? (PH & 3) : (R & 3)) * kSeg, o4_1 = (CT ? ((PH - 1) & 3) : ((R - 1) & 3)) * kSeg;
-    const int o4_2 = (CT ? ((PH - 2) & 3) : ((R - 2) & 3)) * kSeg;
-    const int o2 = (CT ? (PH & 1) : (R & 1)) * kSeg;
-    const int hslot = CT ? (PH & 1) : (R & 1);
+    const int hslot = SLOT(0) & 1;
     const unsigned hpar = CT ? ((PH >> 1) & 1) : ((R >> 1) & 1);
-    mbar_wait(bar0 + 8 * (CT ? (PH & 3) : (R & 3)), bpar);  // staged inputs of front row R have landed
+    mbar_wait(full0 + 8 * SLOT(0), bpar);  // staged inputs of front row R have landed
     const bool act = f_own & F_ACT;
     const bool row_own = (R >= ya && R <= yb);
     const bool row2_own = (R - 2 >= ya && R - 2 <= yb);
@@ -304,30 +356,29 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
       __stcs(reinterpret_cast<double *>(o_hlay + off0), hn_0);
       __stcs(reinterpret_cast<double *>(o_rs + off0), rs_3);
     }
-    sh_h[((size_t)hslot * nlay + l) * tcols + tcol] = hn_0;
+    HN(0, 0) = hn_0;
     __syncwarp();
     if (lane == 0) mbar_arrive(gbar0 + 8 * hslot);  // split-phase: waited for at the end of the row
-    AT(hn, 0) = hn_0;
 
     // -------------------------------------------------------------------------------- rvor, dive, row R (pm:2388, 2435)
     const double u_0 = LD4(S_U, 0, 0), uE_0 = LD4(S_U, 0, 1), u_m1 = LD4(S_U, 1, 0);
     const double v_p1 = LD4(S_V, 0, 0), v_0 = LD4(S_V, 1, 0), vW_0 = LD4(S_V, 1, -1);
     const double rv_0 = SELM(act && (f_own & F_PE), (v_0 - vW_0 - u_0 + u_m1) * D.i_dl);
     const double dv_0 = SELM(act, (uE_0 - u_0 + v_p1 - v_0) * D.i_dl);
+    const double ke = kin * (uE_0 * uE_0 + u_0 * u_0 + v_p1 * v_p1 + v_0 * v_0);  // kinetic part of the Bernoulli potential (pm:2381)
 
     // -------------------------------------------------------------------------------- d2hx, pvor, row R; d2hy, row R-1
-    const double hnE_0 = shdn(hn_0), hnW_0 = shup(hn_0);
-    AT(hnW, 0) = hnW_0;
+    const double hnE_0 = HN(0, 1), hnW_0 = HN(0, -1), hn_m1 = HN(1, 0), hn_m2 = HN(2, 0);
     double d2x_0 = SELM((fw_0 & (F_N << 16)) && (fw_0 & (F_N << 8)) && (f_own & F_N), hnE_0 + hnW_0 - hn_0 * 2.0);
     if (ocrp && (hnE_0 < D.two_hs || hnW_0 < D.two_hs || hn_0 < D.two_hs)) d2x_0 = 0.0;
     d2x_0 = SELM(act, d2x_0);
-    AT(Fx, 0) = 0.16667 * d2x_0;
-    double d2y_m1 = SELM((f_own & F_N) && (fw_m2 & F_N) && (fw_m1 & F_N), hn_0 + AT(hn, 2) - AT(hn, 1) * 2.0);
-    if (ocrp && (hn_0 < D.two_hs || AT(hn, 2) < D.two_hs || AT(hn, 1) < D.two_hs)) d2y_m1 = 0.0;
+    WR(W_FX, 0, 0) = 0.16667 * d2x_0;
+    double d2y_m1 = SELM((f_own & F_N) && (fw_m2 & F_N) && (fw_m1 & F_N), hn_0 + hn_m2 - hn_m1 * 2.0);
+    if (ocrp && (hn_0 < D.two_hs || hn_m2 < D.two_hs || hn_m1 < D.two_hs)) d2y_m1 = 0.0;
     d2y_m1 = SELM(fw_m1 & F_ACT, d2y_m1);
     AT(Gy, 1) = 0.16667 * d2y_m1;
     {
-      const double have = hn_0 + hnW_0 + AT(hnW, 1) + AT(hn, 1);
+      const double have = hn_0 + hnW_0 + HN(1, -1) + hn_m1;
       const double msum = MKN((uint8_t)f_own) + MKN((uint8_t)(fw_0 >> 8)) + MKN((uint8_t)(fw_m1 >> 8)) + MKN((uint8_t)fw_m1);
       const double pv_0 = SELM(act, SELM(f_own & F_PI, LD2(S_FCOR, 0) + rv_0 * D.uadv) * msum / have);
       AT(qp, 0) = 0.25 * pv_0;
@@ -335,6 +386,7 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
     if (UFIRST) AT(Tc, 0) = AT(qp, 0) * (hv_0 + LD4(S_HV, 1, -1));  // Coriolis term of u with h_v at time n (pm:1461-1462)
 
     // -------------------------------------------------------------------------------- Leith viscosity, row R-1 (pm:2477-2502)
+    double P_m1 = 0.0;
     if (VISC) {
       AT(A1, 0) = sq(shdn(rv_0) - rv_0);
       AT(A3, 0) = sq(rv_0 - AT(rv, 1));
@@ -345,7 +397,8 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
       const bool a = fw_m1 & F_ACT;
       const double vll_m1 = SELM(a, sqrt(tll) * D.dvis * D.dl * D.dl + D.bvis);
       const double vcc_m1 = SELM(a, sqrt(tcc) * D.dvis * D.dl * D.dl + D.bvis);
-      AT(Pv, 1) = vcc_m1 * AT(dv, 1);
+      P_m1 = vcc_m1 * AT(dv, 1);
+      WR(W_PV, 1, 0) = P_m1;
       AT(Qv, 1) = vll_m1 * AT(rv, 1);
     }
     AT(rv, 0) = rv_0;
@@ -372,12 +425,14 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
     }
     const double ux1 = LD2(S_DX1, 0), ux2 = LD2(S_DX2, 0), ux3 = LD2(S_DX3, 0);
     const double vy1 = LD2(S_DY1, 0), vy2 = LD2(S_DY2, 0), vy3 = LD2(S_DY3, 0);
+    const double mo_m2 = WR(W_MO, 2, 0), P_m2 = VISC ? WR(W_PV, 2, 0) : 0.0, PW_m2 = VISC ? WR(W_PV, 2, -1) : 0.0;
+    const double hn_m2b = HN(2, 0);
     if (UFIRST) {
       // ---- u at row R-2 (pm:1422-1503) ----
       double un, hun, dm;
-      momentum<true, VISC, MASKED, LEAN>(D, wind, MASKED ? m_u((uint8_t)fw_m2) : 1.0, AT(hnW, 2) + AT(hn, 2), shup(AT(mo, 2)), AT(mo, 2),
-                                         AT(Tc, 2), AT(Tc, 1), LD4(S_U, 2, 0), ux1, ux2, ux3, AT(Pv, 2), shup(AT(Pv, 2)), AT(Qv, 1),
-                                         AT(Qv, 2), shup(AT(Fx, 2)), AT(Fx, 2), xu, un, hun, dm);
+      momentum<true, VISC, MASKED, LEAN>(D, wind, MASKED ? m_u((uint8_t)fw_m2) : 1.0, HN(2, -1) + hn_m2b, WR(W_MO, 2, -1), mo_m2,
+                                         AT(Tc, 2), AT(Tc, 1), LD4(S_U, 2, 0), ux1, ux2, ux3, P_m2, PW_m2, AT(Qv, 1),
+                                         AT(Qv, 2), WR(W_FX, 2, -1), WR(W_FX, 2, 0), xu, un, hun, dm);
       hun = SELM(a2, hun);
       if (sto2) {
         __stcs(reinterpret_cast<double *>(o_u + off2), un);
@@ -388,9 +443,9 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
       // ---- v at row R-2 (pm:1505-1591), using the new h_u of rows R-2 and R-3 ----
       const double wc = AT(qp, 2) * (hun + AT(fl, 3));
       double vn, hvn;
-      momentum<false, VISC, MASKED, LEAN>(D, wind, MASKED ? m_v((uint8_t)fw_m2) : 1.0, AT(hn, 2) + AT(hn, 3), AT(mo, 3), AT(mo, 2), wc,
-                                          shdn(wc), vold, vy1, vy2, vy3, AT(Pv, 2), AT(Pv, 3), shdn(AT(Qv, 2)), AT(Qv, 2), AT(Gy, 3),
-                                          AT(Gy, 2), xv, vn, hvn, dm);
+      momentum<false, VISC, MASKED, LEAN>(D, wind, MASKED ? m_v((uint8_t)fw_m2) : 1.0, hn_m2b + HN(3, 0), WR(W_MO, 3, 0), mo_m2, wc,
+                                          shdn(wc), vold, vy1, vy2, vy3, P_m2, VISC ? WR(W_PV, 3, 0) : 0.0, shdn(AT(Qv, 2)), AT(Qv, 2),
+                                          AT(Gy, 3), AT(Gy, 2), xv, vn, hvn, dm);
       if (sto2) {
         __stcs(reinterpret_cast<double *>(o_v + off2), vn);
         __stcs(reinterpret_cast<double *>(o_hv + off2), SELM(a2, hvn));
@@ -402,8 +457,8 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
       const bool a1 = fw_m1 & F_ACT;
       const double wc = AT(qp, 1) * (LD4(S_HU, 1, 0) + LD4(S_HU, 2, 0));
       double vn, hvn, dm;
-      momentum<false, VISC, MASKED, LEAN>(D, wind, MASKED ? m_v((uint8_t)fw_m1) : 1.0, AT(hn, 1) + AT(hn, 2), AT(mo, 2), AT(mo, 1), wc,
-                                          shdn(wc), LD4(S_V, 2, 0), vy1, vy2, vy3, AT(Pv, 1), AT(Pv, 2), shdn(AT(Qv, 1)), AT(Qv, 1),
+      momentum<false, VISC, MASKED, LEAN>(D, wind, MASKED ? m_v((uint8_t)fw_m1) : 1.0, hn_m1 + hn_m2b, mo_m2, WR(W_MO, 1, 0), wc,
+                                          shdn(wc), LD4(S_V, 2, 0), vy1, vy2, vy3, P_m1, P_m2, shdn(AT(Qv, 1)), AT(Qv, 1),
                                           AT(Gy, 2), AT(Gy, 1), xv, vn, hvn, dm);
       hvn = SELM(a1, hvn);
       if (col_ok && (!MASKED || a1) && (R - 1 >= ya) && (R - 1 <= yb)) {
@@ -414,9 +469,9 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
       AT(Tc, 1) = AT(qp, 1) * (hvn + shup(hvn));  // Coriolis term of u with the new h_v (pm:1461-1462)
       // ---- u at row R-2 (pm:1422-1503), using the new h_v of rows R-2 and R-1 ----
       double un, hun;
-      momentum<true, VISC, MASKED, LEAN>(D, wind, MASKED ? m_u((uint8_t)fw_m2) : 1.0, AT(hnW, 2) + AT(hn, 2), shup(AT(mo, 2)), AT(mo, 2),
-                                         AT(Tc, 2), AT(Tc, 1), LD4(S_U, 2, 0), ux1, ux2, ux3, AT(Pv, 2), shup(AT(Pv, 2)), AT(Qv, 1),
-                                         AT(Qv, 2), shup(AT(Fx, 2)), AT(Fx, 2), xu, un, hun, dm);
+      momentum<true, VISC, MASKED, LEAN>(D, wind, MASKED ? m_u((uint8_t)fw_m2) : 1.0, HN(2, -1) + hn_m2b, WR(W_MO, 2, -1), mo_m2,
+                                         AT(Tc, 2), AT(Tc, 1), LD4(S_U, 2, 0), ux1, ux2, ux3, P_m2, PW_m2, AT(Qv, 1),
+                                         AT(Qv, 2), WR(W_FX, 2, -1), WR(W_FX, 2, 0), xu, un, hun, dm);
       if (sto2) {
         __stcs(reinterpret_cast<double *>(o_u + off2), un);
         __stcs(reinterpret_cast<double *>(o_hu + off2), SELM(a2, hun));
@@ -434,26 +489,29 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
       mpot = -0.0;
     }
     mpot = mpot - 0.0;
-    const double ke = kin * (uE_0 * uE_0 + u_0 * u_0 + v_p1 * v_p1 + v_0 * v_0);
     const double hth = LD2(S_HTH, 0);
     mbar_wait(gbar0 + 8 * hslot, hpar);  // every layer of this column group has published hn(R)
     {
-      const double *col = sh_h + (size_t)hslot * nlay * tcols + tcol;
+      const double *col = sh_h + (size_t)SLOT(0) * nlay * tpad + 1 + tcol;
       double hcol = 0.0;
 #pragma unroll
       for (int i = 0; i < (NL > 0 ? NL : kMaxLay); i++) {
         if (i < nlay) {
-          const double hi = col[(size_t)i * tcols];
+          const double hi = col[(size_t)i * tpad];
           if (i < l) mpot = mpot - cb[i] * hi;
           hcol = hcol + hi;
         }
       }
       mpot = hcol - hth + mpot;
     }
-    AT(mo, 0) = SELM(act, mpot + ke);
+    WR(W_MO, 0, 0) = SELM(act, mpot + ke);
 
     __syncwarp();
-    if (R + 2 <= Rend) issue(R + 2);  // refill the slots this row was the last to read
+    if (lane == 0) mbar_arrive(empty0 + 8 * SLOT(0));  // this warp has finished reading the slots row R + 2 refills
+    if (R + 2 <= Rend) {
+      mbar_wait(empty0 + 8 * SLOT(0), bpar);           // ... and so has every other column group of the layer
+      issue(R + 2);
+    }
     off0 += row_bytes;
     off2 += row_bytes;
   };
@@ -461,6 +519,9 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
 #undef LD2
 #undef LD4
 #undef AT
+#undef SLOT
+#undef HN
+#undef WR
 #undef SELM
 #undef MKN
 
@@ -512,7 +573,7 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
       else       row(ic<0>{}, Ft{}, Tt{}, R, f_own, fw_0, bpar);
       fw_m2 = fw_m1; fw_m1 = fw_0;
 #define ROT(a) a[1] = a[2]; a[2] = a[3]; a[3] = a[0];
-      ROT(hn) ROT(hnW) ROT(rv) ROT(dv) ROT(A1) ROT(A3) ROT(B1) ROT(B3) ROT(Pv) ROT(Qv) ROT(mo) ROT(qp) ROT(Fx) ROT(Gy) ROT(Tc) ROT(fl)
+      ROT(rv) ROT(dv) ROT(A1) ROT(A3) ROT(B1) ROT(B3) ROT(Qv) ROT(qp) ROT(Gy) ROT(Tc) ROT(fl)
 #undef ROT
     }
   }
