@@ -131,6 +131,7 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=10)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--trace", type=int, default=0, help="diagnostic: time N further blocks of 10 steps each and log clocks/power")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -251,6 +252,17 @@ def main():
             ms = float(t.item())
         ms_per_step = ms / steps
         value = updates_per_step * steps / (ms * 1.0e-3)
+        if args.trace and world == 1:  # diagnostic: how the step time evolves under sustained load (power cap)
+            t = warm + steps
+            for k in range(args.trace):
+                gm.mark(0)
+                gm.advance(t + 1, t + 10)
+                gm.mark(1)
+                gm.sync()
+                t += 10
+                q = subprocess.run(["nvidia-smi", "-i", str(local_rank), "--query-gpu=clocks.sm,clocks.mem,power.draw,temperature.gpu",
+                                    "--format=csv,noheader,nounits"], capture_output=True, text=True).stdout.strip()
+                log("[trace] block %d: %.3f ms/step   sm,mem MHz, W, C = %s" % (k, gm.elapsed_ms() / 10.0, q))
 
         # ---- end to end through the C ABI with host buffers: upload_state + K steps + download_state
         e2e = None

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIBDIR = os.path.join(HERE, "lib")
+LIBDIR = os.environ.get("BEOM_LIBDIR") or os.path.join(HERE, "lib")
 MAXLAY = 16
 
 c_double_p = C.POINTER(C.c_double)

@@ -15,7 +15,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
-LIBDIR = os.path.join(HERE, "lib")
+LIBDIR = os.environ.get("BEOM_LIBDIR") or os.path.join(HERE, "lib")  # BEOM_LIBDIR / BEOM_NVCC_DEFS: experiment builds
 GPU_SRC = os.path.join(HERE, "csrc", "gpu")
 HOST_SRC = os.path.join(HERE, "csrc", "host")
 
@@ -50,7 +50,10 @@ def build_gpu(force: bool = False, verbose_ptxas: bool = False) -> str:
     hdrs = _sources(GPU_SRC, (".cuh", ".h")) + [os.path.join(ROOT, "include", "beom_gpu.h")]
     objdir = os.path.join(ROOT, "build", "gpu")
     os.makedirs(objdir, exist_ok=True)
-    extra = ["-Xptxas", "-v"] if verbose_ptxas else []
+    extra = (["-Xptxas", "-v"] if verbose_ptxas else []) + os.environ.get("BEOM_NVCC_DEFS", "").split()
+    if os.environ.get("BEOM_LIBDIR"):
+        objdir = os.path.join(LIBDIR, "obj")
+        os.makedirs(objdir, exist_ok=True)
     # one nvcc per translation unit, in parallel (the fused-step instantiations dominate the build time)
     jobs, objs = [], []
     for cu in cus:

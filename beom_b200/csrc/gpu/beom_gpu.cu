@@ -75,6 +75,7 @@ struct Ctx {
   cudaStream_t stream = nullptr;
   double *halo_send[2] = {nullptr, nullptr}, *halo_recv[2] = {nullptr, nullptr};  // [lower, upper] neighbour
   size_t halo_cap = 0;
+  size_t big_allocs = 0;
   cudaEvent_t ev[2] = {nullptr, nullptr};
   long long launches = 0;
   size_t win_first = 0, win_stride = 0;  // host state arrays cover points win_first .. win_first+win_stride-1 per layer
@@ -82,13 +83,28 @@ struct Ctx {
 };
 Ctx g;
 
+// Device allocation.  Large planes are staggered: allocation k starts (k mod 8) x 2 MiB + (k mod 5) x 4 KiB into its
+// block, so that the ~90 row streams the fused step reads and writes at the same time do not all sit at the same
+// offset modulo the page / TLB-set / DRAM-bank interleave (every field has the same size, so without the stagger
+// their bases are congruent modulo any power of two up to 2 MiB x 8).
 template <class T>
 int dalloc(T **p, size_t n, bool zero = true) {
   void *q = nullptr;
   n += 1024;  // slack: the fused step stages whole-CTA row segments that may run past the last row of a plane
-  CK(cudaMalloc(&q, n * sizeof(T)));
-  if (zero) CK(cudaMemsetAsync(q, 0, n * sizeof(T), g.stream));
+  size_t bytes = n * sizeof(T), shift = 0;
+  static int stagger = -1;
+  if (stagger < 0) {
+    const char *e = getenv("BEOM_STAGGER");
+    stagger = e ? atoi(e) : 1;
+  }
+  if (stagger && bytes >= ((size_t)64 << 20)) {
+    const size_t k = g.big_allocs++;
+    shift = (k % 8) * ((size_t)2 << 20) + (k % 5) * 4096;
+  }
+  CK(cudaMalloc(&q, bytes + shift));
   g.allocs.push_back(q);
+  q = (char *)q + shift;
+  if (zero) CK(cudaMemsetAsync(q, 0, bytes, g.stream));
   *p = (T *)q;
   return 0;
 }
@@ -349,7 +365,7 @@ int beom_gpu_init(const beom_params *par, const beom_fields *fld, const beom_gpu
     g.j1 = g.j0 + base + (g.rank < rem ? 1 : 0) - 1;
     if (g.j1 < g.j0) return fail(-5, "beom_gpu_init: more ranks than grid rows");
   }
-  g.NX = ((lm + 40) + 15) / 16 * 16;  // room for the fused kernel's 36-column staged segments past x_hi
+  g.NX = ((lm + GX0 + 34) + 15) / 16 * 16;  // room for the fused kernel's last 28-column tile (+ 4 staged columns) past x_hi
   g.NY = (g.j1 - g.j0 + 1) + 2 * G;
   g.plane = (size_t)g.NX * g.NY;
   if (g.plane > 0x7fffffffull) return fail(-6, "beom_gpu_init: plane too large for 32-bit cell offsets");

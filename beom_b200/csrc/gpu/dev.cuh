@@ -19,7 +19,7 @@
 namespace beom {
 
 constexpr int G = 4;    // halo width (cells); the fused step needs 3
-constexpr int GX0 = 3;  // X = i + GX0  -> i = 1 sits at X = 4 (32-byte aligned rows)
+constexpr int GX0 = 15;  // X = i + GX0  -> i = 1 sits at X = 16: the fused step's row segments start on 128-byte lines
 
 // per-cell flag bits (the reference's 0./1. masks, private_mod.f95:54-58, plus "is a vector point")
 enum : uint8_t { F_N = 1, F_U = 2, F_V = 4, F_PE = 8, F_PI = 16, F_ACT = 32 };
