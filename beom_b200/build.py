@@ -93,6 +93,9 @@ def build_host(force: bool = False) -> str:
 
 
 def build_all(force: bool = False) -> None:
+    if os.environ.get("BEOM_LIBDIR") and not force and all(
+            os.path.exists(os.path.join(LIBDIR, f)) for f in ("libbeom_gpu.so", "libbeom_host.so")):
+        return  # an experiment build (tools/ab.sh): use it as it is, never rebuild it from the current sources
     build_gpu(force)
     build_host(force)
 

@@ -52,7 +52,7 @@ constexpr int kUse = 32 - 2 * kHalo;  // 28 result columns per warp
 constexpr int kMaxLay = 8;            // layers per CTA (shared-memory exchange, warps per CTA)
 constexpr int kOBitsB = 128;  // per-warp open-water bitmap (32 words)
 #ifndef BEOM_PF_ROWS
-#define BEOM_PF_ROWS 4   // rows ahead of the TMA staging that are prefetched into L2 (0 = off)
+#define BEOM_PF_ROWS 0   // rows ahead of the TMA staging that are prefetched into L2 (0 = off)
 #endif
 #ifndef BEOM_FUSED_WARPS
 #define BEOM_FUSED_WARPS 16
@@ -221,8 +221,10 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
   const int lane = threadIdx.x & 31;
   const int wid = threadIdx.x >> 5;
   const int groups = GROUPS > 0 ? GROUPS : groups_rt;
-  const int grp = wid % groups;
   const int l = wid / groups;  // layer of this warp
+  // column group, rotated by the layer: the warps that share a scheduler (wid mod 4) then belong to different layers
+  // AND different column groups, so no two of them wait for each other at the same barrier
+  const int grp = (wid + l) % groups;
   const int nlay = NL > 0 ? NL : D.nlay;
   const int NX = D.NX, NY = D.NY;
   const int wseg = seg_doubles(groups);   // doubles per staged row segment (whole CTA width)
@@ -245,7 +247,6 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
   const bool wind = D.has_wind && ((wind_layers >> l) & 1);
   const int nstr = wind ? T.n : T.n_nowind;
 
-  const bool tile_ok = xs + kPad + grp * kUse <= D.x_hi;  // this warp has result columns inside the domain
 
   double cb[kMaxLay];  // (rhon(l) - rhon(i)) * i_rn(l), private_mod.f95:2359
 #pragma unroll
@@ -272,15 +273,17 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
   const unsigned my_dst = ring0 + (unsigned)(my_s < 4 ? my_s * 4 : 16 + (my_s - 4) * 2) * segb;
   const int my_mask = my_s < 4 ? 3 : 1;
   const unsigned my_bytes = (unsigned)nstr * segb;  // one row of this layer's inputs
-  // ---- output side: lane k < 8 sends this warp's 28 columns of output k (kOutStream) ----
+  // ---- output side: lane k < 8 of the warp that stages its results last sends the CTA's columns of output k
+  // (kOutStream) of this layer with one bulk copy ----
   constexpr int LVc = UFIRST ? 2 : 1;
   const int my_olag = lane < 2 ? 0 : (lane < 5 ? 2 : LVc);
   double *my_out = nullptr;
   unsigned my_osrc = 0;
   if (lane < 8) {
-    my_out = T.out[lane] + L + (xs + kPad + grp * kUse);
-    my_osrc = ring0 + (unsigned)(16 + (kOutStream[lane] - 4) * 2) * segb + (unsigned)(kPad + grp * kUse) * 8;
+    my_out = T.out[lane] + L + (xs + kPad);
+    my_osrc = ring0 + (unsigned)(16 + (kOutStream[lane] - 4) * 2) * segb + (unsigned)kPad * 8;
   }
+  const unsigned out_bytes = (unsigned)min(groups * kUse, NX - (xs + kPad)) * 8;  // never past the end of the row
   {  // rows below the chunk read as 0 until staged; so do the state rings
     const int n = (int)(sp.ring_bytes(l) / 8);
     for (int i = grp * 32 + lane; i < n; i += groups * 32) ring[i] = 0.0;
@@ -331,7 +334,10 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
 #endif
     }
   };
-  if (grp == 0) issue(Rs);  // row Rs + 1 is staged by the row-epilogue logic inside row Rs
+  if (grp == 0) {
+    issue(Rs);
+    issue(Rs + 1);
+  }
 
   // ---- values carried from earlier rows: X[(phase - age) & 3] is X of row R - age ----
   double rv[4] = {0, 0, 0, 0}, dv[4] = {0, 0, 0, 0};
@@ -392,18 +398,6 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
     HN(0, 0) = hn_0;
     __syncwarp();
     if (lane == 0) mbar_arrive(gbar0 + 8 * hslot);  // split-phase: waited for at the end of the row
-    {  // epilogue of row R-1: once its bulk stores have read their slots, the LAST column group of the layer to get
-       // here stages row R+1 for the whole layer (nobody waits for a slower warp)
-      if (lane < 8) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      __syncwarp();
-      unsigned last = 0;
-      if (lane == 0) {
-        unsigned old;
-        asm volatile("atom.acq_rel.cta.shared.inc.u32 %0, [%1], %2;" : "=r"(old) : "r"(done0 + 8 * SLOT(1)), "r"((unsigned)(groups - 1)) : "memory");
-        last = old == (unsigned)(groups - 1);
-      }
-      if (__shfl_sync(0xffffffffu, last, 0) && R + 1 <= Rend) issue(R + 1);
-    }
 
     // -------------------------------------------------------------------------------- rvor, dive, row R (pm:2388, 2435)
     const double u_0 = LD4(S_U, 0, 0), uE_0 = LD4(S_U, 0, 1), u_m1 = LD4(S_U, 1, 0);
@@ -560,10 +554,23 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the results in the ring become visible to the copy engine
     __syncwarp();
-    if (lane < 8 && tile_ok) {
-      const int ro = R - my_olag;
-      if (ro >= ya && ro <= yb) bulk_s2g(my_out + (size_t)ro * NX, my_osrc + (unsigned)(SLOT(0) & 1) * segb, kUse * 8);
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    // The column group that stages its results LAST sends the layer's row to global memory and, once the copy
+    // engine has read the slots, refills them with the inputs of row R+2 (nobody waits for a slower warp).
+    unsigned last = 0;
+    if (lane == 0) {
+      unsigned old;
+      asm volatile("atom.acq_rel.cta.shared.inc.u32 %0, [%1], %2;" : "=r"(old) : "r"(done0 + 8 * SLOT(0)), "r"((unsigned)(groups - 1)) : "memory");
+      last = old == (unsigned)(groups - 1);
+    }
+    if (__shfl_sync(0xffffffffu, last, 0)) {
+      if (lane < 8) {
+        const int ro = R - my_olag;
+        if (ro >= ya && ro <= yb) bulk_s2g(my_out + (size_t)ro * NX, my_osrc + (unsigned)(SLOT(0) & 1) * segb, out_bytes);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      }
+      __syncwarp();
+      if (R + 2 <= Rend) issue(R + 2);
     }
   };
 #undef LDX
