@@ -6,7 +6,6 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
-#include <cstdlib>
 #include <cstring>
 
 #include "fused_kernel.cuh"
@@ -27,9 +26,6 @@ struct FusedCfg {
   bool visc = false;    // Leith viscosity recomputed every step
   int wind_layers = 0;  // bit l set: tt3d of layer l may be non-zero
   uint8_t *open = nullptr;  // [tiles][NY]: bit 0 = rows R-2..R open water on the tile's 32 columns, bit 1 = the same for R..R+3
-  unsigned long long *probe = nullptr;  // BEOM_FUSED_PROBE=1: device buffer of 4 words
-  unsigned *open4 = nullptr;  // [tiles][open4_words]: bit g of the row-group bitmap = bit 1 of open[4g]
-  int open4_words = 0;
 } cfg;
 
 // open-water summary of the flag plane, one byte per (warp tile, row)
@@ -54,20 +50,9 @@ __global__ void k_open_groups(uint8_t *__restrict__ open, int NY, int ntiles) {
   if (all) o[R] |= 2;  // bit 1 is read by nobody in this kernel
 }
 
-__global__ void k_open_bits(const uint8_t *__restrict__ open, unsigned *__restrict__ open4, int NY, int nwords) {
-  const int w = blockIdx.x * blockDim.x + threadIdx.x, tile = blockIdx.y;
-  if (w >= nwords) return;
-  unsigned bits = 0;
-  for (int b = 0; b < 32; b++) {
-    const int R = (w * 32 + b) * 4;
-    if (R < NY && (open[(size_t)tile * NY + R] & 2)) bits |= 1u << b;
-  }
-  open4[(size_t)tile * nwords + w] = bits;
-}
-
 // Stream table for one step: where each staged row segment comes from (pointers follow the state
 // double buffering, so the table is rebuilt per launch; it is ~20 entries).
-StreamTab make_streams(const Dev &D, const Dev &O, bool ufirst) {
+StreamTab make_streams(const Dev &D, bool ufirst) {
   StreamTab T;
   memset(&T, 0, sizeof T);
   for (auto &s : T.slot) s = -1;
@@ -99,9 +84,6 @@ StreamTab make_streams(const Dev &D, const Dev &O, bool ufirst) {
     add(S_TTYV, D.tt3d + pl, LV, 2); add(S_TTYVS, D.tt3d + pl, LV + 1, 2);
     if (D.has_nudg) { add(S_TTYU, D.tt3d + pl, 2, 2); add(S_TTXV, D.tt3d, LV, 2); add(S_TTXVS, D.tt3d, LV + 1, 2); }
   }
-  double *outs[8] = {O.hlay, D.rs_new, O.u, O.h_u, D.dx_new, O.v, O.h_v, D.dy_new};
-  for (int k = 0; k < 8; k++) T.out[k] = outs[k];
-  T.probe = cfg.probe;
   return T;
 }
 size_t fused_smem_bytes(int nlay, int groups, const StreamTab &T, int wind_layers) {
@@ -111,8 +93,6 @@ size_t fused_smem_bytes(int nlay, int groups, const StreamTab &T, int wind_layer
 
 void fused_release() {
   if (cfg.open) cudaFree(cfg.open);
-  if (cfg.open4) cudaFree(cfg.open4);
-  if (cfg.probe) cudaFree(cfg.probe);
   cfg = FusedCfg();
 }
 
@@ -151,7 +131,7 @@ int fused_configure(const Dev &D, const beom_params &P, int nmir, int nranks, bo
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  const StreamTab T0 = make_streams(D, D, true);
+  const StreamTab T0 = make_streams(D, true);
   if (T0.n > 32) return 0;
   const int width = D.x_hi - D.x_lo + 1, rows = D.y_hi - D.y_lo + 1;
   const int wl = D.has_wind ? cfg.wind_layers : 0;
@@ -164,7 +144,6 @@ int fused_configure(const Dev &D, const beom_params &P, int nmir, int nranks, bo
   cfg.strips = (width + groups * kUse - 1) / (groups * kUse);
   int chunks = std::max(1, (2 * sms + cfg.strips / 2) / cfg.strips);  // about two CTAs' worth of work per SM
   chunks = std::min(chunks, std::max(1, rows / 16));
-  chunks = std::max(chunks, (rows + 3839) / 3840);  // the lean kernel keeps a chunk's open-water bitmap in one warp (32 x 128 rows)
   cfg.rows_per_chunk = (rows + chunks - 1) / chunks;
   cfg.chunks = (rows + cfg.rows_per_chunk - 1) / cfg.rows_per_chunk;
   {
@@ -172,12 +151,8 @@ int fused_configure(const Dev &D, const beom_params &P, int nmir, int nranks, bo
     if (cudaMalloc(&cfg.open, (size_t)ntiles * D.NY) != cudaSuccess) return -62;
     k_open_rows<<<dim3((unsigned)ntiles, (unsigned)((D.NY + 7) / 8)), dim3(32, 8)>>>(D.flags, cfg.open, D.NX, D.NY, D.x_lo);
     k_open_groups<<<dim3((unsigned)((D.NY + 127) / 128), (unsigned)ntiles), 128>>>(cfg.open, D.NY, ntiles);
-    cfg.open4_words = (D.NY + 127) / 128;
-    if (cudaMalloc(&cfg.open4, (size_t)ntiles * cfg.open4_words * sizeof(unsigned)) != cudaSuccess) return -62;
-    k_open_bits<<<dim3((unsigned)((cfg.open4_words + 63) / 64), (unsigned)ntiles), 64>>>(cfg.open, cfg.open4, D.NY, cfg.open4_words);
     if (cudaDeviceSynchronize() != cudaSuccess) return -63;
   }
-  if (getenv("BEOM_FUSED_PROBE") && cudaMalloc(&cfg.probe, 32) != cudaSuccess) return -62;
   cfg.ok = true;
   *enabled = true;
   return 0;
@@ -191,9 +166,9 @@ int fused_step(const Dev &in, const Dev &out, int tstp, bool first_three, cudaSt
   a.grid = dim3((unsigned)cfg.strips, (unsigned)cfg.chunks, 1);
   a.block = dim3((unsigned)(cfg.groups * 32 * in.nlay), 1, 1);
   const bool ufirst = (tstp % 2 == 0);
-  const StreamTab T = make_streams(in, out, ufirst);
+  const StreamTab T = make_streams(in, ufirst);
   a.shmem = fused_smem_bytes(in.nlay, cfg.groups, T, in.has_wind ? cfg.wind_layers : 0);
-  a.in = &in; a.out = &out; a.tab = &T; a.open = cfg.open; a.open4 = cfg.open4; a.open4_words = cfg.open4_words;
+  a.in = &in; a.out = &out; a.tab = &T; a.open = cfg.open;
   a.groups = cfg.groups; a.rows_per_chunk = cfg.rows_per_chunk; a.wind_layers = cfg.wind_layers;
   a.stream = s;
   // the lean instantiation assumes gene = 1 (tstp >= 4 with g_fb = 1; beom_gpu_step passes gene explicitly)
@@ -210,13 +185,6 @@ int fused_step(const Dev &in, const Dev &out, int tstp, bool first_three, cudaSt
     rc = fused_launch_general(a, ufirst, cfg.visc, in.nlay);
   }
   if (rc) return rc;
-  if (cfg.probe) {  // diagnostics only: effective SM clock while the first wave of the step ran
-    unsigned long long h[4];
-    cudaStreamSynchronize(s);
-    cudaMemcpy(h, cfg.probe, 32, cudaMemcpyDeviceToHost);
-    fprintf(stderr, "[fused probe] tstp %d: CTA(0,0) %.3f ms, %.0f MHz\n", tstp, (double)(h[3] - h[1]) * 1e-6,
-            (double)(h[2] - h[0]) / ((double)(h[3] - h[1]) * 1e-3));
-  }
   *nlaunch = 1;
   return cudaGetLastError() == cudaSuccess ? 0 : -60;
 }

@@ -50,10 +50,6 @@ namespace fusedk {
 constexpr int kHalo = 2;              // halo lanes on each side of a warp
 constexpr int kUse = 32 - 2 * kHalo;  // 28 result columns per warp
 constexpr int kMaxLay = 8;            // layers per CTA (shared-memory exchange, warps per CTA)
-constexpr int kOBitsB = 128;  // per-warp open-water bitmap (32 words)
-#ifndef BEOM_PF_ROWS
-#define BEOM_PF_ROWS 0   // rows ahead of the TMA staging that are prefetched into L2 (0 = off)
-#endif
 #ifndef BEOM_FUSED_WARPS
 #define BEOM_FUSED_WARPS 16
 #endif
@@ -81,13 +77,7 @@ struct StreamTab {
   const double *base[S_COUNT];  // by slot
   short lag[S_COUNT];          // row = R - lag
   unsigned char lstride[S_COUNT];  // layer stride in planes (0 = 2-D field, 1, or 2 for [nlay][2] arrays)
-  double *out[8];              // output planes, in the order of kOutStream
-  unsigned long long *probe;   // diagnostics (BEOM_FUSED_PROBE=1): clock64 / globaltimer at the start and end of CTA (0,0)
 };
-// Results are written IN PLACE over the staged input they replace (same field family, same row), then each warp
-// sends its 28 columns of every output to global memory with one bulk shared->global copy per stream.
-//                                  hlay   rs_3   u      h_u    dmd4x  v      h_v    dmd4y
-__device__ constexpr int kOutStream[8] = {S_HL, S_R1, S_DX1, S_DX2, S_DX3, S_DY1, S_DY2, S_DY3};
 
 __host__ __device__ constexpr int ring_segments(int nstreams) { return 16 + (nstreams - 4) * 2; }
 
@@ -113,9 +103,6 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
       "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar),
       "r"(parity)
       : "memory");
-}
-__device__ __forceinline__ void bulk_s2g(void *dst, unsigned src, unsigned bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
@@ -198,10 +185,10 @@ __host__ __device__ inline SmemPlan smem_plan(int nlay, int groups, int n_all, i
   p.tpad = groups * 32 + 2;
   size_t o = (size_t)4 * nlay * p.tpad * 8;          // thickness ring [4][nlay][tpad]
   p.off_bars = o;
-  o += (size_t)(10 * nlay + 2 * groups) * 8;          // full[nlay][4], done[nlay][4] (counters), rdone[nlay][2], gbar[groups][2]
+  o += (size_t)(8 * nlay + 2 * groups) * 8;           // full[nlay][4], empty[nlay][4], gbar[groups][2]
   o = (o + 15) & ~(size_t)15;
   p.off_wring = o;
-  o += (size_t)nlay * groups * (kWRings * 4 * kWRow * 8 + kOBitsB);  // per-warp state rings + open-water bitmap (32 words)
+  o += (size_t)nlay * groups * kWRings * 4 * kWRow * 8;  // per-warp state rings
   o = (o + 127) & ~(size_t)127;
   p.off_ring = o;
   p.seg_bytes = (size_t)seg_doubles(groups) * 8;
@@ -215,8 +202,7 @@ __host__ __device__ inline SmemPlan smem_plan(int nlay, int groups, int n_all, i
 template <bool UFIRST, bool VISC, int NL, bool LEAN, int GROUPS>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1)
 k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const __grid_constant__ StreamTab T,
-             const uint8_t *__restrict__ open, const unsigned *__restrict__ open4, int open4_words, int groups_rt, int rows_per_chunk,
-             int wind_layers) {
+             const uint8_t *__restrict__ open, int groups_rt, int rows_per_chunk, int wind_layers) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int wid = threadIdx.x >> 5;
@@ -233,8 +219,7 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
   const SmemPlan sp = smem_plan(nlay, groups, T.n, T.n_nowind, D.has_wind ? wind_layers : 0);
   double *sh_h = reinterpret_cast<double *>(smem_raw);
   unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem_raw + sp.off_bars);
-  double *wring = reinterpret_cast<double *>(smem_raw + sp.off_wring) + (size_t)wid * (kWRings * 4 * kWRow + kOBitsB / 8);
-  unsigned *obits = reinterpret_cast<unsigned *>(wring + kWRings * 4 * kWRow);  // [32]: open-water bit of every 4-row group
+  double *wring = reinterpret_cast<double *>(smem_raw + sp.off_wring) + (size_t)wid * kWRings * 4 * kWRow;
   double *ring = reinterpret_cast<double *>(smem_raw + sp.ring_off(l));  // input ring of this layer
 
   const int tile = blockIdx.x * groups + grp;
@@ -247,6 +232,11 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
   const bool wind = D.has_wind && ((wind_layers >> l) & 1);
   const int nstr = wind ? T.n : T.n_nowind;
 
+  // output planes of this layer as byte pointers; off0 / off2 are the running byte offsets of (R, x) / (R-2, x)
+  char *__restrict__ o_hlay = reinterpret_cast<char *>(O.hlay + L), *__restrict__ o_u = reinterpret_cast<char *>(O.u + L);
+  char *__restrict__ o_v = reinterpret_cast<char *>(O.v + L), *__restrict__ o_hu = reinterpret_cast<char *>(O.h_u + L);
+  char *__restrict__ o_hv = reinterpret_cast<char *>(O.h_v + L), *__restrict__ o_rs = reinterpret_cast<char *>(D.rs_new + L);
+  char *__restrict__ o_dx = reinterpret_cast<char *>(D.dx_new + L), *__restrict__ o_dy = reinterpret_cast<char *>(D.dy_new + L);
 
   double cb[kMaxLay];  // (rhon(l) - rhon(i)) * i_rn(l), private_mod.f95:2359
 #pragma unroll
@@ -254,14 +244,12 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
   const double kin = 0.25 * D.uadv * D.i_gr;  // private_mod.f95:2381
   const bool ocrp = !LEAN && D.ocrp > 0.5;
 
-  // ---- producer side: the warps of a layer share the staging.  The column group that finishes a row LAST stages
-  // the row two ahead for the whole layer (nobody waits for a slower warp); lane j owns stream j. ----
+  // ---- producer side: the warps of a layer share the staging; lane j of warp (l, grp) owns stream grp + j*groups ----
   const unsigned full0 = smem_u32(bars + 4 * l);               // [4]: inputs of front row R & 3 have landed (tx)
-  const unsigned done0 = smem_u32(bars + 4 * nlay + 4 * l);     // [4] counters (8-byte stride): column groups done with row R & 3
-  const unsigned rdone0 = smem_u32(bars + 8 * nlay + 2 * l);   // [2]: every column group has read the inputs its neighbours overwrite in place
-  const unsigned gbar0 = smem_u32(bars + 10 * nlay + 2 * grp);  // [2]: thickness exchange of a column group (split-phase)
+  const unsigned empty0 = smem_u32(bars + 4 * nlay + 4 * l);   // [4]: every column group has finished row R & 3
+  const unsigned gbar0 = smem_u32(bars + 8 * nlay + 2 * grp);  // [2]: thickness exchange of a column group (split-phase)
   const unsigned ring0 = smem_u32(ring);
-  const int my_s = lane;  // slots are compact and wind-only streams come last
+  const int my_s = grp + lane * groups;  // slots are compact and wind-only streams come last
   const bool my_on = my_s < nstr;
   const char *my_src = nullptr;
   int my_lag = 0;
@@ -272,18 +260,7 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
   const unsigned segb = (unsigned)(wseg * 8);
   const unsigned my_dst = ring0 + (unsigned)(my_s < 4 ? my_s * 4 : 16 + (my_s - 4) * 2) * segb;
   const int my_mask = my_s < 4 ? 3 : 1;
-  const unsigned my_bytes = (unsigned)nstr * segb;  // one row of this layer's inputs
-  // ---- output side: lane k < 8 of the warp that stages its results last sends the CTA's columns of output k
-  // (kOutStream) of this layer with one bulk copy ----
-  constexpr int LVc = UFIRST ? 2 : 1;
-  const int my_olag = lane < 2 ? 0 : (lane < 5 ? 2 : LVc);
-  double *my_out = nullptr;
-  unsigned my_osrc = 0;
-  if (lane < 8) {
-    my_out = T.out[lane] + L + (xs + kPad);
-    my_osrc = ring0 + (unsigned)(16 + (kOutStream[lane] - 4) * 2) * segb + (unsigned)kPad * 8;
-  }
-  const unsigned out_bytes = (unsigned)min(groups * kUse, NX - (xs + kPad)) * 8;  // never past the end of the row
+  const unsigned my_bytes = (grp < nstr ? (unsigned)((nstr - grp + groups - 1) / groups) : 0u) * segb;  // this warp's share of a row
   {  // rows below the chunk read as 0 until staged; so do the state rings
     const int n = (int)(sp.ring_bytes(l) / 8);
     for (int i = grp * 32 + lane; i < n; i += groups * 32) ring[i] = 0.0;
@@ -294,11 +271,9 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
     if (grp == 0) {
 #pragma unroll
       for (int k = 0; k < 4; k++) {
-        mbar_init(full0 + 8 * k, 1);
-        asm volatile("st.shared.u32 [%0], %1;" ::"r"(done0 + 8 * k), "r"(0u) : "memory");
+        mbar_init(full0 + 8 * k, (unsigned)groups);
+        mbar_init(empty0 + 8 * k, (unsigned)groups);
       }
-      mbar_init(rdone0, (unsigned)groups);
-      mbar_init(rdone0 + 8, (unsigned)groups);
     }
     if (l == 0) {
       mbar_init(gbar0, (unsigned)nlay);
@@ -308,36 +283,19 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
-  if (T.probe && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    T.probe[0] = clock64();
-    T.probe[1] = t;
-  }
   const int R0 = ya - 3, R1 = yb + 2;
   const int Rs = R0 & ~3;  // the row loop starts on a multiple of 4: ring slot = R & 3 = unroll phase
   const int Rend = LEAN ? (R1 | 3) : R1;  // last row the loop visits (the unrolled loop works in groups of 4)
   const size_t row_bytes = (size_t)NX * 8;
-  auto issue = [&](int Rt) {  // stage the inputs of front row Rt for the whole layer
+  auto issue = [&](int Rt) {  // stage this warp's share of the inputs of front row Rt
     const unsigned bar = full0 + 8 * (Rt & 3);
     if (lane == 0) mbar_expect_tx(bar, my_bytes);
-    if (my_on) {
-      bulk_g2s(my_dst + (unsigned)(Rt & my_mask) * segb, my_src + (size_t)min(max(Rt - my_lag, 0), NY - 1) * row_bytes, segb, bar);
-#if BEOM_PF_ROWS > 0
-      // The ring holds one row in flight (shared memory is full), far less than the bandwidth-delay product of
-      // HBM: pull the row BEOM_PF_ROWS further ahead into L2 so that the bulk copy above finds it there.
-      const char *pf = my_src + (size_t)min(max(Rt + BEOM_PF_ROWS - my_lag, 0), NY - 1) * row_bytes;
-      const int nlines = (int)(segb + 127) / 128;
-#pragma unroll
-      for (int k = 0; k < (GROUPS > 0 ? (seg_doubles(GROUPS) * 8 + 127) / 128 : 32); k++)
-        if (k < nlines) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf + 128 * k));
-#endif
-    }
+    if (my_on) bulk_g2s(my_dst + (unsigned)(Rt & my_mask) * segb, my_src + (size_t)min(max(Rt - my_lag, 0), NY - 1) * row_bytes, segb, bar);
   };
-  if (grp == 0) {
-    issue(Rs);
-    issue(Rs + 1);
-  }
+  issue(Rs);
+  issue(Rs + 1);
+  size_t off0 = ((size_t)Rs * NX + x) * 8;                   // only dereferenced for rows this chunk owns
+  size_t off2 = off0 - 2 * row_bytes;
 
   // ---- values carried from earlier rows: X[(phase - age) & 3] is X of row R - age ----
   double rv[4] = {0, 0, 0, 0}, dv[4] = {0, 0, 0, 0};
@@ -347,7 +305,7 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
   double vold = 0.0;              // v(R-2) at time n when u goes first (its ring slot is being refilled)
   unsigned fw_m1 = 0, fw_m2 = 0;  // flags of (own | W<<8 | E<<16), masked rows only
 
-  double *sgp = ring + 2 + grp * kUse + lane;
+  const double *sgp = ring + 2 + grp * kUse + lane;
   double *shp = sh_h + (size_t)l * tpad + 1 + tcol;  // + slot*nlay*tpad: this thread's thickness of row slot
   double *wrp = wring + 1 + lane;                     // + (ring*4 + slot)*kWRow
   const int tt_base = LEAN ? kMandatory : (int)T.slot[S_TTXU];  // wind streams keep their order: TTXU, TTYV, TTYVS
@@ -357,7 +315,6 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
 #define LD4(s, age, dx) sgp[((s) * 4 + SLOT(age)) * wseg + (dx)]
 #define LD2(slot, dx) sgp[(16 + ((slot)-4) * 2 + (SLOT(0) & 1)) * wseg + (dx)]
 #define LDX(stream, dx) LD2((int)T.slot[stream], dx)
-#define ST2(slot) LD2(slot, 0)  // results overwrite the staged input of the same family in place
 #define HN(age, dx) shp[SLOT(age) * nlay * tpad + (dx)]
 #define WR(ring_id, age, dx) wrp[((ring_id)*4 + SLOT(age)) * kWRow + (dx)]
 #define SELM(p, a) (MASKED ? sel((p), (a)) : (a))
@@ -374,6 +331,8 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
     const unsigned hpar = CT ? ((PH >> 1) & 1) : ((R >> 1) & 1);
     mbar_wait(full0 + 8 * SLOT(0), bpar);  // staged inputs of front row R have landed
     const bool act = f_own & F_ACT;
+    const bool row_own = (R >= ya && R <= yb);
+    const bool row2_own = (R - 2 >= ya && R - 2 <= yb);
 
     // -------------------------------------------------------------------------------- update_h, row R (pm:1610-1643)
     const double hu_0 = LD4(S_HU, 0, 0), huE_0 = LD4(S_HU, 0, 1);
@@ -395,6 +354,10 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
       }
     }
     hn_0 = SELM(act, hn_0);
+    if (col_ok && row_own && (!MASKED || act)) {
+      __stcs(reinterpret_cast<double *>(o_hlay + off0), hn_0);
+      __stcs(reinterpret_cast<double *>(o_rs + off0), rs_3);
+    }
     HN(0, 0) = hn_0;
     __syncwarp();
     if (lane == 0) mbar_arrive(gbar0 + 8 * hslot);  // split-phase: waited for at the end of the row
@@ -446,7 +409,7 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
     // -------------------------------------------------------------------------------- momentum
     constexpr int LV = UFIRST ? 2 : 1;  // v is updated at row R - LV
     const bool a2 = fw_m2 & F_ACT;
-    const bool sto2 = col_ok && (!MASKED || a2);
+    const bool sto2 = col_ok && (!MASKED || a2) && row2_own;
     MomX xu, xv;
     if (wind) {
       xu.tw_b = LD2(tt_base, 0); xu.tw_a = LD2(tt_base, -1);
@@ -464,12 +427,6 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
     }
     const double ux1 = LD2(S_DX1, 0), ux2 = LD2(S_DX2, 0), ux3 = LD2(S_DX3, 0);
     const double vy1 = LD2(S_DY1, 0), vy2 = LD2(S_DY2, 0), vy3 = LD2(S_DY3, 0);
-    // The results of this row go IN PLACE over HL, R1, DX1-3, DY1-3 (below).  The halo lanes of the neighbouring
-    // column groups read those inputs at this warp's columns, so every group first reports that it has read them.
-    __syncwarp();
-    if (lane == 0) mbar_arrive(rdone0 + 8 * hslot);
-    double o_un, o_hun, o_dmu, o_vn, o_hvn, o_dmv;
-    bool g_v = sto2;
     const double mo_m2 = WR(W_MO, 2, 0), P_m2 = VISC ? WR(W_PV, 2, 0) : 0.0, PW_m2 = VISC ? WR(W_PV, 2, -1) : 0.0;
     const double hn_m2b = HN(2, 0);
     if (UFIRST) {
@@ -479,7 +436,11 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
                                          AT(Tc, 2), AT(Tc, 1), LD4(S_U, 2, 0), ux1, ux2, ux3, P_m2, PW_m2, AT(Qv, 1),
                                          AT(Qv, 2), WR(W_FX, 2, -1), WR(W_FX, 2, 0), xu, un, hun, dm);
       hun = SELM(a2, hun);
-      o_un = un; o_hun = hun; o_dmu = dm;
+      if (sto2) {
+        __stcs(reinterpret_cast<double *>(o_u + off2), un);
+        __stcs(reinterpret_cast<double *>(o_hu + off2), hun);
+        __stcs(reinterpret_cast<double *>(o_dx + off2), dm);
+      }
       AT(fl, 2) = hun;
       // ---- v at row R-2 (pm:1505-1591), using the new h_u of rows R-2 and R-3 ----
       const double wc = AT(qp, 2) * (hun + AT(fl, 3));
@@ -487,7 +448,11 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
       momentum<false, VISC, MASKED, LEAN>(D, wind, MASKED ? m_v((uint8_t)fw_m2) : 1.0, hn_m2b + HN(3, 0), WR(W_MO, 3, 0), mo_m2, wc,
                                           shdn(wc), vold, vy1, vy2, vy3, P_m2, VISC ? WR(W_PV, 3, 0) : 0.0, shdn(AT(Qv, 2)), AT(Qv, 2),
                                           AT(Gy, 3), AT(Gy, 2), xv, vn, hvn, dm);
-      o_vn = vn; o_hvn = SELM(a2, hvn); o_dmv = dm;
+      if (sto2) {
+        __stcs(reinterpret_cast<double *>(o_v + off2), vn);
+        __stcs(reinterpret_cast<double *>(o_hv + off2), SELM(a2, hvn));
+        __stcs(reinterpret_cast<double *>(o_dy + off2), dm);
+      }
       vold = LD4(S_V, 2, 0);  // v(R-1): the old v of the next row's update
     } else {
       // ---- v at row R-1 (pm:1505-1591), h_u at time n ----
@@ -498,15 +463,22 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
                                           shdn(wc), LD4(S_V, 2, 0), vy1, vy2, vy3, P_m1, P_m2, shdn(AT(Qv, 1)), AT(Qv, 1),
                                           AT(Gy, 2), AT(Gy, 1), xv, vn, hvn, dm);
       hvn = SELM(a1, hvn);
-      o_vn = vn; o_hvn = hvn; o_dmv = dm;
-      g_v = col_ok && (!MASKED || a1);
+      if (col_ok && (!MASKED || a1) && (R - 1 >= ya) && (R - 1 <= yb)) {
+        __stcs(reinterpret_cast<double *>(o_v + (off2 + row_bytes)), vn);
+        __stcs(reinterpret_cast<double *>(o_hv + (off2 + row_bytes)), hvn);
+        __stcs(reinterpret_cast<double *>(o_dy + (off2 + row_bytes)), dm);
+      }
       AT(Tc, 1) = AT(qp, 1) * (hvn + shup(hvn));  // Coriolis term of u with the new h_v (pm:1461-1462)
       // ---- u at row R-2 (pm:1422-1503), using the new h_v of rows R-2 and R-1 ----
       double un, hun;
       momentum<true, VISC, MASKED, LEAN>(D, wind, MASKED ? m_u((uint8_t)fw_m2) : 1.0, HN(2, -1) + hn_m2b, WR(W_MO, 2, -1), mo_m2,
                                          AT(Tc, 2), AT(Tc, 1), LD4(S_U, 2, 0), ux1, ux2, ux3, P_m2, PW_m2, AT(Qv, 1),
                                          AT(Qv, 2), WR(W_FX, 2, -1), WR(W_FX, 2, 0), xu, un, hun, dm);
-      o_un = un; o_hun = SELM(a2, hun); o_dmu = dm;
+      if (sto2) {
+        __stcs(reinterpret_cast<double *>(o_u + off2), un);
+        __stcs(reinterpret_cast<double *>(o_hu + off2), SELM(a2, hun));
+        __stcs(reinterpret_cast<double *>(o_dx + off2), dm);
+      }
     }
 
     // -------------------------------------------------------------------------------- mont, row R (pm:2351-2383)
@@ -536,45 +508,16 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
     }
     WR(W_MO, 0, 0) = SELM(act, mpot + ke);
 
-    // -------------------------------------------------------------------------------- results -> global memory
-    mbar_wait(rdone0 + 8 * hslot, hpar);  // nobody reads the inputs of this row that are overwritten now
-    if (col_ok && (!MASKED || act)) {
-      ST2(S_HL) = hn_0;
-      ST2(S_R1) = rs_3;
-    }
-    if (sto2) {
-      ST2(S_DX1) = o_un;
-      ST2(S_DX2) = o_hun;
-      ST2(S_DX3) = o_dmu;
-    }
-    if (g_v) {
-      ST2(S_DY1) = o_vn;
-      ST2(S_DY2) = o_hvn;
-      ST2(S_DY3) = o_dmv;
-    }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the results in the ring become visible to the copy engine
     __syncwarp();
-    // The column group that stages its results LAST sends the layer's row to global memory and, once the copy
-    // engine has read the slots, refills them with the inputs of row R+2 (nobody waits for a slower warp).
-    unsigned last = 0;
-    if (lane == 0) {
-      unsigned old;
-      asm volatile("atom.acq_rel.cta.shared.inc.u32 %0, [%1], %2;" : "=r"(old) : "r"(done0 + 8 * SLOT(0)), "r"((unsigned)(groups - 1)) : "memory");
-      last = old == (unsigned)(groups - 1);
+    if (lane == 0) mbar_arrive(empty0 + 8 * SLOT(0));  // this warp has finished reading the slots row R + 2 refills
+    if (R + 2 <= Rend) {
+      mbar_wait(empty0 + 8 * SLOT(0), bpar);           // ... and so has every other column group of the layer
+      issue(R + 2);
     }
-    if (__shfl_sync(0xffffffffu, last, 0)) {
-      if (lane < 8) {
-        const int ro = R - my_olag;
-        if (ro >= ya && ro <= yb) bulk_s2g(my_out + (size_t)ro * NX, my_osrc + (unsigned)(SLOT(0) & 1) * segb, out_bytes);
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      }
-      __syncwarp();
-      if (R + 2 <= Rend) issue(R + 2);
-    }
+    off0 += row_bytes;
+    off2 += row_bytes;
   };
 #undef LDX
-#undef ST2
 #undef LD2
 #undef LD4
 #undef AT
@@ -591,16 +534,20 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
   using Ft = std::false_type;
   auto flags_of = [&](int R) -> unsigned { return (unsigned)fl_p[(size_t)min(R, NY - 1) * NX]; };
   auto widen = [&](unsigned f) -> unsigned { return f | (__shfl_up_sync(0xffffffffu, f, 1) << 8) | (__shfl_down_sync(0xffffffffu, f, 1) << 16); };
+  // open-water byte of a row (group): a pinned load, so that the compiler cannot sink it to its use a whole group later
+  auto open_of = [&](int R) -> unsigned {
+    unsigned v;
+    asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(op + min(R, NY - 1)));
+    return v;
+  };
   if (LEAN) {
     unsigned bpar = 0;
-    // open-water bit of every 4-row group of the chunk: word k covers groups 32k .. 32k+31 past the first
-    const int w0 = Rs >> 7;
-    obits[lane] = (w0 + lane < open4_words) ? open4[(size_t)tile * open4_words + w0 + lane] : 0u;
-    __syncwarp();
+    unsigned o_next = open_of(Rs);
 #pragma unroll 1
     for (int R = Rs; R <= R1; R += 4) {
-      const unsigned o = obits[(R >> 7) - w0] >> ((R >> 2) & 31);
-      if (o & 1) {  // rows R-2 .. R+3 are open water on all 32 columns
+      const unsigned o = o_next;
+      o_next = open_of(R + 4);
+      if (o & 2) {  // rows R-2 .. R+3 are open water on all 32 columns
         row(ic<0>{}, Tt{}, Ft{}, R, kAllMasks, kAllMasks, bpar);
         row(ic<1>{}, Tt{}, Ft{}, R + 1, kAllMasks, kAllMasks, bpar);
         row(ic<2>{}, Tt{}, Ft{}, R + 2, kAllMasks, kAllMasks, bpar);
@@ -622,12 +569,12 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
     }
   } else {
     unsigned f_next = flags_of(Rs);
-    unsigned o_next = op[min(Rs, NY - 1)];
+    unsigned o_next = open_of(Rs);
 #pragma unroll 1
     for (int R = Rs; R <= R1; R++) {
       const unsigned f_own = f_next, o = o_next;
       f_next = flags_of(R + 1);
-      o_next = op[min(R + 1, NY - 1)];
+      o_next = open_of(R + 1);
       const unsigned fw_0 = widen(f_own);
       const unsigned bpar = (unsigned)(((R - Rs) >> 2) & 1);
       if (o & 1) row(ic<0>{}, Ft{}, Ft{}, R, f_own, fw_0, bpar);
@@ -637,13 +584,6 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
       ROT(rv) ROT(dv) ROT(A1) ROT(A3) ROT(B1) ROT(B3) ROT(Qv) ROT(qp) ROT(Gy) ROT(Tc) ROT(fl)
 #undef ROT
     }
-  }
-  if (lane < 8) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // shared memory must outlive the last bulk stores
-  if (T.probe && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    T.probe[2] = clock64();
-    T.probe[3] = t;
   }
 }
 

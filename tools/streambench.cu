@@ -50,6 +50,54 @@ __global__ void k_strips(Ptrs P, int NX, int NY, size_t plane, int rows_per, int
   }
 }
 
+// store-shape variants of the 4 x 28-column strips (loads as in k_strips):
+//  VAR 0: 14 lanes store 16 bytes each (same 224 bytes per warp)      VAR 1: warp g writes columns [32g, 32g+28) (no line shared by two warps)
+//  VAR 2: the four 28-column results go through shared memory and ONE warp per layer writes the 112 columns with full 32-lane stores
+template <int NR, int NW, int VAR>
+__global__ void k_strips_var(Ptrs P, int NX, int NY, size_t plane, int rows_per) {
+  __shared__ double stage[4][NW][112];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, grp = wid & 3, l = wid >> 2;
+  const int cw = (VAR == 1) ? 32 : 28;
+  const int x = 16 + blockIdx.x * 4 * cw + grp * cw + lane;
+  const bool on = lane < 28 && x < NX;
+  const int y0 = blockIdx.y * rows_per, y1 = min(y0 + rows_per, NY);
+  const size_t L = (size_t)l * plane;
+  for (int y = y0; y < y1; y++) {
+    const size_t c = L + (size_t)y * NX + x;
+    double acc = 0.0;
+    if (on) {
+#pragma unroll
+      for (int s = 0; s < NR; s++) acc += __ldg(P.r[s] + c);
+    }
+    if (VAR == 0) {
+      const double nb = __shfl_down_sync(0xffffffffu, acc, 1);
+      if (on && !(lane & 1)) {
+#pragma unroll
+        for (int s = 0; s < NW; s++) __stcs(reinterpret_cast<double2 *>(P.w[s] + c), make_double2(acc + s, nb + s));
+      }
+    } else if (VAR == 1) {
+      if (on) {
+#pragma unroll
+        for (int s = 0; s < NW; s++) __stcs(P.w[s] + c, acc + s);
+      }
+    } else {
+      if (lane < 28) {
+#pragma unroll
+        for (int s = 0; s < NW; s++) stage[l][s][grp * 28 + lane] = acc + s;
+      }
+      __syncthreads();
+      if (grp == 0) {
+        const size_t c0 = L + (size_t)y * NX + 16 + blockIdx.x * 112;
+#pragma unroll
+        for (int s = 0; s < NW; s++)
+          for (int k = lane; k < 112; k += 32)
+            if (16 + blockIdx.x * 112 + k < NX) __stcs(P.w[s] + c0 + k, stage[l][s][k]);
+      }
+      __syncthreads();
+    }
+  }
+}
+
 // wide: one warp per layer moves the CTA's whole 128-column row segment (1 KiB) with 32-byte lanes
 template <int NR, int NW>
 __global__ void k_wide(Ptrs P, int NX, int NY, size_t plane, int rows_per) {
@@ -187,6 +235,9 @@ int main(int argc, char **argv) {
   timeit("flat 13R+8W", 21 * b1, [&] { k_flat<13, 8><<<148 * 16, 512>>>(P, n / 2); });
   timeit("strips 4x28 cols 13R+8W, x0 = 4 (fused kernel today)", 21 * b1 * 8192 / 8240, [&] { k_strips<13, 8, 28><<<dim3(73, 4), 512>>>(P, NX, NY, plane, rp4, 4); });
   timeit("strips 4x28 cols 13R+8W, x0 = 16 (CTA 128B-aligned)", 21 * b1 * 8176 / 8240, [&] { k_strips<13, 8, 28><<<dim3(73, 4), 512>>>(P, NX, NY, plane, rp4, 16); });
+  timeit("strips 4x28 13R+8W, 14 lanes x 16 B stores", 21 * b1 * 8176 / 8240, [&] { k_strips_var<13, 8, 0><<<dim3(73, 4), 512>>>(P, NX, NY, plane, rp4); });
+  timeit("strips 4x28 13R+8W, warps 32 columns apart", 21 * b1 * 7168 / 8240, [&] { k_strips_var<13, 8, 1><<<dim3(64, 4), 512>>>(P, NX, NY, plane, rp4); });
+  timeit("strips 4x28 13R+8W, smem + one warp stores 112 cols", 21 * b1 * 8176 / 8240, [&] { k_strips_var<13, 8, 2><<<dim3(73, 4), 512>>>(P, NX, NY, plane, rp4); });
   timeit("strips 4x28 13R+8W plain st.global", 21 * b1 * 8176 / 8240, [&] { k_strips<13, 8, 28, 1><<<dim3(73, 4), 512>>>(P, NX, NY, plane, rp4, 4); });
   timeit("strips 4x28 13R+8W st.global.cg", 21 * b1 * 8176 / 8240, [&] { k_strips<13, 8, 28, 2><<<dim3(73, 4), 512>>>(P, NX, NY, plane, rp4, 4); });
   timeit("strips 4x28 13R+8W st.global.wt", 21 * b1 * 8176 / 8240, [&] { k_strips<13, 8, 28, 3><<<dim3(73, 4), 512>>>(P, NX, NY, plane, rp4, 4); });
