@@ -73,6 +73,8 @@ struct Ctx {
   bool visc_valid = false;
   bool stress_const_done = false;  // tt3d = taus*layt does not change when ocrp = 0 and no drag
   cudaStream_t stream = nullptr;
+  cudaStream_t comm_stream = nullptr;  // halo exchange of the fused step, overlapped with the interior rows
+  cudaEvent_t ev_edge = nullptr, ev_comm = nullptr;
   double *halo_send[2] = {nullptr, nullptr}, *halo_recv[2] = {nullptr, nullptr};  // [lower, upper] neighbour
   size_t halo_cap = 0;
   size_t big_allocs = 0;
@@ -136,11 +138,12 @@ struct Item {
 // Make the cells that shadow other cells consistent after `items' were written: periodic aliases on
 // this device (k_mirror) and, with y-slabs, the G halo rows owned by the neighbouring ranks (one packed
 // NCCL send/recv per neighbour).
-int sync_fields(std::initializer_list<Item> items, bool remote = true) {
+int sync_fields(std::initializer_list<Item> items, bool remote = true, cudaStream_t st = nullptr) {
+  if (!st) st = g.stream;
   if (g.nmir) {
     for (const Item &it : items) {
       if (!it.p) continue;
-      k_mirror<<<(g.nmir + 127) / 128, 128, 0, g.stream>>>(it.p, g.plane, it.planes, g.d_mir_dst, g.d_mir_src, g.nmir);
+      k_mirror<<<(g.nmir + 127) / 128, 128, 0, st>>>(it.p, g.plane, it.planes, g.d_mir_dst, g.d_mir_src, g.nmir);
       g.launches++;
     }
   }
@@ -161,11 +164,11 @@ int sync_fields(std::initializer_list<Item> items, bool remote = true) {
     if (count > g.halo_cap) return fail(-71, "sync_fields: halo buffer too small");
     const int lo = g.rank > 0 ? g.rank - 1 : -1, hi = g.rank < g.nranks - 1 ? g.rank + 1 : -1;
     const unsigned blocks = (unsigned)((per_plane + 255) / 256);
-    k_halo_pack<<<dim3(blocks, (unsigned)t.total, 2), 256, 0, g.stream>>>(t, g.plane, g.NX, g.D.y_lo, g.D.y_hi, g.halo_send[0], g.halo_send[1]);
+    k_halo_pack<<<dim3(blocks, (unsigned)t.total, 2), 256, 0, st>>>(t, g.plane, g.NX, g.D.y_lo, g.D.y_hi, g.halo_send[0], g.halo_send[1]);
     g.launches++;
-    int rc = comm_exchange(g.halo_send[0], g.halo_recv[0], lo, g.halo_send[1], g.halo_recv[1], hi, count, g.stream, &g_err);
+    int rc = comm_exchange(g.halo_send[0], g.halo_recv[0], lo, g.halo_send[1], g.halo_recv[1], hi, count, st, &g_err);
     if (rc) return rc;
-    k_halo_unpack<<<dim3(blocks, (unsigned)t.total, 2), 256, 0, g.stream>>>(t, g.plane, g.NX, g.D.y_lo, g.D.y_hi, g.halo_recv[0], g.halo_recv[1], lo >= 0, hi >= 0);
+    k_halo_unpack<<<dim3(blocks, (unsigned)t.total, 2), 256, 0, st>>>(t, g.plane, g.NX, g.D.y_lo, g.D.y_hi, g.halo_recv[0], g.halo_recv[1], lo >= 0, hi >= 0);
     g.launches++;
   }
   return 0;
@@ -315,6 +318,9 @@ int beom_gpu_finalize(void) {
   for (auto &e : g.ev)
     if (e) { cudaEventDestroy(e); e = nullptr; }
   if (g.stream) { cudaStreamDestroy(g.stream); g.stream = nullptr; }
+  if (g.comm_stream) { cudaStreamDestroy(g.comm_stream); g.comm_stream = nullptr; }
+  if (g.ev_edge) { cudaEventDestroy(g.ev_edge); g.ev_edge = nullptr; }
+  if (g.ev_comm) { cudaEventDestroy(g.ev_comm); g.ev_comm = nullptr; }
   fused_release();
   g = Ctx();
   return 0;
@@ -351,6 +357,13 @@ int beom_gpu_init(const beom_params *par, const beom_fields *fld, const beom_gpu
   g.rank = opt.nranks > 1 ? opt.rank : 0;
   g.nranks = opt.nranks > 1 ? opt.nranks : 1;
   CK(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+  {
+    int lo_pri = 0, hi_pri = 0;
+    CK(cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri));
+    CK(cudaStreamCreateWithPriority(&g.comm_stream, cudaStreamNonBlocking, hi_pri));
+    CK(cudaEventCreateWithFlags(&g.ev_edge, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&g.ev_comm, cudaEventDisableTiming));
+  }
   CK(cudaEventCreate(&g.ev[0]));
   CK(cudaEventCreate(&g.ev[1]));
 
@@ -685,22 +698,42 @@ int beom_gpu_step(int tstp, double ctim, double ramp, double gene, int upst, int
     Dev Dout = D;
     const int nxt = g.cur ^ 1;
     Dout.hlay = g.st[0][nxt]; Dout.u = g.st[1][nxt]; Dout.v = g.st[2][nxt]; Dout.h_u = g.st[3][nxt]; Dout.h_v = g.st[4][nxt];
-    int nlaunch = 0;
-    int rc = fused_step(D, Dout, tstp, first_three != 0, g.stream, &nlaunch);
-    if (rc) return fail(rc, "fused_step failed: %s", cudaGetErrorString(cudaGetLastError()));
-    g.launches += nlaunch;
-    if (g.D.has_nudg && g.P.mcbc < 0.5 && g.nseg > 0) {  // no_gradient_obc after both components (pm:2285-2288)
-      Dev Dobc = D;
-      Dobc.hlay = Dout.hlay; Dobc.u = Dout.u; Dobc.v = Dout.v; Dobc.h_u = Dout.h_u; Dobc.h_v = Dout.h_v;
-      for (int pass = 0; pass < 2; pass++) {
-        k_obc<<<(g.nseg + 63) / 64, 64, 0, g.stream>>>(Dobc, g.d_seg, g.nseg, pass);
-        g.launches++;
-      }
-    }
-    if (g.nranks > 1) {
+    int nlaunch = 0, rc;
+    const bool obc = g.D.has_nudg && g.P.mcbc < 0.5 && g.nseg > 0;
+    // BEOM_OVERLAP=1: exchange the edge rows while the interior rows are computed (measured slower than the plain
+    // sequence at 2 GPUs: NCCL's copy kernels displace CTAs of a grid sized for exactly two waves)
+    static const bool want_overlap = getenv("BEOM_OVERLAP") && atoi(getenv("BEOM_OVERLAP")) > 0;
+    const bool overlap = want_overlap && g.nranks > 1 && !obc && (D.y_hi - D.y_lo + 1) >= 4 * G;
+    if (overlap) {
+      // y-slabs: the G rows next to each neighbour first, then their exchange on the communication stream while the
+      // rows in between are computed (the interior reads time level n only, the exchange touches halo rows of n+1)
+      if ((rc = fused_step(D, Dout, tstp, false, g.stream, &nlaunch, 1, G))) return fail(rc, "fused_step (edge rows) failed: %s", cudaGetErrorString(cudaGetLastError()));
+      CK(cudaEventRecord(g.ev_edge, g.stream));
+      CK(cudaStreamWaitEvent(g.comm_stream, g.ev_edge, 0));
       rc = sync_fields({{Dout.hlay, g.nlay}, {Dout.u, g.nlay}, {Dout.v, g.nlay}, {Dout.h_u, g.nlay}, {Dout.h_v, g.nlay},
-                        {D.rs_new, g.nlay}, {D.dx_new, g.nlay}, {D.dy_new, g.nlay}});
+                        {D.rs_new, g.nlay}, {D.dx_new, g.nlay}, {D.dy_new, g.nlay}}, true, g.comm_stream);
       if (rc) return rc;
+      CK(cudaEventRecord(g.ev_comm, g.comm_stream));
+      if ((rc = fused_step(D, Dout, tstp, false, g.stream, &nlaunch, 2, G))) return fail(rc, "fused_step (interior rows) failed: %s", cudaGetErrorString(cudaGetLastError()));
+      CK(cudaStreamWaitEvent(g.stream, g.ev_comm, 0));
+      g.launches += nlaunch;
+    } else {
+      rc = fused_step(D, Dout, tstp, first_three != 0, g.stream, &nlaunch);
+      if (rc) return fail(rc, "fused_step failed: %s", cudaGetErrorString(cudaGetLastError()));
+      g.launches += nlaunch;
+      if (obc) {  // no_gradient_obc after both components (pm:2285-2288)
+        Dev Dobc = D;
+        Dobc.hlay = Dout.hlay; Dobc.u = Dout.u; Dobc.v = Dout.v; Dobc.h_u = Dout.h_u; Dobc.h_v = Dout.h_v;
+        for (int pass = 0; pass < 2; pass++) {
+          k_obc<<<(g.nseg + 63) / 64, 64, 0, g.stream>>>(Dobc, g.d_seg, g.nseg, pass);
+          g.launches++;
+        }
+      }
+      if (g.nranks > 1) {
+        rc = sync_fields({{Dout.hlay, g.nlay}, {Dout.u, g.nlay}, {Dout.v, g.nlay}, {Dout.h_u, g.nlay}, {Dout.h_v, g.nlay},
+                          {D.rs_new, g.nlay}, {D.dx_new, g.nlay}, {D.dy_new, g.nlay}});
+        if (rc) return rc;
+      }
     }
     g.cur = nxt;
     g.rs_o = (g.rs_o + 1) % 3;

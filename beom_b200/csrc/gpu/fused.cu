@@ -160,16 +160,32 @@ int fused_configure(const Dev &D, const beom_params &P, int nmir, int nranks, bo
 
 bool fused_supports(bool first_three, bool upst) { return cfg.ok && !first_three && upst; }
 
-int fused_step(const Dev &in, const Dev &out, int tstp, bool first_three, cudaStream_t s, int *nlaunch) {
+// part: 0 = every row of the slab, 1 = only the `edge` rows next to each neighbouring rank (two chunks), 2 = the rows
+// in between (the part whose computation hides the halo exchange of part 1)
+int fused_step(const Dev &in_, const Dev &out, int tstp, bool first_three, cudaStream_t s, int *nlaunch, int part, int edge) {
   if (!cfg.ok || first_three) return -1;
+  Dev in = in_;
   FusedLaunch a;
-  a.grid = dim3((unsigned)cfg.strips, (unsigned)cfg.chunks, 1);
+  int chunks = cfg.chunks, rpc = cfg.rows_per_chunk;
+  if (part == 1) {
+    chunks = 2;
+    rpc = -edge;
+  } else if (part == 2) {
+    in.y_lo += edge;
+    in.y_hi -= edge;
+    const int rows = in.y_hi - in.y_lo + 1;
+    if (rows <= 0) return 0;
+    chunks = std::max(1, std::min(cfg.chunks, rows / 16));
+    rpc = (rows + chunks - 1) / chunks;
+    chunks = (rows + rpc - 1) / rpc;
+  }
+  a.grid = dim3((unsigned)cfg.strips, (unsigned)chunks, 1);
   a.block = dim3((unsigned)(cfg.groups * 32 * in.nlay), 1, 1);
   const bool ufirst = (tstp % 2 == 0);
   const StreamTab T = make_streams(in, ufirst);
   a.shmem = fused_smem_bytes(in.nlay, cfg.groups, T, in.has_wind ? cfg.wind_layers : 0);
   a.in = &in; a.out = &out; a.tab = &T; a.open = cfg.open;
-  a.groups = cfg.groups; a.rows_per_chunk = cfg.rows_per_chunk; a.wind_layers = cfg.wind_layers;
+  a.groups = cfg.groups; a.rows_per_chunk = rpc; a.wind_layers = cfg.wind_layers;
   a.stream = s;
   // the lean instantiation assumes gene = 1 (tstp >= 4 with g_fb = 1; beom_gpu_step passes gene explicitly)
   const bool lean = cfg.lean && in.gene == 1.0;
@@ -185,7 +201,7 @@ int fused_step(const Dev &in, const Dev &out, int tstp, bool first_three, cudaSt
     rc = fused_launch_general(a, ufirst, cfg.visc, in.nlay);
   }
   if (rc) return rc;
-  *nlaunch = 1;
+  *nlaunch += 1;
   return cudaGetLastError() == cudaSuccess ? 0 : -60;
 }
 

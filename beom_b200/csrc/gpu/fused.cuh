@@ -9,7 +9,7 @@ namespace beom {
 // Decides whether the case can run on the fused path and prepares it.
 int fused_configure(const Dev &D, const beom_params &P, int nmir, int nranks, bool *enabled);
 bool fused_supports(bool first_three, bool upst);
-int fused_step(const Dev &in, const Dev &out, int tstp, bool first_three, cudaStream_t s, int *nlaunch);
+int fused_step(const Dev &in, const Dev &out, int tstp, bool first_three, cudaStream_t s, int *nlaunch, int part = 0, int edge = 0);
 void fused_release();
 
 // ---- dispatch into the instantiation translation units (fused_inst_*.cu, compiled in parallel) ----

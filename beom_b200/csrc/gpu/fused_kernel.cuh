@@ -226,8 +226,10 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
   const int xs = D.x_lo + blockIdx.x * groups * kUse - kPad;  // first staged column of the CTA (even)
   const int x = xs + 2 + grp * kUse + lane;                    // lane 0 = first result column - 2
   const bool col_ok = lane >= kHalo && lane < 32 - kHalo && x <= D.x_hi;
-  const int ya = D.y_lo + blockIdx.y * rows_per_chunk;
-  const int yb = min(ya + rows_per_chunk - 1, D.y_hi);
+  // rows of this CTA.  rows_per_chunk < 0: the two "edge" chunks of a y-slab (the -rows_per_chunk rows next to each
+  // neighbouring rank), which are computed first so that their exchange overlaps the interior rows
+  const int ya = rows_per_chunk > 0 ? D.y_lo + blockIdx.y * rows_per_chunk : (blockIdx.y == 0 ? D.y_lo : D.y_hi + rows_per_chunk + 1);
+  const int yb = rows_per_chunk > 0 ? min(ya + rows_per_chunk - 1, D.y_hi) : ya - rows_per_chunk - 1;
   const size_t L = (size_t)l * D.plane;
   const bool wind = D.has_wind && ((wind_layers >> l) & 1);
   const int nstr = wind ? T.n : T.n_nowind;
@@ -407,7 +409,6 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
     AT(dv, 0) = dv_0;
 
     // -------------------------------------------------------------------------------- momentum
-    constexpr int LV = UFIRST ? 2 : 1;  // v is updated at row R - LV
     const bool a2 = fw_m2 & F_ACT;
     const bool sto2 = col_ok && (!MASKED || a2) && row2_own;
     MomX xu, xv;
