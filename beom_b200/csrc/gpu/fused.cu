@@ -26,6 +26,8 @@ struct FusedCfg {
   bool visc = false;    // Leith viscosity recomputed every step
   int wind_layers = 0;  // bit l set: tt3d of layer l may be non-zero
   uint8_t *open = nullptr;  // [tiles][NY]: bit 0 = rows R-2..R open water on the tile's 32 columns, bit 1 = the same for R..R+3
+  unsigned *open4 = nullptr;  // [tiles][open4_words]: bit g of the row-group bitmap = bit 1 of open[4g]
+  int open4_words = 0;
 } cfg;
 
 // open-water summary of the flag plane, one byte per (warp tile, row)
@@ -48,6 +50,17 @@ __global__ void k_open_groups(uint8_t *__restrict__ open, int NY, int ntiles) {
   bool all = R + 3 < NY;
   for (int k = 0; all && k < 4; k++) all = o[R + k] & 1;
   if (all) o[R] |= 2;  // bit 1 is read by nobody in this kernel
+}
+
+__global__ void k_open_bits(const uint8_t *__restrict__ open, unsigned *__restrict__ open4, int NY, int nwords) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x, tile = blockIdx.y;
+  if (w >= nwords) return;
+  unsigned bits = 0;
+  for (int b = 0; b < 32; b++) {
+    const int R = (w * 32 + b) * 4;
+    if (R < NY && (open[(size_t)tile * NY + R] & 2)) bits |= 1u << b;
+  }
+  open4[(size_t)tile * nwords + w] = bits;
 }
 
 // Stream table for one step: where each staged row segment comes from (pointers follow the state
@@ -93,6 +106,7 @@ size_t fused_smem_bytes(int nlay, int groups, const StreamTab &T, int wind_layer
 
 void fused_release() {
   if (cfg.open) cudaFree(cfg.open);
+  if (cfg.open4) cudaFree(cfg.open4);
   cfg = FusedCfg();
 }
 
@@ -144,6 +158,7 @@ int fused_configure(const Dev &D, const beom_params &P, int nmir, int nranks, bo
   cfg.strips = (width + groups * kUse - 1) / (groups * kUse);
   int chunks = std::max(1, (2 * sms + cfg.strips / 2) / cfg.strips);  // about two CTAs' worth of work per SM
   chunks = std::min(chunks, std::max(1, rows / 16));
+  chunks = std::max(chunks, (rows + 3839) / 3840);  // the lean kernel keeps a chunk's open-water bitmap in 32 words (32 x 128 rows)
   cfg.rows_per_chunk = (rows + chunks - 1) / chunks;
   cfg.chunks = (rows + cfg.rows_per_chunk - 1) / cfg.rows_per_chunk;
   {
@@ -151,6 +166,9 @@ int fused_configure(const Dev &D, const beom_params &P, int nmir, int nranks, bo
     if (cudaMalloc(&cfg.open, (size_t)ntiles * D.NY) != cudaSuccess) return -62;
     k_open_rows<<<dim3((unsigned)ntiles, (unsigned)((D.NY + 7) / 8)), dim3(32, 8)>>>(D.flags, cfg.open, D.NX, D.NY, D.x_lo);
     k_open_groups<<<dim3((unsigned)((D.NY + 127) / 128), (unsigned)ntiles), 128>>>(cfg.open, D.NY, ntiles);
+    cfg.open4_words = (D.NY + 127) / 128;
+    if (cudaMalloc(&cfg.open4, (size_t)ntiles * cfg.open4_words * sizeof(unsigned)) != cudaSuccess) return -62;
+    k_open_bits<<<dim3((unsigned)((cfg.open4_words + 63) / 64), (unsigned)ntiles), 64>>>(cfg.open, cfg.open4, D.NY, cfg.open4_words);
     if (cudaDeviceSynchronize() != cudaSuccess) return -63;
   }
   cfg.ok = true;
@@ -184,7 +202,7 @@ int fused_step(const Dev &in_, const Dev &out, int tstp, bool first_three, cudaS
   const bool ufirst = (tstp % 2 == 0);
   const StreamTab T = make_streams(in, ufirst);
   a.shmem = fused_smem_bytes(in.nlay, cfg.groups, T, in.has_wind ? cfg.wind_layers : 0);
-  a.in = &in; a.out = &out; a.tab = &T; a.open = cfg.open;
+  a.in = &in; a.out = &out; a.tab = &T; a.open = cfg.open; a.open4 = cfg.open4; a.open4_words = cfg.open4_words;
   a.groups = cfg.groups; a.rows_per_chunk = rpc; a.wind_layers = cfg.wind_layers;
   a.stream = s;
   // the lean instantiation assumes gene = 1 (tstp >= 4 with g_fb = 1; beom_gpu_step passes gene explicitly)

@@ -20,6 +20,8 @@ struct FusedLaunch {
   const Dev *in, *out;
   const fusedk::StreamTab *tab;
   const uint8_t *open;
+  const unsigned *open4;
+  int open4_words;
   int groups, rows_per_chunk, wind_layers;
   cudaStream_t stream;
 };

@@ -13,7 +13,7 @@ int fused_launch_one(const FusedLaunch &a) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.shmem) != cudaSuccess) return -61;
     configured = a.shmem;
   }
-  kern<<<a.grid, a.block, a.shmem, a.stream>>>(*a.in, *a.out, *a.tab, a.open, a.groups, a.rows_per_chunk, a.wind_layers);
+  kern<<<a.grid, a.block, a.shmem, a.stream>>>(*a.in, *a.out, *a.tab, a.open, a.open4, a.open4_words, a.groups, a.rows_per_chunk, a.wind_layers);
   return 0;
 }
 }  // namespace beom

@@ -188,7 +188,7 @@ __host__ __device__ inline SmemPlan smem_plan(int nlay, int groups, int n_all, i
   o += (size_t)(8 * nlay + 2 * groups) * 8;           // full[nlay][4], empty[nlay][4], gbar[groups][2]
   o = (o + 15) & ~(size_t)15;
   p.off_wring = o;
-  o += (size_t)nlay * groups * kWRings * 4 * kWRow * 8;  // per-warp state rings
+  o += (size_t)nlay * groups * (kWRings * 4 * kWRow * 8 + 128);  // per-warp state rings + open-water bitmap (32 words)
   o = (o + 127) & ~(size_t)127;
   p.off_ring = o;
   p.seg_bytes = (size_t)seg_doubles(groups) * 8;
@@ -202,7 +202,8 @@ __host__ __device__ inline SmemPlan smem_plan(int nlay, int groups, int n_all, i
 template <bool UFIRST, bool VISC, int NL, bool LEAN, int GROUPS>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1)
 k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const __grid_constant__ StreamTab T,
-             const uint8_t *__restrict__ open, int groups_rt, int rows_per_chunk, int wind_layers) {
+             const uint8_t *__restrict__ open, const unsigned *__restrict__ open4, int open4_words, int groups_rt, int rows_per_chunk,
+             int wind_layers) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31;
   const int wid = threadIdx.x >> 5;
@@ -219,7 +220,8 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
   const SmemPlan sp = smem_plan(nlay, groups, T.n, T.n_nowind, D.has_wind ? wind_layers : 0);
   double *sh_h = reinterpret_cast<double *>(smem_raw);
   unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem_raw + sp.off_bars);
-  double *wring = reinterpret_cast<double *>(smem_raw + sp.off_wring) + (size_t)wid * kWRings * 4 * kWRow;
+  double *wring = reinterpret_cast<double *>(smem_raw + sp.off_wring) + (size_t)wid * (kWRings * 4 * kWRow + 16);
+  unsigned *obits = reinterpret_cast<unsigned *>(wring + kWRings * 4 * kWRow);  // [32]: open-water bit of every 4-row group of the chunk
   double *ring = reinterpret_cast<double *>(smem_raw + sp.ring_off(l));  // input ring of this layer
 
   const int tile = blockIdx.x * groups + grp;
@@ -543,12 +545,15 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
   };
   if (LEAN) {
     unsigned bpar = 0;
-    unsigned o_next = open_of(Rs);
+    // open-water bit of every 4-row group of the chunk, kept in shared memory: word k covers groups 32k .. 32k+31
+    // past the first (a global load per group would sit on the critical path of every group)
+    const int w0 = Rs >> 7;
+    obits[lane] = (w0 + lane < open4_words) ? open4[(size_t)tile * open4_words + w0 + lane] : 0u;
+    __syncwarp();
 #pragma unroll 1
     for (int R = Rs; R <= R1; R += 4) {
-      const unsigned o = o_next;
-      o_next = open_of(R + 4);
-      if (o & 2) {  // rows R-2 .. R+3 are open water on all 32 columns
+      const unsigned o = obits[(R >> 7) - w0] >> ((R >> 2) & 31);
+      if (o & 1) {  // rows R-2 .. R+3 are open water on all 32 columns
         row(ic<0>{}, Tt{}, Ft{}, R, kAllMasks, kAllMasks, bpar);
         row(ic<1>{}, Tt{}, Ft{}, R + 1, kAllMasks, kAllMasks, bpar);
         row(ic<2>{}, Tt{}, Ft{}, R + 2, kAllMasks, kAllMasks, bpar);
