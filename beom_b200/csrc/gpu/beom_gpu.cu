@@ -17,6 +17,7 @@
 #include "dev.cuh"
 #include "fused.cuh"
 #include "split.cuh"
+#include "diag.cuh"
 
 using namespace beom;
 
@@ -78,6 +79,11 @@ struct Ctx {
   double *halo_send[2] = {nullptr, nullptr}, *halo_recv[2] = {nullptr, nullptr};  // [lower, upper] neighbour
   size_t halo_cap = 0;
   size_t big_allocs = 0;
+  float *rec_f32 = nullptr;        // [nlay] dense float32 planes: one diagnostic record
+  float *rec_stage = nullptr;      // vector-layout staging of one layer of a record
+  double *diag_h0 = nullptr;       // [nlay] dense h_0 (beom_gpu_diagnostics)
+  double *diag_partial = nullptr, *diag_out = nullptr;
+  size_t diag_blocks = 0;
   cudaEvent_t ev[2] = {nullptr, nullptr};
   long long launches = 0;
   size_t win_first = 0, win_stride = 0;  // host state arrays cover points win_first .. win_first+win_stride-1 per layer
@@ -836,9 +842,51 @@ int beom_gpu_download_aux(double *h_u, double *h_v, double *rs_h, double *dmdx, 
   return 0;
 }
 
+// One float32 record: out[l*ndeg + (p-1)] for the vector points p this rank holds (whole-array layout).
+static int download_record(float *out) {
+  const int n = g.p_hi - std::max(g.p_lo, 1) + 1, p0 = std::max(g.p_lo, 1);
+  if (n <= 0) return 0;
+  for (int l = 0; l < g.nlay; l++) {
+    k_gather<float><<<(n + 255) / 256, 256, 0, g.stream>>>(g.rec_stage, g.rec_f32 + (size_t)l * g.plane, g.d_cell, p0, n);
+    g.launches++;
+    CK(cudaMemcpyAsync(out + (size_t)l * g.ndeg + (p0 - 1), g.rec_stage, (size_t)n * sizeof(float), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));  // the staging buffer is reused
+  }
+  return 0;
+}
 int beom_gpu_download_diag(float *pvor, float *mont, float *v_cc) {
-  (void)pvor; (void)mont; (void)v_cc;
-  return fail(-31, "beom_gpu_download_diag: not implemented yet");
+  if (!g.ready) return fail(-20, "beom_gpu_download_diag: not initialised");
+  int rc;
+  const size_t pl = g.plane, nl = (size_t)g.nlay;
+  if (!g.rec_f32) {
+    if ((rc = dalloc(&g.rec_f32, pl * nl)) || (rc = dalloc(&g.rec_stage, (size_t)(g.p_hi - g.p_lo + 1), false))) return rc;
+  }
+  Dev D = g.D;
+  set_state_pointers(D);
+  const dim3 grid = cell_grid(D, g.nlay, kBlock);
+  if (pvor) {
+    k_rec_pvor<<<grid, kBlock, 0, g.stream>>>(D, g.rec_f32);
+    g.launches++;
+    if ((rc = download_record(pvor))) return rc;
+  }
+  if (mont) {
+    k_rec_mont<<<grid, kBlock, 0, g.stream>>>(D, g.rec_f32);
+    g.launches++;
+    if ((rc = download_record(mont))) return rc;
+  }
+  if (v_cc) {
+    if ((rc = alloc_split_buffers())) return rc;  // wrk1 / wrk2 live in the split path's rvor / dive planes
+    D = g.D;
+    set_state_pointers(D);
+    k_rec_vort_dive<<<cell_grid(D, g.nlay, kBlock, 2, 2), kBlock, 0, g.stream>>>(D, D.rvor, D.dive);
+    g.launches++;
+    if ((rc = sync_fields({{D.rvor, g.nlay}, {D.dive, g.nlay}}))) return rc;
+    k_rec_vcc<<<grid, kBlock, 0, g.stream>>>(D, D.rvor, D.dive, g.rec_f32);
+    g.launches++;
+    if ((rc = download_record(v_cc))) return rc;
+  }
+  CK(cudaGetLastError());
+  return 0;
 }
 int beom_gpu_download_pi_s(double *pi_s) {
   if (!g.ready) return fail(-20, "beom_gpu_download_pi_s: not initialised");
@@ -851,8 +899,39 @@ int beom_gpu_download_pi_s(double *pi_s) {
   return rc;
 }
 int beom_gpu_diagnostics(const double *h_0, double *vol, double *ke, double *pe) {
-  (void)h_0; (void)vol; (void)ke; (void)pe;
-  return fail(-31, "beom_gpu_diagnostics: not implemented yet");
+  if (!g.ready) return fail(-20, "beom_gpu_diagnostics: not initialised");
+  int rc;
+  const size_t pl = g.plane, nl = (size_t)g.nlay;
+  Dev D = g.D;
+  set_state_pointers(D);
+  const int p0 = std::max(g.p_lo, 1), np = g.p_hi - p0 + 1;  // this rank's vector points (the kernel keeps the rows it owns)
+  const dim3 block(256, 1, 1);
+  const dim3 grid((unsigned)((std::max(np, 1) + 255) / 256), (unsigned)g.nlay, 1);
+  const size_t per_layer = (size_t)grid.x;
+  if (!g.diag_h0) {
+    if ((rc = dalloc(&g.diag_h0, pl * nl)) || (rc = dalloc(&g.diag_partial, 3 * per_layer * nl)) || (rc = dalloc(&g.diag_out, 3 * nl))) return rc;
+    g.diag_blocks = per_layer;
+  }
+  if (h_0) {  // rest thickness h_0(0:ndeg, nlay), reference layout; static, but cheap enough to refresh per call
+    const size_t keep_first = g.win_first, keep_stride = g.win_stride;
+    g.win_first = 0; g.win_stride = (size_t)g.ndeg + 1;
+    rc = upload_planes(g.diag_h0, h_0, g.nlay);
+    g.win_first = keep_first; g.win_stride = keep_stride;
+    if (rc) return rc;
+  }
+  k_conservation<<<grid, block, 0, g.stream>>>(D, g.diag_h0, g.d_cell, p0, np, g.diag_partial);
+  k_sum_partials<<<(unsigned)g.nlay, 32, 0, g.stream>>>(g.diag_partial, (int)per_layer, g.diag_out);
+  g.launches += 2;
+  if (g.nranks > 1 && (rc = comm_allreduce_sum(g.diag_out, 3 * nl, g.stream, &g_err))) return fail(rc, "beom_gpu_diagnostics: %s", g_err.c_str());
+  std::vector<double> h(3 * nl);
+  CK(cudaMemcpyAsync(h.data(), g.diag_out, 3 * nl * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  for (int l = 0; l < g.nlay; l++) {
+    if (vol) vol[l] = h[3 * l + 0];
+    if (ke) ke[l] = h[3 * l + 1];
+  }
+  if (pe) pe[0] = h[2];
+  return 0;
 }
 
 int beom_gpu_point_range(int *first, int *count, int *own_first, int *own_count) {

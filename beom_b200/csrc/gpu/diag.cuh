@@ -1,0 +1,131 @@
+// diag.cuh -- output-side kernels: the diagnostic records of write_array (float32 'pvor', 'mont', 'v_cc';
+// private_mod.f95:2884-2974) and the conservation integrals of testcases/conservation.m:116-211.
+// Same conventions as split.cuh: dense planes, E/W = +-1, N/S = +-NX, expressions in the reference's order
+// (here with its '/ dl' divisions and its float32 roundings, so the records are bit-identical to the oracle's).
+#ifndef BEOM_DIAG_CUH
+#define BEOM_DIAG_CUH
+#include "dev.cuh"
+
+namespace beom {
+
+#define BEOM_CELL_PAD(D)                                                    \
+  const int x = (D).x_lo - 1 + blockIdx.x * blockDim.x + threadIdx.x;       \
+  const int y = (D).y_lo - 1 + blockIdx.y * blockDim.y + threadIdx.y;       \
+  if (x > (D).x_hi + 1 || y > (D).y_hi + 1) return;                         \
+  const int NX = (D).NX;                                                    \
+  const size_t c = (size_t)y * NX + x;                                      \
+  const uint8_t f = (D).flags[c];
+
+// wrk1 (relative vorticity) and wrk2 (divergence) of the 'v_cc' record, pm:2893-2905; 0 outside the vector points
+__global__ void k_rec_vort_dive(const __grid_constant__ Dev D, double *__restrict__ w1, double *__restrict__ w2) {
+  BEOM_CELL_PAD(D)
+  const size_t L = (size_t)blockIdx.z * D.plane;
+  double a = 0.0, b = 0.0;
+  if (f & F_ACT) {
+    const double *u = D.u + L, *v = D.v + L;
+    a = ((v[c] - v[c - 1]) / D.dl - (u[c] - u[c - NX]) / D.dl) * m_pe(f);
+    b = (u[c + 1] - u[c]) / D.dl + (v[c + NX] - v[c]) / D.dl;
+  }
+  w1[L + c] = a;
+  w2[L + c] = b;
+}
+// 'v_cc' record, pm:2907-2926
+__global__ void k_rec_vcc(const __grid_constant__ Dev D, const double *__restrict__ w1, const double *__restrict__ w2, float *__restrict__ out) {
+  BEOM_CELL(D)
+  const size_t L = (size_t)blockIdx.z * D.plane;
+  const double *p = w1 + L, *q = w2 + L;
+  const double a = p[c + 1] - p[c], b = p[c + NX + 1] - p[c + NX], cc = p[c + NX] - p[c], d = p[c + NX + 1] - p[c + 1];
+  const double e = q[c + 1] - q[c], g2 = q[c] - q[c - 1], h = q[c + NX] - q[c], k = q[c] - q[c - NX];
+  out[L + c] = (float)(D.bvis + D.dvis * (D.dl * D.dl) * sqrt(a * a + b * b + cc * cc + d * d + e * e + g2 * g2 + h * h + k * k));
+}
+// 'mont' record, pm:2930-2950 (float32 accumulation of the baroclinic terms)
+__global__ void k_rec_mont(const __grid_constant__ Dev D, float *__restrict__ out) {
+  BEOM_CELL(D)
+  const int l = blockIdx.z;
+  const double mk = m_n(f);
+  const double hl = D.hlay[(size_t)l * D.plane + c];
+  float r = (float)(-D.ocrp / (double)(D.nsal - 1) * D.hsal * mk * cube(D.hsal / (D.hmin * (1.0 - mk) + hl)));
+  double s = 0.0;
+  for (int i = 0; i < l; i++) r = r - (float)((D.rhon[l] - D.rhon[i]) * D.hlay[(size_t)i * D.plane + c] / D.rhon[l]);
+  for (int i = 0; i < D.nlay; i++) s += D.hlay[(size_t)i * D.plane + c];
+  r = r + (float)(s - D.h_th[c]);
+  out[(size_t)l * D.plane + c] = r;
+}
+// 'pvor' record, pm:2951-2974
+__global__ void k_rec_pvor(const __grid_constant__ Dev D, float *__restrict__ out) {
+  BEOM_CELL(D)
+  const size_t L = (size_t)blockIdx.z * D.plane;
+  const double *u = D.u + L, *v = D.v + L, *h = D.hlay + L;
+  const double zeta = ((v[c] - v[c - 1]) / D.dl - (u[c] - u[c - NX]) / D.dl) * m_pe(f);
+  const double msum = m_n(f) + m_n(D.flags[c - 1]) + m_n(D.flags[c - NX]) + m_n(D.flags[c - NX - 1]);
+  out[L + c] = (float)((D.fcor[c] + zeta * D.uadv) * m_pi(f) * msum / (h[c] + h[c - 1] + h[c - NX - 1] + h[c - NX]));
+}
+
+// ---- conservation integrals (testcases/conservation.m:116-211) over the vector points whose rows this rank owns ----
+// per layer l: q[0] = sum over wet points of hlay, q[1] = 0.5 sum(0.5 (U + U(E))) + 0.5 sum(0.5 (V + V(N))) with
+// U = u^2 * 0.5 (h(W) + h), V = v^2 * 0.5 (h(S) + h) (dry or missing thickness counts as 0); layer 0 also q[2] =
+// sum over wet points of eta_1^2, eta_1 = sum over layers of (hlay - h_0).  One thread per vector point (frozen
+// periodic duplicates have no cell and are skipped, as conservation.m:196-201 discards them); neighbours are the
+// dense cells around it, so periodic aliases are honoured.  Warp-shuffle tree + one partial per block; the partials
+// are added in block order by k_sum_partials, so the result does not depend on scheduling.
+__device__ __forceinline__ double wet_h(const Dev &D, const double *h, size_t c) { return (D.flags[c] & F_N) ? h[c] : 0.0; }
+__global__ void k_conservation(const __grid_constant__ Dev D, const double *__restrict__ h_0, const int *__restrict__ cell, int p0, int n,
+                               double *__restrict__ partial) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int l = blockIdx.y, NX = D.NX;
+  double q0 = 0.0, q1 = 0.0, q2 = 0.0;
+  const int cc = t < n ? cell[p0 + t] : -1;
+  if (cc >= 0 && cc / NX >= D.y_lo && cc / NX <= D.y_hi) {
+    const size_t c = (size_t)cc, L = (size_t)l * D.plane;
+    const double *h = D.hlay + L, *u = D.u + L, *v = D.v + L;
+    const bool wet = D.flags[c] & F_N;
+    if (wet) q0 = h[c];
+    const double hc = wet_h(D, h, c), hW = wet_h(D, h, c - 1), hE = wet_h(D, h, c + 1), hS = wet_h(D, h, c - NX), hN = wet_h(D, h, c + NX);
+    const double U0 = u[c] * u[c] * (0.5 * (hW + hc)), U1 = u[c + 1] * u[c + 1] * (0.5 * (hc + hE));
+    const double V0 = v[c] * v[c] * (0.5 * (hS + hc)), V1 = v[c + NX] * v[c + NX] * (0.5 * (hc + hN));
+    q1 = 0.5 * (0.5 * (U0 + U1)) + 0.5 * (0.5 * (V0 + V1));
+    if (l == 0 && wet) {
+      double eta = 0.0;
+      for (int i = D.nlay - 1; i >= 0; i--) eta += D.hlay[(size_t)i * D.plane + c] - h_0[(size_t)i * D.plane + c];
+      q2 = eta * eta;
+    }
+  }
+  __shared__ double sh[3][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    q0 += __shfl_xor_sync(0xffffffffu, q0, o);
+    q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+    q2 += __shfl_xor_sync(0xffffffffu, q2, o);
+  }
+  if (lane == 0) { sh[0][w] = q0; sh[1][w] = q1; sh[2][w] = q2; }
+  __syncthreads();
+  if (w == 0) {
+    q0 = lane < nw ? sh[0][lane] : 0.0; q1 = lane < nw ? sh[1][lane] : 0.0; q2 = lane < nw ? sh[2][lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      q0 += __shfl_xor_sync(0xffffffffu, q0, o);
+      q1 += __shfl_xor_sync(0xffffffffu, q1, o);
+      q2 += __shfl_xor_sync(0xffffffffu, q2, o);
+    }
+    if (lane == 0) {
+      const size_t b = (size_t)l * gridDim.x + blockIdx.x;
+      partial[3 * b + 0] = q0; partial[3 * b + 1] = q1; partial[3 * b + 2] = q2;
+    }
+  }
+}
+// one block per layer: adds the layer's partials in a fixed order (lane-strided, then a shuffle tree)
+__global__ void k_sum_partials(const double *__restrict__ partial, int per_layer, double *__restrict__ out) {
+  const int l = blockIdx.x, lane = threadIdx.x;
+  double q[3] = {0.0, 0.0, 0.0};
+  for (int b = lane; b < per_layer; b += 32)
+    for (int k = 0; k < 3; k++) q[k] += partial[3 * ((size_t)l * per_layer + b) + k];
+  for (int k = 0; k < 3; k++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q[k] += __shfl_xor_sync(0xffffffffu, q[k], o);
+    if (lane == 0) out[3 * l + k] = q[k];
+  }
+}
+
+}  // namespace beom
+#endif

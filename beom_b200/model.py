@@ -177,6 +177,20 @@ class GpuModel:
         self._ck(self.lib.beom_gpu_download_aux(_dp(h_u), _dp(h_v), _dp(rs_h), _dp(dmdx), _dp(dmdy)), "download_aux")
         return h_u, h_v, rs_h, dmdx, dmdy
 
+    def download_diag(self, which=("pvor", "mont", "v_cc")):
+        """The float32 diagnostic records of write_array (private_mod.f95:2884-2974): dict of (nlay, ndeg) arrays."""
+        out = {k: np.zeros((self.nlay, self.ndeg), dtype=np.float32) for k in which}
+        ptr = lambda k: out[k].ctypes.data_as(C.POINTER(C.c_float)) if k in out else None
+        self._ck(self.lib.beom_gpu_download_diag(ptr("pvor"), ptr("mont"), ptr("v_cc")), "download_diag")
+        return out
+
+    def diagnostics(self, h_0):
+        """Conservation integrals (testcases/conservation.m:116-211): (vol[nlay], ke[nlay], sum of eta_1^2)."""
+        h_0 = np.ascontiguousarray(h_0, dtype=np.float64)
+        vol, ke, pe = np.zeros(self.nlay), np.zeros(self.nlay), np.zeros(1)
+        self._ck(self.lib.beom_gpu_diagnostics(_dp(h_0), _dp(vol), _dp(ke), _dp(pe)), "diagnostics")
+        return vol, ke, float(pe[0])
+
     def download_pi_s(self):
         out = np.zeros(self.ndeg + 1)
         self._ck(self.lib.beom_gpu_download_pi_s(_dp(out)), "download_pi_s")

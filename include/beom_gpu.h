@@ -146,9 +146,14 @@ int beom_gpu_download_diag(float *pvor, float *mont, float *v_cc);
 /* Rigid-lid surface pressure pi_s(0:ndeg) (private_mod.f95:91). */
 int beom_gpu_download_pi_s(double *pi_s);
 
-/* Conservation integrals (testcases/conservation.m:116-211), per layer: sum over wet cells of hlay
- * (vol), kinetic energy proxy (ke), and, in pe[0], sum of eta_1^2.  Device reduction with
- * warp shuffles, fixed order; all-reduced over ranks. */
+/* Conservation integrals (testcases/conservation.m:116-211) over the vector points (frozen periodic duplicates
+ * excluded, as the script does at :196-201), per layer l:
+ *   vol[l] = sum over wet points of hlay                      (the script's `volu` times the number of wet points)
+ *   ke[l]  = 0.5 sum 0.5 (U + U(E)) + 0.5 sum 0.5 (V + V(N)),  U = u^2 0.5 (h(W) + h),  V = v^2 0.5 (h(S) + h), dry h = 0
+ *            (the script's `kine` before the factor rhon(l) dl^2)
+ *   pe[0]  = sum over wet points of eta_1^2, eta_1 = sum_l (hlay - h_0)   (`pote` before 0.5 rhon(1) grav dl^2)
+ * h_0(0:ndeg, nlay) is the rest thickness in the reference layout (NULL = the one passed before).  Device reduction:
+ * warp-shuffle trees, block partials added in a fixed order; ncclAllReduce(SUM) over the ranks. */
 int beom_gpu_diagnostics(const double *h_0, double *vol, double *ke, double *pe);
 
 /* y-slab runs: the vector points this rank holds (owned rows + halo rows: first,count) and owns
