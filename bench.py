@@ -295,7 +295,15 @@ def main():
 
     peak, peak_src = measured_peak_gbs()
     achieved = ALGO_BYTES_PER_UPDATE * value / 1.0e9 / world  # per GPU
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    traffic = None  # DRAM bytes per launch from the committed ncu capture of this kernel on this grid (not measured live)
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_fused_traffic.json")) as f:
+            tj = json.load(f)
+        if path == "fused" and world == tj["n_gpus"] and [n, n, nlay] == tj["grid"]:
+            traffic = tj["dram_bytes_per_launch"]
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "kernel": "k_fused_step" if path == "fused" else "whole step (split path: one kernel per reference loop)",
                 "bytes_per_launch_algorithmic": ALGO_BYTES_PER_UPDATE * updates_per_step / world,
                 "launch_ms": ms_per_step, "per_gpu": True}
