@@ -118,7 +118,25 @@ def cpu_baseline(sample_n, nlay, steps, tmp):
             "seconds": dt}
 
 
+def emit(line: dict) -> None:
+    """The ONE JSON line of the contract, on the real stdout (see _quiet_stdout)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
+def _quiet_stdout() -> None:
+    """Everything else that writes to fd 1 (NCCL's version banner, compiler output of the in-tree build) goes to
+    stderr, so that stdout carries exactly one line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
 def main():
+    _quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -165,7 +183,7 @@ def main():
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                 "cpu_baseline": cb, "gpu_launches": 0,
                 "e2e": {"value": cb["value"], "unit": "cell-layer updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return 0
 
     # ---------------------------------------------------------------------------------- our arm
@@ -318,7 +336,7 @@ def main():
             "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": dict(config, path=path), "roofline": roofline, "cpu_baseline": cb,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
