@@ -79,6 +79,7 @@ struct Ctx {
   double *halo_send[2] = {nullptr, nullptr}, *halo_recv[2] = {nullptr, nullptr};  // [lower, upper] neighbour
   size_t halo_cap = 0;
   size_t big_allocs = 0;
+  bool torus = false;              // periodic domain whose aliases form a complete torus: deep ghost cells exist, the fused step may run
   float *rec_f32 = nullptr;        // [nlay] dense float32 planes: one diagnostic record
   float *rec_stage = nullptr;      // vector-layout staging of one layer of a record
   double *diag_h0 = nullptr;       // [nlay] dense h_0 (beom_gpu_diagnostics)
@@ -246,7 +247,7 @@ int step_split(int tstp, bool upst, bool first_three) {
   k_update_h<<<grid1, kBlock, 0, g.stream>>>(D);  // pm:2181 / 2259
   g.launches++;
   if (rgld) { k_rgld_correct<<<grid1, kBlock, 0, g.stream>>>(D); g.launches++; }
-  sync_fields({{D.hlay, nl}, {g.nranks > 1 ? D.rs_new : nullptr, nl}});
+  sync_fields({{D.hlay, nl}, {(g.nranks > 1 || g.torus) ? D.rs_new : nullptr, nl}});
   g.rs_o = (g.rs_o + 1) % 3;
 
   k_diag<<<gridL, kBlock, 0, g.stream>>>(D);  // pm:2187 / 2266
@@ -268,11 +269,11 @@ int step_split(int tstp, bool upst, bool first_three) {
     if (do_u) {
       k_update_u<<<gridL, kBlock, 0, g.stream>>>(D);
       g.launches++;
-      sync_fields({{D.u, nl}, {D.h_u, nl}, {g.nranks > 1 ? D.dx_new : nullptr, nl}});
+      sync_fields({{D.u, nl}, {D.h_u, nl}, {(g.nranks > 1 || g.torus) ? D.dx_new : nullptr, nl}});
     } else {
       k_update_v<<<gridL, kBlock, 0, g.stream>>>(D);
       g.launches++;
-      sync_fields({{D.v, nl}, {D.h_v, nl}, {g.nranks > 1 ? D.dy_new : nullptr, nl}});
+      sync_fields({{D.v, nl}, {D.h_v, nl}, {(g.nranks > 1 || g.torus) ? D.dy_new : nullptr, nl}});
     }
   }
   g.dx_o = (g.dx_o + 1) % 4;
@@ -462,8 +463,43 @@ int beom_gpu_init(const beom_params *par, const beom_fields *fld, const beom_gpu
     // a mirror's source may itself have been turned into a mirror/orphan: forbid chains
     for (size_t k = 0; k < msrc.size(); k++)
       if (msrc[k] < 0) return fail(-9, "beom_gpu_init: chained periodic aliases are not supported");
+    // Deep torus ghosts.  The fused step recomputes its halo (2 columns, 3-4 rows) instead of re-reading it, so on a
+    // periodic domain the cells up to 3 columns / 4 rows outside the core must show periodic images too -- cells the
+    // reference never indexes.  Only when the reference's own aliases (above) form a complete torus: every row
+    // 1..mm aliased in x (xper), every column 1..lm aliased in y (yper).
+    g.torus = false;
+    if (!mdst.empty() && g.nranks == 1 && (par->xper > 0.5 || par->yper > 0.5)) {
+      const bool xp = par->xper > 0.5, yp = par->yper > 0.5;
+      auto wrap = [](int k, int n) { return ((k - 1) % n + n) % n + 1; };
+      auto cell = [&](int i, int j) { return (j + j_off) * g.NX + (i + GX0); };
+      std::vector<int> img(g.plane, -1);
+      for (size_t k = 0; k < mdst.size(); k++) img[mdst[k]] = msrc[k];
+      bool complete = true;
+      if (xp) for (int j = 1; j <= mm && complete; j++) complete = img[cell(0, j)] == cell(lm, j) && img[cell(lm + 1, j)] == cell(1, j);
+      if (yp) for (int i = 1; i <= lm && complete; i++) complete = img[cell(i, 0)] == cell(i, mm) && img[cell(i, mm + 1)] == cell(i, 1);
+      for (size_t k = 0; k < mdst.size() && complete; k++) {  // and nothing else: every alias is the torus image
+        const int X = mdst[k] % g.NX - GX0, Y = mdst[k] / g.NX - j_off;
+        complete = msrc[k] == cell(xp ? wrap(X, lm) : X, yp ? wrap(Y, mm) : Y);
+      }
+      if (complete) {
+        for (int j = 1 - G; j <= mm + 1 + G; j++)
+          for (int i = -3; i <= lm + 4; i++) {
+            if (j + j_off < 0 || j + j_off >= g.NY || i + GX0 < 0 || i + GX0 >= g.NX) continue;
+            const int c = cell(i, j);
+            if (img[c] >= 0 || point_of_cell[c] != 0) continue;  // an alias of the reference, or a vector point of its own
+            const int is = xp ? wrap(i, lm) : i, js = yp ? wrap(j, mm) : j;
+            if ((is == i && js == j) || is < 0 || is > lm + 1 || js < 0 || js > mm + 1) continue;
+            const int src = cell(is, js);
+            if (point_of_cell[src] == 0 || img[src] >= 0) continue;  // nothing there, or itself a mirror
+            mdst.push_back(c);
+            msrc.push_back(src);
+          }
+        g.torus = true;
+      }
+    }
     g.nmir = (int)mdst.size();
-    for (int k = 0; k < g.nmir; k++) hflags[mdst[k]] = (uint8_t)(hflags[msrc[k]] & ~F_ACT);
+    for (int k = 0; k < g.nmir; k++)
+      hflags[mdst[k]] = (uint8_t)((hflags[msrc[k]] & ~F_ACT) | ((hflags[msrc[k]] & F_ACT) ? F_GHOST : 0));
     if (g.nmir) {
       int rc;
       if ((rc = dalloc(&g.d_mir_dst, (size_t)g.nmir, false)) || (rc = dalloc(&g.d_mir_src, (size_t)g.nmir, false))) return rc;
@@ -500,6 +536,9 @@ int beom_gpu_init(const beom_params *par, const beom_fields *fld, const beom_gpu
   if ((rc = dalloc(&tmp, pl))) return rc;
   if ((rc = upload_planes(tmp, fld->h_th, 1))) return rc;
   D.h_th = tmp;
+  if (g.torus) {  // the fused step reads the 2-D statics at its (recomputed) halo cells
+    sync_fields({{const_cast<double *>(D.fcor), 1}, {const_cast<double *>(D.h_th), 1}}, false);
+  }
   D.has_nudg = 0;
   if (fld->nudg) {
     bool any = false;
@@ -509,6 +548,7 @@ int beom_gpu_init(const beom_params *par, const beom_fields *fld, const beom_gpu
       if ((rc = upload_planes(tmp, fld->nudg, 3))) return rc;
       D.nudg = tmp;
       D.has_nudg = 1;
+      if (g.torus) sync_fields({{tmp, 3}}, false);
     }
   }
   D.has_tide = 0;
@@ -528,6 +568,7 @@ int beom_gpu_init(const beom_params *par, const beom_fields *fld, const beom_gpu
     if ((rc = dalloc(&tmp, pl * nl * 3))) return rc;
     if ((rc = upload_planes(tmp, fld->fnud, 3 * nlay))) return rc;
     D.fnud = tmp;
+    if (g.torus) sync_fields({{tmp, 3 * nlay}}, false);
   }
   D.has_hdot = 0;
   if (fld->hdot) {
@@ -538,6 +579,7 @@ int beom_gpu_init(const beom_params *par, const beom_fields *fld, const beom_gpu
       if ((rc = upload_planes(tmp, fld->hdot, nlay))) return rc;
       D.hdot = tmp;
       D.has_hdot = 1;
+      if (g.torus) sync_fields({{tmp, nlay}}, false);
     }
   }
   g.any_taus = false;  // any(abs(taus) > 1.e-7), private_mod.f95:1945
@@ -643,7 +685,7 @@ int beom_gpu_init(const beom_params *par, const beom_fields *fld, const beom_gpu
 
   g.use_fused = false;
   if (opt.fused) {
-    rc = fused_configure(g.D, g.P, g.nmir, g.nranks, &g.use_fused);
+    rc = fused_configure(g.D, g.P, g.torus ? 0 : g.nmir, g.nranks, &g.use_fused);
     if (rc) return rc;
     if (g.use_fused)
       for (int f = 0; f < 5; f++)
@@ -735,7 +777,7 @@ int beom_gpu_step(int tstp, double ctim, double ramp, double gene, int upst, int
           g.launches++;
         }
       }
-      if (g.nranks > 1) {
+      if (g.nranks > 1 || g.nmir) {  // halo rows of the neighbouring ranks / periodic images (deep torus ghosts)
         rc = sync_fields({{Dout.hlay, g.nlay}, {Dout.u, g.nlay}, {Dout.v, g.nlay}, {Dout.h_u, g.nlay}, {Dout.h_v, g.nlay},
                           {D.rs_new, g.nlay}, {D.dx_new, g.nlay}, {D.dy_new, g.nlay}});
         if (rc) return rc;

@@ -334,7 +334,8 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
     const int hslot = SLOT(0) & 1;
     const unsigned hpar = CT ? ((PH >> 1) & 1) : ((R >> 1) & 1);
     mbar_wait(full0 + 8 * SLOT(0), bpar);  // staged inputs of front row R have landed
-    const bool act = f_own & F_ACT;
+    const bool act = f_own & (F_ACT | F_GHOST);  // evaluated (ghost cells: like the cell they mirror) ...
+    const bool own = f_own & F_ACT;              // ... and stored
     const bool row_own = (R >= ya && R <= yb);
     const bool row2_own = (R - 2 >= ya && R - 2 <= yb);
 
@@ -358,7 +359,7 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
       }
     }
     hn_0 = SELM(act, hn_0);
-    if (col_ok && row_own && (!MASKED || act)) {
+    if (col_ok && row_own && (!MASKED || own)) {
       __stcs(reinterpret_cast<double *>(o_hlay + off0), hn_0);
       __stcs(reinterpret_cast<double *>(o_rs + off0), rs_3);
     }
@@ -381,7 +382,7 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
     WR(W_FX, 0, 0) = 0.16667 * d2x_0;
     double d2y_m1 = SELM((f_own & F_N) && (fw_m2 & F_N) && (fw_m1 & F_N), hn_0 + hn_m2 - hn_m1 * 2.0);
     if (ocrp && (hn_0 < D.two_hs || hn_m2 < D.two_hs || hn_m1 < D.two_hs)) d2y_m1 = 0.0;
-    d2y_m1 = SELM(fw_m1 & F_ACT, d2y_m1);
+    d2y_m1 = SELM(fw_m1 & (F_ACT | F_GHOST), d2y_m1);
     AT(Gy, 1) = 0.16667 * d2y_m1;
     {
       const double have = hn_0 + hnW_0 + HN(1, -1) + hn_m1;
@@ -400,7 +401,7 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
       AT(B3, 0) = sq(dv_0 - AT(dv, 1));
       const double tll = AT(A1, 1) + shup(AT(A1, 1)) + AT(A3, 0) + AT(A3, 1) + AT(B1, 1) + AT(B1, 2) + AT(B3, 1) + shup(AT(B3, 1));
       const double tcc = AT(A1, 1) + AT(A1, 0) + AT(A3, 0) + shdn(AT(A3, 0)) + shdn(AT(B1, 1)) + AT(B1, 1) + AT(B3, 0) + AT(B3, 1);
-      const bool a = fw_m1 & F_ACT;
+      const bool a = fw_m1 & (F_ACT | F_GHOST);
       const double vll_m1 = SELM(a, sqrt(tll) * D.dvis * D.dl * D.dl + D.bvis);
       const double vcc_m1 = SELM(a, sqrt(tcc) * D.dvis * D.dl * D.dl + D.bvis);
       P_m1 = vcc_m1 * AT(dv, 1);
@@ -411,8 +412,8 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
     AT(dv, 0) = dv_0;
 
     // -------------------------------------------------------------------------------- momentum
-    const bool a2 = fw_m2 & F_ACT;
-    const bool sto2 = col_ok && (!MASKED || a2) && row2_own;
+    const bool a2 = fw_m2 & (F_ACT | F_GHOST);
+    const bool sto2 = col_ok && (!MASKED || (fw_m2 & F_ACT)) && row2_own;
     MomX xu, xv;
     if (wind) {
       xu.tw_b = LD2(tt_base, 0); xu.tw_a = LD2(tt_base, -1);
@@ -459,14 +460,14 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
       vold = LD4(S_V, 2, 0);  // v(R-1): the old v of the next row's update
     } else {
       // ---- v at row R-1 (pm:1505-1591), h_u at time n ----
-      const bool a1 = fw_m1 & F_ACT;
+      const bool a1 = fw_m1 & (F_ACT | F_GHOST);
       const double wc = AT(qp, 1) * (LD4(S_HU, 1, 0) + LD4(S_HU, 2, 0));
       double vn, hvn, dm;
       momentum<false, VISC, MASKED, LEAN>(D, wind, MASKED ? m_v((uint8_t)fw_m1) : 1.0, hn_m1 + hn_m2b, mo_m2, WR(W_MO, 1, 0), wc,
                                           shdn(wc), LD4(S_V, 2, 0), vy1, vy2, vy3, P_m1, P_m2, shdn(AT(Qv, 1)), AT(Qv, 1),
                                           AT(Gy, 2), AT(Gy, 1), xv, vn, hvn, dm);
       hvn = SELM(a1, hvn);
-      if (col_ok && (!MASKED || a1) && (R - 1 >= ya) && (R - 1 <= yb)) {
+      if (col_ok && (!MASKED || (fw_m1 & F_ACT)) && (R - 1 >= ya) && (R - 1 <= yb)) {
         __stcs(reinterpret_cast<double *>(o_v + (off2 + row_bytes)), vn);
         __stcs(reinterpret_cast<double *>(o_hv + (off2 + row_bytes)), hvn);
         __stcs(reinterpret_cast<double *>(o_dy + (off2 + row_bytes)), dm);

@@ -43,9 +43,9 @@ def assert_same(name, got, want, mask=None):
 @pytest.mark.parametrize("fused", [False, True])
 def test_bit_exact_small(case_factory, name, nsteps, fused):
     c, hm, orc, (hl, u, v), aux, path = run_pair(case_factory, name, nsteps, fused)
-    # the fused step covers closed / sponge domains; periodic ones run on the split path
-    periodic = hm.params.xper > 0.5 or hm.params.yper > 0.5
-    assert path == ("fused" if fused and not periodic else "split")
+    # the fused step covers closed / sponge domains and periodic ones whose aliases form a complete torus (deep
+    # ghost cells): all five cases
+    assert path == ("fused" if fused else "split")
     assert_same("hlay", hl, orc.array("hlay"))
     assert_same("u", u, orc.array("u"))
     assert_same("v", v, orc.array("v"))
