@@ -747,6 +747,11 @@ int beom_gpu_step(int tstp, double ctim, double ramp, double gene, int upst, int
     const int nxt = g.cur ^ 1;
     Dout.hlay = g.st[0][nxt]; Dout.u = g.st[1][nxt]; Dout.v = g.st[2][nxt]; Dout.h_u = g.st[3][nxt]; Dout.h_v = g.st[4][nxt];
     int nlaunch = 0, rc;
+    if (first_three) {  // pm:2166-2177: the start-up steps first rebuild centred fluxes from u, v, hlay
+      k_centred_flux<<<cell_grid(D, g.nlay, kBlock), kBlock, 0, g.stream>>>(D);
+      g.launches++;
+      if ((rc = sync_fields({{D.h_u, g.nlay}, {D.h_v, g.nlay}}))) return rc;
+    }
     const bool obc = g.D.has_nudg && g.P.mcbc < 0.5 && g.nseg > 0;
     // BEOM_OVERLAP=1: exchange the edge rows while the interior rows are computed (measured slower than the plain
     // sequence at 2 GPUs: NCCL's copy kernels displace CTAs of a grid sized for exactly two waves)

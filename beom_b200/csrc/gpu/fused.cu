@@ -176,12 +176,15 @@ int fused_configure(const Dev &D, const beom_params &P, int nmir, int nranks, bo
   return 0;
 }
 
-bool fused_supports(bool first_three, bool upst) { return cfg.ok && !first_three && upst; }
+// The three start-up steps (plain forward-backward, gene = 0) run on the general instantiation after the caller has
+// rebuilt the centred fluxes (private_mod.f95:2166-2177).
+bool fused_supports(bool first_three, bool upst) { return cfg.ok && (upst || first_three); }
 
 // part: 0 = every row of the slab, 1 = only the `edge` rows next to each neighbouring rank (two chunks), 2 = the rows
 // in between (the part whose computation hides the halo exchange of part 1)
 int fused_step(const Dev &in_, const Dev &out, int tstp, bool first_three, cudaStream_t s, int *nlaunch, int part, int edge) {
-  if (!cfg.ok || first_three) return -1;
+  (void)first_three;
+  if (!cfg.ok) return -1;
   Dev in = in_;
   FusedLaunch a;
   int chunks = cfg.chunks, rpc = cfg.rows_per_chunk;

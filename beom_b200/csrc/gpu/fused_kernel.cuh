@@ -50,6 +50,9 @@ namespace fusedk {
 constexpr int kHalo = 2;              // halo lanes on each side of a warp
 constexpr int kUse = 32 - 2 * kHalo;  // 28 result columns per warp
 constexpr int kMaxLay = 8;            // layers per CTA (shared-memory exchange, warps per CTA)
+#ifndef BEOM_TRYWAIT_HINT
+#define BEOM_TRYWAIT_HINT 20000   // suspend-time hint (ns) of mbarrier.try_wait (the warp sleeps in hardware instead of spinning); 0 = none
+#endif
 #ifndef BEOM_FUSED_WARPS
 #define BEOM_FUSED_WARPS 16
 #endif
@@ -99,9 +102,13 @@ __device__ __forceinline__ void mbar_arrive(unsigned bar) {
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tWAIT_%=:\n\t"
+#if BEOM_TRYWAIT_HINT > 0
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+#else
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+#endif
       "@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}" ::"r"(bar),
-      "r"(parity)
+      "r"(parity), "r"((unsigned)BEOM_TRYWAIT_HINT)
       : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
