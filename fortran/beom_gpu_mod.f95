@@ -47,7 +47,7 @@ module beom_gpu_mod
   end type beom_gpu_options
 
   public :: beom_gpu_default_options, beom_gpu_init, beom_gpu_upload_state, beom_gpu_stress, &
-            beom_gpu_step, beom_gpu_download_state, beom_gpu_download_pi_s, beom_gpu_download_diag, &
+            beom_gpu_step, beom_gpu_download_state, beom_gpu_download_pi_s, beom_gpu_download_diag, beom_gpu_diagnostics, &
             beom_gpu_sync, beom_gpu_finalize, beom_gpu_last_error, beom_gpu_check
 
   interface
@@ -98,6 +98,14 @@ module beom_gpu_mod
     function beom_gpu_download_diag(pvor, mont, v_cc) bind(C, name = 'beom_gpu_download_diag') result(rc)
       import :: c_float, c_int
       real(c_float), intent(inout) :: pvor(*), mont(*), v_cc(*)
+      integer(c_int) :: rc
+    end function
+
+    ! conservation integrals of testcases/conservation.m:116-211 (vol(nlay), ke(nlay), pe(1)); h_0(0:ndeg, nlay)
+    function beom_gpu_diagnostics(h_0, vol, ke, pe) bind(C, name = 'beom_gpu_diagnostics') result(rc)
+      import :: c_double, c_int
+      real(c_double), intent(in) :: h_0(*)
+      real(c_double), intent(inout) :: vol(*), ke(*), pe(*)
       integer(c_int) :: rc
     end function
 
