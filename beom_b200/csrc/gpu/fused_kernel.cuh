@@ -1,4 +1,5 @@
-// fused_kernel.cuh -- the fused single-pass time step (generalized forward-backward regime, tstp >= 4).
+// fused_kernel.cuh -- the fused single-pass time step (gener_forward_backward, private_mod.f95:2225-2316, and, with
+// gene = 0 after the caller's centred-flux rebuild, first_three_timesteps, :2151-2223).
 //
 // One kernel per step.  It reads every persistent field once (hlay,u,v,h_u,h_v, 2 rs_h, 3 dmdx,
 // 3 dmdy: 13 doubles per cell-layer) and writes the 8 new ones (hlay,u,v,h_u,h_v + newest rs_h, dmdx,
@@ -33,8 +34,13 @@
 //
 // A CTA is (column groups) x (layers) warps; the layer-warps of a column group exchange the new layer
 // thickness of the front row through shared memory for the column sums of the Montgomery potential
-// (private_mod.f95:2357-2373) with a split-phase mbarrier.  State is double buffered (in -> out), so
-// halo lanes and neighbouring CTAs always read time level n.
+// (private_mod.f95:2357-2373) with a split-phase mbarrier.  The warps that share a scheduler (warp id mod 4) belong to
+// different layers AND different column groups, so they never wait at the same barrier.  State is double buffered
+// (in -> out), so halo lanes and neighbouring CTAs always read time level n.
+//
+// Masks.  F_ACT cells are evaluated and stored; F_GHOST cells (periodic images, dev.cuh) are evaluated like the
+// cell they mirror -- the halo is recomputed, not re-read -- but never stored.  Rows whose three rows in flight are
+// open water on all 32 columns (a bitmap built at init) take a copy of the row code without any select.
 //
 // Arithmetic: the same expressions in the same order as split.cuh / the reference (-fmad=false), so
 // the two paths agree bit for bit; 0/1 masks are applied as selects (x*1 = x, x*0 = +-0).

@@ -113,3 +113,22 @@ def test_restart_reads_back_the_last_record(tmp_path):
     assert hm.scalar("tres") == 0.25 and hm.scalar("irec") == 2
     assert np.all(hm.array("u")[:, 1:] == 0.0)
     assert np.max(np.abs(hm.array("hlay") - h_before)) < 2e-6  # float32 round trip of eta and h_0
+
+
+def test_bench_reference_arm_prints_one_json_line(tmp_path):
+    """bench.py --impl reference (the CPU port on a bounded sample) runs without a GPU and prints exactly one JSON
+    line carrying the keys of the contract."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--cpu-sample", "96"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["config"]["grid"] == [8192, 8192, 4]
