@@ -1,18 +1,18 @@
-// fused_inst_general.cu -- the general fused step: every option a runtime switch, any layer count <= 8.
-#include "fused_inst.cuh"
+// fused_inst_general.cu -- dispatch of the general fused step by layer count (instantiations: fused_inst_general<N>.cu).
+#include "fused.cuh"
 namespace beom {
-template <int NL>
-static int pick(const FusedLaunch &a, bool ufirst, bool visc) {
-  return visc ? (ufirst ? fused_launch_one<true, true, NL, false, 0>(a) : fused_launch_one<false, true, NL, false, 0>(a))
-              : (ufirst ? fused_launch_one<true, false, NL, false, 0>(a) : fused_launch_one<false, false, NL, false, 0>(a));
-}
+int fused_launch_general0(const FusedLaunch &a, bool ufirst, bool visc);
+int fused_launch_general1(const FusedLaunch &a, bool ufirst, bool visc);
+int fused_launch_general2(const FusedLaunch &a, bool ufirst, bool visc);
+int fused_launch_general3(const FusedLaunch &a, bool ufirst, bool visc);
+int fused_launch_general4(const FusedLaunch &a, bool ufirst, bool visc);
 int fused_launch_general(const FusedLaunch &a, bool ufirst, bool visc, int nlay) {
   switch (nlay) {
-    case 1: return pick<1>(a, ufirst, visc);
-    case 2: return pick<2>(a, ufirst, visc);
-    case 3: return pick<3>(a, ufirst, visc);
-    case 4: return pick<4>(a, ufirst, visc);
-    default: return pick<0>(a, ufirst, visc);
+    case 1: return fused_launch_general1(a, ufirst, visc);
+    case 2: return fused_launch_general2(a, ufirst, visc);
+    case 3: return fused_launch_general3(a, ufirst, visc);
+    case 4: return fused_launch_general4(a, ufirst, visc);
+    default: return fused_launch_general0(a, ufirst, visc);
   }
 }
 }  // namespace beom

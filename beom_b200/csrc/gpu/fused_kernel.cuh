@@ -18,9 +18,10 @@
 //     row R   : update_h, rvor, dive, d2hx, pvor, Montgomery/Bernoulli potential          (front)
 //     row R-1 : d2hy, Leith v_cc / v_ll, and the first momentum component if it is v
 //     row R-2 : u (and v when u goes first)
-// The carried state is kept in 4-entry rings indexed by (phase - age) & 3.  In the LEAN instantiation
-// the row loop is unrolled four times with the phase a compile-time constant, so the rings are plain
-// registers that are never moved and every shared-memory address is an immediate offset.
+// The carried state is kept in 4-entry rings indexed by (phase - age) & 3.  The row loop is unrolled four times
+// with the phase a compile-time constant, so the rings are plain registers that are never moved and (in the LEAN
+// instantiation, whose stream slots and column-group count are compile-time too) every shared-memory address is an
+// immediate offset.
 //
 // What is carried is chosen so that no product or squared difference is evaluated twice (each is the
 // SAME IEEE operation on the SAME operands the reference performs, so results stay bit-identical):
@@ -302,7 +303,7 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
   __syncthreads();
   const int R0 = ya - 3, R1 = yb + 2;
   const int Rs = R0 & ~3;  // the row loop starts on a multiple of 4: ring slot = R & 3 = unroll phase
-  const int Rend = LEAN ? (R1 | 3) : R1;  // last row the loop visits (the unrolled loop works in groups of 4)
+  const int Rend = R1 | 3;  // last row the loop visits (the unrolled loop works in groups of 4)
   const size_t row_bytes = (size_t)NX * 8;
   auto issue = [&](int Rt) {  // stage this warp's share of the inputs of front row Rt
     const unsigned bar = full0 + 8 * (Rt & 3);
@@ -545,19 +546,12 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
 #undef MKN
 
   constexpr unsigned kAllMasks = 0x3f | (0x3f << 8) | (0x3f << 16);
-  const uint8_t *op = open + (size_t)tile * NY;
   const uint8_t *fl_p = D.flags + x;
   using Tt = std::true_type;
   using Ft = std::false_type;
   auto flags_of = [&](int R) -> unsigned { return (unsigned)fl_p[(size_t)min(R, NY - 1) * NX]; };
   auto widen = [&](unsigned f) -> unsigned { return f | (__shfl_up_sync(0xffffffffu, f, 1) << 8) | (__shfl_down_sync(0xffffffffu, f, 1) << 16); };
-  // open-water byte of a row (group): a pinned load, so that the compiler cannot sink it to its use a whole group later
-  auto open_of = [&](int R) -> unsigned {
-    unsigned v;
-    asm volatile("ld.global.nc.u8 %0, [%1];" : "=r"(v) : "l"(op + min(R, NY - 1)));
-    return v;
-  };
-  if (LEAN) {
+  {
     unsigned bpar = 0;
     // open-water bit of every 4-row group of the chunk, kept in shared memory: word k covers groups 32k .. 32k+31
     // past the first (a global load per group would sit on the critical path of every group)
@@ -575,34 +569,17 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
         fw_m1 = fw_m2 = kAllMasks;
       } else {
         const unsigned f0 = flags_of(R), f1 = flags_of(R + 1), f2 = flags_of(R + 2), f3 = flags_of(R + 3);
-        const unsigned w0 = widen(f0), w1 = widen(f1), w2 = widen(f2), w3 = widen(f3);
-        row(ic<0>{}, Tt{}, Tt{}, R, f0, w0, bpar);
-        fw_m2 = fw_m1; fw_m1 = w0;
-        row(ic<1>{}, Tt{}, Tt{}, R + 1, f1, w1, bpar);
-        fw_m2 = fw_m1; fw_m1 = w1;
-        row(ic<2>{}, Tt{}, Tt{}, R + 2, f2, w2, bpar);
-        fw_m2 = fw_m1; fw_m1 = w2;
-        row(ic<3>{}, Tt{}, Tt{}, R + 3, f3, w3, bpar);
-        fw_m2 = fw_m1; fw_m1 = w3;
+        const unsigned e0 = widen(f0), e1 = widen(f1), e2 = widen(f2), e3 = widen(f3);
+        row(ic<0>{}, Tt{}, Tt{}, R, f0, e0, bpar);
+        fw_m2 = fw_m1; fw_m1 = e0;
+        row(ic<1>{}, Tt{}, Tt{}, R + 1, f1, e1, bpar);
+        fw_m2 = fw_m1; fw_m1 = e1;
+        row(ic<2>{}, Tt{}, Tt{}, R + 2, f2, e2, bpar);
+        fw_m2 = fw_m1; fw_m1 = e2;
+        row(ic<3>{}, Tt{}, Tt{}, R + 3, f3, e3, bpar);
+        fw_m2 = fw_m1; fw_m1 = e3;
       }
       bpar ^= 1;
-    }
-  } else {
-    unsigned f_next = flags_of(Rs);
-    unsigned o_next = open_of(Rs);
-#pragma unroll 1
-    for (int R = Rs; R <= R1; R++) {
-      const unsigned f_own = f_next, o = o_next;
-      f_next = flags_of(R + 1);
-      o_next = open_of(R + 1);
-      const unsigned fw_0 = widen(f_own);
-      const unsigned bpar = (unsigned)(((R - Rs) >> 2) & 1);
-      if (o & 1) row(ic<0>{}, Ft{}, Ft{}, R, f_own, fw_0, bpar);
-      else       row(ic<0>{}, Ft{}, Tt{}, R, f_own, fw_0, bpar);
-      fw_m2 = fw_m1; fw_m1 = fw_0;
-#define ROT(a) a[1] = a[2]; a[2] = a[3]; a[3] = a[0];
-      ROT(rv) ROT(dv) ROT(A1) ROT(A3) ROT(B1) ROT(B3) ROT(Qv) ROT(qp) ROT(Gy) ROT(Tc) ROT(fl)
-#undef ROT
     }
   }
 }
