@@ -149,9 +149,12 @@ def main():
     ap.add_argument("--cpu-steps", type=int, default=10)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--fma", action="store_true", help="opt-in: the FMA-contracted copy of the fused step (tolerance parity, not bit-exact)")
     ap.add_argument("--trace", type=int, default=0, help="diagnostic: time N further blocks of 10 steps each and log clocks/power")
     args = ap.parse_args()
 
+    if args.fma:
+        os.environ["BEOM_FMA"] = "1"
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -159,7 +162,8 @@ def main():
     config = {"workload": "synthetic %dx%dx%d-layer closed flat basin (SURVEY.md 8d): dl=1km, Leith dvis=0.2 every step, "
                           "generalized forward-backward, wind 0.1cos(pi y/L) Pa, seed 20261018" % (n, n, nlay),
               "grid": [n, n, nlay], "decomposition": "y-slabs x%d" % args.gpus, "l2": "inputs_exceed_L2",
-              "bytes_per_update_algorithmic": ALGO_BYTES_PER_UPDATE}
+              "bytes_per_update_algorithmic": ALGO_BYTES_PER_UPDATE,
+              "arithmetic": "fma-contracted (tolerance parity 1e-10)" if args.fma else "strict IEEE, no contraction (bit-exact vs the oracle)"}
 
     from beom_b200 import build
     from oracle import build as obuild

@@ -60,7 +60,10 @@ def build_gpu(force: bool = False, verbose_ptxas: bool = False) -> str:
         obj = os.path.join(objdir, os.path.basename(cu)[:-3] + ".o")
         objs.append(obj)
         if force or _newer(obj, [cu] + hdrs):
-            cmd = [nvcc] + NVCC_FLAGS + extra + ["-c", cu, "-o", obj]
+            flags = NVCC_FLAGS
+            if cu.endswith("_fma.cu"):  # the opt-in FMA-contracted copies of the fused step (BEOM_FMA=1)
+                flags = [f for f in NVCC_FLAGS if f != "-fmad=false"] + ["-fmad=true"]
+            cmd = [nvcc] + flags + extra + ["-c", cu, "-o", obj]
             print("+", " ".join(cmd), file=sys.stderr, flush=True)
             log = open(obj + ".log", "w") if verbose_ptxas else None
             jobs.append((cmd, subprocess.Popen(cmd, stderr=log) if log else subprocess.Popen(cmd), log))

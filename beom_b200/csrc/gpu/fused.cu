@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "fused_kernel.cuh"
@@ -212,11 +213,13 @@ int fused_step(const Dev &in_, const Dev &out, int tstp, bool first_three, cudaS
   const bool lean = cfg.lean && in.gene == 1.0;
   int rc;
   if (lean) {
+    // BEOM_FMA=1: the copy compiled with FMA contraction (tolerance parity instead of bit-exact parity; off by default)
+    static const bool fma = getenv("BEOM_FMA") && atoi(getenv("BEOM_FMA")) > 0;
     switch (in.nlay) {
-      case 1: rc = fused_launch_lean1(a, ufirst); break;
-      case 2: rc = fused_launch_lean2(a, ufirst); break;
-      case 3: rc = fused_launch_lean3(a, ufirst); break;
-      default: rc = fused_launch_lean4(a, ufirst); break;
+      case 1: rc = fma ? fused_launch_lean1_fma(a, ufirst) : fused_launch_lean1(a, ufirst); break;
+      case 2: rc = fma ? fused_launch_lean2_fma(a, ufirst) : fused_launch_lean2(a, ufirst); break;
+      case 3: rc = fma ? fused_launch_lean3_fma(a, ufirst) : fused_launch_lean3(a, ufirst); break;
+      default: rc = fma ? fused_launch_lean4_fma(a, ufirst) : fused_launch_lean4(a, ufirst); break;
     }
   } else {
     rc = fused_launch_general(a, ufirst, cfg.visc, in.nlay);

@@ -180,3 +180,16 @@ def test_rigid_lid_bit_exact(case_factory, name, kw, extra):
     assert_same("pi_s", pi_s, orc.array("pi_s")[0])
     if "ocrp" in extra:
         assert np.abs(pi_s).max() > 0
+
+
+@pytest.mark.parametrize("nlay", [1, 4])
+def test_fma_flavour_within_tolerance(nlay):
+    """BEOM_FMA=1 (opt-in): the fused step compiled with FMA contraction, like the reference's own -Ofast build.
+    Tolerance of BASELINE.json's north star: max relative field difference <= 1e-10 after N steps."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "fma_worker.py"), str(nlay), "40"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "fma max relative field difference" in r.stdout
