@@ -146,7 +146,7 @@ def main():
     ap.add_argument("--nlay", type=int, default=4)
     ap.add_argument("--split", action="store_true", help="one kernel per reference loop instead of the fused step")
     ap.add_argument("--cpu-sample", type=int, default=2048)
-    ap.add_argument("--cpu-steps", type=int, default=10)
+    ap.add_argument("--cpu-steps", type=int, default=120, help="steps of the CPU baseline leg on the sample (about 10-15 s of CPU work on 16 threads)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--fma", action="store_true", help="opt-in: the FMA-contracted copy of the fused step (tolerance parity, not bit-exact)")
