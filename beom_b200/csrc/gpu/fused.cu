@@ -209,17 +209,18 @@ int fused_step(const Dev &in_, const Dev &out, int tstp, bool first_three, cudaS
   a.in = &in; a.out = &out; a.tab = &T; a.open = cfg.open; a.open4 = cfg.open4; a.open4_words = cfg.open4_words;
   a.groups = cfg.groups; a.rows_per_chunk = rpc; a.wind_layers = cfg.wind_layers;
   a.stream = s;
-  // the lean instantiation assumes gene = 1 (tstp >= 4 with g_fb = 1; beom_gpu_step passes gene explicitly)
-  const bool lean = cfg.lean && in.gene == 1.0;
+  // the lean instantiations assume gene = 1 (tstp >= 4 with g_fb = 1) or gene = 0 (the start-up steps) exactly
+  const bool g0 = in.gene == 0.0;  // the start-up steps
+  const bool lean = cfg.lean && (in.gene == 1.0 || g0);
   int rc;
   if (lean) {
     // BEOM_FMA=1: the copy compiled with FMA contraction (tolerance parity instead of bit-exact parity; off by default)
     static const bool fma = getenv("BEOM_FMA") && atoi(getenv("BEOM_FMA")) > 0;
     switch (in.nlay) {
-      case 1: rc = fma ? fused_launch_lean1_fma(a, ufirst) : fused_launch_lean1(a, ufirst); break;
-      case 2: rc = fma ? fused_launch_lean2_fma(a, ufirst) : fused_launch_lean2(a, ufirst); break;
-      case 3: rc = fma ? fused_launch_lean3_fma(a, ufirst) : fused_launch_lean3(a, ufirst); break;
-      default: rc = fma ? fused_launch_lean4_fma(a, ufirst) : fused_launch_lean4(a, ufirst); break;
+      case 1: rc = (fma && !g0) ? fused_launch_lean1_fma(a, ufirst) : fused_launch_lean1(a, ufirst, g0); break;
+      case 2: rc = (fma && !g0) ? fused_launch_lean2_fma(a, ufirst) : fused_launch_lean2(a, ufirst, g0); break;
+      case 3: rc = (fma && !g0) ? fused_launch_lean3_fma(a, ufirst) : fused_launch_lean3(a, ufirst, g0); break;
+      default: rc = (fma && !g0) ? fused_launch_lean4_fma(a, ufirst) : fused_launch_lean4(a, ufirst, g0); break;
     }
   } else {
     rc = fused_launch_general(a, ufirst, cfg.visc, in.nlay);

@@ -25,10 +25,10 @@ struct FusedLaunch {
   int groups, rows_per_chunk, wind_layers;
   cudaStream_t stream;
 };
-int fused_launch_lean1(const FusedLaunch &a, bool ufirst);
-int fused_launch_lean2(const FusedLaunch &a, bool ufirst);
-int fused_launch_lean3(const FusedLaunch &a, bool ufirst);
-int fused_launch_lean4(const FusedLaunch &a, bool ufirst);
+int fused_launch_lean1(const FusedLaunch &a, bool ufirst, bool gene0);
+int fused_launch_lean2(const FusedLaunch &a, bool ufirst, bool gene0);
+int fused_launch_lean3(const FusedLaunch &a, bool ufirst, bool gene0);
+int fused_launch_lean4(const FusedLaunch &a, bool ufirst, bool gene0);
 int fused_launch_lean1_fma(const FusedLaunch &a, bool ufirst);  // FMA-contracted copies (BEOM_FMA=1)
 int fused_launch_lean2_fma(const FusedLaunch &a, bool ufirst);
 int fused_launch_lean3_fma(const FusedLaunch &a, bool ufirst);

@@ -1,7 +1,10 @@
-// fused_inst_lean1.cu -- the specialised (4x unrolled, rotation-free) fused step for 1 layer(s).
+// fused_inst_lean1.cu -- the specialised fused step for 1 layer(s): generalized forward-backward (gene = 1) and the
+// plain forward-backward start-up steps (gene = 0).
 #include "fused_inst.cuh"
 namespace beom {
-int fused_launch_lean1(const FusedLaunch &a, bool ufirst) {
-  return ufirst ? fused_launch_one<true, true, 1, true, fusedk::kMaxWarps / 1>(a) : fused_launch_one<false, true, 1, true, fusedk::kMaxWarps / 1>(a);
+int fused_launch_lean1(const FusedLaunch &a, bool ufirst, bool gene0) {
+  constexpr int GR = fusedk::kMaxWarps / 1;
+  if (gene0) return ufirst ? fused_launch_one<true, true, 1, true, GR, 0, true>(a) : fused_launch_one<false, true, 1, true, GR, 0, true>(a);
+  return ufirst ? fused_launch_one<true, true, 1, true, GR>(a) : fused_launch_one<false, true, 1, true, GR>(a);
 }
 }  // namespace beom

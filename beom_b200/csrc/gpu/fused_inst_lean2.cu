@@ -1,7 +1,10 @@
-// fused_inst_lean2.cu -- the specialised (4x unrolled, rotation-free) fused step for 2 layer(s).
+// fused_inst_lean2.cu -- the specialised fused step for 2 layer(s): generalized forward-backward (gene = 1) and the
+// plain forward-backward start-up steps (gene = 0).
 #include "fused_inst.cuh"
 namespace beom {
-int fused_launch_lean2(const FusedLaunch &a, bool ufirst) {
-  return ufirst ? fused_launch_one<true, true, 2, true, fusedk::kMaxWarps / 2>(a) : fused_launch_one<false, true, 2, true, fusedk::kMaxWarps / 2>(a);
+int fused_launch_lean2(const FusedLaunch &a, bool ufirst, bool gene0) {
+  constexpr int GR = fusedk::kMaxWarps / 2;
+  if (gene0) return ufirst ? fused_launch_one<true, true, 2, true, GR, 0, true>(a) : fused_launch_one<false, true, 2, true, GR, 0, true>(a);
+  return ufirst ? fused_launch_one<true, true, 2, true, GR>(a) : fused_launch_one<false, true, 2, true, GR>(a);
 }
 }  // namespace beom

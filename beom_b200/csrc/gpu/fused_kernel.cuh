@@ -134,7 +134,7 @@ struct MomX {  // optional inputs (general instantiation and wind layers)
   double fn = 0.0, nud = 0.0;     // sponge target and rate
   double bodf = 0.0;
 };
-template <bool IS_U, bool VISC, bool MASKED, bool LEAN>
+template <bool IS_U, bool VISC, bool MASKED, bool LEAN, bool G0>
 __device__ __forceinline__ void momentum(const Dev &D, const bool wind, const double mask, const double hsum, const double m_far,
                                          const double m_here, const double c1, const double c2, const double old, const double h1,
                                          const double h2, const double h3, const double Ph, const double Pf, const double Qf,
@@ -144,8 +144,10 @@ __device__ __forceinline__ void momentum(const Dev &D, const bool wind, const do
   dmd4 = (m_far - m_here) * D.i_dl * D.grav;
   if (MASKED) dmd4 = sel(mask != 0.0, dmd4);
   double rhsi;
-  if (LEAN) {  // gene = 1 exactly: dmd4*(1-gene) is an exact zero
+  if (LEAN && !G0) {  // gene = 1 exactly: dmd4*(1-gene) is an exact zero
     rhsi = IS_U ? (c1 + c2) : ((-c1) - c2);
+  } else if (LEAN) {  // gene = 0 exactly (start-up steps): dmd4*(1-gene) = dmd4
+    rhsi = IS_U ? (dmd4 + c1 + c2) : (dmd4 - c1 - c2);
   } else {
     if (IS_U) rhsi = dmd4 * (1.0 - D.gene) + c1 + c2;
     else      rhsi = dmd4 * (1.0 - D.gene) - c1 - c2;
@@ -158,8 +160,8 @@ __device__ __forceinline__ void momentum(const Dev &D, const bool wind, const do
     if (D.has_tdrg) rhsi = rhsi - q.tu * D.i_r0 * i__h;
   }
   const double hist = D.del1 * dmd4 + D.del2 * h3 + D.gamm * h2 + D.epsi * h1;
-  if (LEAN) rhsi = rhsi + hist;  // bodf = 0 and gene = 1 (checked by fused_configure)
-  else      rhsi = rhsi + q.bodf + hist * D.gene;
+  if (LEAN && !G0) rhsi = rhsi + hist;  // bodf = 0 and gene = 1 (checked by fused_configure)
+  else if (!LEAN)  rhsi = rhsi + q.bodf + hist * D.gene;  // (LEAN, gene = 0: + 0 + hist*0 changes nothing)
   if (VISC) {
     if (IS_U) rhsi = rhsi + (Ph - Pf) * D.i_dl - (Qf - Qh) * D.i_dl;
     else      rhsi = rhsi + (Ph - Pf) * D.i_dl + (Qf - Qh) * D.i_dl;
@@ -214,7 +216,7 @@ __host__ __device__ inline SmemPlan smem_plan(int nlay, int groups, int n_all, i
 }
 
 // FLAVOR only distinguishes the symbol of the copy compiled with FMA contraction (fused_inst_lean*_fma.cu, BEOM_FMA=1)
-template <bool UFIRST, bool VISC, int NL, bool LEAN, int GROUPS, int FLAVOR = 0>
+template <bool UFIRST, bool VISC, int NL, bool LEAN, int GROUPS, int FLAVOR = 0, bool G0 = false>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1)
 k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const __grid_constant__ StreamTab T,
              const uint8_t *__restrict__ open, const unsigned *__restrict__ open4, int open4_words, int groups_rt, int rows_per_chunk,
@@ -364,7 +366,8 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
     rs_3 = SELM(f_own & F_N, rs_3);
     const double r1 = LD2(S_R1, 0), r2 = LD2(S_R2, 0);
     double rhs_h;
-    if (LEAN) rhs_h = (D.c_ab1 * rs_3 - D.c_ab2 * r2 + D.beta * r1) * D.dt;  // gene = 1: the plain term is an exact zero
+    if (LEAN && G0) rhs_h = rs_3 * D.dt;  // gene = 0 (start-up steps): the extrapolated term is an exact zero
+    else if (LEAN) rhs_h = (D.c_ab1 * rs_3 - D.c_ab2 * r2 + D.beta * r1) * D.dt;  // gene = 1: the plain term is an exact zero
     else      rhs_h = (D.c_ab1 * rs_3 - D.c_ab2 * r2 + D.beta * r1) * D.dt * D.gene + rs_3 * D.dt * (1.0 - D.gene);
     double hn_0 = LD2(S_HL, 0) + rhs_h;
     if (!LEAN) {
@@ -451,7 +454,7 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
     if (UFIRST) {
       // ---- u at row R-2 (pm:1422-1503) ----
       double un, hun, dm;
-      momentum<true, VISC, MASKED, LEAN>(D, wind, MASKED ? m_u((uint8_t)fw_m2) : 1.0, HN(2, -1) + hn_m2b, WR(W_MO, 2, -1), mo_m2,
+      momentum<true, VISC, MASKED, LEAN, G0>(D, wind, MASKED ? m_u((uint8_t)fw_m2) : 1.0, HN(2, -1) + hn_m2b, WR(W_MO, 2, -1), mo_m2,
                                          AT(Tc, 2), AT(Tc, 1), LD4(S_U, 2, 0), ux1, ux2, ux3, P_m2, PW_m2, AT(Qv, 1),
                                          AT(Qv, 2), WR(W_FX, 2, -1), WR(W_FX, 2, 0), xu, un, hun, dm);
       hun = SELM(a2, hun);
@@ -464,7 +467,7 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
       // ---- v at row R-2 (pm:1505-1591), using the new h_u of rows R-2 and R-3 ----
       const double wc = AT(qp, 2) * (hun + AT(fl, 3));
       double vn, hvn;
-      momentum<false, VISC, MASKED, LEAN>(D, wind, MASKED ? m_v((uint8_t)fw_m2) : 1.0, hn_m2b + HN(3, 0), WR(W_MO, 3, 0), mo_m2, wc,
+      momentum<false, VISC, MASKED, LEAN, G0>(D, wind, MASKED ? m_v((uint8_t)fw_m2) : 1.0, hn_m2b + HN(3, 0), WR(W_MO, 3, 0), mo_m2, wc,
                                           shdn(wc), vold, vy1, vy2, vy3, P_m2, VISC ? WR(W_PV, 3, 0) : 0.0, shdn(AT(Qv, 2)), AT(Qv, 2),
                                           AT(Gy, 3), AT(Gy, 2), xv, vn, hvn, dm);
       if (sto2) {
@@ -478,7 +481,7 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
       const bool a1 = fw_m1 & (F_ACT | F_GHOST);
       const double wc = AT(qp, 1) * (LD4(S_HU, 1, 0) + LD4(S_HU, 2, 0));
       double vn, hvn, dm;
-      momentum<false, VISC, MASKED, LEAN>(D, wind, MASKED ? m_v((uint8_t)fw_m1) : 1.0, hn_m1 + hn_m2b, mo_m2, WR(W_MO, 1, 0), wc,
+      momentum<false, VISC, MASKED, LEAN, G0>(D, wind, MASKED ? m_v((uint8_t)fw_m1) : 1.0, hn_m1 + hn_m2b, mo_m2, WR(W_MO, 1, 0), wc,
                                           shdn(wc), LD4(S_V, 2, 0), vy1, vy2, vy3, P_m1, P_m2, shdn(AT(Qv, 1)), AT(Qv, 1),
                                           AT(Gy, 2), AT(Gy, 1), xv, vn, hvn, dm);
       hvn = SELM(a1, hvn);
@@ -490,7 +493,7 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
       AT(Tc, 1) = AT(qp, 1) * (hvn + shup(hvn));  // Coriolis term of u with the new h_v (pm:1461-1462)
       // ---- u at row R-2 (pm:1422-1503), using the new h_v of rows R-2 and R-1 ----
       double un, hun;
-      momentum<true, VISC, MASKED, LEAN>(D, wind, MASKED ? m_u((uint8_t)fw_m2) : 1.0, HN(2, -1) + hn_m2b, WR(W_MO, 2, -1), mo_m2,
+      momentum<true, VISC, MASKED, LEAN, G0>(D, wind, MASKED ? m_u((uint8_t)fw_m2) : 1.0, HN(2, -1) + hn_m2b, WR(W_MO, 2, -1), mo_m2,
                                          AT(Tc, 2), AT(Tc, 1), LD4(S_U, 2, 0), ux1, ux2, ux3, P_m2, PW_m2, AT(Qv, 1),
                                          AT(Qv, 2), WR(W_FX, 2, -1), WR(W_FX, 2, 0), xu, un, hun, dm);
       if (sto2) {
