@@ -701,7 +701,7 @@ int beom_gpu_init(const beom_params *par, const beom_fields *fld, const beom_gpu
 
 int beom_gpu_upload_state(const double *hlay, const double *u, const double *v) {
   if (!g.ready) return fail(-20, "beom_gpu_upload_state: not initialised");
-  const size_t pl = g.plane, nl = (size_t)g.nlay, nd1 = (size_t)g.ndeg + 1;
+  const size_t pl = g.plane, nl = (size_t)g.nlay;
   const double *src[3] = {hlay, u, v};
   g.cur = 0;
   for (int f = 0; f < 5; f++) CK(cudaMemsetAsync(g.st[f][0], 0, pl * nl * sizeof(double), g.stream));
@@ -834,7 +834,6 @@ int beom_gpu_advance(int tstp0, int tstp1, double tres) {
 static int download_planes(double *dst, const double *dense, int nplanes) {
   // dst: reference layout [nplanes][ndeg+1]; only this rank's owned+halo points are written
   const int n = g.p_hi - g.p_lo + 1;
-  const size_t nd1 = (size_t)g.ndeg + 1;
   for (int p0 = 0; p0 < nplanes; p0 += 3 * g.nlay) {
     const int np = std::min(3 * g.nlay, nplanes - p0);
     for (int p = 0; p < np; p++) {
@@ -851,7 +850,7 @@ static int download_planes(double *dst, const double *dense, int nplanes) {
 int beom_gpu_download_state(double *hlay, double *u, double *v) {
   if (!g.ready) return fail(-20, "beom_gpu_download_state: not initialised");
   double *dst[3] = {hlay, u, v};
-  const size_t nl = (size_t)g.nlay, nd1 = (size_t)g.ndeg + 1, no = g.orphans.size();
+  const size_t nl = (size_t)g.nlay, no = g.orphans.size();
   for (int f = 0; f < 3; f++) {
     if (!dst[f]) continue;
     int rc = download_planes(dst[f], g.st[f][g.cur], g.nlay);
@@ -871,7 +870,6 @@ int beom_gpu_download_aux(double *h_u, double *h_v, double *rs_h, double *dmdx, 
   if (h_u && (rc = download_planes(h_u, g.st[3][g.cur], g.nlay))) return rc;
   if (h_v && (rc = download_planes(h_v, g.st[4][g.cur], g.nlay))) return rc;
   const int n = g.p_hi - g.p_lo + 1;
-  const size_t nd1 = (size_t)g.ndeg + 1;
   auto hist = [&](double *dst, int nh, double *a, double *b, double *c) -> int {
     for (int l = 0; l < g.nlay; l++) {
       const size_t L = (size_t)l * g.plane;
