@@ -414,6 +414,71 @@ def sponge_basin(nlay: int = 3, lm: int = 40, mm: int = 14, dt_s: float = 0.2, o
     return Case("sponge_basin", lm, mm, nlay, ndeg, text, {"h_bo": h_bo, "init": init, "nudg": nudg}, {})
 
 
+def option_basin(nlay: int = 3, lm: int = 36, mm: int = 22, dt_s: float = 0.05, wind: bool = True, sponge: bool = True,
+                 bodf: bool = False, hdot: bool = False, tide: bool = False, beta: bool = False, ocrp: float = 0.0,
+                 dt_r: float = 0.0, f0: float = 1.0e-4) -> Case:
+    """A small closed basin with switchable forcing files.  Not a reference script: it exists to drive the hot-path
+    branches no named config reaches -- wind inside a sponge (the Ekman term of the relaxation target,
+    private_mod.f95:1449-1452, 1534-1537), the dt_r ramp (:1898-1901), body force (bodf.bin), thickness source
+    (hdot.bin), tidal targets (tide.bin, :1453-1454, 1538-1539, 1633-1634), a beta plane (fcor.bin), more than four
+    layers, and wind stress spread over outcropping layers."""
+    dl = 2000.0
+    depth = 600.0
+    h_bo = np.zeros((lm + 2, mm + 2))
+    h_bo[1:-1, 1:-1] = depth
+    h_bo[lm // 2 - 2:lm // 2 + 2, mm // 2 - 1:mm // 2 + 2] = 0.0  # an island: coasts inside the tiles
+    ndeg = get_nbr_deg_freedom(h_bo)
+    xs = (np.arange(lm + 2) - 0.5) / lm
+    ys = (np.arange(mm + 2) - 0.5) / mm
+    init = np.zeros((lm + 2, mm + 2, nlay, 3))
+    init[:, :, 0, 0] = 0.04 * np.sin(5.0 * xs)[:, None] * np.cos(3.0 * ys)[None, :]
+    for k in range(1, nlay):
+        init[:, :, k, 0] = (6.0 * k * (xs - 0.5))[:, None] + 1.5 * np.cos(4.0 * ys + k)[None, :]
+    files = {"h_bo": h_bo, "init": init}
+    if sponge:
+        nudg = np.zeros((lm + 2, mm + 2, 3))
+        ramp = np.clip((np.arange(lm + 2) - (lm - 7)) / 8.0, 0.0, 1.0)  # an eastern sponge, eta, u and v
+        for c3 in range(3):
+            nudg[:, 1:-1, c3] = (0.03 * ramp)[:, None]
+        nudg[0:2, 1:-1, 1] = 0.01  # the reference insists on one open-boundary segment (pm:1226-1231)
+        files["nudg"] = nudg
+    if wind:
+        taus = np.zeros((lm + 2, mm + 2, 2))
+        taus[:, :, 0] = (0.08 * np.cos(math.pi * ys))[None, :]
+        taus[:, :, 1] = (0.03 * np.sin(2.0 * math.pi * xs))[:, None]
+        files["taus"] = taus
+    if bodf:
+        b = np.zeros((nlay, 2))
+        b[:, 0] = [1.0e-6 * (k + 1) for k in range(nlay)]
+        b[:, 1] = [-5.0e-7 * (k + 1) for k in range(nlay)]
+        files["bodf"] = b
+    if hdot:
+        hd = np.zeros((lm + 2, mm + 2, nlay))
+        hd[3:9, 3:9, 0] = 2.0e-5
+        hd[3:9, 3:9, nlay - 1] = -2.0e-5
+        files["hdot"] = hd
+    if tide:
+        td = np.zeros((2, 1, lm + 2, mm + 2, 3))
+        td[0, 0, :, :, 0] = 0.02  # amplitude of eta, u, v; phase below
+        td[0, 0, :, :, 1] = 0.004
+        td[0, 0, :, :, 2] = 0.002
+        td[1, 0, :, :, 0] = (2.0 * math.pi * xs)[:, None]
+        td[1, 0, :, :, 1] = (1.0 + 2.0 * math.pi * ys)[None, :]
+        td[1, 0, :, :, 2] = 0.5
+        td[0, 0, 0, 0, 0] = 2.0 * math.pi * 24.0 / 12.42  # omega, rad/day (element (1,k,0,0,1), tide_ridge.m:79-93)
+        files["tide"] = td
+    if beta:
+        fc = np.zeros((lm + 2, mm + 2))
+        fc[:, :] = (f0 + 2.0e-11 * (ys - 0.5) * mm * dl)[None, :]
+        files["fcor"] = fc
+    rhon = [1026.0 + 0.4 * k for k in range(nlay)]
+    topl = [k / (nlay + 0.5) for k in range(nlay)]
+    cext = math.sqrt(9.8 * depth)
+    text = print_params(lm, mm, nlay, ndeg, dl, cext, f0, rhon, topl, dt_s, dt_s, dt_r, 0.0, 0.0, 0.2, 0.0, 1.0, 10.0, 10.0,
+                        1.0, 1.0, 0.0, ocrp, 0.0, 0.0, 0.0, 0.0, [0, 0], "@DIR@", "@DIR@", "option basin")
+    return Case("option_basin", lm, mm, nlay, ndeg, text, files, {})
+
+
 CASES = {
     "stommel1948": stommel1948,
     "lock_exchange": lock_exchange,
@@ -422,4 +487,5 @@ CASES = {
     "conservation": conservation,
     "synthetic_basin": synthetic_basin,
     "sponge_basin": sponge_basin,
+    "option_basin": option_basin,
 }

@@ -193,3 +193,38 @@ def test_fma_flavour_within_tolerance(nlay):
     r = subprocess.run([sys.executable, os.path.join(root, "tests", "fma_worker.py"), str(nlay), "40"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "fma max relative field difference" in r.stdout
+
+
+OPTION_MATRIX = {
+    "ekman_sponge": dict(),                      # wind inside a sponge: the Ekman term of the relaxation target
+    "ramp": dict(dt_r=0.2),                      # dt_r ramp of the forcing (ramp < 1 during the whole test)
+    "bodf": dict(bodf=True),                     # body force per layer
+    "hdot": dict(hdot=True),                     # thickness source
+    "beta": dict(beta=True),                     # fcor.bin (psi-point averaging in float32)
+    "six_layers": dict(nlay=6),                  # the any-layer-count instantiation
+    "outcrop_wind": dict(ocrp=1.0),              # wind stress spread over outcropping layers (every layer stages tt3d)
+    "no_sponge": dict(sponge=False),             # wind only: the specialised instantiation with an island inside the tiles
+    "no_wind": dict(wind=False),
+    "tide": dict(tide=True),                     # tidal targets (cos per point and step): split path
+}
+
+
+@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("opt", sorted(OPTION_MATRIX))
+def test_option_matrix_bit_exact(case_factory, opt, fused):
+    """cases.option_basin: the forcing files and switches no named config reaches, each against the oracle."""
+    c, hm, orc, st, aux, path = run_pair(case_factory, "option_basin", 30, fused, small=False, **OPTION_MATRIX[opt])
+    assert path == ("fused" if fused and opt != "tide" else "split")
+    if opt == "tide":
+        # cos() is the one libm-dependent operation of the path (CUDA's and glibc's differ in the last ulp, DESIGN.md
+        # section 3): tolerance 1e-11 relative to the field's magnitude instead of bit-exact
+        for nm, a in zip(("hlay", "u", "v"), st):
+            w = orc.array(nm).reshape(a.shape)
+            assert np.abs(a - w).max() <= 1.0e-11 * np.abs(w).max(), nm
+        return
+    _check_state("option_basin[%s]" % opt, st, orc)
+    assert_same("h_u", aux[0], orc.array("h_u"))
+    assert_same("h_v", aux[1], orc.array("h_v"))
+    assert_same("rs_h", aux[2], orc.array("rs_h"))
+    assert_same("dmdx", aux[3], orc.array("dmdx"))
+    assert_same("dmdy", aux[4], orc.array("dmdy"))
