@@ -5,6 +5,7 @@
 // Layout reminders (private_mod.f95:27-93): point index 0 is the discarded cell; x(0:ndeg,nlay) is
 // stored [nlay][ndeg+1]; neig(8,0:ndeg) is [ndeg+1][8]; fnud(0:ndeg,nlay,3) is [3][nlay][ndeg+1].
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -14,6 +15,17 @@
 #include "host_model.h"
 
 namespace {
+// BEOM_HOST_TIMING=1: wall-clock of the stages of read_input_data on stderr (diagnostics only)
+struct StageTimer {
+  const char *what;
+  double t0;
+  static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+  explicit StageTimer(const char *w) : what(w), t0(now()) {}
+  ~StageTimer() {
+    static const bool on = getenv("BEOM_HOST_TIMING") != nullptr;
+    if (on) std::fprintf(stderr, "[host init] %-28s %.2f s\n", what, now() - t0);
+  }
+};
 
 struct Fail {
   std::string msg;
@@ -455,10 +467,14 @@ void read_input_data(beom_host *h) {
   const size_t n = h->nd1;
 
   // initialize_variables (pm:252-307): only what the host keeps
+  StageTimer t_all("read_input_data");
+  {
+  StageTimer t("initialize_variables");
   h->neig.assign(n * 8, 0); h->subc.assign(n * 2, 0); h->posc.assign(n, 0);
   for (auto *v : {&h->mk_u, &h->mk_v, &h->mk_n, &h->mkpe, &h->mkpi, &h->h_th, &h->Ow, &h->Os, &h->Osum_, &h->pi_s}) v->assign(n, 0.0);
   h->fcor.assign(n, P.f0);
   for (auto *v : {&h->h_0, &h->hlay, &h->u, &h->v}) v->assign(n * nlay, 0.0);
+  }
 
   // default flat bottom of depth cext**2/grav (pm:119-121), replaced by h_bo.bin if present
   h->h2d.reset(-1, lm + 2, -1, mm + 2, 0.0);
@@ -483,7 +499,10 @@ void read_input_data(beom_host *h) {
       }
   }
 
-  index_grid_points(h);
+  {
+    StageTimer t("index_grid_points");
+    index_grid_points(h);
+  }
 
   double dmin = std::numeric_limits<double>::infinity(), dmax = -dmin;  // pm:134-135
   for (double d : h->h2d.d) {
@@ -520,7 +539,10 @@ void read_input_data(beom_host *h) {
   for (int l = 0; l < nlay; l++)  // pm:198-200
     for (size_t q = 0; q < n; q++) h->hlay[(size_t)l * n + q] = h->h_0[(size_t)l * n + q] * h->mk_n[q];
 
-  read_forcing_files(h);  // pm:204-216
+  {
+    StageTimer t("read_forcing_files");
+    read_forcing_files(h);  // pm:204-216
+  }
 
   double acc = 0.0;  // pm:223-229
   for (size_t q = 0; q < n; q++) acc += h->fcor[q];
