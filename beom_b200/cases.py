@@ -356,6 +356,56 @@ def conservation(outc: float = 0.0, topo: bool = True, lx: float = 600.0e3, dl: 
     return Case("conservation", lm, mm, nlay, ndeg, text, files, {})
 
 
+def soliton(dl: float = 20.0e3, dt_s: float = 60.0) -> Case:
+    """testcases/soliton.m:8-93 -- the equatorial Rossby soliton of Lavelle & Thacker (2008) after Boyd (1980): one layer
+    of 1 m equivalent depth on an equatorial beta plane (fcor.bin), periodic in x, no dissipation.  ``info`` carries the
+    asymptotic westward phase speed -(1/3 + 0.395 B^2) sqrt(g H) the soliton should travel at."""
+    rhon = 1029.0
+    lx = 0.5 * 12.24e6
+    ly = 1.5 * 2.04e6
+    H = 1.0
+    grav = 9.8
+    a_rd = 6371.0e3
+    omeg = 2.0 * math.pi / (24.0 * 3600.0)
+    x_0 = 0.0
+    parB = 0.394
+    parA = 0.772 * parB ** 2
+    Elam = 4.0 * omeg ** 2 * a_rd ** 2 / grav / H
+    L_ls = a_rd / Elam ** 0.25
+    lm = _mround(lx / dl)
+    mm = _mround(ly / dl)
+    if lm % 2 == 0:
+        lm += 1
+    if mm % 2 == 0:
+        mm += 1
+    h_bo = np.zeros((lm + 2, mm + 2))
+    h_bo[1:-1, 1:-1] = H
+    ndeg = get_nbr_deg_freedom(h_bo)
+    xs = (np.arange(1, lm + 3) - 1.5) * dl
+    ys = (np.arange(1, mm + 3) - 1.5) * dl
+    xx = np.broadcast_to(xs[:, None], (lm + 2, mm + 2)).copy()
+    yy = np.broadcast_to(ys[None, :], (lm + 2, mm + 2)).copy()
+    xx -= xx.mean()
+    yy -= yy.mean()
+    sech2 = 1.0 / np.cosh(parB * (xx - x_0) / L_ls) ** 2
+    gauss = np.exp(-yy ** 2 / (2.0 * L_ls ** 2))
+    n = parA * H * sech2 * (6.0 * yy ** 2 + 3.0 * L_ls ** 2) / (4.0 * L_ls ** 2) * gauss
+    u = parA * math.sqrt(grav * H) * sech2 * (6.0 * yy ** 2 - 9.0 * L_ls ** 2) / (4.0 * L_ls ** 2) * gauss
+    v = -2.0 * parA * parB * math.sqrt(grav * H) * np.tanh(parB * (xx - x_0) / L_ls) * sech2 * 2.0 * yy / L_ls * gauss
+    init = np.zeros((lm + 2, mm + 2, 1, 3))
+    init[:, :, 0, 0], init[:, :, 0, 1], init[:, :, 0, 2] = n, u, v
+    cext = math.sqrt(grav * (h_bo + n).max())
+    deld = 0.25 * ly / 40.0e6
+    beta = 2.0 * omeg * math.sin(math.radians(deld)) - 2.0 * omeg * math.sin(math.radians(-deld))
+    beta = beta / (2.0 * deld * 40.0e6 / 360.0)
+    fcor = beta * yy
+    text = print_params(lm, mm, 1, ndeg, dl, cext, 0.0, [rhon], [0.0], dt_s, 2.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.05, 10.0, 10.0,
+                        1.0, 1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, [0, 0], "@DIR@", "@DIR@", "Test-case for equatorial soliton")
+    speed = -(1.0 / 3.0 + 0.395 * parB ** 2) * math.sqrt(grav * H)  # Boyd (1980), to first order in the amplitude
+    return Case("soliton", lm, mm, 1, ndeg, text, {"h_bo": h_bo, "fcor": fcor, "init": init},
+                {"speed": speed, "amplitude": float(n.max()), "dl": dl, "x0_index": int(np.argmax(n[:, (mm + 2) // 2]))})
+
+
 def synthetic_basin(n: int = 8192, nlay: int = 4, seed: int = 20261018, dt_s: float = 1.0, wind: bool = True,
                     mm: int | None = None) -> Case:
     """The throughput workload of BASELINE.json / SURVEY.md section 8(d): an n x n closed flat basin,
@@ -485,6 +535,7 @@ CASES = {
     "unstable_jet": unstable_jet,
     "sill_exchange3D": sill_exchange3D,
     "conservation": conservation,
+    "soliton": soliton,
     "synthetic_basin": synthetic_basin,
     "sponge_basin": sponge_basin,
     "option_basin": option_basin,

@@ -50,6 +50,32 @@ def test_lock_exchange_front_speed():
     assert h2.min() > 0.5 * hm.params.hmin  # the guard of private_mod.f95:2798-2808
 
 
+def test_equatorial_soliton_travels_west_at_boyds_speed():
+    """testcases/soliton.m (Lavelle & Thacker 2008, after Boyd 1980): on the equatorial beta plane (fcor.bin, periodic
+    in x, advection on, no dissipation) the Rossby soliton keeps its shape and moves west at about
+    -(1/3 + 0.395 B^2) sqrt(g H); the script only animates it, the speed is the analytical reference."""
+    c = cases.soliton(dl=40.0e3)
+    hm, orc = make(c)
+    assert hm.params.xper > 0.5 and c.ndeg == hm.params.ndeg
+
+    def peak():
+        eta = readers.vector_to_grid(orc.array("hlay")[0] - orc.array("h_0")[0], orc.iarray("subc"), c.lm, c.mm)[1:-1, 1:-1]
+        prof = np.nan_to_num(eta).max(axis=1)
+        i = int(np.argmax(prof))
+        a, b, d = prof[(i - 1) % c.lm], prof[i], prof[(i + 1) % c.lm]
+        return (i + 0.5 * (a - d) / (a - 2.0 * b + d)) * c.info["dl"], float(np.nanmax(eta))
+
+    x0, a0 = peak()
+    assert abs(a0 / c.info["amplitude"] - 1.0) < 1.0e-3
+    nsteps = int(round(20.0 * 86400.0 / hm.params.dt))
+    orc.advance(1, nsteps)
+    x1, a1 = peak()
+    L = c.lm * c.info["dl"]
+    speed = (((x1 - x0 + 0.5 * L) % L) - 0.5 * L) / (nsteps * hm.params.dt)
+    assert speed < 0.0 and abs(speed / c.info["speed"] - 1.0) < 0.04  # Boyd's first-order speed, -1.2355 m/s
+    assert a1 / a0 > 0.90                                               # the soliton holds together
+
+
 def test_volume_is_conserved_to_roundoff():
     """doc p.4-6 / testcases/conservation.m:116-141: the area-mean layer thickness stays within ~1e-10 m."""
     c = cases.conservation(dl=30.0e3)
