@@ -406,6 +406,463 @@ def soliton(dl: float = 20.0e3, dt_s: float = 60.0) -> Case:
                 {"speed": speed, "amplitude": float(n.max()), "dl": dl, "x0_index": int(np.argmax(n[:, (mm + 2) // 2]))})
 
 
+def _frs(n: int, npts: int, dt: float, cext: float, widt: float, upper: bool) -> np.ndarray:
+    """The flow-relaxation coefficient of the scripts' sponge loops (e.g. wave_sponge.m:57-86), Eq. 29 of Modave et al.
+    2010: ``dt cext / widt * xpos / (npts - xpos)`` with ``xpos`` the clipped depth (grid points) into the sponge, for
+    the 1-based index 1..n+2 along one axis; ``upper`` = the sponge sits at the high-index end."""
+    i = np.arange(1, n + 3, dtype=np.float64)
+    xpos = (i - 1.5 + npts - n) if upper else (npts - (i - 1.5))
+    xpos = np.minimum(np.maximum(xpos, 0.0), npts - 0.5)
+    return dt * cext / widt * xpos / (npts - xpos)
+
+
+def _weak(n: int, npts: int, dt: float, upper: bool) -> np.ndarray:
+    """The one-month relaxation ``dt / (31 d) * xpos / npts`` of mixed_open_bc.m:64, 71, 78 / sill_exchange3D.m."""
+    i = np.arange(1, n + 3, dtype=np.float64)
+    xpos = (i - 1.5 + npts - n) if upper else (npts - (i - 1.5))
+    xpos = np.minimum(np.maximum(xpos, 0.0), npts - 0.5)
+    return dt / (31.0 * 24.0 * 3600.0) * xpos / npts
+
+
+def _centred_axes(lm: int, mm: int, dl: float):
+    """[xx, yy] = meshgrid((1:lm+2)' - 1.5, (1:mm+2) - 1.5); xx = xx' * dl; ...; xx = xx - mean(xx(:))."""
+    xs = (np.arange(1, lm + 3) - 1.5) * dl
+    ys = (np.arange(1, mm + 3) - 1.5) * dl
+    xx = np.broadcast_to(xs[:, None], (lm + 2, mm + 2)).copy()
+    yy = np.broadcast_to(ys[None, :], (lm + 2, mm + 2)).copy()
+    return xx - xx.mean(), yy - yy.mean()
+
+
+def _dry_margins(h_bo: np.ndarray) -> np.ndarray:
+    h_bo[:, 0] = 0.0
+    h_bo[:, -1] = 0.0
+    h_bo[0, :] = 0.0
+    h_bo[-1, :] = 0.0
+    return h_bo
+
+
+def baines_ridge(scale: float = 1.0, dt_s: float = 10.0) -> Case:
+    """testcases/baines_ridge.m:8-153 -- rotating two-layer flow over a cosine ridge (Baines & Leonard 1989): channel
+    periodic in y (mm = 1), uniform inflow U_0 held by east/west sponges, body force balancing f U_0.  ``info`` holds the
+    steady analytical lower-layer thickness (their Eq. 5.1-5.5).  ``scale`` < 1 shortens the domain (150 Rossby radii)."""
+    hmax, U_0, nlay = 110.0, 1.2, 2
+    rhon = [1025.0, 1030.0]
+    topl = [0.0, 1.0 / 1.1]
+    fcor, grav = 1.0e-4, 9.8
+    gp = grav * (rhon[1] - rhon[0]) / rhon[1]
+    d_0 = hmax * (1.0 - topl[1])
+    Lros = math.sqrt(gp * d_0) / abs(fcor)
+    lx = 150.0 * scale * Lros
+    dl = Lros / 5.0
+    lm = _mround(lx / dl)
+    lm += (lm % 2 == 0)
+    npts, mm = 15, 1
+    H_m = 0.1
+    F_0 = U_0 / math.sqrt(gp * d_0)
+    dksi = dl / Lros
+    xx, yy = _centred_axes(lm, mm, dl)
+    X = xx[:, 1] / Lros
+    h_bo = H_m * d_0 * np.cos(math.pi * xx / (10.0 * Lros))
+    h_bo[(xx < -5.0 * Lros) | (xx > 5.0 * Lros)] = 0.0
+    H = h_bo[:, 1] / d_0
+    h_bo = _dry_margins(hmax - h_bo)
+    ndeg = get_nbr_deg_freedom(h_bo)
+    cext = math.sqrt(grav * h_bo.max())
+    n = np.zeros((lm + 2, mm + 2, nlay))
+    u = np.ones((lm + 2, mm + 2, nlay)) * U_0
+    v = np.zeros_like(n)
+    bodf = np.zeros((nlay, 2))
+    bodf[:, 1] = fcor * U_0
+    dt = 0.5 * dl / cext
+    widt = npts * dl
+    nudg = np.zeros((lm + 2, mm + 2, 3))
+    prof = np.maximum(_frs(lm, npts, dt, cext, widt, True), _frs(lm, npts, dt, cext, widt, False))
+    nudg[:, :, 0] = prof[:, None]
+    nudg[:, :, 1] = prof[:, None]
+    # Eq. 5.1-5.5 of Baines & Leonard (1989), baines_ridge.m:100-138
+    Dtil = np.zeros(lm + 2)
+    if F_0 < 1.0:
+        r = math.sqrt(1.0 - F_0 ** 2)
+        for ix in range(lm + 2):
+            Dtil[ix] = (-H[ix] / (1.0 - F_0 ** 2) + 0.5 * (1.0 - F_0 ** 2) ** (-1.5)
+                        * (dksi * np.sum(np.exp((X[ix] - X[ix:]) / r) * H[ix:])
+                           + dksi * np.sum(np.exp(-(X[ix] - X[:ix + 1]) / r) * H[:ix + 1])))
+    elif F_0 > 1.0:
+        r = math.sqrt(F_0 ** 2 - 1.0)
+        for ix in range(lm + 2):
+            Dtil[ix] = H[ix] / (F_0 ** 2 - 1.0) + (F_0 ** 2 - 1.0) ** (-1.5) * dksi * np.sum(H[:ix + 1] * np.sin((X[:ix + 1] - X[ix]) / r))
+    d_an = (1.0 + Dtil) * d_0
+    u_an = U_0 * d_0 / d_an
+    init = np.stack([n, u, v], axis=3)
+    text = print_params(lm, mm, nlay, ndeg, dl, cext, fcor, rhon, topl, dt_s, 0.2, 0.0, 0.0, 0.0, 0.0, 0.0, 0.1, 10.0, 10.0,
+                        1.0, 1.0, 0.0, 0.0, 0, 0.0, 1.0, 0.0, [0, 0], "@DIR@", "@DIR@", "Test-case for flow over a ridge")
+    return Case("baines_ridge", lm, mm, nlay, ndeg, text, {"h_bo": h_bo, "init": init, "nudg": nudg, "bodf": bodf},
+                {"d_an": d_an, "u_an": u_an, "F_0": F_0, "Lros": Lros, "X": X, "d_0": d_0, "npts": npts})
+
+
+def carrier_beach(dt_s: float = 0.08, mesh: float = 50.0) -> Case:
+    """testcases/carrier_beach.m:11-172 -- wetting and drying: a mound of water released on a sloping beach (Carrier &
+    Greenspan 1958).  One layer with outcropping (``ocrp = 1``: the shoreline is where the layer thins to Salmon's
+    thickness), sponge on the western open boundary.  ``info`` holds the analytical shoreline track (their Eq. 3.23-3.29):
+    ``t_sl`` (s) and ``x_sl`` (m from the mean shoreline).  ``mesh`` = grid points per length scale l_0 (50 in the script)."""
+    alph, l_0, epsi = 1.0e-3, 3.0e3, 0.1
+    dl = l_0 / mesh
+    hhti = 3.0 * epsi * alph * l_0
+    l_x = 10.0 * l_0 + hhti / alph
+    lm = _mround(l_x / dl)
+    mm = 1
+    hsal = 0.2 * alph * dl
+    hmin = hsal / 10.0
+    ix_0 = int(math.ceil(0.5 * (mm + 2)))  # 1-based
+    nlay, grav = 1, 9.8
+    v_0 = math.sqrt(grav * l_0 * alph)
+    T = v_0 / (alph * grav)
+    p = 1.0 / 8.0 / (1.0 + epsi)
+    npts = 15
+    h_bo = np.repeat((np.arange(lm + 1, -1, -1, dtype=np.float64) * dl * alph)[:, None], mm + 2, axis=1)
+    h_bo[:npts, ix_0 - 1] = h_bo[npts - 1, ix_0 - 1]
+    h_bo[:, 0] = 0.0
+    h_bo[:, -1] = 0.0
+    h_bo[-1, :] = 0.0
+    h_bo[0, :] = 0.0
+    ndeg = get_nbr_deg_freedom(h_bo)
+    col = h_bo[:, ix_0 - 1]
+    i_sl = int(np.argmin(np.abs(col - hhti)))  # first index of the minimum, 0-based
+    hhti = float(col[i_sl])
+    topl = hhti / h_bo.max()
+    cext = math.sqrt(grav * h_bo.max())
+    xref = np.arange(1, lm + 3, dtype=np.float64) * dl
+    xref = xref - xref[i_sl]
+    sigm = 10.0 - 0.1 * np.arange(101, dtype=np.float64)  # (10 : -1.e-1 : 0)'
+    x = 0.25 * epsi * math.exp(2.0) * p ** 2 * sigm ** 4 * np.exp(-sigm ** 2 * p) - sigm ** 2 / 16.0
+    eta = 0.25 * epsi * p ** 2 * math.exp(2.0) * sigm ** 4 * np.exp(-sigm ** 2 * p)
+    n1 = np.interp(xref, x * l_0, eta * alph * l_0, left=np.nan, right=np.nan)  # x is increasing as sigm decreases
+    n1 = np.nan_to_num(n1, nan=0.0)
+    n = np.repeat(n1[:, None], mm + 2, axis=1)[:, :, None]
+    # shoreline, Eq. 3.23-3.29 (carrier_beach.m:93-114)
+    dlam = 1.0e-3
+    lamb = np.arange(0, 20001, dtype=np.float64) * dlam
+    lmid = 0.5 * (lamb[:-1] + lamb[1:])
+    E_la = np.concatenate([[0.0], np.cumsum(np.exp(0.25 * lmid ** 2)) * dlam])
+    f_la = (-lamb ** 2 + 0.5 * lamb ** 4 + np.exp(-0.25 * lamb ** 2) * E_la * (lamb + lamb ** 3 - 0.25 * lamb ** 5)) / 16.0
+    dfdl = (-lamb + 3.0 * lamb ** 3 - 0.25 * lamb ** 5
+            + np.exp(-0.25 * lamb ** 2) * E_la * (1.0 + 2.5 * lamb ** 2 - 7.0 * lamb ** 4 / 4.0 + 0.125 * lamb ** 6)) / 16.0
+    v_sl = math.sqrt(math.pi * p) * epsi * math.exp(2.0) * dfdl
+    t_sl = 0.25 * lamb / math.sqrt(p) - math.sqrt(math.pi * p) * epsi * math.exp(2.0) * dfdl
+    x_sl = -v_sl ** 2 / 16.0 + epsi * math.exp(2.0) * math.sqrt(math.pi) * 0.25 * f_la
+    dt = 0.5 * dl / cext
+    widt = npts * dl
+    nudg = np.zeros((lm + 2, mm + 2, 3))
+    prof = _frs(lm, npts, dt, cext, widt, False)
+    nudg[:, :, 0] = prof[:, None]
+    nudg[:, :, 1] = prof[:, None]
+    init = np.stack([n, np.zeros_like(n), np.zeros_like(n)], axis=3)
+    text = print_params(lm, mm, nlay, ndeg, dl, cext, 0.0, [1030.0], [topl], dt_s, 5.0e-4, 0.0, 0.0, 0.0, 0.0, 0.0, hmin, 10.0,
+                        10.0, 1.0, 1.0, 0.0, 1.0, 0.0, 0.0, 0.0, 0.0, [0, 0], "@DIR@", "@DIR@",
+                        "Test-case for wave on sloping beach")
+    return Case("carrier_beach", lm, mm, nlay, ndeg, text, {"h_bo": h_bo, "init": init, "nudg": nudg},
+                {"t_sl": t_sl * T, "x_sl": x_sl * l_0, "xref": xref, "hsal": hsal, "hhti": hhti, "T": T, "l_0": l_0})
+
+
+def _millot_crepon(lm: int, hfla: float, topl, rhon, tauw, f0: float, dl: float, grav: float = 9.8) -> dict:
+    """Steady two-layer response to a seaward wind (Millot & Crepon 1981), upwelling_seaward_wind.m:57-81: interface
+    displacement and along-shore velocity against the distance from the coast, for undisturbed thicknesses from topl."""
+    h1 = (topl[1] - topl[0]) * hfla
+    h2 = (1.0 - topl[1]) * hfla
+    gpri = grav * (rhon[1] - rhon[0]) / rhon[1]
+    r_1 = math.sqrt(grav * hfla) / f0
+    r_2 = math.sqrt(gpri * h1 * h2 / hfla) / abs(f0)
+    x = (np.arange(1, lm + 3) - 1.5) * dl
+    t_eta2 = np.exp(-x / r_2) * (-1.0) * tauw[0] / rhon[0] / (r_1 * f0 ** 2) * h2 / hfla * (-1.0) * r_1 / r_2
+    t_eta1 = (-1.0) * tauw[0] / rhon[0] / (r_1 * f0 ** 2) * (np.exp(-x / r_1) + h2 / h1 * r_2 / r_1 * np.exp(-x / r_2))
+    t_v1 = tauw[0] / rhon[0] / f0 / hfla * h2 / h1 * (np.exp(-x / r_2) - 1.0)
+    t_v2 = t_v1 * (h1 / h2) * (-1.0)
+    return {"x": x, "t_eta": np.stack([t_eta1, t_eta2]), "t_v": np.stack([t_v1, t_v2]), "r_1": r_1, "r_2": r_2}
+
+
+def upwelling_seaward_wind(lm: int = 200, dt_s: float = 6.0) -> Case:
+    """testcases/upwelling_seaward_wind.m:10-36 -- two layers, coast on the western edge, uniform seaward wind ``tauw``
+    ramped over ``dt_r`` = 4 days, channel periodic in y (mm = 1).  No input file at all: parameters only."""
+    mm, nlay, dl, f0 = 1, 2, 1.0e3, 1.0e-4
+    dt_o, hfla = 0.16667, 40.0
+    topl = [0.0, 0.5]
+    rhon = [1028.95, 1030.0]
+    tauw = [0.1, 0.0]
+    grav = 9.8
+    h_bo = np.zeros((lm + 2, mm + 2))
+    h_bo[1:-1, 1:-1] = hfla
+    ndeg = get_nbr_deg_freedom(h_bo)
+    cext = math.sqrt(grav * h_bo.max())
+    text = print_params(lm, mm, nlay, ndeg, dl, cext, f0, rhon, topl, dt_s, dt_o, 4.0, 0.0, 0.0, 0.0, 0.0, 1.0, 10.0, 10.0,
+                        1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0, 0.0, tauw, "@DIR@", "@DIR@", "Test-case for upwelling seaward wind")
+    return Case("upwelling_seaward_wind", lm, mm, nlay, ndeg, text, {}, _millot_crepon(lm, hfla, topl, rhon, tauw, f0, dl))
+
+
+def mixed_open_bc(lm: int = 200, mm: int = 100, dt_s: float = 6.0, mcbc: float = 0.0) -> Case:
+    """testcases/mixed_open_bc.m:12-118 -- the seaward-wind upwelling in a basin with a coast (west), a wave sponge
+    (east) and weakly relaxed open boundaries (north, south).  The script predates the ``mcbc`` switch of shared_mod.f95:71
+    (it was written for a model that always applied no_gradient_obc, private_mod.f95:2201, 2285): with the shipped
+    ``mcbc = 1`` the north/south walls are closed, the coastal jet piles up in the north-west corner and the top layer
+    drains after about three days, so the case sets ``mcbc = 0`` (appended to the block; print_params.m has no slot)."""
+    nlay, dl, f0 = 2, 1.0e3, 1.0e-4
+    dt_o, hfla = 0.16667, 40.0
+    topl = [0.0, 0.5]
+    rhon = [1028.95, 1030.0]
+    tauw = [0.1, 0.0]
+    grav, npts = 9.8, 15
+    h_bo = np.zeros((lm + 2, mm + 2))
+    h_bo[1:-1, 1:-1] = hfla
+    ndeg = get_nbr_deg_freedom(h_bo)
+    cext = math.sqrt(grav * h_bo.max())
+    dt = 0.5 * dl / cext
+    widt = npts * dl
+    east = np.zeros((lm + 2, mm + 2, 3))
+    e = _frs(lm, npts, dt, cext, widt, True)
+    east[:, :, 0] = e[:, None]
+    east[:, :, 1] = e[:, None]
+    east[:, :, 2] = _weak(lm, npts, dt, True)[:, None]
+    nort = np.zeros((lm + 2, mm + 2, 3))
+    sout = np.zeros((lm + 2, mm + 2, 3))
+    nort[:, :, :] = _weak(mm, npts, dt, True)[None, :, None]
+    sout[:, :, :] = _weak(mm, npts, dt, False)[None, :, None]
+    nudg = np.maximum(np.maximum(east, nort), sout)
+    nudg[0, :, :] = 0.0
+    text = print_params(lm, mm, nlay, ndeg, dl, cext, f0, rhon, topl, dt_s, dt_o, 4.0, 0.0, 0.0, 0.0, 0.0, 0.001, 1.0, 1.0,
+                        1.0, 0.0, 0.0, 0.0, 0, 0.0, 0.0, 0.0, tauw, "@DIR@", "@DIR@",
+                        "Test-case: Upwelling seaward wind with mixed open boundary conditions",
+                        extra={"mcbc": "%#0.0f" % mcbc})
+    return Case("mixed_open_bc", lm, mm, nlay, ndeg, text, {"nudg": nudg}, _millot_crepon(lm, hfla, topl, rhon, tauw, f0, dl))
+
+
+def morel_upwelling(dl: float = 1.0e3) -> Case:
+    """testcases/morel_upwelling.m:13-63 -- upwelling driven by an along-shore wind up to and past the outcropping of the
+    interface (Morel, Darr & Talandier 2006): two layers, periodic in x (lm = 1), coast at y = y_max, the wind applied
+    as a body force on the top layer (bodf.bin), ``ocrp = 1``.  ``info`` has the constants of the analytical solution."""
+    nlay = 2
+    topl = [0.0, 0.5]
+    rhon = [1015.0, 1030.0]
+    hfla, hsal, f0, grav = 50.0, 0.5, 1.0e-4, 9.8
+    rext = math.sqrt(grav * hfla) / abs(f0)
+    ly = 1.0 * rext
+    mm = _mround(ly / dl)
+    lm = 1
+    h_bo = np.zeros((lm + 2, mm + 2))
+    h_bo[1:-1, 1:-1] = hfla
+    ndeg = get_nbr_deg_freedom(h_bo)
+    cext = math.sqrt(grav * h_bo.max())
+    hmin = hsal / 10.0
+    H_1 = topl[1] * hfla
+    H_2 = (1.0 - topl[1]) * hfla
+    R_d = math.sqrt(grav * (rhon[1] - rhon[0]) / rhon[1] * H_1 * H_2 / hfla) / abs(f0)
+    delt = H_1 / H_2
+    T_w = 0.05 / rhon[0] / H_1
+    t_o = abs(f0) * R_d * (1.0 + delt) / T_w
+    dt_s = float(_mround(3.0 * t_o / 3600.0 / 24.0))
+    bodf = np.zeros((nlay, 2))
+    bodf[0, 0] = T_w
+    text = print_params(lm, mm, nlay, ndeg, dl, cext, f0, rhon, topl, dt_s, 0.05 * dt_s, 0.0, 0.0, 0.0, 0.0, 0.0, hmin, 10.0,
+                        10.0, 1.0, 0.0, 0.0, 1.0, 0.0, 1.0, 0.0, 1.0, [0, 0], "@DIR@", "@DIR@",
+                        "Test-case: Upwelling in presence of outcrop")
+    return Case("morel_upwelling", lm, mm, nlay, ndeg, text, {"bodf": bodf},
+                {"H_1": H_1, "H_2": H_2, "R_d": R_d, "delt": delt, "T_w": T_w, "t_o": t_o, "f0": f0, "dl": dl})
+
+
+def outcrop_seamount(lx: float = 600.0e3, dl: float = 5.0e3, nlay: int = 5, threed: bool = False, dt_s: float = 15.0) -> Case:
+    """testcases/outcrop_seamount.m:9-104 -- a stratified state of rest over a seamount and sloping coasts with
+    isopycnals outcropping into the bottom (Salmon 2002): h_0 from the Newton solve must stay at rest (du/dt = 0).
+    ``threed`` selects the script's commented 3-D option (mm = lm)."""
+    fcor = 1.0e-4
+    if nlay == 1:
+        rhon, topl = [1000.0], [0.0]
+    else:
+        rhon = [1000.0 + 30.0 * k / (nlay - 1) for k in range(nlay)]
+        topl = [k / nlay for k in range(nlay)]
+    grav, hmax = 9.8, 300.0
+    lm = _mround(lx / dl)
+    lm += (lm % 2 == 0)
+    mm = lm if threed else 1
+    xi = np.arange(1, lm + 3, dtype=np.float64)
+    yi = np.arange(1, mm + 3, dtype=np.float64)
+    xx = np.broadcast_to(xi[:, None], (lm + 2, mm + 2)).copy()
+    yy = np.broadcast_to(yi[None, :], (lm + 2, mm + 2)).copy()
+    xx = (xx - xx.mean()) * dl
+    yy = (yy - yy.mean()) * dl
+    ix_0 = int(math.ceil(0.5 * (mm + 2))) - 1
+    h_bo = np.sqrt(xx ** 2 + yy ** 2) / dl
+    h_bo = h_bo / h_bo[:, ix_0].max() * hmax
+    h_bo = h_bo[:, ix_0].max() - h_bo
+    smnt = hmax - np.exp(-(xx ** 2 + yy ** 2) / 50.0e3 ** 2) * 0.75 * hmax
+    h_bo = np.minimum(h_bo, smnt)
+    h_bo[h_bo < h_bo[:, ix_0].min()] = 0.0
+    dhdx = np.zeros((lm + 2, mm + 2))
+    dhdy = np.zeros((lm + 2, mm + 2))
+    dhdx[1:-1, :] = (h_bo[2:, :] - h_bo[:-2, :]) / (2.0 * dl)
+    dhdy[:, 1:-1] = (h_bo[:, 2:] - h_bo[:, :-2]) / (2.0 * dl)
+    slop = np.sqrt(dhdx ** 2 + dhdy ** 2)
+    hsal = 1.0 * slop[h_bo > 1.0e-3].max() * dl * (rhon[1] - rhon[0]) / rhon[1] if nlay > 1 else 1.0
+    hmin = hsal / 10.0
+    dryd = 10.0 * hsal + (nlay - 1) * hsal
+    h_bo[h_bo < dryd] = 0.0
+    h_bo[0, :] = 0.0
+    h_bo[-1, :] = 0.0
+    h_bo[:, -1] = 0.0
+    h_bo[:, 0] = 0.0
+    cext = math.sqrt(grav * h_bo.max())
+    ndeg = get_nbr_deg_freedom(h_bo)
+    text = print_params(lm, mm, nlay, ndeg, dl, cext, fcor, rhon, topl, dt_s, 0.2, 0.0, 0.0, 0.0, 0.0, 0.0, hmin, 10.0, 10.0,
+                        1.0, 1.0, 0.0, 1.0, 0.0, 0.0, 0.0, 0.0, [0, 0], "@DIR@", "@DIR@",
+                        "Test-case for state of rest allowing isopycnal outcrop")
+    return Case("outcrop_seamount", lm, mm, nlay, ndeg, text, {"h_bo": h_bo}, {"hsal": hsal})
+
+
+def _m2_tide(lm: int, mm: int) -> np.ndarray:
+    """tide.bin of sill_exchange2Dtides.m:84-97 / tide_ridge.m:73-92: an M2 current of 0.1 m/s along x starting from
+    rest (phase pi/2); the constituent frequency (rad/day) sits in element (1,1,1,1,1)."""
+    tide = np.zeros((2, 1, lm + 2, mm + 2, 3))
+    tide[0, 0, :, :, 1] = 0.1
+    tide[1, 0, :, :, 1] = math.pi / 2.0
+    tide[1, 0, :, :, 2] = math.pi / 2.0
+    tide[0, 0, 0, 0, 0] = 2.0 * math.pi / (12.4206012 / 24.0)
+    return tide
+
+
+def _sill2d(tides: bool, lx: float, dl: float, dt_s: float) -> Case:
+    ocrp, hmax, dt_r, bdrg, nlay = 1, 700.0, 0.0, 0.0, 2
+    fcor = 0.00014087
+    mm = 1
+    lm = _mround(lx / dl)
+    lm += (lm % 2 == 0)
+    npts = 15 if tides else 200
+    grav = 9.8
+    rhon = [1027.47, 1027.75]
+    hsill = 400.0
+    topl = [0.0, 0.5] if tides else [0.0, 0.1428]
+    xx, yy = _centred_axes(lm, mm, dl)
+    h_bo = _dry_margins(hmax - hsill * np.exp(-(xx / (200.0 * dl)) ** 2))
+    ndeg = get_nbr_deg_freedom(h_bo)
+    cext = math.sqrt(grav * h_bo.max())
+    dhdx = np.zeros((lm + 2, mm + 2))
+    dhdx[2:-2, :] = h_bo[3:-1, :] - h_bo[1:-3, :]
+    dhdx = dhdx / (2.0 * dl)
+    n = np.zeros((lm + 2, mm + 2, nlay))
+    hsal = 20.0 * dhdx.max() * dl * (rhon[-1] - rhon[0]) / rhon[0]
+    hmin = hsal / 10.0
+    if tides:  # sill_exchange2Dtides.m:60-66
+        k = _mround(0.5 * (lm + 2))
+        n[:k, :, 1] = 0.5 * hmax - 4.0 * hsal - 100.0
+        n[k:, :, 1] = (-0.5 * hmax + 4.0 * hsal + 450.0 + (hmax - h_bo[k:, 1]))[:, None]
+        n[k:, :, 1] = np.minimum(n[k:, :, 1], 0.5 * hmax - 4.0 * hsal - 100.0)
+    else:      # sill_exchange2D.m:67-69
+        k = _mround(0.6 * (lm + 2))
+        n[:k, :, 1] = 0.0
+        n[k:, :, 1] = (-h_bo[k:, 1] + 500.0 + 4.0 * hsal)[:, None]
+    dt = 0.5 * dl / cext
+    widt = npts * dl
+    nudg = np.zeros((lm + 2, mm + 2, 3))
+    prof = np.maximum(_frs(lm, npts, dt, cext, widt, True), _frs(lm, npts, dt, cext, widt, False))
+    nudg[:, :, 0] = prof[:, None]
+    nudg[:, :, 1] = prof[:, None]
+    init = np.stack([n, np.zeros_like(n), np.zeros_like(n)], axis=3)
+    files = {"init": init, "h_bo": h_bo, "nudg": nudg}
+    if tides:
+        files["tide"] = _m2_tide(lm, mm)
+    text = print_params(lm, mm, nlay, ndeg, dl, cext, fcor, rhon, topl, dt_s, 0.01, dt_r, 0.0, 0.0, 0.5 if tides else 0.9, bdrg,
+                        hmin, 5.0, 5.0, 1.0, 1.0, 1.0, ocrp, 0.0, 0.0, 0.0, 0.0, [0, 0], "@DIR@", "@DIR@",
+                        "Test-case for tidal flow over a ridge" if tides else "Test-case: 2D sill exchange")
+    return Case("sill_exchange2Dtides" if tides else "sill_exchange2D", lm, mm, nlay, ndeg, text, files, {"hsal": hsal})
+
+
+def sill_exchange2D(lx: float = 200.0e3, dl: float = 100.0, dt_s: float = 3.0) -> Case:
+    """testcases/sill_exchange2D.m:7-137 -- two-layer exchange over a Gaussian sill in an x-z channel (mm = 1) with
+    200-point sponges at both ends, outcropping, quadratic drag switch on (bdrg = 0)."""
+    return _sill2d(False, lx, dl, dt_s)
+
+
+def sill_exchange2Dtides(lx: float = 100.0e3, dl: float = 100.0, dt_s: float = 10.0) -> Case:
+    """testcases/sill_exchange2Dtides.m:7-166 -- the 2-D sill with a lock-exchange initial state, 15-point sponges and an
+    M2 tidal current in the relaxation target (tide.bin)."""
+    return _sill2d(True, lx, dl, dt_s)
+
+
+def tide_ridge(lm: int = 500, ocrp: int = 1, dt_s: float = 3.0) -> Case:
+    """testcases/tide_ridge.m:8-156 -- semidiurnal tidal flow over a Gaussian ridge in 30 m of water: seven layers cut from
+    an exponential density profile (three without outcropping), no rotation, M2 current in the sponges' target ramped
+    over 0.75 dt_s days."""
+    hmax = 30.0
+    dt_r = 0.75 * dt_s
+    bdrg = 0.0
+    nlay = 7 if ocrp == 1 else 3
+    fcor, dl, mm = 0.0, 100.0, 1
+    lm += (lm % 2 == 0)
+    npts, grav = 15, 9.8
+    z = np.arange(0.0, hmax + 0.5, 1.0)
+    rhop = 1028.0 - 6.0 * np.exp(-z / (0.2 * hmax))
+    drho = (rhop.max() - rhop.min()) / nlay
+    rhon = rhop.min() + (np.arange(nlay) + 0.5) * drho
+    xx, yy = _centred_axes(lm, mm, dl)
+    h_bo = _dry_margins(hmax - 0.75 * hmax * np.exp(-(xx / (75.0 * dl)) ** 2))
+    ndeg = get_nbr_deg_freedom(h_bo)
+    cext = math.sqrt(grav * h_bo.max())
+    dhdx = np.zeros((lm + 2, mm + 2))
+    dhdx[2:-2, :] = h_bo[3:-1, :] - h_bo[1:-3, :]
+    dhdx = dhdx / (2.0 * dl)
+    hsal = 20.0 * dhdx.max() * dl * (rhon[-1] - rhon[0]) / rhon[0]
+    hmin = hsal / 10.0
+    topl = np.interp(rhop.min() + np.arange(nlay) * drho, rhop, z)
+    if topl[1] < 10.0 * hsal:
+        topl[1:] = topl[1:] + (10.0 * hsal - topl[1])
+    topl = topl / hmax
+    dt = 0.5 * dl / cext
+    widt = npts * dl
+    nudg = np.zeros((lm + 2, mm + 2, 3))
+    prof = np.maximum(_frs(lm, npts, dt, cext, widt, True), _frs(lm, npts, dt, cext, widt, False))
+    nudg[:, :, 0] = prof[:, None]
+    nudg[:, :, 1] = prof[:, None]
+    text = print_params(lm, mm, nlay, ndeg, dl, cext, fcor, rhon, topl, dt_s, 0.01, dt_r, 0.0, 0.0, 0.5, bdrg, hmin, 5.0, 5.0,
+                        1.0, 1.0, 1.0, ocrp, 0.0, 0.0, 0.0, 0.0, [0, 0], "@DIR@", "@DIR@", "Test-case for tidal flow over a ridge")
+    return Case("tide_ridge", lm, mm, nlay, ndeg, text, {"h_bo": h_bo, "nudg": nudg, "tide": _m2_tide(lm, mm)},
+                {"hsal": hsal, "omega": 2.0 * math.pi / (12.4206012 / 24.0)})
+
+
+def wave_sponge(lx: float = 600.0e3, dl: float = 10.0e3, npts: int = 15, dt_s: float = 0.25) -> Case:
+    """testcases/wave_sponge.m:12-116 -- a Gaussian mound adjusting in a rotating two-layer basin whose four sides are
+    flow-relaxation sponges (eta and the normal velocity): the radiated gravity waves must leave without reflection."""
+    ly = lx
+    nlay = 2
+    fcor = 1.0e-4
+    rhon = [1000.0, 1030.0]
+    topl = [0.0, 0.5]
+    hfla, grav = 200.0, 9.8
+    lm = _mround(lx / dl)
+    mm = _mround(ly / dl)
+    lm += (lm % 2 == 0)
+    mm += (mm % 2 == 0)
+    lm += 2 * npts
+    mm += 2 * npts
+    n = np.zeros((lm + 2, mm + 2, nlay))
+    h_bo = np.zeros((lm + 2, mm + 2))
+    h_bo[1:-1, 1:-1] = hfla
+    cext = math.sqrt(grav * hfla)
+    ndeg = get_nbr_deg_freedom(h_bo)
+    xs = np.arange(1, lm + 3) - 1.5
+    ys = np.arange(1, mm + 3) - 1.5
+    xx = np.broadcast_to((xs - np.median(xs))[:, None], (lm + 2, mm + 2)) * dl
+    yy = np.broadcast_to((ys - np.median(ys))[None, :], (lm + 2, mm + 2)) * dl
+    n[:, :, 0] = 1.0 * np.exp(-(xx ** 2 + yy ** 2) / 50.0e3 ** 2)
+    dt = 0.5 * dl / cext
+    widt = npts * dl
+    ew = np.maximum(_frs(lm, npts, dt, cext, widt, True), _frs(lm, npts, dt, cext, widt, False))
+    ns = np.maximum(_frs(mm, npts, dt, cext, widt, True), _frs(mm, npts, dt, cext, widt, False))
+    nudg = np.zeros((lm + 2, mm + 2, 3))
+    nudg[:, :, 0] = np.maximum(ew[:, None], ns[None, :])
+    nudg[:, :, 1] = ew[:, None]
+    nudg[:, :, 2] = ns[None, :]
+    init = np.stack([n, np.zeros_like(n), np.zeros_like(n)], axis=3)
+    text = print_params(lm, mm, nlay, ndeg, dl, cext, fcor, rhon, topl, dt_s, 4.17e-3, 0.0, 0.0, 0.0, 0.0, 0.0, 1.0, 10.0, 10.0,
+                        1.0, 1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, [0, 0], "@DIR@", "@DIR@", "Test-case for wave sponge")
+    return Case("wave_sponge", lm, mm, nlay, ndeg, text, {"init": init, "nudg": nudg}, {"npts": npts, "rhon": rhon, "hfla": hfla})
+
+
 def synthetic_basin(n: int = 8192, nlay: int = 4, seed: int = 20261018, dt_s: float = 1.0, wind: bool = True,
                     mm: int | None = None) -> Case:
     """The throughput workload of BASELINE.json / SURVEY.md section 8(d): an n x n closed flat basin,
@@ -536,6 +993,16 @@ CASES = {
     "sill_exchange3D": sill_exchange3D,
     "conservation": conservation,
     "soliton": soliton,
+    "baines_ridge": baines_ridge,
+    "carrier_beach": carrier_beach,
+    "upwelling_seaward_wind": upwelling_seaward_wind,
+    "mixed_open_bc": mixed_open_bc,
+    "morel_upwelling": morel_upwelling,
+    "outcrop_seamount": outcrop_seamount,
+    "sill_exchange2D": sill_exchange2D,
+    "sill_exchange2Dtides": sill_exchange2Dtides,
+    "tide_ridge": tide_ridge,
+    "wave_sponge": wave_sponge,
     "synthetic_basin": synthetic_basin,
     "sponge_basin": sponge_basin,
     "option_basin": option_basin,

@@ -28,6 +28,17 @@ SMALL = {
     "unstable_jet": dict(dl=60.0e3),
     "sill_exchange3D": dict(lx=6.0e3, ly=100.0e3),
     "conservation": dict(dl=30.0e3),
+    "soliton": dict(dl=80.0e3),
+    "baines_ridge": dict(scale=0.3),
+    "carrier_beach": dict(mesh=20.0),
+    "upwelling_seaward_wind": dict(lm=80),
+    "mixed_open_bc": dict(lm=60, mm=40),
+    "morel_upwelling": dict(dl=4.0e3),
+    "outcrop_seamount": dict(),
+    "sill_exchange2D": dict(lx=140.0e3),
+    "sill_exchange2Dtides": dict(lx=60.0e3),
+    "tide_ridge": dict(lm=200),
+    "wave_sponge": dict(dl=20.0e3),
 }
 
 

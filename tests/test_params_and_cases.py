@@ -86,12 +86,24 @@ def test_print_params_reproduces_the_script_rounding():
 
 @pytest.mark.parametrize("name,lm,mm,nlay,ndeg", [("stommel1948", 100, 63, 1, 6464), ("lock_exchange", 160, 1, 2, 322),
                                                    ("unstable_jet", 201, 267, 1, 54136), ("sill_exchange3D", 125, 501, 2, 63252),
-                                                   ("conservation", 61, 61, 2, 3844)])
+                                                   ("conservation", 61, 61, 2, 3844), ("soliton", 307, 153, 1, 47432),
+                                                   ("baines_ridge", 751, 1, 2, 1504), ("carrier_beach", 515, 1, 1, 1032),
+                                                   ("upwelling_seaward_wind", 200, 1, 2, 402), ("mixed_open_bc", 200, 100, 2, 20301),
+                                                   ("morel_upwelling", 1, 221, 2, 444), ("outcrop_seamount", 121, 1, 5, 244),
+                                                   ("sill_exchange2D", 2001, 1, 2, 4004), ("sill_exchange2Dtides", 1001, 1, 2, 2004),
+                                                   ("tide_ridge", 501, 1, 7, 1004), ("wave_sponge", 91, 91, 2, 8464)])
 def test_case_sizes_match_the_reference_scripts(name, lm, mm, nlay, ndeg):
+    """lm, mm, nlay as the scripts compute them; ndeg from get_nbr_deg_freedom.m -- and the reference's own check
+    (i_c == ndeg, private_mod.f95:604-610, restated by the host driver) accepts it."""
     c = cases.CASES[name]()
     assert (c.lm, c.mm, c.nlay, c.ndeg) == (lm, mm, nlay, ndeg)
-    for arr in c.files.values():
-        assert arr.shape[:2] == (lm + 2, mm + 2)
+    for key, arr in c.files.items():
+        if key == "bodf":
+            assert arr.shape == (nlay, 2)
+        elif key == "tide":
+            assert arr.shape == (2, 1, lm + 2, mm + 2, 3)
+        else:
+            assert arr.shape[:2] == (lm + 2, mm + 2)
 
 
 def test_input_files_are_column_major_float32(tmp_path):
@@ -105,7 +117,9 @@ def test_input_files_are_column_major_float32(tmp_path):
     assert np.all(a[1:] == 0)
 
 
-@pytest.mark.parametrize("name", ["stommel1948", "lock_exchange", "unstable_jet", "sill_exchange3D", "conservation"])
+@pytest.mark.parametrize("name", ["stommel1948", "lock_exchange", "unstable_jet", "sill_exchange3D", "conservation", "soliton",
+                                  "baines_ridge", "carrier_beach", "upwelling_seaward_wind", "mixed_open_bc", "morel_upwelling",
+                                  "outcrop_seamount", "sill_exchange2D", "sill_exchange2Dtides", "tide_ridge", "wave_sponge"])
 def test_host_read_input_data_equals_oracle(case_factory, name):
     """Two independent restatements of read_input_data (C++ host driver, C oracle) agree bit for bit:
     connectivity, masks, rest thickness (Newton solve when ocrp = 1), sponge, segments, forcing."""
