@@ -18,6 +18,7 @@
 #include "fused.cuh"
 #include "split.cuh"
 #include "diag.cuh"
+#include "orphans.h"
 
 using namespace beom;
 
@@ -55,7 +56,7 @@ struct Ctx {
   std::vector<int> cell_of_point;  // [ndeg+1], -1 = not on this device, -2 = orphan (periodic duplicate)
   int *d_cell = nullptr;
   std::vector<int> orphans;        // vector indices whose dense cell is a periodic mirror
-  std::vector<double> orphan_val;  // [3][nlay][norph] frozen hlay,u,v
+  Orphans orph;                    // their hlay,u,v (host side): frozen, or following the sponge recurrence (orphans.h)
   int nmir = 0;
   int *d_mir_dst = nullptr, *d_mir_src = nullptr;
   SegDev *d_seg = nullptr;
@@ -449,9 +450,8 @@ int beom_gpu_init(const beom_params *par, const beom_fields *fld, const beom_gpu
         alias_of_cell[c] = q;
         if (point_of_cell[c] != 0) {  // orphan
           const int o = point_of_cell[c];
-          if (fld->mk_n[o] > 0.5 || fld->mk_u[o] > 0.5 || fld->mk_v[o] > 0.5 ||
-              (fld->nudg && (fld->nudg[o] != 0.0 || fld->nudg[nd1 + o] != 0.0 || fld->nudg[2 * nd1 + o] != 0.0)))
-            return fail(-9, "beom_gpu_init: unsupported periodic connectivity (aliased point %d is not frozen)", o);
+          if (fld->mk_n[o] > 0.5 || fld->mk_u[o] > 0.5 || fld->mk_v[o] > 0.5)
+            return fail(-9, "beom_gpu_init: unsupported periodic connectivity (aliased point %d is not masked)", o);
           g.orphans.push_back(o);
           g.cell_of_point[o] = -2;
           point_of_cell[c] = 0;
@@ -506,7 +506,10 @@ int beom_gpu_init(const beom_params *par, const beom_fields *fld, const beom_gpu
       CK(cudaMemcpy(g.d_mir_dst, mdst.data(), sizeof(int) * g.nmir, cudaMemcpyHostToDevice));
       CK(cudaMemcpy(g.d_mir_src, msrc.data(), sizeof(int) * g.nmir, cudaMemcpyHostToDevice));
     }
-    g.orphan_val.assign((size_t)3 * nlay * g.orphans.size(), 0.0);
+    g.orph = Orphans();
+    g.orph.nlay = nlay;
+    g.orph.n = g.orphans.size();
+    g.orph.val.assign((size_t)3 * nlay * g.orphans.size(), 0.0);
   }
 
   int rc;
@@ -588,6 +591,39 @@ int beom_gpu_init(const beom_params *par, const beom_fields *fld, const beom_gpu
   D.has_wind = g.any_taus;
   D.has_bdrg = par->bdrg > 1.e-7;
   D.has_tdrg = par->tdrg > 1.e-7;
+  // periodic duplicates inside a sponge are not frozen: the relaxation moves them (orphans.h)
+  if (D.has_nudg && !g.orphans.empty()) {
+    Orphans &O = g.orph;
+    const size_t no = O.n;
+    O.nud.assign(3 * no, 0.0);
+    bool uv = false;
+    for (int f = 0; f < 3; f++)
+      for (size_t k = 0; k < no; k++) {
+        const double c = fld->nudg[(size_t)f * nd1 + g.orphans[k]];
+        O.nud[(size_t)f * no + k] = c;
+        O.live = O.live || c != 0.0;
+        uv = uv || (f > 0 && c != 0.0);
+      }
+    if (O.live) {
+      if (!fld->fnud) return fail(-9, "beom_gpu_init: nudged periodic duplicates need fnud");
+      if (par->variant != BEOM_VARIANT_STANDARD || par->rgld > 0.5)
+        return fail(-9, "beom_gpu_init: unsupported periodic connectivity (a sponge over the duplicate row/column with the 1d/3d/plume variants or the rigid lid)");
+      if (uv && D.has_wind && fld->invf != 0.0)
+        return fail(-9, "beom_gpu_init: unsupported periodic connectivity (a velocity sponge over the duplicate row/column under wind stress: the Ekman term of its target, private_mod.f95:1449-1452)");
+      O.fnud.resize(3 * nl * no);
+      for (int f = 0; f < 3; f++)
+        for (int l = 0; l < nlay; l++)
+          for (size_t k = 0; k < no; k++) O.fnud[((size_t)f * nl + l) * no + k] = fld->fnud[((size_t)f * nl + l) * nd1 + g.orphans[k]];
+      O.has_tide = D.has_tide != 0;
+      O.w_ti = fld->w_ti;
+      if (O.has_tide) {
+        O.tide.resize(6 * no);
+        for (int f = 0; f < 3; f++)
+          for (size_t k = 0; k < no; k++)
+            for (int a = 0; a < 2; a++) O.tide[((size_t)f * no + k) * 2 + a] = fld->tide[((size_t)f * nd1 + g.orphans[k]) * 2 + a];
+      }
+    }
+  }
   if (D.has_wind) {
     if ((rc = dalloc(&tmp, pl * 2))) return rc;
     if ((rc = upload_planes(tmp, fld->taus, 2))) return rc;
@@ -726,7 +762,8 @@ int beom_gpu_upload_state(const double *hlay, const double *u, const double *v) 
   const size_t no = g.orphans.size();
   for (int f = 0; f < 3; f++)
     for (int l = 0; l < g.nlay; l++)
-      for (size_t k = 0; k < no; k++) g.orphan_val[((size_t)f * nl + l) * no + k] = src[f][(size_t)l * g.win_stride + (g.orphans[k] - g.win_first)];
+      for (size_t k = 0; k < no; k++) g.orph.val[((size_t)f * nl + l) * no + k] = src[f][(size_t)l * g.win_stride + (g.orphans[k] - g.win_first)];
+  g.orph.forget();
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(g.stream));
   return 0;
@@ -740,6 +777,7 @@ int beom_gpu_stress(void) {
 int beom_gpu_step(int tstp, double ctim, double ramp, double gene, int upst, int first_three) {
   if (!g.ready) return fail(-20, "beom_gpu_step: not initialised");
   g.D.ctim = ctim; g.D.ramp = ramp; g.D.gene = gene;
+  g.orph.record(ctim, ramp);
   if (g.use_fused && fused_supports(first_three != 0, upst != 0)) {
     Dev D = g.D;
     set_state_pointers(D);
@@ -851,13 +889,14 @@ int beom_gpu_download_state(double *hlay, double *u, double *v) {
   if (!g.ready) return fail(-20, "beom_gpu_download_state: not initialised");
   double *dst[3] = {hlay, u, v};
   const size_t nl = (size_t)g.nlay, no = g.orphans.size();
+  g.orph.replay();  // the steps since the last download, for the duplicates a sponge moves
   for (int f = 0; f < 3; f++) {
     if (!dst[f]) continue;
     int rc = download_planes(dst[f], g.st[f][g.cur], g.nlay);
     if (rc) return rc;
     for (int l = 0; l < g.nlay; l++) {
       if (g.win_first == 0) dst[f][(size_t)l * g.win_stride] = 0.0;  // the discarded cell
-      for (size_t k = 0; k < no; k++) dst[f][(size_t)l * g.win_stride + (g.orphans[k] - g.win_first)] = g.orphan_val[((size_t)f * nl + l) * no + k];
+      for (size_t k = 0; k < no; k++) dst[f][(size_t)l * g.win_stride + (g.orphans[k] - g.win_first)] = g.orph.val[((size_t)f * nl + l) * no + k];
     }
   }
   CK(cudaGetLastError());

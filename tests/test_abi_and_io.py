@@ -8,7 +8,7 @@ import re
 import numpy as np
 import pytest
 
-from beom_b200 import _lib, model, readers
+from beom_b200 import _lib, cases, model, readers
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -161,3 +161,65 @@ def test_fused_step_shared_memory_plan_fits_one_sm(tmp_path):
             assert p["off_ring"] % 128 == 0 and p["seg_bytes"] % 16 == 0 and p["off_wring"] % 16 == 0
             assert p["seg_bytes"] == (groups * 28 + 8) * 8
     assert q["mandatory"] == 15 and q["streams"] <= 32
+
+
+@pytest.mark.parametrize("tide", [False, True])
+def test_nudged_periodic_duplicates_follow_the_sponge_recurrence(tmp_path, tide):
+    """beom_b200/csrc/gpu/orphans.h on the CPU: baines_ridge.m's east/west sponges cover the duplicate row j = mm + 1 of
+    its y-periodic channel, so those vector points (all masks 0, read by nobody, written to every record) relax toward
+    their targets each step (private_mod.f95:1633-1638, 1482, 1567).  The GPU library replays that recurrence on the host
+    at download time; here the same code, compiled without CUDA, must reproduce the oracle bit for bit -- also with a
+    tidal target (cos) and a dt_r ramp."""
+    import ctypes as C
+    import subprocess
+    from oracle.pyoracle import Oracle
+    so = str(tmp_path / "liborphans_host.so")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", os.path.join(ROOT, "tools", "orphans_host.cc"),
+                    "-o", so], check=True, capture_output=True, timeout=300)
+    lib = C.CDLL(so)
+    dp = C.POINTER(C.c_double)
+    lib.orphans_replay.argtypes = [C.c_int, C.c_int, dp, dp, dp, C.c_double, C.c_int, dp, dp]
+    c = cases.baines_ridge(scale=0.3)
+    if tide:
+        td = cases._m2_tide(c.lm, c.mm)
+        td[0, 0, :, :, 0] = 0.05  # a tidal target for eta too (layer 1 only, private_mod.f95:1634) ...
+        td[1, 0, :, :, 0] = 0.3
+        td[0, 0, 0, 0, 0] = 2.0 * np.pi / (12.4206012 / 24.0)  # ... the frequency keeps its slot
+        c.files["tide"] = td
+        c.params_text = c.params_text.replace("dt_r       = 0.", "dt_r       = 0.050000")
+    d = str(tmp_path / "case")
+    hm = model.HostModel.from_block(c.write(d))
+    orc = Oracle(hm.params, d)
+    sub = hm.iarray("subc")
+    dup = np.nonzero(sub[1] == c.mm + 1)[0]
+    dup = dup[dup > 0]
+    assert len(dup) == c.lm + 1
+    for nm in ("mk_n", "mk_u", "mk_v"):
+        assert not np.any(hm.array(nm)[0][dup])            # masked ...
+    nud = np.ascontiguousarray(hm.array("nudg")[:, dup])
+    assert np.count_nonzero(nud) > 20                       # ... but inside the sponges
+    nlay, n = c.nlay, len(dup)
+    fnud = np.ascontiguousarray(hm.array("fnud").reshape(3, nlay, -1)[:, :, dup])
+    tid = np.ascontiguousarray(hm.array("tide")[:, dup, :]) if tide else None
+    val = np.ascontiguousarray(np.stack([hm.array(k)[:, dup] for k in ("hlay", "u", "v")]))
+    start = val.copy()
+    nstep = 200
+    p = hm.params
+    dtd8 = p.dt / 24.0 / 3600.0
+    log, ramp = [], 1.0
+    for tstp in range(1, nstep + 1):  # ctim and ramp as integrate_time computes them (private_mod.f95:1862-1901)
+        ctim = dtd8 * tstp
+        if tstp == 1 or tstp > 3:
+            ramp = ctim / p.dt_r if (p.rsta < 0.5 and ctim < p.dt_r) else 1.0
+        log += [ctim, ramp]
+    log = np.array(log)
+    assert (min(log[1::2]) < 1.0) == tide
+    live = lib.orphans_replay(nlay, n, nud.ctypes.data_as(dp), fnud.ctypes.data_as(dp), tid.ctypes.data_as(dp) if tide else None,
+                              hm.scalar("w_ti") if tide else 0.0, nstep, log.ctypes.data_as(dp), val.ctypes.data_as(dp))
+    assert live == 1
+    orc.advance(1, nstep)
+    for f, nm in enumerate(("hlay", "u", "v")):
+        want = orc.array(nm)[:, dup]
+        assert np.array_equal(val[f], want), nm
+    if tide:
+        assert np.abs(val - start).max() > 1.0e-3  # the duplicates really moved

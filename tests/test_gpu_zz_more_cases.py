@@ -1,0 +1,47 @@
+"""GPU parity on the rest of the reference's test scripts (testcases/*.m beyond the five named configs): every
+script's small version through the C ABI against the CPU oracle, both kernel paths, bit for bit (tidal cases: 1e-11,
+cos).  Each run is its own process with a timeout, so a kernel that wedges on an unusual shape (one-row channels,
+lm = 1, seven layers) fails its test instead of hanging the suite."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+CASES = [
+    ("soliton", 40, {}),                    # periodic in x only, beta plane from fcor.bin
+    ("baines_ridge", 60, {}),               # one-row channel periodic in y, bodf.bin, sponges, moving initial state
+    ("baines_ridge", 60, {"mcbc": "0."}),   # + no_gradient_obc at the two open ends
+    ("carrier_beach", 80, {}),              # wetting/drying: one layer with outcropping, nonzero topl(1)
+    ("upwelling_seaward_wind", 40, {}),     # no input file: uniform tauw, dt_r ramp
+    ("mixed_open_bc", 40, {}),              # mcbc = 0: segments on three sides of a 2-D basin
+    ("morel_upwelling", 60, {}),            # lm = 1 periodic in x, outcropping, body force
+    ("outcrop_seamount", 40, {}),           # five layers, most of them grounded
+    ("sill_exchange2D", 40, {}),            # 200-point sponges, Leith viscosity, quadratic-drag switch
+    ("sill_exchange2Dtides", 40, {}),       # tide.bin
+    ("tide_ridge", 40, {}),                 # seven layers, tide.bin, dt_r ramp
+    ("wave_sponge", 40, {}),                # sponges on four sides
+]
+
+
+# Written after round 1's GPU budget was spent: none of these has run on hardware yet (the CPU side of each -- case
+# set-up, oracle, the connectivity / segment analysis of beom_gpu_init restated in Python, the comparison logic of the
+# worker -- has).  Non-strict xfail keeps the suite's verdict on the tests that HAVE been observed; an XPASS here is
+# new evidence, an XFAIL a bug to fix.  To be promoted to plain tests as soon as they have been seen on a B200.
+@pytest.mark.xfail(strict=False, reason="not yet observed on a GPU (round-1 GPU budget exhausted before these cases existed)")
+@pytest.mark.parametrize("fused", [0, 1])
+@pytest.mark.parametrize("name,nsteps,extra", CASES, ids=["%s%s" % (n, "-obc" if e else "") for n, _, e in CASES])
+def test_reference_script_bit_exact(name, nsteps, extra, fused):
+    cmd = [sys.executable, os.path.join(ROOT, "tests", "case_worker.py"), name, str(nsteps), str(fused), json.dumps(extra)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert lines, r.stdout[-2000:] + r.stderr[-2000:]
+    res = json.loads(lines[-1])
+    assert r.returncode == 0 and not res["bad"], res
+    assert res["path"] in ("fused", "split") and (fused or res["path"] == "split")
+    assert res["moved"] > 0.0  # the case is not a trivial state of rest after nsteps ... except where it should be
