@@ -357,6 +357,7 @@ void read_forcing_files(beom_host *h) {
     auto at = [&](int i, int j, int c) { return f[((size_t)c * (mm + 2) + j) * (lm + 2) + i]; };
     h->nudg.assign(n * 3, 0.0);
     bool live = false;
+#pragma omp parallel for schedule(static) reduction(|| : live)
     for (int p = 1; p <= ndeg; p++) {
       const int i = si[p], j = sj[p];
       const double ne = (double)at(i, j, 0);
@@ -373,16 +374,21 @@ void read_forcing_files(beom_host *h) {
       index_boundary_points(h, f);
     }
     h->fnud.assign(n * nlay * 3, 0.0);
+#pragma omp parallel for collapse(2) schedule(static)
     for (int l = 0; l < nlay; l++)
       for (int p = 1; p <= ndeg; p++) h->fnud[(size_t)l * n + p] = h->hlay[(size_t)l * n + p];
   }
 
+  StageTimer *t_init = new StageTimer("  init.bin: read");
   f = slurp(h->idir, "init", plane * nlay * 3, &present);  // pm:882-910
+  delete t_init;
   h->has_init = present;
   if (present) {
+    StageTimer t_g("  init.bin: gather");
     if (h->fnud.empty()) h->fnud.assign(n * nlay * 3, 0.0);
     auto at = [&](int i, int j, int l, int c) { return (double)f[(((size_t)c * nlay + l) * (mm + 2) + j) * (lm + 2) + i]; };
     double *fn = h->fnud.data(), *fu = fn + n * nlay, *fv = fu + n * nlay;
+#pragma omp parallel for collapse(2) schedule(static)
     for (int l = 0; l < nlay; l++)
       for (int p = 1; p <= ndeg; p++) {
         const int i = si[p], j = sj[p];
@@ -410,6 +416,7 @@ void read_forcing_files(beom_host *h) {
   h->has_hdot = present;
   if (present) {
     h->hdot.assign(n * nlay, 0.0);
+#pragma omp parallel for collapse(2) schedule(static)
     for (int l = 0; l < nlay; l++)
       for (int p = 1; p <= ndeg; p++) h->hdot[(size_t)l * n + p] = (double)f[((size_t)l * (mm + 2) + sj[p]) * (lm + 2) + si[p]];
   }
@@ -421,6 +428,7 @@ void read_forcing_files(beom_host *h) {
   h->has_taus = present;
   if (present) {
     std::fill(h->taus.begin(), h->taus.end(), 0.0);
+#pragma omp parallel for schedule(static)
     for (int p = 1; p <= ndeg; p++) {
       const size_t k = (size_t)sj[p] * (lm + 2) + si[p];
       h->taus[p] = (double)f[k];
@@ -447,6 +455,7 @@ void read_forcing_files(beom_host *h) {
     for (size_t k = 0; k < plane; k++) acc = acc + f[k];
     h->fcor[0] = (double)(acc / (float)plane);
     auto at = [&](int i, int j) { return f[(size_t)j * (lm + 2) + i]; };
+#pragma omp parallel for schedule(static)
     for (int p = 1; p <= ndeg; p++) {
       const int i = si[p], j = sj[p];
       if (i > 0 && j > 0) {
@@ -470,10 +479,18 @@ void read_input_data(beom_host *h) {
   StageTimer t_all("read_input_data");
   {
   StageTimer t("initialize_variables");
-  h->neig.assign(n * 8, 0); h->subc.assign(n * 2, 0); h->posc.assign(n, 0);
-  for (auto *v : {&h->mk_u, &h->mk_v, &h->mk_n, &h->mkpe, &h->mkpi, &h->h_th, &h->Ow, &h->Os, &h->Osum_, &h->pi_s}) v->assign(n, 0.0);
-  h->fcor.assign(n, P.f0);
-  for (auto *v : {&h->h_0, &h->hlay, &h->u, &h->v}) v->assign(n * nlay, 0.0);
+  // first touch of ~250 bytes per point: one vector per thread at a time (4 GB at 4096 x 4096 x 4)
+  std::vector<double> *dv[] = {&h->mk_u, &h->mk_v, &h->mk_n, &h->mkpe, &h->mkpi, &h->h_th, &h->Ow, &h->Os, &h->Osum_, &h->pi_s,
+                               &h->fcor, &h->h_0, &h->hlay, &h->u, &h->v};
+  const int ndv = (int)(sizeof dv / sizeof dv[0]);
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int k = 0; k < ndv + 3; k++) {
+    if (k == ndv) h->neig.assign(n * 8, 0);
+    else if (k == ndv + 1) h->subc.assign(n * 2, 0);
+    else if (k == ndv + 2) h->posc.assign(n, 0);
+    else if (k == 10) dv[k]->assign(n, P.f0);
+    else dv[k]->assign(k > 10 ? n * nlay : n, 0.0);
+  }
   }
 
   // default flat bottom of depth cext**2/grav (pm:119-121), replaced by h_bo.bin if present
@@ -517,6 +534,7 @@ void read_input_data(beom_host *h) {
   }
 
   if (P.ocrp < 0.5) {  // pm:154-175: layers stacked from the bottom, no outcrop
+#pragma omp parallel for schedule(static)
     for (int p = 1; p <= h->ndeg; p++) {
       if (!(h->mk_n[p] > 0.5)) continue;
       const double depth = h->h2d(h->subc[p], h->subc[n + p]);
@@ -533,9 +551,11 @@ void read_input_data(beom_host *h) {
 
   // h_0.bin holds float32 (pm:185-194); write_array reads it back (pm:2839-2846)
   h->h_0_r4.resize((size_t)h->ndeg * nlay);
+#pragma omp parallel for collapse(2) schedule(static)
   for (int l = 0; l < nlay; l++)
     for (int p = 1; p <= h->ndeg; p++) h->h_0_r4[(size_t)l * h->ndeg + (p - 1)] = (float)h->h_0[(size_t)l * n + p];
 
+#pragma omp parallel for collapse(2) schedule(static)
   for (int l = 0; l < nlay; l++)  // pm:198-200
     for (size_t q = 0; q < n; q++) h->hlay[(size_t)l * n + q] = h->h_0[(size_t)l * n + q] * h->mk_n[q];
 
