@@ -223,3 +223,39 @@ def test_nudged_periodic_duplicates_follow_the_sponge_recurrence(tmp_path, tide)
         assert np.array_equal(val[f], want), nm
     if tide:
         assert np.abs(val - start).max() > 1.0e-3  # the duplicates really moved
+
+
+def test_conservation_integrals_from_the_output_files(tmp_path):
+    """readers.conservation_integrals = testcases/conservation.m:116-211 on the files write_outputs produces (the state
+    here comes from the oracle; pvor.bin is the diag = 1 record).  The reference's documentation (p.4-6) claims for this
+    case: layer volumes conserved to round-off (here limited by the float32 records), K + P within a few per cent,
+    potential enstrophy nearly conserved; the mean relative vorticity of a doubly periodic domain is zero."""
+    from oracle.pyoracle import Oracle
+    from tests.conftest import SMALL
+    c = cases.conservation(**SMALL["conservation"])
+    blk = c.write(str(tmp_path))
+    hm = model.HostModel.from_block(blk, write_outputs=True)
+    orc = Oracle(hm.params, str(tmp_path))
+    lib = hm.lib
+    lib.beom_host_write_diag_record.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_float)]
+    nrec, per = 6, 400
+    for r in range(nrec):
+        if r:
+            orc.advance((r - 1) * per + 1, r * per)
+        for k in ("hlay", "u", "v"):
+            hm.array(k)[:] = orc.array(k)
+        assert lib.beom_host_write_outputs(hm.h, r * per * hm.params.dt / 86400.0) == 0
+        pv = orc.record("pvor")
+        assert lib.beom_host_write_diag_record(hm.h, b"pvor", pv.ctypes.data_as(C.POINTER(C.c_float))) == 0
+    ci = readers.conservation_integrals(str(tmp_path))
+    assert ci["volu"].shape == (nrec, c.nlay) and ci["taxi"].size == nrec
+    assert np.all(np.abs(ci["volu"] - ci["volu"][0]) < 2.0e-6)            # metres of ~100: float32 eta records
+    assert ci["vstd"][-1, 0] > 1.0e-3                                      # while the layers themselves move
+    etot = ci["pote"][:, 0] + ci["kine"].sum(axis=1)
+    assert ci["kine"][0].sum() == 0.0 and ci["kine"][-1].sum() > 0.1 * etot[0]
+    # K + barotropic P as the script plots them: over the seamount some energy sits in the interface (baroclinic P, which
+    # the script leaves out), so the sum wanders by up to ~10 % on this coarse 30 km grid instead of staying put
+    assert np.all(np.abs(etot / etot[0] - 1.0) < 0.15)
+    assert np.all(np.abs(ci["enst"] / ci["enst"][0] - 1.0) < 0.02)
+    f0 = hm.params.f0
+    assert np.all(np.abs(ci["rvor"]) < 1.0e-6 * f0) and ci["rstd"][-1, 0] > 1.0e-4 * f0
