@@ -18,6 +18,7 @@
 #include "fused.cuh"
 #include "split.cuh"
 #include "diag.cuh"
+#include "layout.h"
 #include "orphans.h"
 
 using namespace beom;
@@ -81,6 +82,8 @@ struct Ctx {
   size_t halo_cap = 0;
   size_t big_allocs = 0;
   bool torus = false;              // periodic domain whose aliases form a complete torus: deep ghost cells exist, the fused step may run
+  bool ring = false;               // y-periodic domain split into y-slabs: the halo exchange is ring-closed (layout.h)
+  HaloRows halo;                   // peers and rows of the packed halo exchange
   float *rec_f32 = nullptr;        // [nlay] dense float32 planes: one diagnostic record
   float *rec_stage = nullptr;      // vector-layout staging of one layer of a record
   double *diag_h0 = nullptr;       // [nlay] dense h_0 (beom_gpu_diagnostics)
@@ -170,13 +173,14 @@ int sync_fields(std::initializer_list<Item> items, bool remote = true, cudaStrea
     if (t.n == 0) return 0;
     const size_t per_plane = (size_t)G * g.NX, count = per_plane * t.total;
     if (count > g.halo_cap) return fail(-71, "sync_fields: halo buffer too small");
-    const int lo = g.rank > 0 ? g.rank - 1 : -1, hi = g.rank < g.nranks - 1 ? g.rank + 1 : -1;
+    const HaloRows &h = g.halo;  // plain slab neighbours, or the ring of a y-periodic domain (layout.h)
+    const int lo = h.peer_lo, hi = h.peer_hi;
     const unsigned blocks = (unsigned)((per_plane + 255) / 256);
-    k_halo_pack<<<dim3(blocks, (unsigned)t.total, 2), 256, 0, st>>>(t, g.plane, g.NX, g.D.y_lo, g.D.y_hi, g.halo_send[0], g.halo_send[1]);
+    k_halo_pack<<<dim3(blocks, (unsigned)t.total, 2), 256, 0, st>>>(t, g.plane, g.NX, h.send_lo, h.send_hi, g.halo_send[0], g.halo_send[1]);
     g.launches++;
     int rc = comm_exchange(g.halo_send[0], g.halo_recv[0], lo, g.halo_send[1], g.halo_recv[1], hi, count, st, &g_err);
     if (rc) return rc;
-    k_halo_unpack<<<dim3(blocks, (unsigned)t.total, 2), 256, 0, st>>>(t, g.plane, g.NX, g.D.y_lo, g.D.y_hi, g.halo_recv[0], g.halo_recv[1], lo >= 0, hi >= 0);
+    k_halo_unpack<<<dim3(blocks, (unsigned)t.total, 2), 256, 0, st>>>(t, g.plane, g.NX, h.recv_lo, h.recv_hi, g.halo_recv[0], g.halo_recv[1], lo >= 0, hi >= 0);
     g.launches++;
   }
   return 0;
@@ -377,142 +381,35 @@ int beom_gpu_init(const beom_params *par, const beom_fields *fld, const beom_gpu
 
   const int lm = g.lm, mm = g.mm, nlay = g.nlay, ndeg = g.ndeg;
   const size_t nd1 = (size_t)ndeg + 1;
-  const int32_t *si = fld->subc, *sj = fld->subc + nd1;
+  const int32_t *sj = fld->subc + nd1;
 
-  // y-slab owned by this rank: rows 1..mm+1 split evenly
-  {
-    const int rows = mm + 1, base = rows / g.nranks, rem = rows % g.nranks;
-    g.j0 = 1 + g.rank * base + std::min(g.rank, rem);
-    g.j1 = g.j0 + base + (g.rank < rem ? 1 : 0) - 1;
-    if (g.j1 < g.j0) return fail(-5, "beom_gpu_init: more ranks than grid rows");
-  }
-  g.NX = ((lm + GX0 + 34) + 15) / 16 * 16;  // room for the fused kernel's last 28-column tile (+ 4 staged columns) past x_hi
-  g.NY = (g.j1 - g.j0 + 1) + 2 * G;
-  g.plane = (size_t)g.NX * g.NY;
-  if (g.plane > 0x7fffffffull) return fail(-6, "beom_gpu_init: plane too large for 32-bit cell offsets");
-  const int j_off = G - g.j0;  // Y = j + j_off
-
-  // vector points on this device: rows j0-G .. j1+G (vector order is j outer, i inner: contiguous)
-  g.cell_of_point.assign(nd1, -1);
-  g.p_lo = ndeg + 1; g.p_hi = 0;
-  for (int p = 1; p <= ndeg; p++) {
-    const int j = sj[p], i = si[p];
-    if (j < g.j0 - G || j > g.j1 + G) continue;
-    if (i < 1 - GX0 || i + GX0 >= g.NX) return fail(-7, "beom_gpu_init: subc out of range at point %d", p);
-    g.cell_of_point[p] = (j + j_off) * g.NX + (i + GX0);
-    g.p_lo = std::min(g.p_lo, p);
-    g.p_hi = std::max(g.p_hi, p);
-  }
-  if (g.p_hi < g.p_lo) return fail(-8, "beom_gpu_init: no grid points on rank %d", g.rank);
-
-  // dense flags + point-of-cell map
-  std::vector<uint8_t> hflags(g.plane, 0);
-  std::vector<int> point_of_cell(g.plane, 0);
-  for (int p = g.p_lo; p <= g.p_hi; p++) {
-    const int c = g.cell_of_point[p];
-    if (c < 0) continue;
-    uint8_t f = F_ACT;
-    if (fld->mk_n[p] > 0.5) f |= F_N;
-    if (fld->mk_u[p] > 0.5) f |= F_U;
-    if (fld->mk_v[p] > 0.5) f |= F_V;
-    if (fld->mkpe[p] > 0.5) f |= F_PE;
-    if (fld->mkpi[p] > 0.5) f |= F_PI;
-    hflags[c] = f;
-    point_of_cell[c] = p;
-  }
-  // mirror cells: wherever neig(k,p) is not the point sitting at (i+di, j+dj) (periodic aliases,
-  // private_mod.f95:614-685).  A vector point whose own cell must show another point's values is an
-  // "orphan": nothing ever reads it and its masks are zero, so its state is frozen.
-  {
-    static const int di[8] = {1, 1, 0, -1, -1, -1, 0, 1}, dj[8] = {0, 1, 1, 1, 0, -1, -1, -1};
-    std::vector<int> mdst, msrc;
-    std::vector<int> alias_of_cell(g.plane, -1);
-    for (int p = g.p_lo; p <= g.p_hi; p++) {
-      if (g.cell_of_point[p] < 0) continue;
-      const int j = sj[p], i = si[p];
-      if (j < g.j0 - 1 || j > g.j1 + 1) continue;  // only cells whose neighbours are read
-      for (int k = 0; k < 8; k++) {
-        const int q = fld->neig[(size_t)p * 8 + k];
-        const int c = (j + dj[k] + j_off) * g.NX + (i + di[k] + GX0);
-        if (q == point_of_cell[c] && alias_of_cell[c] < 0) continue;
-        if (q == 0) {
-          if (alias_of_cell[c] == 0 || point_of_cell[c] == 0) continue;
-          return fail(-9, "beom_gpu_init: neig(%d,%d) = 0 but a grid point exists there", k + 1, p);
-        }
-        if (alias_of_cell[c] >= 0) {
-          if (alias_of_cell[c] != q) return fail(-9, "beom_gpu_init: inconsistent connectivity at point %d", p);
-          continue;
-        }
-        if (q < g.p_lo || q > g.p_hi || g.cell_of_point[q] < 0) {
-          if (g.nranks > 1) continue;  // alias source lives on another rank: filled by the halo exchange
-          return fail(-9, "beom_gpu_init: neig(%d,%d) = %d is out of range", k + 1, p, q);
-        }
-        alias_of_cell[c] = q;
-        if (point_of_cell[c] != 0) {  // orphan
-          const int o = point_of_cell[c];
-          if (fld->mk_n[o] > 0.5 || fld->mk_u[o] > 0.5 || fld->mk_v[o] > 0.5)
-            return fail(-9, "beom_gpu_init: unsupported periodic connectivity (aliased point %d is not masked)", o);
-          g.orphans.push_back(o);
-          g.cell_of_point[o] = -2;
-          point_of_cell[c] = 0;
-        }
-        mdst.push_back(c);
-        msrc.push_back(g.cell_of_point[q]);
-      }
-    }
-    // a mirror's source may itself have been turned into a mirror/orphan: forbid chains
-    for (size_t k = 0; k < msrc.size(); k++)
-      if (msrc[k] < 0) return fail(-9, "beom_gpu_init: chained periodic aliases are not supported");
-    // Deep torus ghosts.  The fused step recomputes its halo (2 columns, 3-4 rows) instead of re-reading it, so on a
-    // periodic domain the cells up to 3 columns / 4 rows outside the core must show periodic images too -- cells the
-    // reference never indexes.  Only when the reference's own aliases (above) form a complete torus: every row
-    // 1..mm aliased in x (xper), every column 1..lm aliased in y (yper).
-    g.torus = false;
-    if (!mdst.empty() && g.nranks == 1 && (par->xper > 0.5 || par->yper > 0.5)) {
-      const bool xp = par->xper > 0.5, yp = par->yper > 0.5;
-      auto wrap = [](int k, int n) { return ((k - 1) % n + n) % n + 1; };
-      auto cell = [&](int i, int j) { return (j + j_off) * g.NX + (i + GX0); };
-      std::vector<int> img(g.plane, -1);
-      for (size_t k = 0; k < mdst.size(); k++) img[mdst[k]] = msrc[k];
-      bool complete = true;
-      if (xp) for (int j = 1; j <= mm && complete; j++) complete = img[cell(0, j)] == cell(lm, j) && img[cell(lm + 1, j)] == cell(1, j);
-      if (yp) for (int i = 1; i <= lm && complete; i++) complete = img[cell(i, 0)] == cell(i, mm) && img[cell(i, mm + 1)] == cell(i, 1);
-      for (size_t k = 0; k < mdst.size() && complete; k++) {  // and nothing else: every alias is the torus image
-        const int X = mdst[k] % g.NX - GX0, Y = mdst[k] / g.NX - j_off;
-        complete = msrc[k] == cell(xp ? wrap(X, lm) : X, yp ? wrap(Y, mm) : Y);
-      }
-      if (complete) {
-        for (int j = 1 - G; j <= mm + 1 + G; j++)
-          for (int i = -3; i <= lm + 4; i++) {
-            if (j + j_off < 0 || j + j_off >= g.NY || i + GX0 < 0 || i + GX0 >= g.NX) continue;
-            const int c = cell(i, j);
-            if (img[c] >= 0 || point_of_cell[c] != 0) continue;  // an alias of the reference, or a vector point of its own
-            const int is = xp ? wrap(i, lm) : i, js = yp ? wrap(j, mm) : j;
-            if ((is == i && js == j) || is < 0 || is > lm + 1 || js < 0 || js > mm + 1) continue;
-            const int src = cell(is, js);
-            if (point_of_cell[src] == 0 || img[src] >= 0) continue;  // nothing there, or itself a mirror
-            mdst.push_back(c);
-            msrc.push_back(src);
-          }
-        g.torus = true;
-      }
-    }
-    g.nmir = (int)mdst.size();
-    for (int k = 0; k < g.nmir; k++)
-      hflags[mdst[k]] = (uint8_t)((hflags[msrc[k]] & ~F_ACT) | ((hflags[msrc[k]] & F_ACT) ? F_GHOST : 0));
-    if (g.nmir) {
-      int rc;
-      if ((rc = dalloc(&g.d_mir_dst, (size_t)g.nmir, false)) || (rc = dalloc(&g.d_mir_src, (size_t)g.nmir, false))) return rc;
-      CK(cudaMemcpy(g.d_mir_dst, mdst.data(), sizeof(int) * g.nmir, cudaMemcpyHostToDevice));
-      CK(cudaMemcpy(g.d_mir_src, msrc.data(), sizeof(int) * g.nmir, cudaMemcpyHostToDevice));
-    }
-    g.orph = Orphans();
-    g.orph.nlay = nlay;
-    g.orph.n = g.orphans.size();
-    g.orph.val.assign((size_t)3 * nlay * g.orphans.size(), 0.0);
-  }
-
+  // dense layout of this rank: slab rows, cell map, flags, periodic images, duplicates (layout.h)
+  Layout lay;
+  if (analyse_layout(lay, lm, mm, ndeg, par->xper > 0.5, par->yper > 0.5, g.rank, g.nranks, fld->subc, fld->neig, fld->mk_n, fld->mk_u,
+                     fld->mk_v, fld->mkpe, fld->mkpi))
+    return fail(lay.rc, "%s", lay.error.c_str());
+  g.j0 = lay.j0; g.j1 = lay.j1;
+  g.NX = lay.NX; g.NY = lay.NY; g.plane = lay.plane;
+  g.p_lo = lay.p_lo; g.p_hi = lay.p_hi;
+  g.cell_of_point = lay.cell_of_point;
+  g.orphans = lay.orphans;
+  g.torus = lay.torus;
+  g.ring = lay.ring;
+  g.halo = halo_rows(g.rank, g.nranks, g.ring, G, G + (g.j1 - g.j0));
+  const int j_off = lay.j_off;  // Y = j + j_off
+  const std::vector<uint8_t> &hflags = lay.flags;
   int rc;
+  g.nmir = (int)lay.mdst.size();
+  if (g.nmir) {
+    if ((rc = dalloc(&g.d_mir_dst, (size_t)g.nmir, false)) || (rc = dalloc(&g.d_mir_src, (size_t)g.nmir, false))) return rc;
+    CK(cudaMemcpy(g.d_mir_dst, lay.mdst.data(), sizeof(int) * g.nmir, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(g.d_mir_src, lay.msrc.data(), sizeof(int) * g.nmir, cudaMemcpyHostToDevice));
+  }
+  g.orph = Orphans();
+  g.orph.nlay = nlay;
+  g.orph.n = g.orphans.size();
+  g.orph.val.assign((size_t)3 * nlay * g.orphans.size(), 0.0);
+
   if ((rc = dalloc(&g.flags, g.plane, false))) return rc;
   CK(cudaMemcpy(g.flags, hflags.data(), g.plane, cudaMemcpyHostToDevice));
   if ((rc = dalloc(&g.d_cell, nd1, false))) return rc;
@@ -721,7 +618,8 @@ int beom_gpu_init(const beom_params *par, const beom_fields *fld, const beom_gpu
 
   g.use_fused = false;
   if (opt.fused) {
-    rc = fused_configure(g.D, g.P, g.torus ? 0 : g.nmir, g.nranks, &g.use_fused);
+    // periodic images that are not a complete single-rank torus (incl. the ring of a y-periodic slab chain): split path
+    rc = fused_configure(g.D, g.P, g.torus ? 0 : g.nmir + (g.ring ? 1 : 0), g.nranks, &g.use_fused);
     if (rc) return rc;
     if (g.use_fused)
       for (int f = 0; f < 5; f++)
@@ -757,8 +655,9 @@ int beom_gpu_upload_state(const double *hlay, const double *u, const double *v) 
       k_scatter<double><<<(n + 255) / 256, 256, 0, g.stream>>>(g.st[f][0] + (size_t)l * pl, g.stage + ((size_t)f * nl + l) * n, g.d_cell, g.p_lo, n);
       g.launches++;
     }
-  // halo rows come straight from the caller's arrays: no exchange here (upload is not a collective)
-  for (int f = 0; f < 3; f++) sync_fields({{g.st[f][0], g.nlay}}, false);
+  // halo rows come straight from the caller's arrays: no exchange here (upload is not a collective) -- except across the
+  // seam of a y-periodic slab chain, whose images are another rank's rows (every rank uploads, so the ring closes)
+  for (int f = 0; f < 3; f++) sync_fields({{g.st[f][0], g.nlay}}, g.ring);
   const size_t no = g.orphans.size();
   for (int f = 0; f < 3; f++)
     for (int l = 0; l < g.nlay; l++)

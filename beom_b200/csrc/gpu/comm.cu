@@ -101,15 +101,13 @@ int comm_size() { return g_size; }
 int comm_exchange(const double *send_lo, double *recv_lo, int peer_lo, const double *send_hi, double *recv_hi, int peer_hi,
                   size_t count, cudaStream_t s, std::string *err) {
   if (!g_comm) { if (err) *err = "comm_exchange: communicator not initialised"; return -44; }
+  // Sends in the order (lo, hi), receives in the order (hi, lo): on a two-rank ring both peers are the same rank, and
+  // messages between one pair match in posting order -- what this rank sends "down" is what the peer receives "from above".
   NC(api.GroupStart(), "ncclGroupStart");
-  if (peer_lo >= 0) {
-    NC(api.Send(send_lo, count, ncclDouble, peer_lo, g_comm, s), "ncclSend");
-    NC(api.Recv(recv_lo, count, ncclDouble, peer_lo, g_comm, s), "ncclRecv");
-  }
-  if (peer_hi >= 0) {
-    NC(api.Send(send_hi, count, ncclDouble, peer_hi, g_comm, s), "ncclSend");
-    NC(api.Recv(recv_hi, count, ncclDouble, peer_hi, g_comm, s), "ncclRecv");
-  }
+  if (peer_lo >= 0) NC(api.Send(send_lo, count, ncclDouble, peer_lo, g_comm, s), "ncclSend");
+  if (peer_hi >= 0) NC(api.Send(send_hi, count, ncclDouble, peer_hi, g_comm, s), "ncclSend");
+  if (peer_hi >= 0) NC(api.Recv(recv_hi, count, ncclDouble, peer_hi, g_comm, s), "ncclRecv");
+  if (peer_lo >= 0) NC(api.Recv(recv_lo, count, ncclDouble, peer_lo, g_comm, s), "ncclRecv");
   NC(api.GroupEnd(), "ncclGroupEnd");
   return 0;
 }

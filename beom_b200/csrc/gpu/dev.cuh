@@ -15,16 +15,9 @@
 #include <cstdint>
 
 #include "../../../include/beom_gpu.h"
+#include "layout.h"  // G, GX0 and the per-cell flag bits F_N .. F_GHOST
 
 namespace beom {
-
-constexpr int G = 4;    // halo width (cells); the fused step needs 3
-constexpr int GX0 = 15;  // X = i + GX0  -> i = 1 sits at X = 16: the fused step's row segments start on 128-byte lines
-
-// per-cell flag bits (the reference's 0./1. masks, private_mod.f95:54-58, plus "is a vector point")
-// F_GHOST: the cell shows a periodic image of an active cell (a mirror cell): never updated in place, but the fused
-// step, which recomputes its halo instead of re-reading it, evaluates it like the cell it mirrors
-enum : uint8_t { F_N = 1, F_U = 2, F_V = 4, F_PE = 8, F_PI = 16, F_ACT = 32, F_GHOST = 64 };
 
 struct Dev {
   // geometry

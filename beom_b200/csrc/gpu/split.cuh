@@ -548,22 +548,23 @@ __device__ __forceinline__ double *halo_plane(const HaloTab &t, int gp, size_t p
   while (k + 1 < t.n && gp >= t.off[k + 1]) k++;
   return t.p[k] + (size_t)(gp - t.off[k]) * plane;
 }
-// blockIdx.z = 0: rows y_lo .. y_lo+G-1 -> send_lo; 1: rows y_hi-G+1 .. y_hi -> send_hi
-__global__ void k_halo_pack(const __grid_constant__ HaloTab t, size_t plane, int NX, int y_lo, int y_hi, double *send_lo, double *send_hi) {
+// blockIdx.z = 0: G rows from row_lo -> send_lo; 1: G rows from row_hi -> send_hi (layout.h: halo_rows; plain slabs send
+// y_lo .. y_lo+G-1 and y_hi-G+1 .. y_hi, the last rank of a y-periodic ring one row lower)
+__global__ void k_halo_pack(const __grid_constant__ HaloTab t, size_t plane, int NX, int row_lo, int row_hi, double *send_lo, double *send_hi) {
   const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x, n = (size_t)G * NX;
   if (k >= n) return;
   const int gp = blockIdx.y;
-  const double *src = halo_plane(t, gp, plane) + (size_t)(blockIdx.z == 0 ? y_lo : y_hi - G + 1) * NX;
+  const double *src = halo_plane(t, gp, plane) + (size_t)(blockIdx.z == 0 ? row_lo : row_hi) * NX;
   (blockIdx.z == 0 ? send_lo : send_hi)[(size_t)gp * n + k] = src[k];
 }
-// blockIdx.z = 0: recv_lo -> rows y_lo-G .. y_lo-1; 1: recv_hi -> rows y_hi+1 .. y_hi+G
-__global__ void k_halo_unpack(const __grid_constant__ HaloTab t, size_t plane, int NX, int y_lo, int y_hi, const double *recv_lo, const double *recv_hi,
+// blockIdx.z = 0: recv_lo -> G rows from row_lo (plain: y_lo-G); 1: recv_hi -> G rows from row_hi (plain: y_hi+1)
+__global__ void k_halo_unpack(const __grid_constant__ HaloTab t, size_t plane, int NX, int row_lo, int row_hi, const double *recv_lo, const double *recv_hi,
                               int has_lo, int has_hi) {
   const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x, n = (size_t)G * NX;
   if (k >= n) return;
   if (blockIdx.z == 0 ? !has_lo : !has_hi) return;
   const int gp = blockIdx.y;
-  double *dst = halo_plane(t, gp, plane) + (size_t)(blockIdx.z == 0 ? y_lo - G : y_hi + 1) * NX;
+  double *dst = halo_plane(t, gp, plane) + (size_t)(blockIdx.z == 0 ? row_lo : row_hi) * NX;
   dst[k] = (blockIdx.z == 0 ? recv_lo : recv_hi)[(size_t)gp * n + k];
 }
 

@@ -24,7 +24,8 @@ def main():
     if name == "synthetic_basin":
         c = cases.synthetic_basin(n=300, mm=170, nlay=4)
     else:
-        c = cases.sill_exchange3D(lx=6.0e3, ly=100.0e3)
+        from tests.conftest import SMALL
+        c = cases.CASES[name](**SMALL.get(name, {}))
     d = tempfile.mkdtemp(prefix="beom_mg%d_" % rank)
     blk = c.write(d)
     hm = model.HostModel.from_block(blk)
@@ -37,14 +38,20 @@ def main():
     hl, u, v = gm.download_state()
     aux = gm.download_aux()
     sl = slice(own_first, own_first + own_count)
+    # frozen periodic duplicates carry no meaningful fluxes or histories (their state proper is compared)
+    keep = np.ones(own_count, dtype=bool)
+    if hm.params.xper > 0.5 or hm.params.yper > 0.5:
+        sub = hm.iarray("subc")[:, sl]
+        keep = ~((sub[0] == c.lm + 1) | (sub[1] == c.mm + 1))
     bad = []
     for nm, got in (("hlay", hl), ("u", u), ("v", v), ("h_u", aux[0]), ("h_v", aux[1])):
         want = orc.array(nm)
-        if not np.array_equal(got[:, sl], want[:, sl]):
-            bad.append("%s (max abs %.3e)" % (nm, float(np.max(np.abs(got[:, sl] - want[:, sl])))))
+        m = keep if nm in ("h_u", "h_v") else slice(None)
+        if not np.array_equal(got[:, sl][:, m], want[:, sl][:, m]):
+            bad.append("%s (max abs %.3e)" % (nm, float(np.max(np.abs(got[:, sl][:, m] - want[:, sl][:, m])))))
     for nm, got in (("rs_h", aux[2]), ("dmdx", aux[3]), ("dmdy", aux[4])):
         want = orc.array(nm)
-        if not np.array_equal(got[:, sl], want[:, sl]):
+        if not np.array_equal(got[:, sl][:, keep], want[:, sl][:, keep]):
             bad.append(nm)
     path = gm.path
     gm.close()

@@ -55,8 +55,15 @@ def test_rendezvous_over_gloo():
     assert out[0][2] == out[1][2] == [(1, 251), (252, 502)]
 
 
+_UNSEEN = pytest.mark.xfail(strict=False, reason="not yet observed on GPUs (written after round 1's GPU budget was spent); the index "
+                                                 "logic of the ring / x-periodic slabs is checked on the CPU in tests/test_layout.py")
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,nsteps,fused", [("synthetic_basin", 12, 1), ("synthetic_basin", 9, 0), ("sill_exchange3D", 12, 1)])
+@pytest.mark.parametrize("name,nsteps,fused", [("synthetic_basin", 12, 1), ("synthetic_basin", 9, 0), ("sill_exchange3D", 12, 1),
+                                               pytest.param("conservation", 12, 0, marks=_UNSEEN),   # y-periodic: ring-closed exchange
+                                               pytest.param("unstable_jet", 12, 1, marks=_UNSEEN),   # (fused asked for, split expected)
+                                               pytest.param("soliton", 12, 0, marks=_UNSEEN)])       # x-periodic slabs
 def test_two_ranks_bit_exact(name, nsteps, fused):
     import torch
     if torch.cuda.device_count() < 2:
