@@ -13,6 +13,8 @@ pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
+_timed_out = []  # a worker that hangs is killed after 120 s; the remaining ones are then skipped
+
 CASES = [
     ("soliton", 40, {}),                    # periodic in x only, beta plane from fcor.bin
     ("baines_ridge", 60, {}),               # one-row channel periodic in y, bodf.bin, sponges, moving initial state
@@ -37,8 +39,14 @@ CASES = [
 @pytest.mark.parametrize("fused", [0, 1])
 @pytest.mark.parametrize("name,nsteps,extra", CASES, ids=["%s%s" % (n, "-obc" if e else "") for n, _, e in CASES])
 def test_reference_script_bit_exact(name, nsteps, extra, fused):
+    if _timed_out:
+        pytest.skip("an earlier worker (%s) ran into its timeout: not spending more GPU time on possibly wedged kernels" % _timed_out[0])
     cmd = [sys.executable, os.path.join(ROOT, "tests", "case_worker.py"), name, str(nsteps), str(fused), json.dumps(extra)]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT)
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=120, cwd=ROOT)
+    except subprocess.TimeoutExpired:
+        _timed_out.append("%s fused=%d" % (name, fused))
+        raise
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert lines, r.stdout[-2000:] + r.stderr[-2000:]
     res = json.loads(lines[-1])
