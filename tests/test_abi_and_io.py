@@ -259,3 +259,57 @@ def test_conservation_integrals_from_the_output_files(tmp_path):
     assert np.all(np.abs(ci["enst"] / ci["enst"][0] - 1.0) < 0.02)
     f0 = hm.params.f0
     assert np.all(np.abs(ci["rvor"]) < 1.0e-6 * f0) and ci["rstd"][-1, 0] > 1.0e-4 * f0
+
+
+def _c_struct_fields(text, name):
+    """(type, name, array length) of every member of `typedef struct name {...}` in the C header, in order."""
+    body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), text, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    out = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        m = re.match(r"(const\s+)?(\w+)\s+(.*)$", decl, flags=re.S)
+        ctype, rest = m.group(2), m.group(3)
+        for item in rest.split(","):
+            item = item.strip()
+            ptr = item.startswith("*")
+            item = item.lstrip("* ")
+            am = re.match(r"(\w+)(?:\[(\w+)\])?$", item)
+            out.append(("ptr" if ptr else ctype, am.group(1), am.group(2)))
+    return out
+
+
+def _fortran_type_fields(text, name):
+    body = re.search(r"type, bind\(C\), public :: %s\n(.*?)end type %s" % (name, name), text, flags=re.S).group(1)
+    out = []
+    for line in body.splitlines():
+        line = line.split("!")[0].strip()
+        if not line:
+            continue
+        m = re.match(r"(integer\(c_int32_t\)|real\(c_double\)|type\(c_ptr\))\s*::\s*(.*)$", line)
+        ftype = {"integer(c_int32_t)": "int32_t", "real(c_double)": "double", "type(c_ptr)": "ptr"}[m.group(1)]
+        for item in re.findall(r"(\w+)(?:\((\w+)\))?", m.group(2)):
+            out.append((ftype, item[0], item[1] or None))
+    return out
+
+
+def test_fortran_binding_mirrors_the_c_header():
+    """fortran/beom_gpu_mod.f95 cannot be compiled here (no Fortran compiler), so its bind(C) types are checked
+    textually against include/beom_gpu.h: same members, same order, same types and array extents; and every interface
+    it declares binds a symbol the library exports."""
+    with open(os.path.join(ROOT, "include", "beom_gpu.h")) as f:
+        hdr = f.read()
+    with open(os.path.join(ROOT, "fortran", "beom_gpu_mod.f95")) as f:
+        f95 = f.read()
+    assert re.search(r"beom_maxlay = (\d+)", f95).group(1) == re.search(r"#define BEOM_MAXLAY (\d+)", hdr).group(1)
+    for name in ("beom_params", "beom_fields", "beom_gpu_options"):
+        c_fields = [(t, n, {"BEOM_MAXLAY": "beom_maxlay"}.get(a, a)) for t, n, a in _c_struct_fields(hdr, name)]
+        assert _fortran_type_fields(f95, name) == c_fields, name
+    lib = _lib.gpu_lib()
+    bound = re.findall(r"bind\(C, name = '(\w+)'\)", f95)
+    assert len(bound) >= 12 and all(hasattr(lib, s) for s in bound), [s for s in bound if not hasattr(lib, s)]
+    # value / reference: beom_gpu_step takes its six scalars by value, exactly as the prototype says
+    assert re.search(r"int\s+beom_gpu_step\(int tstp, double ctim, double ramp, double gene, int upst, int first_three\)", hdr)
+    assert "integer(c_int), value :: tstp, upst, first_three" in f95 and "real(c_double), value :: ctim, ramp, gene" in f95
