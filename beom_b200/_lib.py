@@ -88,7 +88,12 @@ def gpu_lib() -> C.CDLL:
     path = os.path.join(LIBDIR, "libbeom_gpu.so")
     if not os.path.exists(path):
         raise _missing(path)
-    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    _gpu = bind_gpu(C.CDLL(path, mode=C.RTLD_GLOBAL))
+    return _gpu
+
+
+def bind_gpu(lib: C.CDLL) -> C.CDLL:
+    """Declares the prototypes of include/beom_gpu.h on a loaded library."""
     lib.beom_gpu_version.restype = C.c_char_p
     lib.beom_gpu_path.restype = C.c_char_p
     lib.beom_gpu_last_error.argtypes = [C.c_char_p, C.c_int]
@@ -114,7 +119,6 @@ def gpu_lib() -> C.CDLL:
     lib.beom_gpu_host_free.restype = None
     lib.beom_gpu_comm_unique_id.argtypes = [C.c_char_p]
     lib.beom_gpu_comm_init.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int]
-    _gpu = lib
     return lib
 
 

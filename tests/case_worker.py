@@ -1,7 +1,8 @@
 """Runs in its own process, so that a wedged kernel is killed by the caller's timeout instead of hanging the suite:
 one reference test case (small version) through the C ABI on the GPU against the CPU oracle.
 
-usage: case_worker.py <case> <nsteps> <fused 0|1> ['{"param": "value", ...}' appended to the parameter block]
+usage: case_worker.py <case> <nsteps> <fused 0|1> ['{"param": "value", ...}' appended to the parameter block
+                      ['{"kwarg": value, ...}' for the case generator instead of the small defaults [variant]]]
 Prints one JSON line {"path": ..., "exact": ..., "worst": ..., "bad": [...]}; exit status 0 = parity holds."""
 import json
 import os
@@ -19,10 +20,12 @@ from tests.conftest import SMALL  # noqa: E402
 
 name, nsteps, fused = sys.argv[1], int(sys.argv[2]), bool(int(sys.argv[3]))
 extra = json.loads(sys.argv[4]) if len(sys.argv) > 4 else {}
-c = cases.CASES[name](**SMALL.get(name, {}))
+kwargs = json.loads(sys.argv[5]) if len(sys.argv) > 5 else SMALL.get(name, {})
+variant = int(sys.argv[6]) if len(sys.argv) > 6 else 0
+c = cases.CASES[name](**kwargs)
 c.params_text += "".join("%-10s = %s\n" % kv for kv in extra.items())
 with tempfile.TemporaryDirectory() as d:
-    hm = model.HostModel.from_block(c.write(d))
+    hm = model.HostModel.from_block(c.write(d), variant=variant)
     orc = Oracle(hm.params, d)
     orc.advance(1, nsteps)
     gm = model.GpuModel(hm.params, hm.fields(), model.default_options(fused=fused))

@@ -1,0 +1,24 @@
+"""Runs in its own process: one reference test case (small version) on the CPU EMULATION of the library's split path
+(tools/emu: the kernels' source compiled by g++, every launch a serial loop) against the CPU oracle.  Test
+infrastructure: the emulated library is loaded here explicitly, under its own file name; the product never sees it.
+
+usage: emu_worker.py <libbeom_gpu_emu.so> <case> <nsteps> ['{"param": "value", ...}']"""
+import ctypes as C
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from beom_b200 import _lib  # noqa: E402
+
+emu = _lib.bind_gpu(C.CDLL(sys.argv[1], mode=C.RTLD_LOCAL))
+assert b"cpu-emulation" in emu.beom_gpu_version()
+_lib.host_lib()      # the host driver (read_input_data) first: it links the real libbeom_gpu.so, which stays unused here
+_lib._gpu = emu      # from here on model.GpuModel talks to the emulation
+
+sys.argv = [sys.argv[0], sys.argv[2], sys.argv[3], "0"] + sys.argv[4:]
+import runpy  # noqa: E402
+
+runpy.run_path(os.path.join(ROOT, "tests", "case_worker.py"), run_name="__main__")

@@ -1,0 +1,91 @@
+"""The library's split path on the CPU: tools/emu compiles the SOURCE of beom_gpu.cu, split.cuh and diag.cuh with g++
+against a stand-in CUDA runtime in which a kernel launch is a serial loop over its grid, and the result is compared
+with the oracle bit for bit (tides: same libm on both sides here, so also exact).
+
+What this shows without a GPU: the logic of the kernels and of the host plumbing around them -- indexing in the dense
+layout, masks, option switches, upload / download, periodic images and displaced duplicates (incl. the nudged ones of
+baines_ridge), open-boundary segments -- for every reference script and the option matrix.  What it cannot show:
+anything about races, barriers, TMA, the fused step (stubbed out) or speed.  The cases that HAVE run on a B200
+(tests/test_gpu_parity.py) were bit-identical to the same oracle, so agreement here means the emulation reproduces
+the hardware's results on them; the cases written after the GPU budget was spent get their first end-to-end check here.
+
+The emulated library is test infrastructure: built into a temporary directory under its own name, loaded explicitly by
+tests/emu_worker.py, reporting itself as "cpu-emulation"; nothing under beom_b200/ knows about it."""
+import importlib.util
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def emu_so(tmp_path_factory):
+    spec = importlib.util.spec_from_file_location("build_emu", os.path.join(ROOT, "tools", "emu", "build_emu.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod.build(str(tmp_path_factory.mktemp("emu")))
+
+
+def run(emu_so, name, nsteps, extra=None, kwargs=None, variant=0):
+    cmd = [sys.executable, os.path.join(ROOT, "tests", "emu_worker.py"), emu_so, name, str(nsteps), json.dumps(extra or {})]
+    if kwargs is not None or variant:
+        from tests.conftest import SMALL
+        cmd += [json.dumps(kwargs if kwargs is not None else SMALL.get(name, {})), str(variant)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert lines, r.stdout[-2000:] + r.stderr[-2000:]
+    res = json.loads(lines[-1])
+    assert r.returncode == 0 and not res["bad"], res
+    assert res["path"] == "split" and res["worst"] == 0.0
+    return res
+
+
+SCRIPTS = ["stommel1948", "lock_exchange", "unstable_jet", "sill_exchange3D", "conservation", "soliton", "baines_ridge",
+           "carrier_beach", "upwelling_seaward_wind", "mixed_open_bc", "morel_upwelling", "outcrop_seamount", "sill_exchange2D",
+           "sill_exchange2Dtides", "tide_ridge", "wave_sponge"]
+
+
+@pytest.mark.parametrize("name", SCRIPTS)
+def test_every_reference_script_on_the_emulated_split_path(emu_so, name):
+    run(emu_so, name, 30)
+
+
+@pytest.mark.parametrize("name,extra", [("baines_ridge", {"mcbc": "0."}), ("wave_sponge", {"mcbc": "0."}),
+                                        ("sill_exchange3D", {"mcbc": "0."}), ("sill_exchange3D", {"bdrg": "2.e-3", "qdrg": "1."}),
+                                        ("sill_exchange3D", {"bdrg": "1.e-3", "qdrg": "0."}), ("sill_exchange3D", {"tdrg": "1.e-3"}),
+                                        ("sill_exchange3D", {"dt3d": "0.002"}), ("lock_exchange", {"svis": "1.e6"}),
+                                        ("stommel1948", {"rgld": "0.", "g_fb": "0."})])
+def test_options_on_the_emulated_split_path(emu_so, name, extra):
+    run(emu_so, name, 24, extra)
+
+
+OPTION_MATRIX = {
+    "ekman_sponge": dict(), "ramp": dict(dt_r=0.2), "bodf": dict(bodf=True), "hdot": dict(hdot=True), "beta": dict(beta=True),
+    "six_layers": dict(nlay=6), "outcrop_wind": dict(ocrp=1.0), "no_sponge": dict(sponge=False), "no_wind": dict(wind=False),
+    "tide": dict(tide=True),
+}
+
+
+@pytest.mark.parametrize("opt", sorted(OPTION_MATRIX))
+def test_option_matrix_on_the_emulated_split_path(emu_so, opt):
+    run(emu_so, "option_basin", 20, kwargs=OPTION_MATRIX[opt])
+
+
+@pytest.mark.parametrize("variant,nlay,plum", [(1, 2, None), (2, 3, None), (3, 3, "0."), (3, 3, "1.")])
+def test_update_h_variants_on_the_emulated_split_path(emu_so, variant, nlay, plum):
+    run(emu_so, "sponge_basin", 20, {"plum": plum} if plum else {}, kwargs=dict(nlay=nlay), variant=variant)
+
+
+def test_the_emulation_is_not_part_of_the_product():
+    for base, _, files in os.walk(os.path.join(ROOT, "beom_b200")):
+        if os.path.basename(base) in ("lib", "__pycache__"):
+            continue
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h", ".cc")):
+                with open(os.path.join(base, fn), errors="replace") as f:
+                    text = f.read()
+                assert "tools/emu" not in text and "libbeom_gpu_emu" not in text and "BEOM_CUDA_EMULATION" not in text, fn

@@ -1,0 +1,109 @@
+// tools/emu/include/cuda_runtime.h -- TEST INFRASTRUCTURE ONLY.
+//
+// A minimal stand-in for the CUDA runtime that lets g++ compile the SOURCE of the split-path kernels
+// (beom_b200/csrc/gpu/split.cuh, diag.cuh) and of the library's host code (beom_gpu.cu) for the CPU, every kernel
+// launch becoming a serial loop over its grid (tools/emu/build_emu.py rewrites the <<< >>> launches).  Purpose: check
+// the LOGIC of kernels and host plumbing against the oracle on a machine without a GPU -- indexing, masks, option
+// switches, upload/download, periodic images, open-boundary segments.  It cannot say anything about races, barriers,
+// TMA or performance, the fused step is not part of it (stubbed: every case runs the split path), and kernels that
+// cooperate through __syncthreads / shuffles abort if they are ever launched.
+//
+// The product never builds, ships or loads this: beom_b200/build.py does not know it, beom_b200/_lib.py loads
+// beom_b200/lib/libbeom_gpu.so only, and the library built here reports itself as "cpu-emulation" (tests/test_split_emulation.py).
+#pragma once
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#define BEOM_CUDA_EMULATION 1
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __grid_constant__
+#define __launch_bounds__(...)
+#define __shared__ static
+
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
+};
+namespace emu {
+struct Idx { unsigned x, y, z; };
+extern thread_local Idx block_idx, thread_idx;
+extern thread_local dim3 block_dim, grid_dim;
+template <class F>
+void launch(dim3 grid, dim3 block, F &&body) {
+  grid_dim = grid;
+  block_dim = block;
+  for (unsigned bz = 0; bz < grid.z; bz++)
+    for (unsigned by = 0; by < grid.y; by++)
+      for (unsigned bx = 0; bx < grid.x; bx++)
+        for (unsigned tz = 0; tz < block.z; tz++)
+          for (unsigned ty = 0; ty < block.y; ty++)
+            for (unsigned tx = 0; tx < block.x; tx++) {
+              block_idx = Idx{bx, by, bz};
+              thread_idx = Idx{tx, ty, tz};
+              body();
+            }
+}
+[[noreturn]] inline void not_emulated(const char *what) {
+  std::fprintf(stderr, "cuda emulation: %s is not emulated (threads run one after the other)\n", what);
+  std::abort();
+}
+}  // namespace emu
+#define blockIdx (emu::block_idx)
+#define threadIdx (emu::thread_idx)
+#define blockDim (emu::block_dim)
+#define gridDim (emu::grid_dim)
+
+inline void __syncthreads() { emu::not_emulated("__syncthreads"); }
+inline void __syncwarp() {}
+template <class T> inline T __shfl_xor_sync(unsigned, T, int) { emu::not_emulated("__shfl_xor_sync"); }
+template <class T> inline T __shfl_up_sync(unsigned, T, int) { emu::not_emulated("__shfl_up_sync"); }
+template <class T> inline T __shfl_down_sync(unsigned, T, int) { emu::not_emulated("__shfl_down_sync"); }
+template <class T> inline void __stcs(T *p, T v) { *p = v; }
+using std::max;
+using std::min;
+
+enum cudaError_t { cudaSuccess = 0, cudaErrorEmulation = 1 };
+inline const char *cudaGetErrorString(cudaError_t) { return "cuda emulation"; }
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+typedef struct emuStream *cudaStream_t;
+struct emuEvent { std::chrono::steady_clock::time_point t; };
+typedef emuEvent *cudaEvent_t;
+enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaHostAllocDefault = 0 };
+enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
+struct cudaDeviceProp { int major = 10, minor = 0; char name[64] = "cpu-emulation of sm_100a"; };
+
+inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
+inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) { *p = cudaDeviceProp(); return cudaSuccess; }
+inline cudaError_t cudaDeviceGetStreamPriorityRange(int *lo, int *hi) { *lo = 0; *hi = 0; return cudaSuccess; }
+inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = nullptr; return cudaSuccess; }
+inline cudaError_t cudaStreamCreateWithPriority(cudaStream_t *s, unsigned, int) { *s = nullptr; return cudaSuccess; }
+inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new emuEvent(); return cudaSuccess; }
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { return cudaEventCreate(e); }
+inline cudaError_t cudaEventDestroy(cudaEvent_t e) { delete e; return cudaSuccess; }
+inline cudaError_t cudaEventRecord(cudaEvent_t e, cudaStream_t = nullptr) { e->t = std::chrono::steady_clock::now(); return cudaSuccess; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventElapsedTime(float *ms, cudaEvent_t a, cudaEvent_t b) {
+  *ms = std::chrono::duration<float, std::milli>(b->t - a->t).count();
+  return cudaSuccess;
+}
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned = 0) { return cudaSuccess; }
+template <class T> inline cudaError_t cudaMalloc(T **p, size_t n) { *p = static_cast<T *>(std::malloc(n ? n : 1)); return *p ? cudaSuccess : cudaErrorEmulation; }
+inline cudaError_t cudaFree(void *p) { std::free(p); return cudaSuccess; }
+template <class T> inline cudaError_t cudaHostAlloc(T **p, size_t n, unsigned) { return cudaMalloc(p, n); }
+inline cudaError_t cudaFreeHost(void *p) { std::free(p); return cudaSuccess; }
+inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { std::memcpy(d, s, n); return cudaSuccess; }
+inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind k, cudaStream_t = nullptr) { return cudaMemcpy(d, s, n, k); }
+inline cudaError_t cudaMemset(void *d, int v, size_t n) { std::memset(d, v, n); return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t = nullptr) { return cudaMemset(d, v, n); }
