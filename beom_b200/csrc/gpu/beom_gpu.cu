@@ -84,6 +84,7 @@ struct Ctx {
   bool torus = false;              // periodic domain whose aliases form a complete torus: deep ghost cells exist, the fused step may run
   bool ring = false;               // y-periodic domain split into y-slabs: the halo exchange is ring-closed (layout.h)
   HaloRows halo;                   // peers and rows of the packed halo exchange
+  int own_first = 0, own_last = -1;  // vector points of the rows this rank owns (a contiguous range)
   float *rec_f32 = nullptr;        // [nlay] dense float32 planes: one diagnostic record
   float *rec_stage = nullptr;      // vector-layout staging of one layer of a record
   double *diag_h0 = nullptr;       // [nlay] dense h_0 (beom_gpu_diagnostics)
@@ -396,6 +397,9 @@ int beom_gpu_init(const beom_params *par, const beom_fields *fld, const beom_gpu
   g.torus = lay.torus;
   g.ring = lay.ring;
   g.halo = halo_rows(g.rank, g.nranks, g.ring, G, G + (g.j1 - g.j0));
+  g.own_first = 0; g.own_last = -1;
+  for (int p = g.p_lo; p <= g.p_hi; p++)
+    if (sj[p] >= g.j0 && sj[p] <= g.j1) { if (!g.own_first) g.own_first = p; g.own_last = p; }
   const int j_off = lay.j_off;  // Y = j + j_off
   const std::vector<uint8_t> &hflags = lay.flags;
   int rc;
@@ -921,15 +925,9 @@ int beom_gpu_point_range(int *first, int *count, int *own_first, int *own_count)
   if (!g.ready) return fail(-20, "beom_gpu_point_range: not initialised");
   if (first) *first = g.p_lo;
   if (count) *count = g.p_hi - g.p_lo + 1;
-  int of = 0, ol = -1;  // owned = rows j0..j1
-  for (int p = g.p_lo; p <= g.p_hi; p++) {
-    const int c = g.cell_of_point[p];
-    if (c < 0) continue;
-    const int y = c / g.NX;
-    if (y >= g.D.y_lo && y <= g.D.y_hi) { if (!of) of = p; ol = p; }
-  }
-  if (own_first) *own_first = of;
-  if (own_count) *own_count = ol - of + 1;
+  // owned = the vector points of rows j0..j1, periodic duplicates included (their state is patched in by the downloads)
+  if (own_first) *own_first = g.own_first;
+  if (own_count) *own_count = g.own_last - g.own_first + 1;
   return 0;
 }
 int beom_gpu_set_window(int first, int count) {

@@ -89,3 +89,40 @@ def test_the_emulation_is_not_part_of_the_product():
                 with open(os.path.join(base, fn), errors="replace") as f:
                     text = f.read()
                 assert "tools/emu" not in text and "libbeom_gpu_emu" not in text and "BEOM_CUDA_EMULATION" not in text, fn
+
+
+RANKS = [
+    ("synthetic_basin", 9, 2, {}, dict(n=60, mm=40, nlay=2)),   # plain y-slabs (the configuration that HAS run on 2 B200s)
+    ("sill_exchange3D", 12, 2, {}, None),
+    ("wave_sponge", 12, 4, {"mcbc": "0."}, None),               # open-boundary segments spread over four ranks
+    ("soliton", 12, 3, {}, None),                                # x-periodic: images stay inside a rank
+    ("conservation", 12, 2, {}, None),                           # doubly periodic: the halo exchange is ring-closed
+    ("conservation", 12, 3, {}, None),
+    ("conservation", 12, 2, {"xper": "0."}, None),               # periodic in y only
+    ("unstable_jet", 12, 4, {}, None),
+]
+
+
+@pytest.mark.parametrize("name,nsteps,nranks,extra,kwargs", RANKS, ids=["%s-%d%s" % (r[0], r[2], "-" + "".join(r[3]) if r[3] else "") for r in RANKS])
+def test_y_slab_ranks_on_the_emulated_split_path(emu_so, name, nsteps, nranks, extra, kwargs):
+    """One emulated library instance per rank (own file, own globals, own thread); the packed halo exchange goes through
+    a callback that pairs the messages like NCCL.  Every rank's own slab -- periodic duplicates included -- must equal the
+    oracle bit for bit, and the own ranges must tile 1..ndeg (output records are their concatenation)."""
+    cmd = [sys.executable, os.path.join(ROOT, "tests", "emu_ranks_worker.py"), emu_so, name, str(nsteps), str(nranks), json.dumps(extra)]
+    if kwargs is not None:
+        cmd.append(json.dumps(kwargs))
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert lines, r.stdout[-2000:] + r.stderr[-2000:]
+    res = json.loads(lines[-1])
+    assert r.returncode == 0, res
+    ranks = res["ranks"]
+    assert all(not k["bad"] and k["path"] == "split" and k["exchanges"] > 3 * nsteps for k in ranks), res
+    assert ranks[0]["points"][0] == 1 and all(a["points"][1] + 1 == b["points"][0] for a, b in zip(ranks, ranks[1:]))
+    assert res["moved"] > 0
+
+
+def test_ranks_that_cannot_hold_the_seam_fail_loudly(emu_so):
+    cmd = [sys.executable, os.path.join(ROOT, "tests", "emu_ranks_worker.py"), emu_so, "baines_ridge", "5", "2"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 1 and "rows per rank" in r.stdout

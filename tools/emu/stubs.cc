@@ -17,17 +17,32 @@ int fused_configure(const Dev &, const beom_params &, int, int, bool *enabled) {
 bool fused_supports(bool, bool) { return false; }
 int fused_step(const Dev &, const Dev &, int, bool, cudaStream_t, int *, int, int) { return -1; }
 void fused_release() {}
-// one rank only
-int comm_unique_id(char[128], std::string *err) { if (err) *err = "cuda emulation: no communicator"; return -40; }
-int comm_init(const char[128], int, int, int, std::string *err) { if (err) *err = "cuda emulation: no communicator"; return -40; }
-int comm_finalize() { return 0; }
-bool comm_ready() { return false; }
-int comm_rank() { return 0; }
-int comm_size() { return 1; }
-int comm_exchange(const double *, double *, int, const double *, double *, int, size_t, cudaStream_t, std::string *err) {
-  if (err) *err = "cuda emulation: no communicator";
-  return -44;
+// Ranks: each rank is its own copy of the emulated library (loaded from its own file, so with its own globals) driven by
+// its own thread of the test process; the halo exchange is handed to a callback of the test, which pairs the messages
+// the way NCCL does (what a rank sends to its lower neighbour is what that neighbour receives from above).
+typedef int (*emu_exchange_fn)(const double *send_lo, double *recv_lo, int peer_lo, const double *send_hi, double *recv_hi, int peer_hi,
+                               size_t count);
+static emu_exchange_fn g_exchange = nullptr;
+static int g_rank = 0, g_size = 1;
+int comm_unique_id(char[128], std::string *err) { if (err) *err = "cuda emulation: ranks are wired up by emu_comm_set"; return -40; }
+int comm_init(const char[128], int, int, int, std::string *err) { if (err) *err = "cuda emulation: ranks are wired up by emu_comm_set"; return -40; }
+int comm_finalize() { g_exchange = nullptr; g_rank = 0; g_size = 1; return 0; }
+bool comm_ready() { return g_exchange != nullptr; }
+int comm_rank() { return g_rank; }
+int comm_size() { return g_size; }
+int comm_exchange(const double *send_lo, double *recv_lo, int peer_lo, const double *send_hi, double *recv_hi, int peer_hi, size_t count,
+                  cudaStream_t, std::string *err) {
+  if (!g_exchange) { if (err) *err = "cuda emulation: no exchange callback"; return -44; }
+  const int rc = g_exchange(send_lo, recv_lo, peer_lo, send_hi, recv_hi, peer_hi, count);
+  if (rc && err) *err = "cuda emulation: the exchange callback failed";
+  return rc;
 }
 int comm_allreduce_sum(double *, size_t, cudaStream_t, std::string *) { return 0; }
 int comm_allreduce_max(double *, size_t, cudaStream_t, std::string *) { return 0; }
 }  // namespace beom
+
+extern "C" void emu_comm_set(int rank, int size, beom::emu_exchange_fn fn) {
+  beom::g_rank = rank;
+  beom::g_size = size;
+  beom::g_exchange = fn;
+}
