@@ -126,3 +126,51 @@ def test_ranks_that_cannot_hold_the_seam_fail_loudly(emu_so):
     cmd = [sys.executable, os.path.join(ROOT, "tests", "emu_ranks_worker.py"), emu_so, "baines_ridge", "5", "2"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 1 and "rows per rank" in r.stdout
+
+
+@pytest.mark.parametrize("name,dt_o", [("lock_exchange", 0.005), ("conservation", 0.1), ("baines_ridge", 0.01), ("sill_exchange3D", 0.0005)])
+def test_the_executable_end_to_end_on_the_emulation(emu_so, tmp_path, name, dt_o):
+    """beom_run (= main.f95: read_input_data, integrate_time, write_outputs) with the emulated library preloaded in place
+    of libbeom_gpu.so: the output files it leaves behind -- eta_/u___/v___.bin and, with diag = 1, pvor/mont/v_cc.bin,
+    time.txt -- against the oracle's write_array records at the same steps, bit for bit (float32)."""
+    import numpy as np
+    from beom_b200 import cases, model
+    from oracle.pyoracle import Oracle
+    from tests.conftest import SMALL
+    c = cases.CASES[name](**SMALL.get(name, {}))
+    text = c.params_text
+    import re
+    text = re.sub(r"dt_o       = \S+", "dt_o       = %f" % dt_o, text)
+    text = re.sub(r"diag       = \S+", "diag       = 1.", text)
+    c.params_text = text
+    blk = c.write(str(tmp_path))
+    hm = model.HostModel.from_block(blk)
+    nstp, notp, _ = hm.counts()
+    assert 5 <= notp <= 200, notp
+    nrec = 3
+    steps = nrec * notp + 5
+    exe = os.path.join(ROOT, "beom_b200", "lib", "beom_run")
+    env = dict(os.environ, LD_PRELOAD=emu_so)
+    r = subprocess.run([exe, blk, "--steps", str(steps), "--split"], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    assert "record = %d" % (nrec + 1) in r.stdout
+    orc = Oracle(hm.params, str(tmp_path))
+    n, nlay = c.ndeg, c.nlay
+    sub = hm.iarray("subc")
+    dup = np.zeros(n, dtype=bool)  # diag records are not reproduced at the periodic duplicates (conservation.m discards them)
+    if hm.params.xper > 0.5:
+        dup |= (sub[0] == c.lm + 1)[1:]
+    if hm.params.yper > 0.5:
+        dup |= (sub[1] == c.mm + 1)[1:]
+    times = np.atleast_1d(np.loadtxt(tmp_path / "time.txt"))
+    assert times.size == nrec + 1
+    for k in range(nrec + 1):
+        if k:
+            orc.advance((k - 1) * notp + 1, k * notp)
+        assert abs(times[k] - k * notp * hm.params.dt / 86400.0) < 1e-12
+        for var in ("eta_", "u___", "v___", "pvor", "mont", "v_cc"):
+            raw = np.fromfile(tmp_path / (var + ".bin"), dtype="<f4", count=n * nlay, offset=4 * k * n * nlay).reshape(nlay, n)
+            want = orc.record(var)
+            keep = ~dup if var in ("pvor", "mont", "v_cc") else np.ones(n, dtype=bool)
+            same = (raw == want) | (np.isnan(raw) & np.isnan(want)) | ~keep[None, :]
+            assert same.all(), (name, var, k, int((~same).sum()))
