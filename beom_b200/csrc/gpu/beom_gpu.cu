@@ -85,6 +85,7 @@ struct Ctx {
   bool ring = false;               // y-periodic domain split into y-slabs: the halo exchange is ring-closed (layout.h)
   HaloRows halo;                   // peers and rows of the packed halo exchange
   int own_first = 0, own_last = -1;  // vector points of the rows this rank owns (a contiguous range)
+  double adv_ramp = 1.0, adv_gene = 0.0;  // beom_gpu_advance: ramp and gene of the previous step
   float *rec_f32 = nullptr;        // [nlay] dense float32 planes: one diagnostic record
   float *rec_stage = nullptr;      // vector-layout staging of one layer of a record
   double *diag_h0 = nullptr;       // [nlay] dense h_0 (beom_gpu_diagnostics)
@@ -742,7 +743,7 @@ int beom_gpu_advance(int tstp0, int tstp1, double tres) {
   if (!g.ready) return fail(-20, "beom_gpu_advance: not initialised");
   const beom_params &P = g.P;
   const double dtd8 = P.dt / 24.0 / 3600.0;
-  static double ramp = 1.0, gene = 0.0;
+  double &ramp = g.adv_ramp, &gene = g.adv_gene;  // carried from call to call (steps 1-3 keep the ramp of step 1, pm:1862-1866)
   for (int tstp = tstp0; tstp <= tstp1; tstp++) {
     const double ctim = tres + dtd8 * (double)tstp;
     int rc;
