@@ -174,3 +174,48 @@ def test_the_executable_end_to_end_on_the_emulation(emu_so, tmp_path, name, dt_o
             keep = ~dup if var in ("pvor", "mont", "v_cc") else np.ones(n, dtype=bool)
             same = (raw == want) | (np.isnan(raw) & np.isnan(want)) | ~keep[None, :]
             assert same.all(), (name, var, k, int((~same).sum()))
+
+
+def test_restart_continues_the_record_files_on_the_emulation(emu_so, tmp_path):
+    """rsta = 1 (private_mod.f95:236-243, 1299-1420): a second beom_run picks the state up from the last float32 record,
+    keeps counting time from there and appends its records.  The oracle, started from the same float32-rounded state,
+    must produce the appended records bit for bit."""
+    import numpy as np
+    import re
+    from beom_b200 import cases, model
+    from oracle.pyoracle import Oracle
+    c = cases.lock_exchange()
+    c.params_text = re.sub(r"dt_o       = \S+", "dt_o       = 0.005000", c.params_text)
+    blk = c.write(str(tmp_path))
+    hm = model.HostModel.from_block(blk)
+    _, notp, _ = hm.counts()
+    exe = os.path.join(ROOT, "beom_b200", "lib", "beom_run")
+    env = dict(os.environ, LD_PRELOAD=emu_so)
+    r = subprocess.run([exe, blk, "--steps", str(2 * notp + 3), "--split"], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    n, nlay = c.ndeg, c.nlay
+    assert os.path.getsize(tmp_path / "eta_.bin") == 3 * n * nlay * 4
+    # second run: restart from record 3
+    with open(blk) as f:
+        text = f.read()
+    with open(blk, "w") as f:
+        f.write(re.sub(r"rsta       = \S+", "rsta       = 1.", text))
+    # what read_restart_record makes of record 3 (float32 eta -> hlay = h_0 + eta_k - eta_k+1), for the oracle below
+    hm2 = model.HostModel.from_block(blk, write_outputs=True)   # rsta = 1: the directory is left as it is
+    assert hm2.lib.beom_host_read_restart(hm2.h) == 0 and hm2.scalar("irec") == 4
+    start = {k: hm2.array(k).copy() for k in ("hlay", "u", "v")}
+    r = subprocess.run([exe, blk, "--steps", str(2 * notp), "--split"], capture_output=True, text=True, timeout=600, env=env)
+    assert r.returncode == 0 and "Restarting from record number 3" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
+    assert os.path.getsize(tmp_path / "eta_.bin") == 5 * n * nlay * 4
+    times = np.loadtxt(tmp_path / "time.txt")
+    dtd8 = hm.params.dt / 86400.0
+    assert times.size == 5 and abs(times[4] - (times[2] + 2 * notp * dtd8)) < 1e-12
+    # the oracle from the restart state
+    orc = Oracle(hm2.params, str(tmp_path))
+    for k in ("hlay", "u", "v"):
+        orc.array(k)[:] = start[k]
+    for rec in (3, 4):
+        orc.advance((rec - 3) * notp + 1, (rec - 2) * notp)
+        for var in ("eta_", "u___", "v___"):
+            raw = np.fromfile(tmp_path / (var + ".bin"), dtype="<f4", count=n * nlay, offset=4 * rec * n * nlay).reshape(nlay, n)
+            assert np.array_equal(raw, orc.record(var)), (var, rec)
