@@ -30,8 +30,8 @@ def emu_so(tmp_path_factory):
     return mod.build(str(tmp_path_factory.mktemp("emu")))
 
 
-def run(emu_so, name, nsteps, extra=None, kwargs=None, variant=0):
-    cmd = [sys.executable, os.path.join(ROOT, "tests", "emu_worker.py"), emu_so, name, str(nsteps), json.dumps(extra or {})]
+def run(emu_so, name, nsteps, extra=None, kwargs=None, variant=0, fused=0, path="split"):
+    cmd = [sys.executable, os.path.join(ROOT, "tests", "emu_worker.py"), emu_so, name, str(nsteps), str(fused), json.dumps(extra or {})]
     if kwargs is not None or variant:
         from tests.conftest import SMALL
         cmd += [json.dumps(kwargs if kwargs is not None else SMALL.get(name, {})), str(variant)]
@@ -40,7 +40,7 @@ def run(emu_so, name, nsteps, extra=None, kwargs=None, variant=0):
     assert lines, r.stdout[-2000:] + r.stderr[-2000:]
     res = json.loads(lines[-1])
     assert r.returncode == 0 and not res["bad"], res
-    assert res["path"] == "split" and res["worst"] == 0.0
+    assert res["path"] == path and res["worst"] == 0.0, res
     return res
 
 
@@ -219,3 +219,38 @@ def test_restart_continues_the_record_files_on_the_emulation(emu_so, tmp_path):
         for var in ("eta_", "u___", "v___"):
             raw = np.fromfile(tmp_path / (var + ".bin"), dtype="<f4", count=n * nlay, offset=4 * rec * n * nlay).reshape(nlay, n)
             assert np.array_equal(raw, orc.record(var)), (var, rec)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# The FUSED step on the SIMT emulator (tools/emu/include/simt.h): one OS thread per warp, 32 coroutine lanes, warp
+# shuffles and votes, __syncthreads, mbarriers with transaction counts and bulk global->shared copies -- the kernel
+# source of fused_kernel.cuh unchanged except for its six inline-PTX helpers, which build_emu.py redirects.  Shared
+# memory starts filled with a byte pattern, so a read of something never written shows up as garbage.  A protocol error
+# (an mbarrier wait nobody satisfies) is a hang: the workers run under a timeout.
+# ------------------------------------------------------------------------------------------------------------------
+FUSED_SCRIPTS = [n for n in SCRIPTS if n not in ("sill_exchange2Dtides", "tide_ridge")]  # tidal targets: split path
+
+
+@pytest.mark.parametrize("name", FUSED_SCRIPTS)
+def test_every_reference_script_on_the_emulated_fused_step(emu_so, name):
+    """Incl. the shapes that had never run on hardware when this was written: one-row and one-column tori
+    (baines_ridge, upwelling_seaward_wind, morel_upwelling), five layers, a single outcropping layer, the open-boundary
+    kernel after the fused step on three sides, nudged periodic duplicates."""
+    run(emu_so, name, 24, fused=1, path="fused")
+
+
+@pytest.mark.parametrize("nlay", [1, 3, 4])
+def test_the_bench_workload_on_the_emulated_fused_step(emu_so, nlay):
+    """The specialised (lean) instantiations: several x strips and y chunks, wind stress, Leith viscosity, both u/v orders,
+    the gene = 0 start-up steps."""
+    run(emu_so, "synthetic_basin", 9, kwargs=dict(n=130, mm=70, nlay=nlay), fused=1, path="fused")
+
+
+@pytest.mark.parametrize("opt", sorted(k for k in OPTION_MATRIX if k != "tide"))
+def test_option_matrix_on_the_emulated_fused_step(emu_so, opt):
+    run(emu_so, "option_basin", 16, kwargs=OPTION_MATRIX[opt], fused=1, path="fused")
+
+
+@pytest.mark.parametrize("extra", [{"mcbc": "0."}, {"bdrg": "2.e-3", "qdrg": "1."}, {"bdrg": "1.e-3", "qdrg": "0."}, {"tdrg": "1.e-3"}])
+def test_sill_options_on_the_emulated_fused_step(emu_so, extra):
+    run(emu_so, "sill_exchange3D", 16, extra, fused=1, path="fused")

@@ -34,7 +34,7 @@ CASES = [
 # Written after round 1's GPU budget was spent: none of these has run on hardware yet (the CPU side of each -- case
 # set-up, oracle, the connectivity / segment analysis of beom_gpu_init restated in Python, the comparison logic of the
 # worker -- has; and the split path's kernel source, compiled for the CPU, is bit-identical to the oracle on every one of
-# them, tests/test_split_emulation.py).  Non-strict xfail keeps the suite's verdict on the tests that HAVE been observed; an XPASS here is
+# them, tests/test_emulation.py).  Non-strict xfail keeps the suite's verdict on the tests that HAVE been observed; an XPASS here is
 # new evidence, an XFAIL a bug to fix.  To be promoted to plain tests as soon as they have been seen on a B200.
 @pytest.mark.xfail(strict=False, reason="not yet observed on a GPU (round-1 GPU budget exhausted before these cases existed)")
 @pytest.mark.parametrize("fused", [0, 1])

@@ -3,7 +3,7 @@
 ``beom_gpu.cu`` is copied with every ``kernel<<<grid, block, shmem, stream>>>(args);`` rewritten into a serial loop over
 the grid (``emu::launch``), and compiled by g++ (-ffp-contract=off: same arithmetic as nvcc -fmad=false) against
 tools/emu/include/cuda_runtime.h together with tools/emu/stubs.cc (no fused step, no NCCL).  See the header for what
-this can and cannot show.  Used by tests/test_split_emulation.py only; nothing under beom_b200/ refers to it."""
+this can and cannot show.  Used by tests/test_emulation.py only; nothing under beom_b200/ refers to it."""
 from __future__ import annotations
 
 import os
@@ -43,6 +43,10 @@ def _split_top(s: str) -> list[str]:
     return out
 
 
+# kernels whose threads cooperate (shuffles, votes, barriers, mbarriers): launched through the SIMT emulator
+SIMT = {"kern", "k_open_rows", "k_conservation", "k_sum_partials", "k_surf_pressure"}
+
+
 def rewrite_launches(text: str) -> tuple[str, int]:
     out, pos, n = "", 0, 0
     while True:
@@ -59,28 +63,75 @@ def rewrite_launches(text: str) -> tuple[str, int]:
         assert text[a0] == "(", text[k - 40:k + 80]
         a1 = _match(text, a0, "(", ")")
         assert text[a1 + 1] == ";", text[k - 40:a1 + 10]
-        out += text[pos:b] + "emu::launch(dim3(%s), dim3(%s), [&]() { %s%s; })" % (cfg[0], cfg[1], name, text[a0:a1 + 1])
+        call = "%s%s" % (name, text[a0:a1 + 1])
+        if name.split("<")[0] in SIMT:
+            shmem = cfg[2] if len(cfg) > 2 else "0"
+            out += text[pos:b] + "emu::launch_simt(dim3(%s), dim3(%s), (size_t)(%s), [&]() { %s; })" % (cfg[0], cfg[1], shmem, call)
+        else:
+            out += text[pos:b] + "emu::launch(dim3(%s), dim3(%s), [&]() { %s; })" % (cfg[0], cfg[1], call)
         pos = a1 + 1
         n += 1
 
 
+PTX_HELPERS = """
+// (tools/emu/build_emu.py: the inline-PTX helpers of the fused step, redirected to tools/emu/include/simt.h)
+inline unsigned smem_u32(const void *p) { return emu::smem_u32(p); }
+inline void mbar_init(unsigned bar, unsigned count) { emu::mbar_init(bar, count); }
+inline void mbar_expect_tx(unsigned bar, unsigned bytes) { emu::mbar_expect_tx(bar, bytes); }
+inline void mbar_arrive(unsigned bar) { emu::mbar_arrive(bar); }
+inline void mbar_wait(unsigned bar, unsigned parity) { emu::mbar_wait(bar, parity); }
+inline void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) { emu::bulk_g2s(dst, src, bytes, bar); }
+
+"""
+
+
+def rewrite_fused_kernel(text: str) -> str:
+    """fused_kernel.cuh: the PTX helpers, the dynamic shared-memory declaration and the two fences."""
+    a = text.index("__device__ __forceinline__ unsigned smem_u32")
+    b = text.index("// One momentum update")
+    text = text[:a] + PTX_HELPERS + text[b:]
+    decl = "extern __shared__ __align__(128) unsigned char smem_raw[];"
+    assert text.count(decl) == 1
+    text = text.replace(decl, "unsigned char *smem_raw = emu::dyn_smem();")
+    import re
+    text, n = re.subn(r'asm volatile\("fence[^\n]*\n', "/* fence */;\n", text)
+    assert n == 2 and "asm volatile" not in text, n
+    return text
+
+
 def build(outdir: str) -> str:
     os.makedirs(outdir, exist_ok=True)
-    with open(os.path.join(GPU_SRC, "beom_gpu.cu")) as f:
-        src, n = rewrite_launches(f.read())
-    assert n >= 30, n
-    tag = 'return "beom_b200 0.1 (sm_100a)"'  # beom_gpu_version(): the emulated library says what it is
-    assert src.count(tag) == 1
-    src = src.replace(tag, 'return "cpu-emulation of beom_b200 (test infrastructure, tools/emu)"')
-    gen = os.path.join(outdir, "beom_gpu_emu.cc")
-    with open(gen, "w") as f:
-        f.write("// generated by tools/emu/build_emu.py from beom_b200/csrc/gpu/beom_gpu.cu (%d launches rewritten)\n" % n)
-        f.write(src)
+    gens, total = [], 0
+    units = ["beom_gpu.cu", "fused.cu", "fused_inst_general.cu"] + ["fused_inst_general%d.cu" % k for k in range(5)] + \
+            ["fused_inst_lean%d.cu" % k for k in range(1, 5)]
+    for unit in units + ["fused_inst.cuh", "fused_kernel.cuh"]:
+        with open(os.path.join(GPU_SRC, unit)) as f:
+            src, n = rewrite_launches(f.read())
+        total += n
+        if unit == "beom_gpu.cu":
+            tag = 'return "beom_b200 0.1 (sm_100a)"'  # beom_gpu_version(): the emulated library says what it is
+            assert src.count(tag) == 1
+            src = src.replace(tag, 'return "cpu-emulation of beom_b200 (test infrastructure, tools/emu)"')
+        if unit == "fused_kernel.cuh":
+            src = rewrite_fused_kernel(src)
+        gen = os.path.join(outdir, unit.replace(".cu", "_emu.cc") if unit.endswith(".cu") else unit)
+        with open(gen, "w") as f:
+            f.write("// generated by tools/emu/build_emu.py from beom_b200/csrc/gpu/%s\n" % unit)
+            f.write(src)
+        if unit.endswith(".cu"):
+            gens.append(gen)
+    assert total >= 35, total
     so = os.path.join(outdir, "libbeom_gpu_emu.so")
-    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-Wno-unused-function", "-Wno-unknown-pragmas",
-           "-I" + os.path.join(HERE, "include"), "-I" + GPU_SRC, "-I" + os.path.join(ROOT, "include"),
-           gen, os.path.join(HERE, "stubs.cc"), "-Wl,-Bsymbolic", "-o", so]
-    subprocess.run(cmd, check=True)
+    flags = ["-O1", "-std=c++17", "-fPIC", "-ffp-contract=off", "-Wno-unused-function", "-Wno-unknown-pragmas", "-pthread",
+             "-I" + outdir, "-I" + os.path.join(HERE, "include"), "-I" + GPU_SRC, "-I" + os.path.join(ROOT, "include")]
+    objs, jobs = [], []
+    for src in gens + [os.path.join(HERE, "stubs.cc"), os.path.join(HERE, "simt.cc")]:
+        obj = os.path.join(outdir, os.path.basename(src)[:-3] + ".o")
+        objs.append(obj)
+        jobs.append(subprocess.Popen(["g++"] + flags + ["-c", src, "-o", obj]))
+    if any(j.wait() != 0 for j in jobs):
+        raise subprocess.CalledProcessError(1, "g++")
+    subprocess.run(["g++", "-shared", "-pthread"] + objs + ["-Wl,-Bsymbolic", "-o", so], check=True)
     return so
 
 

@@ -9,7 +9,7 @@
 // cooperate through __syncthreads / shuffles abort if they are ever launched.
 //
 // The product never builds, ships or loads this: beom_b200/build.py does not know it, beom_b200/_lib.py loads
-// beom_b200/lib/libbeom_gpu.so only, and the library built here reports itself as "cpu-emulation" (tests/test_split_emulation.py).
+// beom_b200/lib/libbeom_gpu.so only, and the library built here reports itself as "cpu-emulation" (tests/test_emulation.py).
 #pragma once
 #include <algorithm>
 #include <chrono>
@@ -61,11 +61,7 @@ void launch(dim3 grid, dim3 block, F &&body) {
 #define blockDim (emu::block_dim)
 #define gridDim (emu::grid_dim)
 
-inline void __syncthreads() { emu::not_emulated("__syncthreads"); }
-inline void __syncwarp() {}
-template <class T> inline T __shfl_xor_sync(unsigned, T, int) { emu::not_emulated("__shfl_xor_sync"); }
-template <class T> inline T __shfl_up_sync(unsigned, T, int) { emu::not_emulated("__shfl_up_sync"); }
-template <class T> inline T __shfl_down_sync(unsigned, T, int) { emu::not_emulated("__shfl_down_sync"); }
+#include "simt.h"  // shuffles, votes, __syncwarp, __syncthreads, mbarriers: only inside emu::launch_simt
 template <class T> inline void __stcs(T *p, T v) { *p = v; }
 using std::max;
 using std::min;
@@ -80,6 +76,11 @@ enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaHostAllocDefau
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
 struct cudaDeviceProp { int major = 10, minor = 0; char name[64] = "cpu-emulation of sm_100a"; };
 
+enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount, cudaDevAttrMaxSharedMemoryPerBlockOptin };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize };
+inline cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
+inline cudaError_t cudaDeviceGetAttribute(int *v, cudaDeviceAttr a, int) { *v = a == cudaDevAttrMultiProcessorCount ? 148 : 227 * 1024; return cudaSuccess; }
+template <class F> inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
 inline cudaError_t cudaGetDeviceCount(int *n) { *n = 1; return cudaSuccess; }
 inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
 inline cudaError_t cudaGetDeviceProperties(cudaDeviceProp *p, int) { *p = cudaDeviceProp(); return cudaSuccess; }

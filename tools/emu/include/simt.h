@@ -1,0 +1,194 @@
+// tools/emu/include/simt.h -- TEST INFRASTRUCTURE ONLY (see cuda_runtime.h in this directory).
+//
+// A small SIMT emulator for the kernels that cooperate: warp shuffles / votes, __syncwarp, __syncthreads, and the
+// sm_90+ machinery the fused step is built on (mbarriers with transaction counts, bulk global->shared copies).
+// A CTA runs as one OS thread per warp; the 32 lanes of a warp are coroutines (ucontext) of that thread, switched at
+// the collective operations, so a shuffle costs a few user-space context switches.  CTAs run one after the other.
+// mbarrier waits spin cooperatively (lane yield + sched_yield): a wait that the hardware would satisfy is satisfied here,
+// a deadlock shows up as a hang (tests run the emulation under a timeout).  Bulk copies complete at once.
+// Nothing here models timing, memory-ordering subtleties of the async proxy, or bank conflicts: it checks LOGIC.
+#pragma once
+#include <ucontext.h>
+
+#include <atomic>
+#include <condition_variable>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+namespace emu {
+
+struct Cta;
+struct Warp {
+  Cta *cta = nullptr;
+  int id = 0;
+  ucontext_t main;
+  ucontext_t lane[32];
+  std::vector<char> stack[32];
+  bool done[32] = {};
+  int active = 32, cur = 0;
+  // collectives
+  uint64_t buf[2][32] = {};
+  int arrived = 0;
+  unsigned gen = 0;
+  int sync_arrived = 0;  // __syncthreads arrivals of this warp's lanes
+  unsigned sync_gen = 0;
+};
+struct MBar {
+  unsigned expected = 0;
+  int pending = 0;
+  long tx = 0;
+  unsigned phase = 0;
+};
+struct Cta {
+  dim3 block, grid;
+  Idx block_idx;
+  std::vector<unsigned char> smem;
+  std::function<void()> *body = nullptr;
+  int nwarps = 0;
+  // CTA barrier over warps
+  std::mutex mu;
+  std::condition_variable cv;
+  int bar_count = 0;
+  unsigned bar_gen = 0;
+  std::map<unsigned, MBar> mbars;  // by shared-memory offset
+};
+
+extern thread_local Warp *cur_warp;   // the warp this OS thread runs (null outside a SIMT launch)
+constexpr unsigned kSmemBase = 0x1000;  // shared-window addresses start here (0 stays invalid)
+
+inline Warp &warp() {
+  if (!cur_warp) not_emulated("a cooperative intrinsic outside a SIMT launch");
+  return *cur_warp;
+}
+inline void set_lane_ids(Warp &w) {
+  const unsigned t = (unsigned)(w.id * 32 + w.cur);
+  thread_idx = Idx{t % w.cta->block.x, (t / w.cta->block.x) % w.cta->block.y, t / (w.cta->block.x * w.cta->block.y)};
+  block_idx = w.cta->block_idx;
+  block_dim = w.cta->block;
+  grid_dim = w.cta->grid;
+}
+inline void lane_yield() {  // back to the warp's scheduler
+  Warp &w = warp();
+  const int me = w.cur;
+  swapcontext(&w.lane[me], &w.main);
+  w.cur = me;
+  set_lane_ids(w);
+}
+inline unsigned char *dyn_smem() { return warp().cta->smem.data(); }
+inline unsigned smem_u32(const void *p) { return kSmemBase + (unsigned)((const unsigned char *)p - warp().cta->smem.data()); }
+inline unsigned char *smem_ptr(unsigned a) { return warp().cta->smem.data() + (a - kSmemBase); }
+
+// ---- warp collectives: every active lane calls; the last one to arrive opens the generation ----
+inline void warp_collect(Warp &w, uint64_t mine) {
+  const unsigned g = w.gen;
+  w.buf[g & 1][w.cur] = mine;
+  if (++w.arrived == w.active) {
+    w.arrived = 0;
+    w.gen++;
+  }
+  while (w.gen == g) lane_yield();
+}
+template <class T> inline uint64_t to_bits(T v) { uint64_t b = 0; static_assert(sizeof(T) <= 8, "shuffle of <= 8 bytes"); std::memcpy(&b, &v, sizeof(T)); return b; }
+template <class T> inline T from_bits(uint64_t b) { T v; std::memcpy(&v, &b, sizeof(T)); return v; }
+template <class T> inline T shfl_idx(T v, int src) {
+  Warp &w = warp();
+  const unsigned g = w.gen;
+  const int me = w.cur;
+  warp_collect(w, to_bits(v));
+  if (src < 0 || src > 31 || w.done[src]) src = me;
+  return from_bits<T>(w.buf[g & 1][src]);
+}
+inline bool vote_all(bool p) {
+  Warp &w = warp();
+  const unsigned g = w.gen;
+  warp_collect(w, p ? 1u : 0u);
+  for (int l = 0; l < 32; l++)
+    if (!w.done[l] && !w.buf[g & 1][l]) return false;
+  return true;
+}
+inline void syncwarp() { warp_collect(warp(), 0); }
+inline void syncthreads() {
+  Warp &w = warp();
+  Cta &c = *w.cta;
+  const unsigned g = w.sync_gen;
+  if (++w.sync_arrived == w.active) {  // last lane of the warp: meet the other warps
+    w.sync_arrived = 0;
+    std::unique_lock<std::mutex> lk(c.mu);
+    const unsigned bg = c.bar_gen;
+    if (++c.bar_count == c.nwarps) {
+      c.bar_count = 0;
+      c.bar_gen++;
+      c.cv.notify_all();
+    } else {
+      c.cv.wait(lk, [&] { return c.bar_gen != bg; });
+    }
+    w.sync_gen++;
+  }
+  while (w.sync_gen == g) lane_yield();
+}
+
+// ---- mbarriers (shared-memory objects; state kept in a side table) ----
+inline void mbar_complete_if_done(MBar &b) {
+  if (b.pending == 0 && b.tx == 0) {
+    b.phase ^= 1;
+    b.pending = (int)b.expected;
+  }
+}
+inline void mbar_init(unsigned bar, unsigned count) {
+  Cta &c = *warp().cta;
+  std::lock_guard<std::mutex> lk(c.mu);
+  MBar &b = c.mbars[bar];
+  b = MBar();
+  b.expected = count;
+  b.pending = (int)count;
+}
+inline void mbar_arrive_tx(unsigned bar, long bytes, bool arrive) {
+  Cta &c = *warp().cta;
+  std::lock_guard<std::mutex> lk(c.mu);
+  auto it = c.mbars.find(bar);
+  if (it == c.mbars.end()) not_emulated("an mbarrier that was never initialised");
+  MBar &b = it->second;
+  b.tx += bytes;
+  if (arrive) {
+    if (b.pending <= 0) not_emulated("more arrivals than the mbarrier expects");
+    b.pending--;
+  }
+  mbar_complete_if_done(b);
+}
+inline void mbar_expect_tx(unsigned bar, unsigned bytes) { mbar_arrive_tx(bar, (long)bytes, true); }
+inline void mbar_arrive(unsigned bar) { mbar_arrive_tx(bar, 0, true); }
+inline bool mbar_test(unsigned bar, unsigned parity) {
+  Cta &c = *warp().cta;
+  std::lock_guard<std::mutex> lk(c.mu);
+  auto it = c.mbars.find(bar);
+  if (it == c.mbars.end()) not_emulated("waiting on an mbarrier that was never initialised");
+  return it->second.phase != (parity & 1u);  // the phase of that parity has completed
+}
+inline void mbar_wait(unsigned bar, unsigned parity) {
+  while (!mbar_test(bar, parity)) {
+    lane_yield();
+    std::this_thread::yield();
+  }
+}
+inline void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+  std::memcpy(smem_ptr(dst), src, bytes);
+  mbar_arrive_tx(bar, -(long)bytes, false);
+}
+
+// ---- launch ----
+void launch_simt(dim3 grid, dim3 block, size_t shmem, std::function<void()> body);
+
+}  // namespace emu
+
+template <class T> inline T __shfl_xor_sync(unsigned, T v, int m) { return emu::shfl_idx(v, emu::warp().cur ^ m); }
+template <class T> inline T __shfl_up_sync(unsigned, T v, int d) { return emu::shfl_idx(v, emu::warp().cur - d); }
+template <class T> inline T __shfl_down_sync(unsigned, T v, int d) { return emu::shfl_idx(v, emu::warp().cur + d); }
+inline bool __all_sync(unsigned, bool p) { return emu::vote_all(p); }
+inline void __syncwarp() { if (emu::cur_warp) emu::syncwarp(); }
+inline void __syncthreads() { emu::syncthreads(); }

@@ -12,11 +12,11 @@ thread_local dim3 block_dim, grid_dim;
 }  // namespace emu
 
 namespace beom {
-// the fused step (TMA, mbarriers, warp shuffles) is hardware: every case runs the split path here
-int fused_configure(const Dev &, const beom_params &, int, int, bool *enabled) { *enabled = false; return 0; }
-bool fused_supports(bool, bool) { return false; }
-int fused_step(const Dev &, const Dev &, int, bool, cudaStream_t, int *, int, int) { return -1; }
-void fused_release() {}
+// the FMA-contracted copies of the fused step are a hardware experiment: not built here
+int fused_launch_lean1_fma(const FusedLaunch &, bool) { return -1; }
+int fused_launch_lean2_fma(const FusedLaunch &, bool) { return -1; }
+int fused_launch_lean3_fma(const FusedLaunch &, bool) { return -1; }
+int fused_launch_lean4_fma(const FusedLaunch &, bool) { return -1; }
 // Ranks: each rank is its own copy of the emulated library (loaded from its own file, so with its own globals) driven by
 // its own thread of the test process; the halo exchange is handed to a callback of the test, which pairs the messages
 // the way NCCL does (what a rank sends to its lower neighbour is what that neighbour receives from above).
