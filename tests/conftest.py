@@ -19,6 +19,16 @@ def _built():
     from oracle import build as obuild
     build.build_all()
     obuild.build_oracle()
+    # tests/test_emulation.py re-runs the GPU test modules on the CPU emulation of the library (tools/emu, test
+    # infrastructure): it starts pytest again with BEOM_TEST_EMU naming the emulated library, which is swapped in here
+    emu = os.environ.get("BEOM_TEST_EMU")
+    if emu:
+        import ctypes
+        from beom_b200 import _lib
+        lib = _lib.bind_gpu(ctypes.CDLL(emu, mode=ctypes.RTLD_LOCAL))
+        assert b"cpu-emulation" in lib.beom_gpu_version()
+        _lib.host_lib()
+        _lib._gpu = lib
 
 
 # small versions of the named configs: same code paths, sizes the CPU oracle finishes in seconds

@@ -254,3 +254,16 @@ def test_option_matrix_on_the_emulated_fused_step(emu_so, opt):
 @pytest.mark.parametrize("extra", [{"mcbc": "0."}, {"bdrg": "2.e-3", "qdrg": "1."}, {"bdrg": "1.e-3", "qdrg": "0."}, {"tdrg": "1.e-3"}])
 def test_sill_options_on_the_emulated_fused_step(emu_so, extra):
     run(emu_so, "sill_exchange3D", 16, extra, fused=1, path="fused")
+
+
+def test_gpu_test_modules_on_the_emulation(emu_so):
+    """The GPU tests themselves, re-run with the emulated library swapped in (tests/conftest.py, BEOM_TEST_EMU): the ones
+    whose kernels nothing above reaches -- the rigid lid (hyperplane Gauss-Seidel with __syncthreads and shuffle
+    reductions), the biharmonic viscosity, the float32 diagnostic records and the conservation integrals (warp-shuffle
+    reductions).  The whole of tests/test_gpu_parity.py and tests/test_gpu_outputs.py passes this way too (about five
+    minutes; `BEOM_TEST_EMU=<libbeom_gpu_emu.so> pytest tests/test_gpu_parity.py tests/test_gpu_outputs.py -m gpu`)."""
+    env = dict(os.environ, BEOM_TEST_EMU=emu_so)
+    cmd = [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), os.path.join(ROOT, "tests", "test_gpu_outputs.py"),
+           "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider", "-k", "rigid_lid or conservation_integrals or diagnostic_records or biharmonic"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=1200, cwd=ROOT, env=env)
+    assert r.returncode == 0 and " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]

@@ -99,17 +99,19 @@ template <class T> inline T from_bits(uint64_t b) { T v; std::memcpy(&v, &b, siz
 template <class T> inline T shfl_idx(T v, int src) {
   Warp &w = warp();
   const unsigned g = w.gen;
-  const int me = w.cur;
+  if (src < 0 || src > 31 || w.done[src]) src = w.cur;  // (decided on arrival: the partner may leave the kernel right after)
   warp_collect(w, to_bits(v));
-  if (src < 0 || src > 31 || w.done[src]) src = me;
   return from_bits<T>(w.buf[g & 1][src]);
 }
 inline bool vote_all(bool p) {
   Warp &w = warp();
   const unsigned g = w.gen;
+  unsigned part = 0;  // the lanes taking part, as of this lane's arrival
+  for (int l = 0; l < 32; l++)
+    if (!w.done[l]) part |= 1u << l;
   warp_collect(w, p ? 1u : 0u);
   for (int l = 0; l < 32; l++)
-    if (!w.done[l] && !w.buf[g & 1][l]) return false;
+    if (((part >> l) & 1u) && !w.buf[g & 1][l]) return false;
   return true;
 }
 inline void syncwarp() { warp_collect(warp(), 0); }
