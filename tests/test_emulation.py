@@ -51,7 +51,7 @@ SCRIPTS = ["stommel1948", "lock_exchange", "unstable_jet", "sill_exchange3D", "c
 
 @pytest.mark.parametrize("name", SCRIPTS)
 def test_every_reference_script_on_the_emulated_split_path(emu_so, name):
-    run(emu_so, name, 30)
+    run(emu_so, name, 16)
 
 
 @pytest.mark.parametrize("name,extra", [("baines_ridge", {"mcbc": "0."}), ("wave_sponge", {"mcbc": "0."}),
@@ -236,7 +236,7 @@ def test_every_reference_script_on_the_emulated_fused_step(emu_so, name):
     """Incl. the shapes that had never run on hardware when this was written: one-row and one-column tori
     (baines_ridge, upwelling_seaward_wind, morel_upwelling), five layers, a single outcropping layer, the open-boundary
     kernel after the fused step on three sides, nudged periodic duplicates."""
-    run(emu_so, name, 24, fused=1, path="fused")
+    run(emu_so, name, 16, fused=1, path="fused")
 
 
 @pytest.mark.parametrize("nlay", [1, 3, 4])

@@ -2,14 +2,12 @@
 //
 // A small SIMT emulator for the kernels that cooperate: warp shuffles / votes, __syncwarp, __syncthreads, and the
 // sm_90+ machinery the fused step is built on (mbarriers with transaction counts, bulk global->shared copies).
-// A CTA runs as one OS thread per warp; the 32 lanes of a warp are coroutines (ucontext) of that thread, switched at
-// the collective operations, so a shuffle costs a few user-space context switches.  CTAs run one after the other.
+// A CTA runs as one OS thread per warp; the 32 lanes of a warp are coroutines of that thread (a dozen instructions of
+// x86-64 stack switching, simt.cc), switched at the collective operations, so a shuffle costs a few user-space switches.  CTAs run one after the other.
 // mbarrier waits spin cooperatively (lane yield + sched_yield): a wait that the hardware would satisfy is satisfied here,
 // a deadlock shows up as a hang (tests run the emulation under a timeout).  Bulk copies complete at once.
 // Nothing here models timing, memory-ordering subtleties of the async proxy, or bank conflicts: it checks LOGIC.
 #pragma once
-#include <ucontext.h>
-
 #include <atomic>
 #include <condition_variable>
 #include <cstdint>
@@ -21,15 +19,17 @@
 #include <thread>
 #include <vector>
 
+extern "C" void emu_switch(void **save_sp, void *load_sp);  // saves the callee-saved registers and swaps stacks
+
 namespace emu {
 
 struct Cta;
 struct Warp {
   Cta *cta = nullptr;
   int id = 0;
-  ucontext_t main;
-  ucontext_t lane[32];
-  std::vector<char> stack[32];
+  void *main_sp = nullptr;     // saved stack pointers of the scheduler and of the lanes (emu_switch)
+  void *lane_sp[32] = {};
+  char *stack[32] = {};
   bool done[32] = {};
   int active = 32, cur = 0;
   // collectives
@@ -38,12 +38,13 @@ struct Warp {
   unsigned gen = 0;
   int sync_arrived = 0;  // __syncthreads arrivals of this warp's lanes
   unsigned sync_gen = 0;
+  bool progress = false;  // some lane got past a wait (or left the kernel) since the scheduler last looked
 };
 struct MBar {
   unsigned expected = 0;
   int pending = 0;
   long tx = 0;
-  unsigned phase = 0;
+  std::atomic<unsigned> phase{0};  // read without the lock by the waiters (they poll)
 };
 struct Cta {
   dim3 block, grid;
@@ -76,7 +77,7 @@ inline void set_lane_ids(Warp &w) {
 inline void lane_yield() {  // back to the warp's scheduler
   Warp &w = warp();
   const int me = w.cur;
-  swapcontext(&w.lane[me], &w.main);
+  emu_switch(&w.lane_sp[me], w.main_sp);
   w.cur = me;
   set_lane_ids(w);
 }
@@ -93,6 +94,7 @@ inline void warp_collect(Warp &w, uint64_t mine) {
     w.gen++;
   }
   while (w.gen == g) lane_yield();
+  w.progress = true;
 }
 template <class T> inline uint64_t to_bits(T v) { uint64_t b = 0; static_assert(sizeof(T) <= 8, "shuffle of <= 8 bytes"); std::memcpy(&b, &v, sizeof(T)); return b; }
 template <class T> inline T from_bits(uint64_t b) { T v; std::memcpy(&v, &b, sizeof(T)); return v; }
@@ -133,22 +135,24 @@ inline void syncthreads() {
     w.sync_gen++;
   }
   while (w.sync_gen == g) lane_yield();
+  w.progress = true;
 }
 
 // ---- mbarriers (shared-memory objects; state kept in a side table) ----
 inline void mbar_complete_if_done(MBar &b) {
   if (b.pending == 0 && b.tx == 0) {
-    b.phase ^= 1;
     b.pending = (int)b.expected;
+    b.phase.store(b.phase.load(std::memory_order_relaxed) ^ 1u, std::memory_order_release);
   }
 }
 inline void mbar_init(unsigned bar, unsigned count) {
   Cta &c = *warp().cta;
   std::lock_guard<std::mutex> lk(c.mu);
   MBar &b = c.mbars[bar];
-  b = MBar();
   b.expected = count;
   b.pending = (int)count;
+  b.tx = 0;
+  b.phase.store(0);
 }
 inline void mbar_arrive_tx(unsigned bar, long bytes, bool arrive) {
   Cta &c = *warp().cta;
@@ -166,17 +170,14 @@ inline void mbar_arrive_tx(unsigned bar, long bytes, bool arrive) {
 inline void mbar_expect_tx(unsigned bar, unsigned bytes) { mbar_arrive_tx(bar, (long)bytes, true); }
 inline void mbar_arrive(unsigned bar) { mbar_arrive_tx(bar, 0, true); }
 inline bool mbar_test(unsigned bar, unsigned parity) {
-  Cta &c = *warp().cta;
-  std::lock_guard<std::mutex> lk(c.mu);
+  Cta &c = *warp().cta;  // (no lock: barriers are only created before the CTA-wide barrier that follows their initialisation)
   auto it = c.mbars.find(bar);
   if (it == c.mbars.end()) not_emulated("waiting on an mbarrier that was never initialised");
-  return it->second.phase != (parity & 1u);  // the phase of that parity has completed
+  return it->second.phase.load(std::memory_order_acquire) != (parity & 1u);  // the phase of that parity has completed
 }
 inline void mbar_wait(unsigned bar, unsigned parity) {
-  while (!mbar_test(bar, parity)) {
-    lane_yield();
-    std::this_thread::yield();
-  }
+  while (!mbar_test(bar, parity)) lane_yield();  // (the warp's scheduler gives the core away when none of its lanes can move)
+  warp().progress = true;
 }
 inline void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
   std::memcpy(smem_ptr(dst), src, bytes);
