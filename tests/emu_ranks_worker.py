@@ -2,7 +2,7 @@
 copy of the emulated library driven by its own thread, the halo exchange handed to a Python callback that pairs the
 messages like NCCL.  Compares every rank's own slab with the CPU oracle bit for bit.  Test infrastructure.
 
-usage: emu_ranks_worker.py <libbeom_gpu_emu.so> <case> <nsteps> <nranks> ['{"param": "value"}' ['{"kwarg": value}']]"""
+usage: emu_ranks_worker.py <libbeom_gpu_emu.so> <case> <nsteps> <nranks> ['{"param": "value"}' ['{"kwarg": value}' [fused 0|1]]]"""
 import ctypes as C
 import json
 import os
@@ -22,7 +22,8 @@ from tests.conftest import SMALL  # noqa: E402
 
 so, name, nsteps, nranks = sys.argv[1], sys.argv[2], int(sys.argv[3]), int(sys.argv[4])
 extra = json.loads(sys.argv[5]) if len(sys.argv) > 5 else {}
-kwargs = json.loads(sys.argv[6]) if len(sys.argv) > 6 else SMALL.get(name, {})
+kwargs = json.loads(sys.argv[6]) if len(sys.argv) > 6 and sys.argv[6] != "null" else SMALL.get(name, {})
+fused = int(sys.argv[7]) if len(sys.argv) > 7 else 0
 
 EXCH = C.CFUNCTYPE(C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
                    C.c_int, C.c_size_t)
@@ -87,7 +88,7 @@ def run_rank(rank):
         lib.emu_comm_set(rank, nranks, cb)
         opt = model.Options()
         lib.beom_gpu_default_options(C.byref(opt))
-        opt.fused, opt.rank, opt.nranks, opt.device = 0, rank, nranks, 0
+        opt.fused, opt.rank, opt.nranks, opt.device = fused, rank, nranks, 0
         gm = EmuRank(lib, hm.params, hm.fields(), opt)
         first, count, own_first, own_count = gm.point_range()
         gm.upload_state(hm.array("hlay"), hm.array("u"), hm.array("v"))

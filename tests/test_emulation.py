@@ -267,3 +267,19 @@ def test_gpu_test_modules_on_the_emulation(emu_so):
            "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider", "-k", "rigid_lid or conservation_integrals or diagnostic_records or biharmonic"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=1200, cwd=ROOT, env=env)
     assert r.returncode == 0 and " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("name,nsteps,nranks,kwargs", [("synthetic_basin", 9, 2, dict(n=60, mm=40, nlay=2)),
+                                                       ("synthetic_basin", 9, 4, dict(n=60, mm=90, nlay=4)),
+                                                       ("sill_exchange3D", 12, 2, None)])
+def test_y_slab_ranks_on_the_emulated_fused_step(emu_so, name, nsteps, nranks, kwargs):
+    """The fused step on y-slabs: one packed exchange of the 8 new fields' four boundary rows per step, the deep halo
+    recomputed locally -- every rank's slab bit-identical to the oracle."""
+    cmd = [sys.executable, os.path.join(ROOT, "tests", "emu_ranks_worker.py"), emu_so, name, str(nsteps), str(nranks), "{}",
+           json.dumps(kwargs), "1"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert lines, r.stdout[-2000:] + r.stderr[-2000:]
+    res = json.loads(lines[-1])
+    assert r.returncode == 0 and all(not k["bad"] and k["path"] == "fused" for k in res["ranks"]), res
+    assert all(k["exchanges"] < 3 * nsteps for k in res["ranks"])  # one exchange per fused step (+ the start-up rebuilds)
