@@ -986,6 +986,49 @@ def option_basin(nlay: int = 3, lm: int = 36, mm: int = 22, dt_s: float = 0.05, 
     return Case("option_basin", lm, mm, nlay, ndeg, text, files, {})
 
 
+def random_coast(seed: int = 1, lm: int = 70, mm: int = 44, nlay: int = 3, land: float = 0.25, wind: bool = True, sponge: bool = False,
+                 ocrp: float = 0.0, dt_s: float = 0.05) -> Case:
+    """A basin with a random coastline (smoothed noise thresholded at the ``land`` quantile: bays, islands, one-cell
+    channels, isolated lakes), tilted interfaces and optional wind / eastern sponge.  Not a reference script: it exists to
+    drive every mask combination (mk_n, mk_u, mk_v, mkpe, mkpi) through the kernels' masked rows."""
+    rng = np.random.default_rng(seed)
+    dl, depth = 2000.0, 500.0
+    z = rng.standard_normal((lm + 2, mm + 2))
+    for _ in range(3):  # cheap smoothing: bays and islands a few cells wide, with ragged one-cell features left over
+        z = 0.25 * (np.roll(z, 1, 0) + np.roll(z, -1, 0) + np.roll(z, 1, 1) + np.roll(z, -1, 1)) + 0.35 * z
+    wet = z > np.quantile(z, land)
+    h_bo = np.where(wet, depth, 0.0)
+    if sponge:
+        h_bo[lm - 9:lm + 1, 1:-1] = depth  # open water under the sponge
+    h_bo = _dry_margins(h_bo)
+    ndeg = get_nbr_deg_freedom(h_bo)
+    xs = (np.arange(lm + 2) - 0.5) / lm
+    ys = (np.arange(mm + 2) - 0.5) / mm
+    init = np.zeros((lm + 2, mm + 2, nlay, 3))
+    init[:, :, 0, 0] = 0.05 * np.sin(7.0 * xs)[:, None] * np.cos(5.0 * ys)[None, :]
+    for k in range(1, nlay):
+        init[:, :, k, 0] = (8.0 * k * (xs - 0.5))[:, None] + 2.0 * np.cos(6.0 * ys + k)[None, :]
+    init[:, :, :, 1] = 0.02 * rng.standard_normal((lm + 2, mm + 2, nlay))
+    init[:, :, :, 2] = 0.02 * rng.standard_normal((lm + 2, mm + 2, nlay))
+    files = {"h_bo": h_bo, "init": init}
+    if wind:
+        taus = np.zeros((lm + 2, mm + 2, 2))
+        taus[:, :, 0] = (0.08 * np.cos(math.pi * ys))[None, :]
+        taus[:, :, 1] = (0.04 * np.sin(2.0 * math.pi * xs))[:, None]
+        files["taus"] = taus
+    if sponge:
+        nudg = np.zeros((lm + 2, mm + 2, 3))
+        ramp = np.clip((np.arange(lm + 2) - (lm - 8)) / 8.0, 0.0, 1.0)
+        for c3 in range(3):
+            nudg[:, 1:-1, c3] = (0.03 * ramp)[:, None]
+        files["nudg"] = nudg
+    rhon = [1026.0 + 0.5 * k for k in range(nlay)]
+    topl = [k / (nlay + 0.5) for k in range(nlay)]
+    text = print_params(lm, mm, nlay, ndeg, dl, math.sqrt(9.8 * depth), 1.0e-4, rhon, topl, dt_s, dt_s, 0.0, 0.0, 0.0, 0.2, 1.0e-3, 1.0,
+                        10.0, 10.0, 1.0, 1.0, 1.0, ocrp, 0.0, 0.0, 0.0, 0.0, [0, 0], "@DIR@", "@DIR@", "random coastline %d" % seed)
+    return Case("random_coast", lm, mm, nlay, ndeg, text, files, {"wet_fraction": float(wet.mean())})
+
+
 CASES = {
     "stommel1948": stommel1948,
     "lock_exchange": lock_exchange,
@@ -1006,4 +1049,5 @@ CASES = {
     "synthetic_basin": synthetic_basin,
     "sponge_basin": sponge_basin,
     "option_basin": option_basin,
+    "random_coast": random_coast,
 }

@@ -49,6 +49,7 @@ SMALL = {
     "sill_exchange2Dtides": dict(lx=60.0e3),
     "tide_ridge": dict(lm=200),
     "wave_sponge": dict(dl=20.0e3),
+    "random_coast": dict(seed=3, lm=150, mm=90),
 }
 
 

@@ -283,3 +283,15 @@ def test_y_slab_ranks_on_the_emulated_fused_step(emu_so, name, nsteps, nranks, k
     res = json.loads(lines[-1])
     assert r.returncode == 0 and all(not k["bad"] and k["path"] == "fused" for k in res["ranks"]), res
     assert all(k["exchanges"] < 3 * nsteps for k in res["ranks"])  # one exchange per fused step (+ the start-up rebuilds)
+
+
+COASTS = [dict(seed=1), dict(seed=5, lm=120, mm=21, nlay=2, sponge=True), dict(seed=6, lm=57, mm=57, nlay=5, ocrp=1.0),
+          dict(seed=7, lm=29, mm=33, nlay=4, land=0.5), dict(seed=9, lm=85, mm=40, nlay=8, land=0.1)]
+
+
+@pytest.mark.parametrize("fused", [0, 1])
+@pytest.mark.parametrize("spec", COASTS, ids=["seed%d" % s["seed"] for s in COASTS])
+def test_random_coastlines_on_the_emulation(emu_so, spec, fused):
+    """cases.random_coast: bays, islands, one-cell channels and lakes drive every combination of the five masks through
+    the masked rows of both paths (wind, quadratic drag, optional sponge and outcropping; 1 to 8 layers)."""
+    run(emu_so, "random_coast", 12, kwargs=spec, fused=fused, path="fused" if fused else "split")

@@ -28,6 +28,7 @@ CASES = [
     ("sill_exchange2Dtides", 40, {}),       # tide.bin
     ("tide_ridge", 40, {}),                 # seven layers, tide.bin, dt_r ramp
     ("wave_sponge", 40, {}),                # sponges on four sides
+    ("random_coast", 30, {}),               # random coastline (not a reference script): every mask combination
 ]
 
 
