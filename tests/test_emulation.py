@@ -295,3 +295,26 @@ def test_random_coastlines_on_the_emulation(emu_so, spec, fused):
     """cases.random_coast: bays, islands, one-cell channels and lakes drive every combination of the five masks through
     the masked rows of both paths (wind, quadratic drag, optional sponge and outcropping; 1 to 8 layers)."""
     run(emu_so, "random_coast", 12, kwargs=spec, fused=fused, path="fused" if fused else "split")
+
+
+def test_no_out_of_bounds_access_under_addresssanitizer(tmp_path_factory):
+    """The emulated library built with -fsanitize=address: "device" memory is malloc'ed and shared memory is a vector, so
+    a kernel reading or writing outside its planes, rings or staged row segments becomes an ASan report (the CPU
+    counterpart of compute-sanitizer's memcheck).  The lean and the general fused step (several strips and chunks, a
+    one-row torus) and the split path with tidal targets."""
+    import shutil
+    spec = importlib.util.spec_from_file_location("build_emu", os.path.join(ROOT, "tools", "emu", "build_emu.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    so = mod.build(str(tmp_path_factory.mktemp("emu_asan")), sanitize=True)
+    asan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(asan) or not os.path.exists(asan):
+        pytest.skip("libasan.so not found")
+    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0:detect_stack_use_after_return=0")
+    for args in (["synthetic_basin", "6", "1", "{}", json.dumps(dict(n=130, mm=70, nlay=3))], ["baines_ridge", "8", "1"],
+                 ["sill_exchange3D", "6", "1", json.dumps({"mcbc": "0."})], ["tide_ridge", "6", "0"]):
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu_worker.py"), so] + args, capture_output=True, text=True,
+                           timeout=900, cwd=ROOT, env=env)
+        assert "AddressSanitizer" not in r.stderr and r.returncode == 0, (args, r.stdout[-500:], r.stderr[-3000:])
+        assert json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])["bad"] == []
+    shutil.rmtree(os.path.dirname(so), ignore_errors=True)

@@ -99,7 +99,9 @@ def rewrite_fused_kernel(text: str) -> str:
     return text
 
 
-def build(outdir: str) -> str:
+def build(outdir: str, sanitize: bool = False) -> str:
+    """sanitize: -fsanitize=address (load the result with LD_PRELOAD=libasan.so, ASAN_OPTIONS=detect_leaks=0): out-of-bounds
+    accesses of the kernels to "device" memory (malloc'ed here) or to the CTA's shared memory become reports."""
     os.makedirs(outdir, exist_ok=True)
     gens, total = [], 0
     units = ["beom_gpu.cu", "fused.cu", "fused_inst_general.cu"] + ["fused_inst_general%d.cu" % k for k in range(5)] + \
@@ -124,6 +126,8 @@ def build(outdir: str) -> str:
     so = os.path.join(outdir, "libbeom_gpu_emu.so")
     flags = ["-O1", "-std=c++17", "-fPIC", "-ffp-contract=off", "-Wno-unused-function", "-Wno-unknown-pragmas", "-pthread",
              "-I" + outdir, "-I" + os.path.join(HERE, "include"), "-I" + GPU_SRC, "-I" + os.path.join(ROOT, "include")]
+    if sanitize:
+        flags += ["-fsanitize=address", "-g", "-fno-omit-frame-pointer"]
     objs, jobs = [], []
     for src in gens + [os.path.join(HERE, "stubs.cc"), os.path.join(HERE, "simt.cc")]:
         obj = os.path.join(outdir, os.path.basename(src)[:-3] + ".o")
@@ -131,9 +135,11 @@ def build(outdir: str) -> str:
         jobs.append(subprocess.Popen(["g++"] + flags + ["-c", src, "-o", obj]))
     if any(j.wait() != 0 for j in jobs):
         raise subprocess.CalledProcessError(1, "g++")
-    subprocess.run(["g++", "-shared", "-pthread"] + objs + ["-Wl,-Bsymbolic", "-o", so], check=True)
+    subprocess.run(["g++", "-shared", "-pthread"] + (["-fsanitize=address"] if sanitize else []) + objs + ["-Wl,-Bsymbolic", "-o", so], check=True)
     return so
 
 
 if __name__ == "__main__":
-    print(build(sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "build", "emu")))
+    asan = "--asan" in sys.argv
+    args = [a for a in sys.argv[1:] if a != "--asan"]
+    print(build(args[0] if args else os.path.join(ROOT, "build", "emu_asan" if asan else "emu"), sanitize=asan))
