@@ -30,12 +30,45 @@ def emu_so(tmp_path_factory):
     return mod.build(str(tmp_path_factory.mktemp("emu")))
 
 
-def run(emu_so, name, nsteps, extra=None, kwargs=None, variant=0, fused=0, path="split"):
+def _cmd(emu_so, name, nsteps, extra, kwargs, variant, fused):
     cmd = [sys.executable, os.path.join(ROOT, "tests", "emu_worker.py"), emu_so, name, str(nsteps), str(fused), json.dumps(extra or {})]
     if kwargs is not None or variant:
         from tests.conftest import SMALL
         cmd += [json.dumps(kwargs if kwargs is not None else SMALL.get(name, {})), str(variant)]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    return cmd
+
+
+# Every single-rank job of this module is known when it is imported (JOBS, filled next to each parametrisation): the first
+# test that needs one runs them all, four worker processes at a time, and the tests then look their verdicts up -- the
+# wall-clock of ~100 short processes is start-up, not emulation.
+JOBS = []
+_done = {}
+
+
+def _key(name, nsteps, extra, kwargs, variant, fused):
+    return json.dumps([name, nsteps, extra or {}, kwargs, variant, fused], sort_keys=True)
+
+
+def job(name, nsteps, extra=None, kwargs=None, variant=0, fused=0):
+    JOBS.append((name, nsteps, extra, kwargs, variant, fused))
+
+
+def _run_one(emu_so, j):
+    r = subprocess.run(_cmd(emu_so, *j), capture_output=True, text=True, timeout=900, cwd=ROOT)
+    return _key(*j), r
+
+
+def run(emu_so, name, nsteps, extra=None, kwargs=None, variant=0, fused=0, path="split"):
+    k = _key(name, nsteps, extra, kwargs, variant, fused)
+    if k not in _done:
+        from concurrent.futures import ThreadPoolExecutor
+        todo = [j for j in JOBS if _key(*j) not in _done] or [(name, nsteps, extra, kwargs, variant, fused)]
+        if k not in {_key(*j) for j in todo}:
+            todo.append((name, nsteps, extra, kwargs, variant, fused))
+        with ThreadPoolExecutor(max_workers=4) as pool:
+            for kk, r in pool.map(lambda j: _run_one(emu_so, j), todo):
+                _done[kk] = r
+    r = _done[k]
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert lines, r.stdout[-2000:] + r.stderr[-2000:]
     res = json.loads(lines[-1])
@@ -49,16 +82,25 @@ SCRIPTS = ["stommel1948", "lock_exchange", "unstable_jet", "sill_exchange3D", "c
            "sill_exchange2Dtides", "tide_ridge", "wave_sponge"]
 
 
+for _n in SCRIPTS:
+    job(_n, 16)
+
+
 @pytest.mark.parametrize("name", SCRIPTS)
 def test_every_reference_script_on_the_emulated_split_path(emu_so, name):
     run(emu_so, name, 16)
 
 
-@pytest.mark.parametrize("name,extra", [("baines_ridge", {"mcbc": "0."}), ("wave_sponge", {"mcbc": "0."}),
-                                        ("sill_exchange3D", {"mcbc": "0."}), ("sill_exchange3D", {"bdrg": "2.e-3", "qdrg": "1."}),
-                                        ("sill_exchange3D", {"bdrg": "1.e-3", "qdrg": "0."}), ("sill_exchange3D", {"tdrg": "1.e-3"}),
-                                        ("sill_exchange3D", {"dt3d": "0.002"}), ("lock_exchange", {"svis": "1.e6"}),
-                                        ("stommel1948", {"rgld": "0.", "g_fb": "0."})])
+SPLIT_OPTIONS = [("baines_ridge", {"mcbc": "0."}), ("wave_sponge", {"mcbc": "0."}),
+                 ("sill_exchange3D", {"mcbc": "0."}), ("sill_exchange3D", {"bdrg": "2.e-3", "qdrg": "1."}),
+                 ("sill_exchange3D", {"bdrg": "1.e-3", "qdrg": "0."}), ("sill_exchange3D", {"tdrg": "1.e-3"}),
+                 ("sill_exchange3D", {"dt3d": "0.002"}), ("lock_exchange", {"svis": "1.e6"}),
+                 ("stommel1948", {"rgld": "0.", "g_fb": "0."})]
+for _n, _e in SPLIT_OPTIONS:
+    job(_n, 24, _e)
+
+
+@pytest.mark.parametrize("name,extra", SPLIT_OPTIONS)
 def test_options_on_the_emulated_split_path(emu_so, name, extra):
     run(emu_so, name, 24, extra)
 
@@ -70,12 +112,23 @@ OPTION_MATRIX = {
 }
 
 
+for _o in OPTION_MATRIX:
+    job("option_basin", 20, kwargs=OPTION_MATRIX[_o])
+    if _o != "tide":
+        job("option_basin", 16, kwargs=OPTION_MATRIX[_o], fused=1)
+
+
 @pytest.mark.parametrize("opt", sorted(OPTION_MATRIX))
 def test_option_matrix_on_the_emulated_split_path(emu_so, opt):
     run(emu_so, "option_basin", 20, kwargs=OPTION_MATRIX[opt])
 
 
-@pytest.mark.parametrize("variant,nlay,plum", [(1, 2, None), (2, 3, None), (3, 3, "0."), (3, 3, "1.")])
+VARIANTS = [(1, 2, None), (2, 3, None), (3, 3, "0."), (3, 3, "1.")]
+for _v, _l, _p in VARIANTS:
+    job("sponge_basin", 20, {"plum": _p} if _p else {}, kwargs=dict(nlay=_l), variant=_v)
+
+
+@pytest.mark.parametrize("variant,nlay,plum", VARIANTS)
 def test_update_h_variants_on_the_emulated_split_path(emu_so, variant, nlay, plum):
     run(emu_so, "sponge_basin", 20, {"plum": plum} if plum else {}, kwargs=dict(nlay=nlay), variant=variant)
 
@@ -231,6 +284,12 @@ def test_restart_continues_the_record_files_on_the_emulation(emu_so, tmp_path):
 FUSED_SCRIPTS = [n for n in SCRIPTS if n not in ("sill_exchange2Dtides", "tide_ridge")]  # tidal targets: split path
 
 
+for _n in FUSED_SCRIPTS:
+    job(_n, 16, fused=1)
+for _l in (1, 3, 4):
+    job("synthetic_basin", 9, kwargs=dict(n=130, mm=70, nlay=_l), fused=1)
+
+
 @pytest.mark.parametrize("name", FUSED_SCRIPTS)
 def test_every_reference_script_on_the_emulated_fused_step(emu_so, name):
     """Incl. the shapes that had never run on hardware when this was written: one-row and one-column tori
@@ -251,7 +310,12 @@ def test_option_matrix_on_the_emulated_fused_step(emu_so, opt):
     run(emu_so, "option_basin", 16, kwargs=OPTION_MATRIX[opt], fused=1, path="fused")
 
 
-@pytest.mark.parametrize("extra", [{"mcbc": "0."}, {"bdrg": "2.e-3", "qdrg": "1."}, {"bdrg": "1.e-3", "qdrg": "0."}, {"tdrg": "1.e-3"}])
+SILL_FUSED = [{"mcbc": "0."}, {"bdrg": "2.e-3", "qdrg": "1."}, {"bdrg": "1.e-3", "qdrg": "0."}, {"tdrg": "1.e-3"}]
+for _e in SILL_FUSED:
+    job("sill_exchange3D", 16, _e, fused=1)
+
+
+@pytest.mark.parametrize("extra", SILL_FUSED)
 def test_sill_options_on_the_emulated_fused_step(emu_so, extra):
     run(emu_so, "sill_exchange3D", 16, extra, fused=1, path="fused")
 
@@ -287,6 +351,11 @@ def test_y_slab_ranks_on_the_emulated_fused_step(emu_so, name, nsteps, nranks, k
 
 COASTS = [dict(seed=1), dict(seed=5, lm=120, mm=21, nlay=2, sponge=True), dict(seed=6, lm=57, mm=57, nlay=5, ocrp=1.0),
           dict(seed=7, lm=29, mm=33, nlay=4, land=0.5), dict(seed=9, lm=85, mm=40, nlay=8, land=0.1)]
+
+
+for _s in COASTS:
+    for _f in (0, 1):
+        job("random_coast", 12, kwargs=_s, fused=_f)
 
 
 @pytest.mark.parametrize("fused", [0, 1])
