@@ -127,8 +127,12 @@ inline int analyse_layout(Layout &L, int lm, int mm, int ndeg, bool xper, bool y
   for (int p = L.p_lo; p <= L.p_hi; p++) {
     if (L.cell_of_point[p] < 0) continue;
     const int j = sj[p], i = si[p];
-    if (j < L.j0 - 1 || j > L.j1 + 1) continue;  // only cells whose neighbours are read
+    // only cells whose neighbours are read -- plus, on the y-slabs of a domain periodic in x only, the east/west images of
+    // the deeper halo rows: the fused step recomputes those rows and must see them exactly as their owner does
+    const bool near = j >= L.j0 - 1 && j <= L.j1 + 1;
+    if (!near && !(xper && !yper && nranks > 1)) continue;
     for (int k = 0; k < 8; k++) {
+      if (!near && dj[k] != 0) continue;
       const int q = neig[(size_t)p * 8 + k];
       const int c = (j + dj[k] + j_off) * NX + (i + di[k] + GX0);
       if (q == point_of_cell[c] && alias_of_cell[c] < 0) continue;
@@ -180,13 +184,13 @@ inline int analyse_layout(Layout &L, int lm, int mm, int ndeg, bool xper, bool y
   // reference never indexes.  Only when the reference's own aliases (above) form a complete torus: every row
   // 1..mm aliased in x (xper), every column 1..lm aliased in y (yper).
   L.torus = false;
-  if (!mdst.empty() && nranks == 1 && (xper || yper)) {
+  if (!mdst.empty() && (xper || yper) && (nranks == 1 || !yper)) {  // (x images stay inside a row, hence inside a slab)
     const bool xp = xper, yp = yper;
     auto cell = [&](int i, int j) { return (j + j_off) * NX + (i + GX0); };
     std::vector<int> img(L.plane, -1);
     for (size_t k = 0; k < mdst.size(); k++) img[mdst[k]] = msrc[k];
     bool complete = true;
-    if (xp) for (int j = 1; j <= mm && complete; j++) complete = img[cell(0, j)] == cell(lm, j) && img[cell(lm + 1, j)] == cell(1, j);
+    if (xp) for (int j = std::max(1, L.j0 - G); j <= std::min(mm, L.j1 + G) && complete; j++) complete = img[cell(0, j)] == cell(lm, j) && img[cell(lm + 1, j)] == cell(1, j);
     if (yp) for (int i = 1; i <= lm && complete; i++) complete = img[cell(i, 0)] == cell(i, mm) && img[cell(i, mm + 1)] == cell(i, 1);
     for (size_t k = 0; k < mdst.size() && complete; k++) {  // and nothing else: every alias is the torus image
       const int X = mdst[k] % NX - GX0, Y = mdst[k] / NX - j_off;

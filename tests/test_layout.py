@@ -143,6 +143,8 @@ def test_y_slabs_show_the_reference_neighbours(shim, name, nranks):
     c, hm, ranks = build(shim, name, nranks, **kw)
     assert all(r.rc == 0 for r in ranks), [r.error for r in ranks]
     assert [r.j0 for r in ranks][0] == 1 and ranks[-1].j1 == c.mm + 1 and not any(r.ring for r in ranks)
+    # periodic in x only: the images stay inside a row, so every slab is a complete torus of its own (fused step allowed)
+    assert all(r.torus == (name == "soliton") for r in ranks)
     assert ranks[0].peer_lo == -1 and ranks[-1].peer_hi == -1
     exchange(ranks)
     owned = sum(np.count_nonzero((r.cell >= 0) & (r.sub[1] >= r.j0) & (r.sub[1] <= r.j1)) for r in ranks)
