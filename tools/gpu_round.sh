@@ -6,6 +6,9 @@
 # 2. the bench line (1 GPU) and the reference arm
 # 3. the ncu launch list of the same bench command and one --set full capture of the fused step
 # Everything lands under gpurun_out/<tag>_*; copy what is to be judged into profiles/.
+# Two GPUs (the ring of y-periodic slabs, x-periodic slabs on the fused step -- so far only seen on the CPU emulation):
+#   /usr/local/graft/bin/gpurun --gpus 2 --timeout 900 -- 'python -m pytest tests/test_multigpu.py -m gpu -q -rxXs > gpurun_out/r2_mgpu.log 2>&1; tail -20 gpurun_out/r2_mgpu.log'
+# Before any of it costs GPU minutes, the same kernels can be run on the CPU: python -m pytest tests/test_emulation.py
 tag=${1:-round}
 out=gpurun_out
 mkdir -p $out
