@@ -388,3 +388,34 @@ def test_no_out_of_bounds_access_under_addresssanitizer(tmp_path_factory):
         assert "AddressSanitizer" not in r.stderr and r.returncode == 0, (args, r.stdout[-500:], r.stderr[-3000:])
         assert json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])["bad"] == []
     shutil.rmtree(os.path.dirname(so), ignore_errors=True)
+
+
+def test_no_race_between_warps_under_threadsanitizer(tmp_path_factory):
+    """The emulated library built with -fsanitize=thread, every lane a TSan fiber (tools/emu/simt.cc): two WARPS (OS
+    threads) touching the same shared-memory word without an mbarrier / __syncthreads in between is a report -- the CPU
+    counterpart of compute-sanitizer's racecheck for the fused step's protocol (input ring refill against its readers,
+    thickness exchange between the layers of a column group, per-warp state rings).  The one race that is there by
+    design (halo lanes peeking at the neighbouring column group's thickness slot; the value only feeds discarded halo
+    results) goes through emu::halo_peek and is reported when it does not (seen while writing this).  Run through
+    beom_run with the host single-threaded: libgomp's barriers are invisible to TSan."""
+    import shutil
+    from beom_b200 import cases
+    spec = importlib.util.spec_from_file_location("build_emu", os.path.join(ROOT, "tools", "emu", "build_emu.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    so = mod.build(str(tmp_path_factory.mktemp("emu_tsan")), tsan=True)
+    tsan = subprocess.run(["gcc", "-print-file-name=libtsan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(tsan) or not os.path.exists(tsan):
+        pytest.skip("libtsan.so not found")
+    exe = os.path.join(ROOT, "beom_b200", "lib", "beom_run")
+    env = dict(os.environ, LD_PRELOAD=tsan + " " + so, OMP_NUM_THREADS="1",
+               TSAN_OPTIONS="halt_on_error=0 report_signal_unsafe=0 history_size=4 exitcode=0")
+    for k, c in enumerate((cases.synthetic_basin(n=130, mm=70, nlay=4),                 # lean, 2 strips x 4 chunks, wind
+                           cases.random_coast(seed=7, lm=29, mm=33, nlay=4, land=0.5),   # general, masked rows, drag
+                           cases.conservation(dl=30.0e3))):                              # torus
+        d = str(tmp_path_factory.mktemp("tsan_case%d" % k))
+        blk = c.write(d)
+        r = subprocess.run([exe, blk, "--steps", "5"], capture_output=True, text=True, timeout=1500, env=env, cwd=d)
+        assert r.returncode == 0 and "record = 1" in r.stdout, r.stdout[-800:] + r.stderr[-2000:]
+        assert "ThreadSanitizer" not in r.stderr, r.stderr[:6000]
+    shutil.rmtree(os.path.dirname(so), ignore_errors=True)

@@ -96,10 +96,13 @@ def rewrite_fused_kernel(text: str) -> str:
     import re
     text, n = re.subn(r'asm volatile\("fence[^\n]*\n', "/* fence */;\n", text)
     assert n == 2 and "asm volatile" not in text, n
+    # reads of the thickness ring one column to the side: across warps at the halo lanes (simt.h, halo_peek)
+    text, n = re.subn(r"\bHN\((\d), (-?1)\)", r"emu::halo_peek(&HN(\1, \2))", text)
+    assert n >= 5, n
     return text
 
 
-def build(outdir: str, sanitize: bool = False) -> str:
+def build(outdir: str, sanitize: bool = False, tsan: bool = False) -> str:
     """sanitize: -fsanitize=address (load the result with LD_PRELOAD=libasan.so, ASAN_OPTIONS=detect_leaks=0): out-of-bounds
     accesses of the kernels to "device" memory (malloc'ed here) or to the CTA's shared memory become reports."""
     os.makedirs(outdir, exist_ok=True)
@@ -128,6 +131,8 @@ def build(outdir: str, sanitize: bool = False) -> str:
              "-I" + outdir, "-I" + os.path.join(HERE, "include"), "-I" + GPU_SRC, "-I" + os.path.join(ROOT, "include")]
     if sanitize:
         flags += ["-fsanitize=address", "-g", "-fno-omit-frame-pointer"]
+    if tsan:  # every lane a TSan fiber (simt.cc): unordered accesses of different warps to shared memory are reported
+        flags += ["-fsanitize=thread", "-g", "-fno-omit-frame-pointer"]
     objs, jobs = [], []
     for src in gens + [os.path.join(HERE, "stubs.cc"), os.path.join(HERE, "simt.cc")]:
         obj = os.path.join(outdir, os.path.basename(src)[:-3] + ".o")
@@ -135,11 +140,11 @@ def build(outdir: str, sanitize: bool = False) -> str:
         jobs.append(subprocess.Popen(["g++"] + flags + ["-c", src, "-o", obj]))
     if any(j.wait() != 0 for j in jobs):
         raise subprocess.CalledProcessError(1, "g++")
-    subprocess.run(["g++", "-shared", "-pthread"] + (["-fsanitize=address"] if sanitize else []) + objs + ["-Wl,-Bsymbolic", "-o", so], check=True)
+    subprocess.run(["g++", "-shared", "-pthread"] + (["-fsanitize=address"] if sanitize else []) + (["-fsanitize=thread"] if tsan else []) + objs + ["-Wl,-Bsymbolic", "-o", so], check=True)
     return so
 
 
 if __name__ == "__main__":
-    asan = "--asan" in sys.argv
-    args = [a for a in sys.argv[1:] if a != "--asan"]
-    print(build(args[0] if args else os.path.join(ROOT, "build", "emu_asan" if asan else "emu"), sanitize=asan))
+    asan, tsan = "--asan" in sys.argv, "--tsan" in sys.argv
+    args = [a for a in sys.argv[1:] if a not in ("--asan", "--tsan")]
+    print(build(args[0] if args else os.path.join(ROOT, "build", "emu_asan" if asan else "emu_tsan" if tsan else "emu"), sanitize=asan, tsan=tsan))

@@ -30,8 +30,33 @@ emu_switch:
 .size emu_switch, .-emu_switch
 )");
 
+// ThreadSanitizer build (build_emu.py --tsan): every lane is a TSan fiber, so that accesses of different WARPS (OS threads) to
+// shared memory that are not ordered by an mbarrier / __syncthreads are reported, while the lanes of one warp -- which only
+// interleave at the switches below, each a happens-before edge -- are not.
+#if defined(__SANITIZE_THREAD__)
+extern "C" {
+void *__tsan_get_current_fiber(void);
+void *__tsan_create_fiber(unsigned flags);
+void __tsan_destroy_fiber(void *fiber);
+void __tsan_switch_to_fiber(void *fiber, unsigned flags);
+}
+#define EMU_TSAN 1
+#else
+#define EMU_TSAN 0
+#endif
+
 namespace emu {
 thread_local Warp *cur_warp = nullptr;
+#if EMU_TSAN
+thread_local void *tsan_main = nullptr;
+thread_local void *tsan_lane[32] = {};
+#endif
+void lane_to_main(Warp &w, int me) {
+#if EMU_TSAN
+  __tsan_switch_to_fiber(tsan_main, 0);
+#endif
+  emu_switch(&w.lane_sp[me], w.main_sp);
+}
 
 namespace {
 constexpr size_t kLaneStack = 512 * 1024;
@@ -51,12 +76,18 @@ void lane_entry() {
   (*w.cta->body)();
   lane_finished(w);
   void *dead = nullptr;
+#if EMU_TSAN
+  __tsan_switch_to_fiber(tsan_main, 0);
+#endif
   emu_switch(&dead, w.main_sp);  // for good: a finished lane is never resumed
   std::abort();
 }
 void run_warp(Warp *wp, int nlanes) {
   Warp &w = *wp;
   cur_warp = wp;
+#if EMU_TSAN
+  tsan_main = __tsan_get_current_fiber();
+#endif
   w.active = nlanes;
   for (int l = 0; l < 32; l++) {
     w.done[l] = l >= nlanes;
@@ -69,6 +100,9 @@ void run_warp(Warp *wp, int nlanes) {
     *--sp = (void *)&lane_entry;     // popped by emu_switch's ret: rsp is then 8 mod 16, as after a call
     for (int k = 0; k < 6; k++) *--sp = nullptr;
     w.lane_sp[l] = (void *)sp;
+#if EMU_TSAN
+    tsan_lane[l] = __tsan_create_fiber(0);
+#endif
   }
   while (w.active > 0) {
     w.progress = false;
@@ -76,10 +110,16 @@ void run_warp(Warp *wp, int nlanes) {
       if (w.done[l]) continue;
       w.cur = l;
       set_lane_ids(w);
+#if EMU_TSAN
+      __tsan_switch_to_fiber(tsan_lane[l], 0);
+#endif
       emu_switch(&w.main_sp, w.lane_sp[l]);
     }
     if (!w.progress && w.active > 0) std::this_thread::yield();  // every lane waits for another warp: let that one run
   }
+#if EMU_TSAN
+  for (int l = 0; l < nlanes; l++) __tsan_destroy_fiber(tsan_lane[l]);
+#endif
   cur_warp = nullptr;
 }
 }  // namespace
