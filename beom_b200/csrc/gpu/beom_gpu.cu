@@ -591,6 +591,14 @@ int beom_gpu_init(const beom_params *par, const beom_fields *fld, const beom_gpu
     g.halo_cap = (size_t)G * g.NX * (size_t)nlay * 12;  // up to 12 layered fields per exchange
     for (int k = 0; k < 2; k++)
       if ((rc = dalloc(&g.halo_send[k], g.halo_cap)) || (rc = dalloc(&g.halo_recv[k], g.halo_cap))) return rc;
+    if (g.ring && g.torus) {
+      // the statics of the deep rows across the seam of a y-periodic slab chain are another rank's rows: one ring
+      // exchange each (every rank initialises, so this is a collective like the rest of a multi-rank init)
+      if ((rc = sync_fields({{const_cast<double *>(D.fcor), 1}, {const_cast<double *>(D.h_th), 1}}))) return rc;
+      if (D.has_nudg && (rc = sync_fields({{const_cast<double *>(D.nudg), 3}}))) return rc;
+      if (D.fnud && (rc = sync_fields({{const_cast<double *>(D.fnud), 3 * nlay}}))) return rc;
+      if (D.has_hdot && (rc = sync_fields({{const_cast<double *>(D.hdot), nlay}}))) return rc;
+    }
   }
 
   // scalars and constants, evaluated like the reference does

@@ -127,10 +127,10 @@ inline int analyse_layout(Layout &L, int lm, int mm, int ndeg, bool xper, bool y
   for (int p = L.p_lo; p <= L.p_hi; p++) {
     if (L.cell_of_point[p] < 0) continue;
     const int j = sj[p], i = si[p];
-    // only cells whose neighbours are read -- plus, on the y-slabs of a domain periodic in x only, the east/west images of
+    // only cells whose neighbours are read -- plus, on the y-slabs of a domain periodic in x, the east/west images of
     // the deeper halo rows: the fused step recomputes those rows and must see them exactly as their owner does
     const bool near = j >= L.j0 - 1 && j <= L.j1 + 1;
-    if (!near && !(xper && !yper && nranks > 1)) continue;
+    if (!near && !(xper && nranks > 1)) continue;
     for (int k = 0; k < 8; k++) {
       if (!near && dj[k] != 0) continue;
       const int q = neig[(size_t)p * 8 + k];
@@ -179,17 +179,42 @@ inline int analyse_layout(Layout &L, int lm, int mm, int ndeg, bool xper, bool y
   // a mirror's source may itself have been turned into a mirror/orphan: forbid chains
   for (size_t k = 0; k < msrc.size(); k++)
     if (msrc[k] < 0) return layout_fail(L, -9, "beom_gpu_init: chained periodic aliases are not supported");
+  // The ring is a property of the parameters, so that every rank takes part in the same exchange.  It copies whole
+  // rows (row mm -> row 0 of the first rank, row 1 -> row mm+1 of the last), which equals the reference's aliasing when
+  // every vector point of the seam rows has been displaced by an image (a seam with dry gaps keeps points of its own
+  // there) and every point of the source rows is imaged; the ranks at the seam need G rows to send.
+  L.ring = yper && nranks > 1;
+  if (L.ring) {
+    if (L.j1 - L.j0 + 1 < G + 1) return layout_fail(L, -9, "beom_gpu_init: a y-periodic domain needs at least %d rows per rank", G + 1);
+    for (int p = L.p_lo; p <= L.p_hi; p++) {
+      const bool seam = (rank == 0 && sj[p] == 0) || (rank == nranks - 1 && sj[p] == mm + 1);
+      if (seam && L.cell_of_point[p] >= 0)
+        return layout_fail(L, -9, "beom_gpu_init: a y-periodic seam with dry gaps cannot be split into y-slabs (point %d keeps a cell of its own)", p);
+    }
+    for (int q = 1; q <= ndeg; q++) {  // every rank knows the whole grid
+      int jc = -1;
+      if (rank == 0 && sj[q] == mm) jc = 0;
+      if (rank == nranks - 1 && sj[q] == 1) jc = mm + 1;
+      if (jc < 0 || si[q] < 1 || si[q] > lm) continue;  // (the margin / duplicate columns show their own images)
+      if (alias_of_cell[(jc + j_off) * NX + (si[q] + GX0)] != q)
+        return layout_fail(L, -9, "beom_gpu_init: unsupported y-periodic connectivity (point %d of the seam is not imaged on rank %d)", q, rank);
+    }
+  }
   // Deep torus ghosts.  The fused step recomputes its halo (2 columns, 3-4 rows) instead of re-reading it, so on a
   // periodic domain the cells up to 3 columns / 4 rows outside the core must show periodic images too -- cells the
   // reference never indexes.  Only when the reference's own aliases (above) form a complete torus: every row
   // 1..mm aliased in x (xper), every column 1..lm aliased in y (yper).
+  // On y-slabs the x images stay inside a row, hence inside a slab; the y images of the seam rows are another rank's rows
+  // (the ring above, already verified), so only the x part is looked at here and the deep rows across the seam get their
+  // flags from the points they show (below).
   L.torus = false;
-  if (!mdst.empty() && (xper || yper) && (nranks == 1 || !yper)) {  // (x images stay inside a row, hence inside a slab)
-    const bool xp = xper, yp = yper;
+  if ((!mdst.empty() || L.ring) && (xper || yper)) {
+    const bool xp = xper, yp = yper && nranks == 1;
     auto cell = [&](int i, int j) { return (j + j_off) * NX + (i + GX0); };
     std::vector<int> img(L.plane, -1);
     for (size_t k = 0; k < mdst.size(); k++) img[mdst[k]] = msrc[k];
     bool complete = true;
+    // (on a ring, the rows next to the seam have already lost their corner images to the remote list: rows 1..mm only)
     if (xp) for (int j = std::max(1, L.j0 - G); j <= std::min(mm, L.j1 + G) && complete; j++) complete = img[cell(0, j)] == cell(lm, j) && img[cell(lm + 1, j)] == cell(1, j);
     if (yp) for (int i = 1; i <= lm && complete; i++) complete = img[cell(i, 0)] == cell(i, mm) && img[cell(i, mm + 1)] == cell(i, 1);
     for (size_t k = 0; k < mdst.size() && complete; k++) {  // and nothing else: every alias is the torus image
@@ -212,31 +237,28 @@ inline int analyse_layout(Layout &L, int lm, int mm, int ndeg, bool xper, bool y
       L.torus = true;
     }
   }
-  // The ring is a property of the parameters, so that every rank takes part in the same exchange.  It copies whole
-  // rows (row mm -> row 0 of the first rank, row 1 -> row mm+1 of the last), which equals the reference's aliasing when
-  // every vector point of the seam rows has been displaced by an image (a seam with dry gaps keeps points of its own
-  // there) and every point of the source rows is imaged; the ranks at the seam need G rows to send.
-  L.ring = yper && nranks > 1;
-  if (L.ring) {
-    if (L.j1 - L.j0 + 1 < G + 1) return layout_fail(L, -9, "beom_gpu_init: a y-periodic domain needs at least %d rows per rank", G + 1);
-    for (int p = L.p_lo; p <= L.p_hi; p++) {
-      const bool seam = (rank == 0 && sj[p] == 0) || (rank == nranks - 1 && sj[p] == mm + 1);
-      if (seam && L.cell_of_point[p] >= 0)
-        return layout_fail(L, -9, "beom_gpu_init: a y-periodic seam with dry gaps cannot be split into y-slabs (point %d keeps a cell of its own)", p);
-    }
-    for (int q = 1; q <= ndeg; q++) {  // every rank knows the whole grid
-      int jc = -1;
-      if (rank == 0 && sj[q] == mm) jc = 0;
-      if (rank == nranks - 1 && sj[q] == 1) jc = mm + 1;
-      if (jc < 0 || si[q] < 1 || si[q] > lm) continue;  // (the margin / duplicate columns show their own images)
-      if (alias_of_cell[(jc + j_off) * NX + (si[q] + GX0)] != q)
-        return layout_fail(L, -9, "beom_gpu_init: unsupported y-periodic connectivity (point %d of the seam is not imaged on rank %d)", q, rank);
-    }
-  }
   for (size_t k = 0; k < mdst.size(); k++)
     hflags[mdst[k]] = (uint8_t)((hflags[msrc[k]] & ~F_ACT) | ((hflags[msrc[k]] & F_ACT) ? F_GHOST : 0));
   // remote images: the masks of the point they show (every rank holds the static fields of the whole domain), never active
   for (size_t k = 0; k < rdst.size(); k++) hflags[rdst[k]] = (uint8_t)((flags_of_point(rsrc[k]) & ~F_ACT) | F_GHOST);
+  if (L.ring && L.torus) {
+    // the deep rows across the seam (the fused step recomputes them): G rows below row 1 on the first rank show rows
+    // mm-G+1..mm, G rows from mm+1 on the last rank show rows 1..G -- flagged with the masks of the points they show
+    std::vector<int> grid((size_t)(lm + 2) * (mm + 2), 0);
+    for (int p = 1; p <= ndeg; p++) grid[(size_t)sj[p] * (lm + 2) + si[p]] = p;
+    for (int k = 0; k < G && (rank == 0 || rank == nranks - 1); k++) {
+      const int js = rank == 0 ? mm - k : 1 + k;        // the row shown ...
+      const int jh = rank == 0 ? -k : mm + 1 + k;       // ... and the row showing it
+      if (jh + j_off < 0 || jh + j_off >= L.NY || js < 1 || js > mm) continue;
+      for (int i = -3; i <= lm + 4; i++) {
+        if (i + GX0 < 0 || i + GX0 >= NX) continue;
+        const int is = xper ? wrap(i, lm) : i;
+        if (is < 0 || is > lm + 1) continue;
+        const int q = grid[(size_t)js * (lm + 2) + is];
+        if (q) hflags[(jh + j_off) * NX + (i + GX0)] = (uint8_t)((flags_of_point(q) & ~F_ACT) | F_GHOST);
+      }
+    }
+  }
   return 0;
 }
 

@@ -336,7 +336,9 @@ def test_gpu_test_modules_on_the_emulation(emu_so):
 @pytest.mark.parametrize("name,nsteps,nranks,kwargs", [("synthetic_basin", 9, 2, dict(n=60, mm=40, nlay=2)),
                                                        ("synthetic_basin", 9, 4, dict(n=60, mm=90, nlay=4)),
                                                        ("sill_exchange3D", 12, 2, None),
-                                                       ("soliton", 12, 3, None)])   # periodic in x: every slab is a torus of its own
+                                                       ("soliton", 12, 3, None),    # periodic in x: every slab is a torus of its own
+                                                       ("conservation", 12, 3, None),  # doubly periodic: deep rows across the ring
+                                                       ("unstable_jet", 12, 4, None)])
 def test_y_slab_ranks_on_the_emulated_fused_step(emu_so, name, nsteps, nranks, kwargs):
     """The fused step on y-slabs: one packed exchange of the 8 new fields' four boundary rows per step, the deep halo
     recomputed locally -- every rank's slab bit-identical to the oracle."""
