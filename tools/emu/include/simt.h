@@ -185,6 +185,13 @@ inline void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar
   mbar_arrive_tx(bar, -(long)bytes, false);
 }
 
+// Shared -> global bulk copies (cp.async.bulk.global.shared::cta with bulk groups), for store-side variants of the fused
+// step: the copy happens at once, so commit / wait are no-ops here -- what the emulation checks is WHAT is stored WHERE,
+// not when the staging buffer may be reused (on hardware: after cp.async.bulk.wait_group.read).
+inline void bulk_s2g(void *dst, unsigned src, unsigned bytes) { std::memcpy(dst, smem_ptr(src), bytes); }
+inline void bulk_commit_group() {}
+inline void bulk_wait_group_read(int) {}
+
 // The thickness ring of the fused step is read one column beyond a warp's own 32 by its halo lanes (lanes 0 and 31 look at
 // the neighbouring column group's slot, which that warp may be rewriting: the value only ever feeds halo-lane results
 // that are thrown away -- fused_kernel.cuh, "lanes 0,1,30,31 are the x halo").  Those reads go through this function so
