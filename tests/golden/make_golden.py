@@ -26,6 +26,18 @@ GOLDEN = {
     "unstable_jet": (dict(dl=60.0e3), 80),
     "sill_exchange3D": (dict(lx=6.0e3, ly=100.0e3), 80),
     "conservation": (dict(dl=30.0e3), 100),
+    # the further reference scripts (small versions as in tests/conftest.py)
+    "soliton": (dict(dl=80.0e3), 60),
+    "baines_ridge": (dict(scale=0.3), 60),
+    "carrier_beach": (dict(mesh=20.0), 80),
+    "upwelling_seaward_wind": (dict(lm=80), 60),
+    "mixed_open_bc": (dict(lm=60, mm=40), 60),
+    "morel_upwelling": (dict(dl=4.0e3), 60),
+    "outcrop_seamount": (dict(), 60),
+    "sill_exchange2D": (dict(lx=140.0e3), 60),
+    "sill_exchange2Dtides": (dict(lx=60.0e3), 60),
+    "tide_ridge": (dict(lm=200), 60),
+    "wave_sponge": (dict(dl=20.0e3), 60),
 }
 
 
@@ -45,5 +57,8 @@ def run(name):
 
 if __name__ == "__main__":
     for name in GOLDEN:
-        np.savez_compressed(os.path.join(HERE, name + ".npz"), **run(name))
+        path = os.path.join(HERE, name + ".npz")
+        if os.path.exists(path) and "--all" not in sys.argv:
+            continue  # frozen: only missing vectors are made (--all regenerates everything)
+        np.savez_compressed(path, **run(name))
         print("wrote", name)

@@ -280,7 +280,9 @@ def test_two_dimensional_sill_cases_run_and_keep_their_layers(name):
     assert np.allclose(h[:, wet].sum(axis=0), h_start[:, wet].sum(axis=0), atol=0.5)  # the free surface barely moves
 
 
-@pytest.mark.parametrize("name", ["stommel1948", "lock_exchange", "unstable_jet", "sill_exchange3D", "conservation"])
+@pytest.mark.parametrize("name", ["stommel1948", "lock_exchange", "unstable_jet", "sill_exchange3D", "conservation", "soliton",
+                                  "baines_ridge", "carrier_beach", "upwelling_seaward_wind", "mixed_open_bc", "morel_upwelling",
+                                  "outcrop_seamount", "sill_exchange2D", "sill_exchange2Dtides", "tide_ridge", "wave_sponge"])
 def test_oracle_reproduces_its_golden_vectors(name):
     import importlib.util
     spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLD, "make_golden.py"))
