@@ -421,3 +421,13 @@ def test_no_race_between_warps_under_threadsanitizer(tmp_path_factory):
         assert r.returncode == 0 and "record = 1" in r.stdout, r.stdout[-800:] + r.stderr[-2000:]
         assert "ThreadSanitizer" not in r.stderr, r.stderr[:6000]
     shutil.rmtree(os.path.dirname(so), ignore_errors=True)
+
+
+def test_halo_overlap_variant_on_emulated_ranks(emu_so):
+    """BEOM_OVERLAP=1 (off by default): the G rows next to each neighbour first, their exchange while
+    the rows in between are computed -- three launches per step instead of one; the result must not change."""
+    cmd = [sys.executable, os.path.join(ROOT, "tests", "emu_ranks_worker.py"), emu_so, "synthetic_basin", "9", "2", "{}",
+           json.dumps(dict(n=60, mm=90, nlay=2)), "1"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=dict(os.environ, BEOM_OVERLAP="1"))
+    res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    assert r.returncode == 0 and all(not k["bad"] and k["path"] == "fused" for k in res["ranks"]), res
