@@ -86,6 +86,7 @@ struct Ctx {
   HaloRows halo;                   // peers and rows of the packed halo exchange
   int own_first = 0, own_last = -1;  // vector points of the rows this rank owns (a contiguous range)
   double adv_ramp = 1.0, adv_gene = 0.0;  // beom_gpu_advance: ramp and gene of the previous step
+  double *fnud_tide = nullptr;     // [3][nlay] planes: the step's relaxation targets with the tidal term (fused step only)
   float *rec_f32 = nullptr;        // [nlay] dense float32 planes: one diagnostic record
   float *rec_stage = nullptr;      // vector-layout staging of one layer of a record
   double *diag_h0 = nullptr;       // [nlay] dense h_0 (beom_gpu_diagnostics)
@@ -702,6 +703,13 @@ int beom_gpu_step(int tstp, double ctim, double ramp, double gene, int upst, int
       g.launches++;
       if ((rc = sync_fields({{D.h_u, g.nlay}, {D.h_v, g.nlay}}))) return rc;
     }
+    const double *fnud_plain = D.fnud;
+    if (D.has_tide) {  // this step's targets with the tidal term (the fused step's stream table has no room for the tidal planes)
+      if (!g.fnud_tide && (rc = dalloc(&g.fnud_tide, g.plane * (size_t)g.nlay * 3))) return rc;
+      k_tide_targets<<<dim3((unsigned)((g.plane + 255) / 256), (unsigned)g.nlay), 256, 0, g.stream>>>(D, g.fnud_tide);
+      g.launches++;
+      D.fnud = g.fnud_tide;
+    }
     const bool obc = g.D.has_nudg && g.P.mcbc < 0.5 && g.nseg > 0;
     // BEOM_OVERLAP=1: exchange the edge rows while the interior rows are computed (measured slower than the plain
     // sequence at 2 GPUs: NCCL's copy kernels displace CTAs of a grid sized for exactly two waves)
@@ -726,6 +734,7 @@ int beom_gpu_step(int tstp, double ctim, double ramp, double gene, int upst, int
       g.launches += nlaunch;
       if (obc) {  // no_gradient_obc after both components (pm:2285-2288)
         Dev Dobc = D;
+        Dobc.fnud = fnud_plain;  // (the open-boundary copy uses the plain targets, pm:2613-2679)
         Dobc.hlay = Dout.hlay; Dobc.u = Dout.u; Dobc.v = Dout.v; Dobc.h_u = Dout.h_u; Dobc.h_v = Dout.h_v;
         for (int pass = 0; pass < 2; pass++) {
           k_obc<<<(g.nseg + 63) / 64, 64, 0, g.stream>>>(Dobc, g.d_seg, g.nseg, pass);

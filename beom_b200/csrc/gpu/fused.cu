@@ -117,7 +117,9 @@ int fused_configure(const Dev &D, const beom_params &P, int nmir, int nranks, bo
   (void)nranks;
   if (nmir != 0) return 0;  // periodic aliases: split path (for now)
   if (P.rgld > 0.5 || P.svis > 0.0 || P.variant != BEOM_VARIANT_STANDARD) return 0;
-  if (D.has_tide) return 0;
+  // tidal targets: the caller hands the step fnud + tide term (k_tide_targets); exact only when the Ekman term of the
+  // target, which the reference adds between the two, is absent or an exact zero; periodic images of the targets are not kept
+  if (D.has_tide && ((D.has_wind && D.invf != 0.0) || P.xper > 0.5 || P.yper > 0.5)) return 0;
   if (D.nlay > kMaxLay) return 0;
   const double dtd8 = P.dt / 24.0 / 3600.0;
   const bool every_step = std::floor(P.dt3d / dtd8 + 0.5) < 2.0;  // n_3d = 1

@@ -27,6 +27,24 @@ __device__ __forceinline__ double tide_term(const Dev &D, size_t c, int comp) {
 }
 __device__ __forceinline__ double single(double x) { return (double)(float)x; }
 
+// The relaxation targets of one step with the tidal term added, for the fused step (whose stream table has no room for
+// the six tidal planes): out[comp][layer] = fnud + ramp*A*cos(phi - w*ctim), the first two terms of the reference's
+// hfor / ufor / vfor (private_mod.f95:1453-1454, 1538-1539, 1633-1634; eta: layer 1 only), same expressions as
+// k_update_h / k_update_u / k_update_v above.  Every cell of the plane: the fused step also reads its halo and ghost cells.
+// (Only used when the Ekman term that would come between the two is absent or exactly zero: fused_configure.)
+__global__ void k_tide_targets(const __grid_constant__ Dev D, double *__restrict__ out) {
+  const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= D.plane) return;
+  const int l = blockIdx.y;
+  for (int comp = 0; comp < 3; comp++) {
+    const size_t k = ((size_t)comp * D.nlay + l) * D.plane + c;
+    double t = D.fnud[k];
+    if (comp == 0) t = t + tide_term(D, c, 0) * (l == 0 ? 1.0 : 0.0);
+    else t = t + tide_term(D, c, comp);
+    out[k] = t;
+  }
+}
+
 // ---- first_three_timesteps flux rebuild, private_mod.f95:2166-2177 (and 2208-2219) ----
 __global__ void k_centred_flux(const __grid_constant__ Dev D) {
   BEOM_CELL(D)

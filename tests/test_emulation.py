@@ -281,7 +281,7 @@ def test_restart_continues_the_record_files_on_the_emulation(emu_so, tmp_path):
 # memory starts filled with a byte pattern, so a read of something never written shows up as garbage.  A protocol error
 # (an mbarrier wait nobody satisfies) is a hang: the workers run under a timeout.
 # ------------------------------------------------------------------------------------------------------------------
-FUSED_SCRIPTS = [n for n in SCRIPTS if n not in ("sill_exchange2Dtides", "tide_ridge")]  # tidal targets: split path
+FUSED_SCRIPTS = list(SCRIPTS)  # all sixteen (tidal targets: the step is handed fnud + tide term, k_tide_targets)
 
 
 for _n in FUSED_SCRIPTS:
@@ -305,9 +305,22 @@ def test_the_bench_workload_on_the_emulated_fused_step(emu_so, nlay):
     run(emu_so, "synthetic_basin", 9, kwargs=dict(n=130, mm=70, nlay=nlay), fused=1, path="fused")
 
 
+job("option_basin", 16, kwargs=dict(tide=True), fused=1)
+job("option_basin", 16, kwargs=dict(tide=True, wind=False), fused=1)
+job("tide_ridge", 16, {"mcbc": "0."}, fused=1)
+
+
 @pytest.mark.parametrize("opt", sorted(k for k in OPTION_MATRIX if k != "tide"))
 def test_option_matrix_on_the_emulated_fused_step(emu_so, opt):
     run(emu_so, "option_basin", 16, kwargs=OPTION_MATRIX[opt], fused=1, path="fused")
+
+
+def test_tidal_targets_on_the_emulated_fused_step(emu_so):
+    """Tides run fused unless the Ekman term of the sponge target (wind stress and f != 0), which the reference adds
+    between fnud and the tidal term, is live: then the sum would associate differently and the split path is kept."""
+    run(emu_so, "option_basin", 16, kwargs=dict(tide=True, wind=False), fused=1, path="fused")
+    run(emu_so, "option_basin", 16, kwargs=dict(tide=True), fused=1, path="split")
+    run(emu_so, "tide_ridge", 16, {"mcbc": "0."}, fused=1, path="fused")  # + no_gradient_obc with the plain targets
 
 
 SILL_FUSED = [{"mcbc": "0."}, {"bdrg": "2.e-3", "qdrg": "1."}, {"bdrg": "1.e-3", "qdrg": "0."}, {"tdrg": "1.e-3"}]
