@@ -22,12 +22,21 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+_sanitizer_builds = {}
+
+
 @pytest.fixture(scope="module")
 def emu_so(tmp_path_factory):
+    from concurrent.futures import ThreadPoolExecutor
     spec = importlib.util.spec_from_file_location("build_emu", os.path.join(ROOT, "tools", "emu", "build_emu.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
-    return mod.build(str(tmp_path_factory.mktemp("emu")))
+    so = mod.build(str(tmp_path_factory.mktemp("emu")))
+    # the two sanitizer variants are compiled in the background while the emulation jobs run
+    pool = ThreadPoolExecutor(max_workers=2)
+    _sanitizer_builds["asan"] = pool.submit(mod.build, str(tmp_path_factory.mktemp("emu_asan")), True, False)
+    _sanitizer_builds["tsan"] = pool.submit(mod.build, str(tmp_path_factory.mktemp("emu_tsan")), False, True)
+    return so
 
 
 def _cmd(emu_so, name, nsteps, extra, kwargs, variant, fused):
@@ -382,16 +391,13 @@ def test_random_coastlines_on_the_emulation(emu_so, spec, fused):
     run(emu_so, "random_coast", 12, kwargs=spec, fused=fused, path="fused" if fused else "split")
 
 
-def test_no_out_of_bounds_access_under_addresssanitizer(tmp_path_factory):
+def test_no_out_of_bounds_access_under_addresssanitizer(emu_so, tmp_path_factory):
     """The emulated library built with -fsanitize=address: "device" memory is malloc'ed and shared memory is a vector, so
     a kernel reading or writing outside its planes, rings or staged row segments becomes an ASan report (the CPU
     counterpart of compute-sanitizer's memcheck).  The lean and the general fused step (several strips and chunks, a
     one-row torus) and the split path with tidal targets."""
     import shutil
-    spec = importlib.util.spec_from_file_location("build_emu", os.path.join(ROOT, "tools", "emu", "build_emu.py"))
-    mod = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mod)
-    so = mod.build(str(tmp_path_factory.mktemp("emu_asan")), sanitize=True)
+    so = _sanitizer_builds["asan"].result(timeout=1200)
     asan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
     if not os.path.isabs(asan) or not os.path.exists(asan):
         pytest.skip("libasan.so not found")
@@ -405,7 +411,7 @@ def test_no_out_of_bounds_access_under_addresssanitizer(tmp_path_factory):
     shutil.rmtree(os.path.dirname(so), ignore_errors=True)
 
 
-def test_no_race_between_warps_under_threadsanitizer(tmp_path_factory):
+def test_no_race_between_warps_under_threadsanitizer(emu_so, tmp_path_factory):
     """The emulated library built with -fsanitize=thread, every lane a TSan fiber (tools/emu/simt.cc): two WARPS (OS
     threads) touching the same shared-memory word without an mbarrier / __syncthreads in between is a report -- the CPU
     counterpart of compute-sanitizer's racecheck for the fused step's protocol (input ring refill against its readers,
@@ -415,10 +421,7 @@ def test_no_race_between_warps_under_threadsanitizer(tmp_path_factory):
     beom_run with the host single-threaded: libgomp's barriers are invisible to TSan."""
     import shutil
     from beom_b200 import cases
-    spec = importlib.util.spec_from_file_location("build_emu", os.path.join(ROOT, "tools", "emu", "build_emu.py"))
-    mod = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(mod)
-    so = mod.build(str(tmp_path_factory.mktemp("emu_tsan")), tsan=True)
+    so = _sanitizer_builds["tsan"].result(timeout=1200)
     tsan = subprocess.run(["gcc", "-print-file-name=libtsan.so"], capture_output=True, text=True).stdout.strip()
     if not os.path.isabs(tsan) or not os.path.exists(tsan):
         pytest.skip("libtsan.so not found")
