@@ -93,29 +93,44 @@ def make_case(n, nlay, workdir, mm=None):
     return c, blk
 
 
-def cpu_baseline(sample_n, nlay, steps, tmp):
+def host_cores() -> int:
+    """Cores this process may use (the affinity mask when there is one), not whatever OMP_NUM_THREADS was inherited."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def cpu_baseline(sample_n, nlay, steps, tmp, warm=1):
     """Times the oracle's OpenMP build (the reference's loops with the reference's `!$OMP PARALLEL DO'
-    placement) on a bounded sample of the same workload."""
+    placement) on a sample_n x sample_n x nlay basin of the same workload, on every host core: torchrun exports
+    OMP_NUM_THREADS=1 to its workers, so the thread count is set explicitly, not inherited."""
     from beom_b200 import model
     from oracle.pyoracle import Oracle
-    d = os.path.join(tmp, "cpu_sample")
+    d = os.path.join(tmp, "cpu_sample_%d" % sample_n)
     c, blk = make_case(sample_n, nlay, d)
     with open(blk) as f:
         p, idir, _, _ = model.parse_params(f.read())
-    cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
-    orc = Oracle(p, idir, omp=True)
-    orc.advance(1, 4)  # start-up steps + one generalized forward-backward step (warm caches)
+    cores = host_cores()
+    os.environ["OMP_NUM_THREADS"] = str(cores)
     t0 = time.perf_counter()
-    orc.advance(5, 4 + steps)
+    orc = Oracle(p, idir, omp=True)
+    try:
+        C.CDLL("libgomp.so.1").omp_set_num_threads(cores)  # (libgomp may have read the environment before this point)
+    except OSError:
+        pass
+    t_init = time.perf_counter() - t0
+    orc.advance(1, 3 + max(warm, 1))  # start-up steps + generalized forward-backward warm-up steps
+    t0 = time.perf_counter()
+    orc.advance(4 + max(warm, 1), 3 + max(warm, 1) + steps)
     dt = time.perf_counter() - t0
     orc.close()
     shutil.rmtree(d, ignore_errors=True)
     ups = float(sample_n) * sample_n * nlay * steps / dt
-    return {"value": ups, "unit": "cell-layer updates/s", "cores": int(os.environ["OMP_NUM_THREADS"]), "kind": "port",
-            "sample": "%dx%dx%d basin of the same workload, %d generalized-FB steps, oracle built -O3 -fopenmp "
-                      "(the reference cannot be compiled here: no Fortran compiler)" % (sample_n, sample_n, nlay, steps),
-            "seconds": dt}
+    return {"value": ups, "unit": "cell-layer updates/s", "cores": cores, "kind": "port",
+            "sample": "%dx%dx%d basin of the same workload, %d generalized-FB steps after %d warm-up steps, oracle built -O3 -fopenmp, "
+                      "%d threads (the reference cannot be compiled here: no Fortran compiler)" % (sample_n, sample_n, nlay, steps, 3 + max(warm, 1), cores),
+            "grid": [sample_n, sample_n, nlay], "seconds": dt, "init_seconds": t_init}
 
 
 def emit(line: dict) -> None:
@@ -147,6 +162,7 @@ def main():
     ap.add_argument("--split", action="store_true", help="one kernel per reference loop instead of the fused step")
     ap.add_argument("--cpu-sample", type=int, default=2048)
     ap.add_argument("--cpu-steps", type=int, default=120, help="steps of the CPU baseline leg on the sample (about 10-15 s of CPU work on 16 threads)")
+    ap.add_argument("--ref-budget", type=float, default=200.0, help="--impl reference: seconds the full-grid CPU run may take (else the sample is the value)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--fma", action="store_true", help="opt-in: the FMA-contracted copy of the fused step (tolerance parity, not bit-exact)")
@@ -178,14 +194,37 @@ def main():
         tmp = tempfile.mkdtemp(prefix="beom_ref_")
         try:
             W = max(args.warmup, 0)
-            cb = cpu_baseline(args.cpu_sample, nlay, max(args.steps, 1), tmp)
+            K = max(args.steps, 1)
+            # a bounded sample first: it says how long the full grid would take on this box
+            sample = cpu_baseline(args.cpu_sample, nlay, min(K, 20), tmp)
+            est_step = float(n) * n * nlay / sample["value"]
+            est_total = est_step * (3 + max(W, 1) + K) + 0.4 * est_step * 20 + 30.0  # + read_input_data + writing the inputs
+            try:
+                import psutil
+                free_gb = psutil.virtual_memory().available / 2.0 ** 30
+            except Exception:
+                free_gb = 0.0
+            need_gb = (30.0 * nlay + 20.0) * (n + 1.0) * (n + 1.0) * 8.0 / 2.0 ** 30
+            full = None
+            if n > args.cpu_sample and est_total < args.ref_budget and free_gb > 1.3 * need_gb:
+                log("[reference] full %dx%dx%d grid: estimated %.0f s, %.0f GB of host memory (%.0f GB free)" % (n, n, nlay, est_total, need_gb, free_gb))
+                full = cpu_baseline(n, nlay, K, tmp, warm=max(W, 1))
+            else:
+                log("[reference] the full grid does not fit (estimated %.0f s against a budget of %.0f s; %.0f GB needed, %.0f GB free): "
+                    "the %d^2 sample is the arm's value" % (est_total, args.ref_budget, need_gb, free_gb, args.cpu_sample))
         finally:
             shutil.rmtree(tmp, ignore_errors=True)
-        ms = 1.0e3 * (float(n) * n * nlay) / cb["value"]  # per step of the full workload at this rate
+        cb = full or sample
+        gn = cb["grid"][0]
+        ms = 1.0e3 * (float(gn) * gn * nlay) / cb["value"]  # per step of the grid that was timed
+        cfg = dict(config, grid=cb["grid"], decomposition="host cores x%d (OpenMP)" % cb["cores"],
+                   timed_on="the full grid" if full else "a %dx%dx%d sample of the workload (the full grid would not finish in the time budget)" % tuple(cb["grid"]))
+        if not full:
+            cfg["workload"] = cfg["workload"] + " -- SAMPLE %dx%dx%d" % tuple(cb["grid"])
         line = {"impl": "reference", "metric": "cell_layer_updates_per_s", "value": cb["value"], "unit": "cell-layer updates/s",
-                "n_gpus": args.gpus, "steps": args.steps, "warmup": W, "ms_per_step": ms, "higher_is_better": True,
-                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-                "cpu_baseline": cb, "gpu_launches": 0,
+                "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+                "cpu_baseline": cb, "sample_leg": sample if full else None, "gpu_launches": 0,
                 "e2e": {"value": cb["value"], "unit": "cell-layer updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         emit(line)
         return 0
@@ -235,6 +274,9 @@ def main():
                 hl[:] = hm.array("hlay")[:, first:first + count]
                 uu[:] = hm.array("u")[:, first:first + count]
                 vv[:] = hm.array("v")[:, first:first + count]
+                # grid row of every own point: the state checksum below is taken row by row, which makes it independent
+                # of how the rows are dealt out to ranks
+                own_rows = np.array(hm.iarray("subc")[1][own_first:own_first + own_count], copy=True)
                 hm.close()
                 log("[rank %d] read_input_data + beom_gpu_init: %.1f s" % (rank, time.perf_counter() - t0))
             if world > 1:
@@ -304,6 +346,30 @@ def main():
             e2e = {"value": updates_per_step * steps / dt, "unit": "cell-layer updates/s", "h2d_bytes_per_step": nbytes / steps,
                    "d2h_bytes_per_step": nbytes / steps, "seconds": dt,
                    "what": "beom_gpu_upload_state (pinned host hlay,u,v) + %d steps + beom_gpu_download_state" % steps}
+        # ---- what the e2e leg computed, as a checksum that does not depend on the decomposition: sha256 per (field,
+        # layer, grid row) of the rows each rank owns, concatenated in global order and hashed again.  The step is
+        # bit-exact, so the line must carry the same state_sha256 at N = 1, 2, 4, 8.
+        state_sha = None
+        if e2e is not None:
+            import hashlib
+            t0 = time.perf_counter()
+            cuts = np.concatenate(([0], np.flatnonzero(np.diff(own_rows)) + 1, [own_count])) + (own_first - first)
+            mine = []
+            for arr in (hl, uu, vv):
+                for l in range(nlay):
+                    row = arr[l]
+                    mine.append(b"".join(hashlib.sha256(row[a:b].tobytes()).digest() for a, b in zip(cuts[:-1], cuts[1:])))
+            parts = [mine]
+            if world > 1:
+                parts = [None] * world if rank == 0 else None
+                dist.gather_object(mine, parts, dst=0)
+            if rank == 0:
+                h = hashlib.sha256()
+                for k in range(3 * nlay):
+                    for r in range(world):
+                        h.update(parts[r][k])
+                state_sha = h.hexdigest()
+                log("[rank 0] state checksum over hlay,u,v after %d steps: %s (%.1f s)" % (steps, state_sha, time.perf_counter() - t0))
         path = gm.path
         gm.close()
     finally:
@@ -339,7 +405,8 @@ def main():
     line = {"metric": "cell_layer_updates_per_s", "value": value, "unit": "cell-layer updates/s", "n_gpus": world, "steps": steps,
             "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": dict(config, path=path), "roofline": roofline, "cpu_baseline": cb,
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "state_sha256": state_sha, "state_sha256_nsteps": steps if state_sha else None}
     emit(line)
     if world > 1:
         dist.destroy_process_group()

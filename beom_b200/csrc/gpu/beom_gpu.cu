@@ -61,7 +61,8 @@ struct Ctx {
   int nmir = 0;
   int *d_mir_dst = nullptr, *d_mir_src = nullptr;
   SegDev *d_seg = nullptr;
-  int nseg = 0;
+  int nseg = 0;          // open-boundary segments whose points this rank owns
+  bool obc_any = false;  // some rank has open-boundary segments: every rank takes part in the exchanges around k_obc
   // buffers
   uint8_t *flags = nullptr;
   double *st[5][2] = {{nullptr}};  // hlay,u,v,h_u,h_v x {A,B}
@@ -227,9 +228,10 @@ int run_stress() {
   if (D.has_tdrg) { k_stress_drag<<<cell_grid(D, 1, kBlock), kBlock, 0, g.stream>>>(D, 1); g.launches++; }
   k_stress_apply<<<cell_grid(D, g.nlay, kBlock), kBlock, 0, g.stream>>>(D);
   g.launches++;
-  if (D.has_wind) mirror(D.tt3d, 2 * g.nlay);
-  if (D.has_bdrg) mirror(D.tb3d, 2 * g.nlay);
-  if (D.has_tdrg) mirror(D.tu3d, 2 * g.nlay);
+  int rc;
+  if (D.has_wind && (rc = mirror(D.tt3d, 2 * g.nlay))) return rc;
+  if (D.has_bdrg && (rc = mirror(D.tb3d, 2 * g.nlay))) return rc;
+  if (D.has_tdrg && (rc = mirror(D.tu3d, 2 * g.nlay))) return rc;
   CK(cudaGetLastError());
   return 0;
 }
@@ -286,8 +288,8 @@ int step_split(int tstp, bool upst, bool first_three) {
   }
   g.dx_o = (g.dx_o + 1) % 4;
   g.dy_o = (g.dy_o + 1) % 4;
-  if (g.D.has_nudg && g.P.mcbc < 0.5 && g.nseg > 0) {  // pm:2201-2204 / 2285-2288
-    for (int pass = 0; pass < 2; pass++) {
+  if (g.D.has_nudg && g.P.mcbc < 0.5 && g.obc_any) {  // pm:2201-2204 / 2285-2288
+    for (int pass = 0; pass < 2 && g.nseg > 0; pass++) {
       k_obc<<<(g.nseg + 63) / 64, 64, 0, g.stream>>>(D, g.d_seg, g.nseg, pass);
       g.launches++;
     }
@@ -341,8 +343,18 @@ int beom_gpu_finalize(void) {
   return 0;
 }
 
+static int init_impl(const beom_params *par, const beom_fields *fld, const beom_gpu_options *opt_in);
 int beom_gpu_init(const beom_params *par, const beom_fields *fld, const beom_gpu_options *opt_in) {
   if (g.ready) beom_gpu_finalize();
+  const int rc = init_impl(par, fld, opt_in);
+  if (rc) {  // release the streams, events and allocations made before the failure; the message survives
+    const std::string keep = g_err;
+    beom_gpu_finalize();
+    g_err = keep;
+  }
+  return rc;
+}
+static int init_impl(const beom_params *par, const beom_fields *fld, const beom_gpu_options *opt_in) {
   if (!par || !fld) return fail(-1, "beom_gpu_init: null argument");
   beom_gpu_options opt;
   if (opt_in) opt = *opt_in;
@@ -539,6 +551,7 @@ int beom_gpu_init(const beom_params *par, const beom_fields *fld, const beom_gpu
     if ((rc = dalloc(&D.tu3d, pl * nl * 2)) || (rc = dalloc(&D.layu, pl * nl)) || (rc = dalloc(&D.taum, pl * 2))) return rc;
 
   if (par->rgld > 0.5) {  // rigid lid: Poisson operators and the start pressure (private_mod.f95:505-563)
+    if (g.nranks > 1 || g.nmir) return fail(-30, "beom_gpu_init: rgld = 1 is supported on one GPU, non-periodic domains only");
     if (!fld->Ow || !fld->Os || !fld->Osum_) return fail(-14, "beom_gpu_init: rgld = 1 needs Ow, Os, Osum_");
     if (nlay != 2) return fail(-14, "beom_gpu_init: the reference's rigid lid is written for two layers (private_mod.f95:1653-1654)");
     double *o1 = nullptr, *o2 = nullptr, *o3 = nullptr;
@@ -550,6 +563,7 @@ int beom_gpu_init(const beom_params *par, const beom_fields *fld, const beom_gpu
 
   // open-boundary segments as dense cells (private_mod.f95:1060-1240, columns 1,4,5,10,13,16)
   g.nseg = 0;
+  g.obc_any = fld->segm && fld->nseg > 0 && fld->flag_nudging;
   if (fld->segm && fld->nseg > 0 && fld->flag_nudging) {
     std::vector<SegDev> segs;
     for (int s = 0; s < fld->nseg; s++) {
@@ -710,7 +724,7 @@ int beom_gpu_step(int tstp, double ctim, double ramp, double gene, int upst, int
       g.launches++;
       D.fnud = g.fnud_tide;
     }
-    const bool obc = g.D.has_nudg && g.P.mcbc < 0.5 && g.nseg > 0;
+    const bool obc = g.D.has_nudg && g.P.mcbc < 0.5 && g.obc_any;  // (decided alike on every rank: the exchanges are collective)
     // BEOM_OVERLAP=1: exchange the edge rows while the interior rows are computed (measured slower than the plain
     // sequence at 2 GPUs: NCCL's copy kernels displace CTAs of a grid sized for exactly two waves)
     static const bool want_overlap = getenv("BEOM_OVERLAP") && atoi(getenv("BEOM_OVERLAP")) > 0;
@@ -732,18 +746,27 @@ int beom_gpu_step(int tstp, double ctim, double ramp, double gene, int upst, int
       rc = fused_step(D, Dout, tstp, first_three != 0, g.stream, &nlaunch);
       if (rc) return fail(rc, "fused_step failed: %s", cudaGetErrorString(cudaGetLastError()));
       g.launches += nlaunch;
+      const bool shadows = g.nranks > 1 || g.nmir;  // halo rows of the neighbouring ranks / periodic images (deep torus ghosts)
       if (obc) {  // no_gradient_obc after both components (pm:2285-2288)
+        // the open-boundary copy reads hlay, u, v at neighbours of the segment points (neig 5 / 7, pm:2635-2676), which
+        // may be periodic images or a neighbouring rank's rows: the step wrote only the rows it owns, so refresh them first
+        if (shadows) {
+          rc = sync_fields({{Dout.hlay, g.nlay}, {Dout.u, g.nlay}, {Dout.v, g.nlay}, {Dout.h_u, g.nlay}, {Dout.h_v, g.nlay},
+                            {D.rs_new, g.nlay}, {D.dx_new, g.nlay}, {D.dy_new, g.nlay}});
+          if (rc) return rc;
+        }
         Dev Dobc = D;
         Dobc.fnud = fnud_plain;  // (the open-boundary copy uses the plain targets, pm:2613-2679)
         Dobc.hlay = Dout.hlay; Dobc.u = Dout.u; Dobc.v = Dout.v; Dobc.h_u = Dout.h_u; Dobc.h_v = Dout.h_v;
-        for (int pass = 0; pass < 2; pass++) {
+        for (int pass = 0; pass < 2 && g.nseg > 0; pass++) {
           k_obc<<<(g.nseg + 63) / 64, 64, 0, g.stream>>>(Dobc, g.d_seg, g.nseg, pass);
           g.launches++;
         }
       }
-      if (g.nranks > 1 || g.nmir) {  // halo rows of the neighbouring ranks / periodic images (deep torus ghosts)
-        rc = sync_fields({{Dout.hlay, g.nlay}, {Dout.u, g.nlay}, {Dout.v, g.nlay}, {Dout.h_u, g.nlay}, {Dout.h_v, g.nlay},
-                          {D.rs_new, g.nlay}, {D.dx_new, g.nlay}, {D.dy_new, g.nlay}});
+      if (shadows) {
+        if (obc) rc = sync_fields({{Dout.u, g.nlay}, {Dout.v, g.nlay}, {Dout.h_u, g.nlay}, {Dout.h_v, g.nlay}});  // what k_obc rewrote
+        else rc = sync_fields({{Dout.hlay, g.nlay}, {Dout.u, g.nlay}, {Dout.v, g.nlay}, {Dout.h_u, g.nlay}, {Dout.h_v, g.nlay},
+                               {D.rs_new, g.nlay}, {D.dx_new, g.nlay}, {D.dy_new, g.nlay}});
         if (rc) return rc;
       }
     }

@@ -181,7 +181,13 @@ int fused_configure(const Dev &D, const beom_params &P, int nmir, int nranks, bo
 
 // The three start-up steps (plain forward-backward, gene = 0) run on the general instantiation after the caller has
 // rebuilt the centred fluxes (private_mod.f95:2166-2177).
-bool fused_supports(bool first_three, bool upst) { return cfg.ok && (upst || first_three); }
+// Whatever fused_configure accepted either recomputes its upst-dependent terms every step (n_3d = 1: Leith viscosity,
+// drag) or does not depend on upst at all (dvis = 0: v_cc = v_ll = bvis for ever, private_mod.f95:2268-2270), so steps
+// between two 3-D updates run here as well -- the split path's stored v_cc / v_ll would never have been filled.
+bool fused_supports(bool first_three, bool upst) {
+  (void)first_three; (void)upst;
+  return cfg.ok;
+}
 
 // part: 0 = every row of the slab, 1 = only the `edge` rows next to each neighbouring rank (two chunks), 2 = the rows
 // in between (the part whose computation hides the halo exchange of part 1)

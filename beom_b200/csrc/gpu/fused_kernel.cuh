@@ -244,7 +244,11 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
   const int tile = blockIdx.x * groups + grp;
   const int xs = D.x_lo + blockIdx.x * groups * kUse - kPad;  // first staged column of the CTA (even)
   const int x = xs + 2 + grp * kUse + lane;                    // lane 0 = first result column - 2
+#ifdef BEOM_DBG_NOSTORE  // timing experiment (tools/ab.sh): every global store predicated off at run time; results are garbage
+  const bool col_ok = lane >= kHalo && lane < 32 - kHalo && x <= D.x_hi && D.dt < -1.0;
+#else
   const bool col_ok = lane >= kHalo && lane < 32 - kHalo && x <= D.x_hi;
+#endif
   // rows of this CTA.  rows_per_chunk < 0: the two "edge" chunks of a y-slab (the -rows_per_chunk rows next to each
   // neighbouring rank), which are computed first so that their exchange overlaps the interior rows
   const int ya = rows_per_chunk > 0 ? D.y_lo + blockIdx.y * rows_per_chunk : (blockIdx.y == 0 ? D.y_lo : D.y_hi + rows_per_chunk + 1);

@@ -157,6 +157,7 @@ RANKS = [
     ("synthetic_basin", 9, 2, {}, dict(n=60, mm=40, nlay=2)),   # plain y-slabs (the configuration that HAS run on 2 B200s)
     ("sill_exchange3D", 12, 2, {}, None),
     ("wave_sponge", 12, 4, {"mcbc": "0."}, None),               # open-boundary segments spread over four ranks
+    ("sill_exchange3D", 12, 3, {"mcbc": "0."}, None),           # ... and a middle rank that owns none (the exchanges stay collective)
     ("soliton", 12, 3, {}, None),                                # x-periodic: images stay inside a rank
     ("conservation", 12, 2, {}, None),                           # doubly periodic: the halo exchange is ring-closed
     ("conservation", 12, 3, {}, None),
@@ -332,7 +333,8 @@ def test_tidal_targets_on_the_emulated_fused_step(emu_so):
     run(emu_so, "tide_ridge", 16, {"mcbc": "0."}, fused=1, path="fused")  # + no_gradient_obc with the plain targets
 
 
-SILL_FUSED = [{"mcbc": "0."}, {"bdrg": "2.e-3", "qdrg": "1."}, {"bdrg": "1.e-3", "qdrg": "0."}, {"tdrg": "1.e-3"}]
+SILL_FUSED = [{"mcbc": "0."}, {"bdrg": "2.e-3", "qdrg": "1."}, {"bdrg": "1.e-3", "qdrg": "0."}, {"tdrg": "1.e-3"},
+              {"dt3d": "0.002", "dvis": "0.", "bvis": "30."}]  # n_3d > 1 with a constant viscosity stays on the fused step
 for _e in SILL_FUSED:
     job("sill_exchange3D", 16, _e, fused=1)
 
@@ -340,6 +342,19 @@ for _e in SILL_FUSED:
 @pytest.mark.parametrize("extra", SILL_FUSED)
 def test_sill_options_on_the_emulated_fused_step(emu_so, extra):
     run(emu_so, "sill_exchange3D", 16, extra, fused=1, path="fused")
+
+
+OBC_FUSED = [("baines_ridge", 24), ("wave_sponge", 16), ("mixed_open_bc", 16)]
+for _n, _k in OBC_FUSED:
+    job(_n, _k, {"mcbc": "0."}, fused=1)
+
+
+@pytest.mark.parametrize("name,nsteps", OBC_FUSED)
+def test_open_boundaries_after_the_emulated_fused_step(emu_so, name, nsteps):
+    """no_gradient_obc reads hlay, u, v at neighbours of the segment points (pm:2635-2676).  After the fused step, which
+    writes only the rows it owns, those may be stale periodic images: in baines_ridge (one row, periodic in y) EVERY
+    southern neighbour is one -- the combination that failed on the B200 in round 1."""
+    run(emu_so, name, nsteps, {"mcbc": "0."}, fused=1, path="fused")
 
 
 def test_gpu_test_modules_on_the_emulation(emu_so):
@@ -355,23 +370,30 @@ def test_gpu_test_modules_on_the_emulation(emu_so):
     assert r.returncode == 0 and " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
 
 
-@pytest.mark.parametrize("name,nsteps,nranks,kwargs", [("synthetic_basin", 9, 2, dict(n=60, mm=40, nlay=2)),
-                                                       ("synthetic_basin", 9, 4, dict(n=60, mm=90, nlay=4)),
-                                                       ("sill_exchange3D", 12, 2, None),
-                                                       ("soliton", 12, 3, None),    # periodic in x: every slab is a torus of its own
-                                                       ("conservation", 12, 3, None),  # doubly periodic: deep rows across the ring
-                                                       ("unstable_jet", 12, 4, None)])
-def test_y_slab_ranks_on_the_emulated_fused_step(emu_so, name, nsteps, nranks, kwargs):
+RANKS_FUSED = [("synthetic_basin", 9, 2, dict(n=60, mm=40, nlay=2), {}),
+               ("synthetic_basin", 9, 4, dict(n=60, mm=90, nlay=4), {}),
+               ("sill_exchange3D", 12, 2, None, {}),
+               ("soliton", 12, 3, None, {}),        # periodic in x: every slab is a torus of its own
+               ("conservation", 12, 3, None, {}),   # doubly periodic: deep rows across the ring
+               ("unstable_jet", 12, 4, None, {}),
+               ("wave_sponge", 12, 4, None, {"mcbc": "0."}),      # open-boundary segments whose neighbours are another rank's rows
+               ("sill_exchange3D", 12, 3, None, {"mcbc": "0."})]
+
+
+@pytest.mark.parametrize("name,nsteps,nranks,kwargs,extra", RANKS_FUSED,
+                         ids=["%s-%d%s" % (r[0], r[2], "-obc" if r[4] else "") for r in RANKS_FUSED])
+def test_y_slab_ranks_on_the_emulated_fused_step(emu_so, name, nsteps, nranks, kwargs, extra):
     """The fused step on y-slabs: one packed exchange of the 8 new fields' four boundary rows per step, the deep halo
-    recomputed locally -- every rank's slab bit-identical to the oracle."""
-    cmd = [sys.executable, os.path.join(ROOT, "tests", "emu_ranks_worker.py"), emu_so, name, str(nsteps), str(nranks), "{}",
+    recomputed locally -- every rank's slab bit-identical to the oracle.  With no_gradient_obc
+    (mcbc = 0) the exchange runs before the open-boundary copy and once more, for u, v, h_u, h_v, after it."""
+    cmd = [sys.executable, os.path.join(ROOT, "tests", "emu_ranks_worker.py"), emu_so, name, str(nsteps), str(nranks), json.dumps(extra),
            json.dumps(kwargs), "1"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert lines, r.stdout[-2000:] + r.stderr[-2000:]
     res = json.loads(lines[-1])
     assert r.returncode == 0 and all(not k["bad"] and k["path"] == "fused" for k in res["ranks"]), res
-    assert all(k["exchanges"] < 3 * nsteps for k in res["ranks"])  # one exchange per fused step (+ the start-up rebuilds)
+    assert all(k["exchanges"] < 3 * nsteps for k in res["ranks"])  # one exchange per fused step (two with mcbc = 0; + the start-up rebuilds)
 
 
 COASTS = [dict(seed=1), dict(seed=5, lm=120, mm=21, nlay=2, sponge=True), dict(seed=6, lm=57, mm=57, nlay=5, ocrp=1.0),

@@ -130,11 +130,12 @@ def _check_state(tag, got, orc, names=("hlay", "u", "v")):
     dict(bdrg="3.e-3", qdrg="1."),                     # a7: quadratic bottom drag with outcropping (layb)
     dict(bdrg="1.e-4", qdrg="0.", tdrg="2.e-4"),       # a7: linear bottom + top drag (layu)
     dict(dt3d="0.001"),                                # stress / viscosity refreshed every n_3d > 1 steps
-], ids=["obc", "quad_drag", "top_drag", "n3d"])
+    dict(dt3d="0.001", dvis="0.", bvis="30."),         # n_3d > 1 with a constant viscosity: nothing depends on upst, fused
+], ids=["obc", "quad_drag", "top_drag", "n3d", "n3d_const_visc"])
 def test_sill_options_bit_exact(case_factory, fused, extra):
     c, hm, orc, st, aux, path = run_pair(case_factory, "sill_exchange3D", 40, fused, extra=extra)
     if "dt3d" in extra:
-        assert orc.counts()[2] > 1 and path == "split"
+        assert orc.counts()[2] > 1 and path == ("fused" if (fused and "bvis" in extra) else "split")
     _check_state("sill" + str(extra), st, orc)
     assert_same("h_u", aux[0], orc.array("h_u"))
     assert_same("h_v", aux[1], orc.array("h_v"))

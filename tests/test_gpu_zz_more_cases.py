@@ -32,12 +32,9 @@ CASES = [
 ]
 
 
-# Written after round 1's GPU budget was spent: none of these has run on hardware yet (the CPU side of each -- case
-# set-up, oracle, the connectivity / segment analysis of beom_gpu_init restated in Python, the comparison logic of the
-# worker -- has; and the split path's kernel source, compiled for the CPU, is bit-identical to the oracle on every one of
-# them, tests/test_emulation.py).  Non-strict xfail keeps the suite's verdict on the tests that HAVE been observed; an XPASS here is
-# new evidence, an XFAIL a bug to fix.  To be promoted to plain tests as soon as they have been seen on a B200.
-@pytest.mark.xfail(strict=False, reason="not yet observed on a GPU (round-1 GPU budget exhausted before these cases existed)")
+# All of these were bit-identical to the oracle on a B200 in round 1's driver run except baines_ridge + mcbc = 0 on the fused
+# step (k_obc read periodic images the fused step had not refreshed yet; fixed in beom_gpu_step, covered on the CPU by
+# tests/test_emulation.py::test_open_boundaries_after_the_emulated_fused_step).  Plain tests: a mismatch fails the suite.
 @pytest.mark.parametrize("fused", [0, 1])
 @pytest.mark.parametrize("name,nsteps,extra", CASES, ids=["%s%s" % (n, "-obc" if e else "") for n, _, e in CASES])
 def test_reference_script_bit_exact(name, nsteps, extra, fused):

@@ -55,18 +55,13 @@ def test_rendezvous_over_gloo():
     assert out[0][2] == out[1][2] == [(1, 251), (252, 502)]
 
 
-_UNSEEN = pytest.mark.xfail(strict=False, reason="not yet observed on GPUs (written after round 1's GPU budget was spent); the index "
-                                                 "logic of the ring / x-periodic slabs is checked on the CPU in tests/test_layout.py and the complete steps on emulated ranks in "
-                                                 "tests/test_emulation.py")
-
-
 @pytest.mark.gpu
 @pytest.mark.parametrize("name,nsteps,fused", [("synthetic_basin", 12, 1), ("synthetic_basin", 9, 0), ("sill_exchange3D", 12, 1),
-                                               pytest.param("conservation", 12, 0, marks=_UNSEEN),   # y-periodic: ring-closed exchange
-                                               pytest.param("conservation", 12, 1, marks=_UNSEEN),   # ... and the fused step across the ring
-                                               pytest.param("unstable_jet", 12, 1, marks=_UNSEEN),
-                                               pytest.param("soliton", 12, 0, marks=_UNSEEN),        # x-periodic slabs
-                                               pytest.param("soliton", 12, 1, marks=_UNSEEN)])       # ... each a torus of its own: fused
+                                               ("conservation", 12, 0),   # y-periodic: ring-closed exchange
+                                               ("conservation", 12, 1),   # ... and the fused step across the ring
+                                               ("unstable_jet", 12, 1),
+                                               ("soliton", 12, 0),        # x-periodic slabs
+                                               ("soliton", 12, 1)])       # ... each a torus of its own: fused
 def test_two_ranks_bit_exact(name, nsteps, fused):
     import torch
     if torch.cuda.device_count() < 2:
