@@ -131,7 +131,10 @@ def test_bench_reference_arm_prints_one_json_line(tmp_path):
               "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
         assert k in d, k
     assert d["impl"] == "reference" and d["value"] > 0 and d["cpu_baseline"]["kind"] == "port"
-    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["config"]["grid"] == [8192, 8192, 4]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0
+    # the full 8192^2 grid does not fit this test's box/time budget: the line must say, truthfully, that it timed the sample
+    assert d["config"]["grid"] == [96, 96, 4] and "SAMPLE 96x96x4" in d["config"]["workload"]
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["grid"] == [96, 96, 4]
 
 
 def test_fused_step_shared_memory_plan_fits_one_sm(tmp_path):
