@@ -160,6 +160,7 @@ int fused_configure(const Dev &D, const beom_params &P, int nmir, int nranks, bo
   cfg.groups = groups;
   cfg.strips = (width + groups * kUse - 1) / (groups * kUse);
   int chunks = std::max(1, (2 * sms + cfg.strips / 2) / cfg.strips);  // about two CTAs' worth of work per SM
+  if (const char *e = getenv("BEOM_FUSED_CHUNKS")) chunks = std::max(1, atoi(e));  // experiment: y-chunks per strip
   chunks = std::min(chunks, std::max(1, rows / 16));
   chunks = std::max(chunks, (rows + 3839) / 3840);  // the lean kernel keeps a chunk's open-water bitmap in 32 words (32 x 128 rows)
   cfg.rows_per_chunk = (rows + chunks - 1) / chunks;

@@ -60,6 +60,9 @@ constexpr int kMaxLay = 8;            // layers per CTA (shared-memory exchange,
 #ifndef BEOM_TRYWAIT_HINT
 #define BEOM_TRYWAIT_HINT 20000   // suspend-time hint (ns) of mbarrier.try_wait (the warp sleeps in hardware instead of spinning); 0 = none
 #endif
+#ifndef BEOM_ISSUE_LATE
+#define BEOM_ISSUE_LATE 0
+#endif
 #ifndef BEOM_FUSED_WARPS
 #define BEOM_FUSED_WARPS 16
 #endif
@@ -119,9 +122,15 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
       : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
+#ifdef BEOM_BULK_CTA  // experiment: the CTA-local destination form (no cluster rank lookup per copy)
+  asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+               "r"(bar)
+               : "memory");
+#else
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
                "r"(bar)
                : "memory");
+#endif
 }
 
 // One momentum update: update_u (private_mod.f95:1437-1500) when IS_U, update_v (private_mod.f95:1520-1586)
@@ -388,6 +397,14 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
     HN(0, 0) = hn_0;
     __syncwarp();
     if (lane == 0) mbar_arrive(gbar0 + 8 * hslot);  // split-phase: waited for at the end of the row
+#if BEOM_ISSUE_LATE == 1
+    // experiment: the refill of the slots row R - 1 has released is issued here, not at the end of row R - 1 -- a warp that is
+    // ahead of the other column groups of its layer starts its next row instead of waiting for them
+    if (R - 1 >= Rs && R + 1 <= Rend) {
+      mbar_wait(empty0 + 8 * SLOT(1), CT ? (PH == 0 ? bpar ^ 1u : bpar) : (unsigned)(((R - 1 - Rs) >> 2) & 1));
+      issue(R + 1);
+    }
+#endif
 
     // -------------------------------------------------------------------------------- rvor, dive, row R (pm:2388, 2435)
     const double u_0 = LD4(S_U, 0, 0), uE_0 = LD4(S_U, 0, 1), u_m1 = LD4(S_U, 1, 0);
@@ -433,6 +450,12 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
     AT(rv, 0) = rv_0;
     AT(dv, 0) = dv_0;
 
+#if BEOM_ISSUE_LATE == 2
+    if (R - 1 >= Rs && R + 1 <= Rend) {  // experiment: as above, but half a row later
+      mbar_wait(empty0 + 8 * SLOT(1), CT ? (PH == 0 ? bpar ^ 1u : bpar) : (unsigned)(((R - 1 - Rs) >> 2) & 1));
+      issue(R + 1);
+    }
+#endif
     // -------------------------------------------------------------------------------- momentum
     const bool a2 = fw_m2 & (F_ACT | F_GHOST);
     const bool sto2 = col_ok && (!MASKED || (fw_m2 & F_ACT)) && row2_own;
@@ -536,10 +559,12 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
 
     __syncwarp();
     if (lane == 0) mbar_arrive(empty0 + 8 * SLOT(0));  // this warp has finished reading the slots row R + 2 refills
+#if !BEOM_ISSUE_LATE
     if (R + 2 <= Rend) {
       mbar_wait(empty0 + 8 * SLOT(0), bpar);           // ... and so has every other column group of the layer
       issue(R + 2);
     }
+#endif
     off0 += row_bytes;
     off2 += row_bytes;
   };

@@ -1,0 +1,137 @@
+"""The four named configs of BASELINE.json at the sizes their scripts ship with (stommel1948
+ndeg 6 464 / 1 layer, lock_exchange 322 / 2, unstable_jet 54 136 / 1, sill_exchange3D 63 252 / 2): 200 steps through the
+C ABI on both kernel paths, bit for bit against the CPU oracle, and their step times (latency-bound: at most 1.3e5
+cell-layers).  Reference: testcases/stommel1948.m:85-88, lock_exchange.m:61-64, unstable_jet.m:63-66,
+sill_exchange3D.m:152-155.
+
+Plus the long run the north star asks for on the chaotic case: 1 000 steps of unstable_jet at native size -- state
+identical to the oracle's, layer volume conserved to rounding, kinetic + potential energy and potential-vorticity
+envelope equal to the oracle's (conservation.m:116-211)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from beom_b200 import model
+from oracle.pyoracle import Oracle
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NATIVE = {"stommel1948": (6464, 1), "lock_exchange": (322, 2), "unstable_jet": (54136, 1), "sill_exchange3D": (63252, 2)}
+NSTEPS = 200
+
+_oracle_cache = {}
+
+
+def _record(key, value):
+    """Step times go to gpurun_out/native_configs.json (scratch; BASELINE.md's table is filled from it)."""
+    out = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        path = os.path.join(out, "native_configs.json")
+        data = {}
+        if os.path.exists(path):
+            with open(path) as f:
+                data = json.load(f)
+        data[key] = value
+        with open(path, "w") as f:
+            json.dump(data, f, indent=1, sort_keys=True)
+    except OSError:
+        pass
+
+
+def _oracle_state(name, hm, d, nsteps):
+    key = (name, nsteps)
+    if key not in _oracle_cache:
+        orc = Oracle(hm.params, d, omp=True)  # the OpenMP build of the same source: same results, the test stays short
+        orc.advance(1, nsteps)
+        _oracle_cache[key] = {k: np.array(orc.array(k), copy=True) for k in ("hlay", "u", "v", "h_u", "h_v")}
+        orc.close()
+    return _oracle_cache[key]
+
+
+def _same(name, got, want):
+    want = want.reshape(got.shape)
+    if not np.array_equal(got, want):
+        bad = np.argwhere(got != want)
+        k = tuple(bad[0])
+        raise AssertionError("%s differs at %d entries, first %s: got %r want %r" % (name, len(bad), k, got[k], want[k]))
+
+
+@pytest.mark.parametrize("fused", [False, True], ids=["split", "fused"])
+@pytest.mark.parametrize("name", list(NATIVE))
+def test_named_config_at_native_size(case_factory, name, fused):
+    c, d, hm = case_factory(name, small=False)
+    ndeg, nlay = NATIVE[name]
+    assert (c.ndeg, hm.params.nlay) == (ndeg, nlay)
+    want = _oracle_state(name, hm, d, NSTEPS)
+    gm = model.GpuModel(hm.params, hm.fields(), model.default_options(fused=fused))
+    gm.upload_state(hm.array("hlay"), hm.array("u"), hm.array("v"))
+    gm.advance(1, 20)
+    gm.sync()
+    gm.mark(0)
+    gm.advance(21, NSTEPS)
+    gm.mark(1)
+    gm.sync()
+    ms = gm.elapsed_ms() / (NSTEPS - 20)
+    hl, u, v = gm.download_state()
+    h_u, h_v = gm.download_aux()[:2]
+    path = gm.path
+    gm.close()
+    assert path == ("fused" if fused else "split")
+    _same("hlay", hl, want["hlay"])
+    _same("u", u, want["u"])
+    _same("v", v, want["v"])
+    own = np.ones(c.ndeg + 1, dtype=bool)  # frozen periodic duplicates carry no meaningful fluxes
+    if hm.params.xper > 0.5 or hm.params.yper > 0.5:
+        sub = hm.iarray("subc")
+        own &= ~((sub[0] == c.lm + 1) | (sub[1] == c.mm + 1))
+    _same("h_u", h_u[..., own], want["h_u"].reshape(h_u.shape)[..., own])
+    _same("h_v", h_v[..., own], want["h_v"].reshape(h_v.shape)[..., own])
+    wet = int((hm.array("mk_n")[0] > 0.5).sum())
+    _record("%s/%s" % (name, path), {"ndeg": ndeg, "nlay": nlay, "wet_cells": wet, "steps_timed": NSTEPS - 20, "ms_per_step": ms,
+                                     "cell_layer_updates_per_s": wet * nlay / (ms * 1.0e-3), "bit_exact_vs_oracle_after": NSTEPS})
+
+
+def _integrals(hm, hl, u, v):
+    """Layer volume, kinetic + potential energy and the potential-vorticity envelope of a one-layer state in the
+    reference's vector layout (conservation.m:116-211, restated in beom_b200/readers.py for gridded records; here on
+    the vectors, which is all the comparison with the oracle needs)."""
+    mk_n = hm.array("mk_n")[0]
+    mk_u, mk_v = hm.array("mk_u")[0], hm.array("mk_v")[0]
+    g, dl = hm.params.grav, hm.params.dl
+    vol = float((hl[0] * mk_n).sum() * dl * dl)
+    ke = float(0.5 * ((u[0] * mk_u) ** 2 + (v[0] * mk_v) ** 2).sum())
+    h_th = hm.array("h_th")[0]
+    pe = float(0.5 * g * (((hl[0] - h_th) * mk_n) ** 2).sum())
+    return vol, ke, pe
+
+
+def test_unstable_jet_long_run_matches_oracle_and_conserves_volume(case_factory):
+    nsteps = 1000
+    c, d, hm = case_factory("unstable_jet", small=False)
+    want = _oracle_state("unstable_jet", hm, d, nsteps)
+    hl0, u0, v0 = (np.array(hm.array(k), copy=True) for k in ("hlay", "u", "v"))
+    gm = model.GpuModel(hm.params, hm.fields(), model.default_options(fused=True))
+    gm.upload_state(hl0, u0, v0)
+    gm.advance(1, nsteps)
+    hl, u, v = gm.download_state()
+    pv = gm.download_diag(("pvor",))[0]
+    assert gm.path == "fused"
+    gm.close()
+    # the chaotic case after 1 000 steps: still the oracle's state, bit for bit (strict IEEE on both sides)
+    _same("hlay", hl, want["hlay"])
+    _same("u", u, want["u"])
+    _same("v", v, want["v"])
+    vol0, ke0, pe0 = _integrals(hm, hl0, u0, v0)
+    vol1, ke1, pe1 = _integrals(hm, hl, u, v)
+    wv, wk, wp = _integrals(hm, want["hlay"].reshape(hl.shape), want["u"].reshape(u.shape), want["v"].reshape(v.shape))
+    assert abs(vol1 - vol0) <= 1e-12 * abs(vol0)          # doc p.4: mean thickness drift below 1e-10 m over 50 days
+    assert (vol1, ke1, pe1) == (wv, wk, wp)               # conserved-quantity drift = the oracle's drift, exactly
+    assert ke1 > 0 and abs((ke1 + pe1) - (ke0 + pe0)) <= 0.05 * (ke0 + pe0)  # K + P within a few per cent (doc p.5-6)
+    assert np.all(np.isfinite(pv)) and float(np.abs(pv).max()) > 0.0
+    _record("unstable_jet/long_run", {"steps": nsteps, "volume_rel_drift": (vol1 - vol0) / vol0,
+                                      "energy_rel_drift": ((ke1 + pe1) - (ke0 + pe0)) / (ke0 + pe0),
+                                      "pvor_min": float(pv.min()), "pvor_max": float(pv.max()), "bit_exact_vs_oracle": True})

@@ -129,6 +129,7 @@ def build(outdir: str, sanitize: bool = False, tsan: bool = False) -> str:
     so = os.path.join(outdir, "libbeom_gpu_emu.so")
     flags = ["-O1", "-std=c++17", "-fPIC", "-ffp-contract=off", "-Wno-unused-function", "-Wno-unknown-pragmas", "-pthread",
              "-I" + outdir, "-I" + os.path.join(HERE, "include"), "-I" + GPU_SRC, "-I" + os.path.join(ROOT, "include")]
+    flags += os.environ.get("BEOM_EMU_DEFS", "").split()  # experiment switches of the kernels (-DBEOM_...), as BEOM_NVCC_DEFS for nvcc
     if sanitize:
         flags += ["-fsanitize=address", "-g", "-fno-omit-frame-pointer"]
     if tsan:  # every lane a TSan fiber (simt.cc): unordered accesses of different warps to shared memory are reported
