@@ -926,7 +926,7 @@ int beom_gpu_download_pi_s(double *pi_s) {
   if (!rc) pi_s[0] = 0.0;
   return rc;
 }
-int beom_gpu_diagnostics(const double *h_0, double *vol, double *ke, double *pe) {
+int beom_gpu_diagnostics_all(const double *h_0, double *vol, double *ke, double *pe, double *enst, double *zeta, double *zeta2, double *npts) {
   if (!g.ready) return fail(-20, "beom_gpu_diagnostics: not initialised");
   int rc;
   const size_t pl = g.plane, nl = (size_t)g.nlay;
@@ -937,7 +937,7 @@ int beom_gpu_diagnostics(const double *h_0, double *vol, double *ke, double *pe)
   const dim3 grid((unsigned)((std::max(np, 1) + 255) / 256), (unsigned)g.nlay, 1);
   const size_t per_layer = (size_t)grid.x;
   if (!g.diag_h0) {
-    if ((rc = dalloc(&g.diag_h0, pl * nl)) || (rc = dalloc(&g.diag_partial, 3 * per_layer * nl)) || (rc = dalloc(&g.diag_out, 3 * nl))) return rc;
+    if ((rc = dalloc(&g.diag_h0, pl * nl)) || (rc = dalloc(&g.diag_partial, kNQ * per_layer * nl)) || (rc = dalloc(&g.diag_out, kNQ * nl + 1))) return rc;
     g.diag_blocks = per_layer;
   }
   if (h_0) {  // rest thickness h_0(0:ndeg, nlay), reference layout; static, but cheap enough to refresh per call
@@ -950,16 +950,23 @@ int beom_gpu_diagnostics(const double *h_0, double *vol, double *ke, double *pe)
   k_conservation<<<grid, block, 0, g.stream>>>(D, g.diag_h0, g.d_cell, p0, np, g.diag_partial);
   k_sum_partials<<<(unsigned)g.nlay, 32, 0, g.stream>>>(g.diag_partial, (int)per_layer, g.diag_out);
   g.launches += 2;
-  if (g.nranks > 1 && (rc = comm_allreduce_sum(g.diag_out, 3 * nl, g.stream, &g_err))) return fail(rc, "beom_gpu_diagnostics: %s", g_err.c_str());
-  std::vector<double> h(3 * nl);
-  CK(cudaMemcpyAsync(h.data(), g.diag_out, 3 * nl * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
+  if (g.nranks > 1 && (rc = comm_allreduce_sum(g.diag_out, kNQ * nl, g.stream, &g_err))) return fail(rc, "beom_gpu_diagnostics: %s", g_err.c_str());
+  std::vector<double> h(kNQ * nl);
+  CK(cudaMemcpyAsync(h.data(), g.diag_out, kNQ * nl * sizeof(double), cudaMemcpyDeviceToHost, g.stream));
   CK(cudaStreamSynchronize(g.stream));
   for (int l = 0; l < g.nlay; l++) {
-    if (vol) vol[l] = h[3 * l + 0];
-    if (ke) ke[l] = h[3 * l + 1];
+    if (vol) vol[l] = h[kNQ * l + 0];
+    if (ke) ke[l] = h[kNQ * l + 1];
+    if (enst) enst[l] = h[kNQ * l + 3];
+    if (zeta) zeta[l] = h[kNQ * l + 4];
+    if (zeta2) zeta2[l] = h[kNQ * l + 5];
   }
   if (pe) pe[0] = h[2];
+  if (npts) *npts = h[6];  // vector points that are not frozen periodic duplicates
   return 0;
+}
+int beom_gpu_diagnostics(const double *h_0, double *vol, double *ke, double *pe) {
+  return beom_gpu_diagnostics_all(h_0, vol, ke, pe, nullptr, nullptr, nullptr, nullptr);
 }
 
 int beom_gpu_point_range(int *first, int *count, int *own_first, int *own_count) {

@@ -64,66 +64,86 @@ __global__ void k_rec_pvor(const __grid_constant__ Dev D, float *__restrict__ ou
 // ---- conservation integrals (testcases/conservation.m:116-211) over the vector points whose rows this rank owns ----
 // per layer l: q[0] = sum over wet points of hlay, q[1] = 0.5 sum(0.5 (U + U(E))) + 0.5 sum(0.5 (V + V(N))) with
 // U = u^2 * 0.5 (h(W) + h), V = v^2 * 0.5 (h(S) + h) (dry or missing thickness counts as 0); layer 0 also q[2] =
-// sum over wet points of eta_1^2, eta_1 = sum over layers of (hlay - h_0).  One thread per vector point (frozen
-// periodic duplicates have no cell and are skipped, as conservation.m:196-201 discards them); neighbours are the
-// dense cells around it, so periodic aliases are honoured.  Warp-shuffle tree + one partial per block; the partials
-// are added in block order by k_sum_partials, so the result does not depend on scheduling.
+// sum over wet points of eta_1^2, eta_1 = sum over layers of (hlay - h_0); and, conservation.m:169-211,
+// q[3] = sum of 0.5 pvor^2 hatp (potential enstrophy), q[4] = sum of zeta = pvor hatp - fcor (relative vorticity),
+// q[5] = sum of zeta^2, with pvor as write_array computes it (private_mod.f95:2951-2974, here kept in double) and hatp the mean
+// thickness of the cells around the psi point that hold a value (vector points and periodic images).
+// One thread per vector point (frozen periodic duplicates have no cell and are skipped, as conservation.m:196-201
+// discards them); neighbours are the dense cells around it, so periodic aliases are honoured.  Warp-shuffle tree + one
+// partial per block; the partials are added in block order by k_sum_partials, so the result does not depend on scheduling.
+constexpr int kNQ = 7;  // + q[6] = number of points counted
 __device__ __forceinline__ double wet_h(const Dev &D, const double *h, size_t c) { return (D.flags[c] & F_N) ? h[c] : 0.0; }
 __global__ void k_conservation(const __grid_constant__ Dev D, const double *__restrict__ h_0, const int *__restrict__ cell, int p0, int n,
                                double *__restrict__ partial) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const int l = blockIdx.y, NX = D.NX;
-  double q0 = 0.0, q1 = 0.0, q2 = 0.0;
+  double q[kNQ];
+#pragma unroll
+  for (int k = 0; k < kNQ; k++) q[k] = 0.0;
   const int cc = t < n ? cell[p0 + t] : -1;
   if (cc >= 0 && cc / NX >= D.y_lo && cc / NX <= D.y_hi) {
     const size_t c = (size_t)cc, L = (size_t)l * D.plane;
     const double *h = D.hlay + L, *u = D.u + L, *v = D.v + L;
-    const bool wet = D.flags[c] & F_N;
-    if (wet) q0 = h[c];
+    const uint8_t f = D.flags[c];
+    const bool wet = f & F_N;
+    if (wet) q[0] = h[c];
+    q[6] = 1.0;
     const double hc = wet_h(D, h, c), hW = wet_h(D, h, c - 1), hE = wet_h(D, h, c + 1), hS = wet_h(D, h, c - NX), hN = wet_h(D, h, c + NX);
     const double U0 = u[c] * u[c] * (0.5 * (hW + hc)), U1 = u[c + 1] * u[c + 1] * (0.5 * (hc + hE));
     const double V0 = v[c] * v[c] * (0.5 * (hS + hc)), V1 = v[c + NX] * v[c + NX] * (0.5 * (hc + hN));
-    q1 = 0.5 * (0.5 * (U0 + U1)) + 0.5 * (0.5 * (V0 + V1));
+    q[1] = 0.5 * (0.5 * (U0 + U1)) + 0.5 * (0.5 * (V0 + V1));
     if (l == 0 && wet) {
       double eta = 0.0;
       for (int i = D.nlay - 1; i >= 0; i--) eta += D.hlay[(size_t)i * D.plane + c] - h_0[(size_t)i * D.plane + c];
-      q2 = eta * eta;
+      q[2] = eta * eta;
+    }
+    {
+      const uint8_t fW = D.flags[c - 1], fS = D.flags[c - NX], fSW = D.flags[c - NX - 1];
+      const double zr = ((v[c] - v[c - 1]) / D.dl - (u[c] - u[c - NX]) / D.dl) * m_pe(f);
+      const double msum = m_n(f) + m_n(fW) + m_n(fS) + m_n(fSW);
+      const double pv = (D.fcor[c] + zr * D.uadv) * m_pi(f) * msum / (h[c] + h[c - 1] + h[c - NX - 1] + h[c - NX]);
+      const uint8_t val = F_ACT | F_GHOST;  // cells that hold a value (get_field leaves NaN elsewhere)
+      double cnt = 1.0 + ((fW & val) ? 1.0 : 0.0) + ((fS & val) ? 1.0 : 0.0) + ((fSW & val) ? 1.0 : 0.0);
+      const double hsum = h[c] + ((fW & val) ? h[c - 1] : 0.0) + ((fS & val) ? h[c - NX] : 0.0) + ((fSW & val) ? h[c - NX - 1] : 0.0);
+      const double hatp = hsum / cnt;
+      const double z = pv * hatp - D.fcor[c];
+      if (pv == pv) {  // (a psi point with no thickness around it: 0/0, which nanmean skips)
+        q[3] = pv * pv * hatp * 0.5;
+        q[4] = z;
+        q[5] = z * z;
+      }
     }
   }
-  __shared__ double sh[3][32];
+  __shared__ double sh[kNQ][32];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    q0 += __shfl_xor_sync(0xffffffffu, q0, o);
-    q1 += __shfl_xor_sync(0xffffffffu, q1, o);
-    q2 += __shfl_xor_sync(0xffffffffu, q2, o);
+  for (int k = 0; k < kNQ; k++) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q[k] += __shfl_xor_sync(0xffffffffu, q[k], o);
+    if (lane == 0) sh[k][w] = q[k];
   }
-  if (lane == 0) { sh[0][w] = q0; sh[1][w] = q1; sh[2][w] = q2; }
   __syncthreads();
   if (w == 0) {
-    q0 = lane < nw ? sh[0][lane] : 0.0; q1 = lane < nw ? sh[1][lane] : 0.0; q2 = lane < nw ? sh[2][lane] : 0.0;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      q0 += __shfl_xor_sync(0xffffffffu, q0, o);
-      q1 += __shfl_xor_sync(0xffffffffu, q1, o);
-      q2 += __shfl_xor_sync(0xffffffffu, q2, o);
-    }
-    if (lane == 0) {
-      const size_t b = (size_t)l * gridDim.x + blockIdx.x;
-      partial[3 * b + 0] = q0; partial[3 * b + 1] = q1; partial[3 * b + 2] = q2;
+    for (int k = 0; k < kNQ; k++) {
+      double s = lane < nw ? sh[k][lane] : 0.0;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+      if (lane == 0) partial[kNQ * ((size_t)l * gridDim.x + blockIdx.x) + k] = s;
     }
   }
 }
 // one block per layer: adds the layer's partials in a fixed order (lane-strided, then a shuffle tree)
 __global__ void k_sum_partials(const double *__restrict__ partial, int per_layer, double *__restrict__ out) {
   const int l = blockIdx.x, lane = threadIdx.x;
-  double q[3] = {0.0, 0.0, 0.0};
+  double q[kNQ];
+  for (int k = 0; k < kNQ; k++) q[k] = 0.0;
   for (int b = lane; b < per_layer; b += 32)
-    for (int k = 0; k < 3; k++) q[k] += partial[3 * ((size_t)l * per_layer + b) + k];
-  for (int k = 0; k < 3; k++) {
+    for (int k = 0; k < kNQ; k++) q[k] += partial[kNQ * ((size_t)l * per_layer + b) + k];
+  for (int k = 0; k < kNQ; k++) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) q[k] += __shfl_xor_sync(0xffffffffu, q[k], o);
-    if (lane == 0) out[3 * l + k] = q[k];
+    if (lane == 0) out[kNQ * l + k] = q[k];
   }
 }
 

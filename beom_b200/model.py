@@ -191,6 +191,17 @@ class GpuModel:
         self._ck(self.lib.beom_gpu_diagnostics(_dp(h_0), _dp(vol), _dp(ke), _dp(pe)), "diagnostics")
         return vol, ke, float(pe[0])
 
+    def diagnostics_all(self, h_0):
+        """diagnostics() plus the vorticity integrals of conservation.m:169-211: a dict with vol, ke, enst, zeta, zeta2
+        (per layer), pe (sum of eta_1^2) and npts (points counted); enst / npts, zeta / npts are the script's `enst`, `rvor`."""
+        h_0 = np.ascontiguousarray(h_0, dtype=np.float64)
+        o = {k: np.zeros(self.nlay) for k in ("vol", "ke", "enst", "zeta", "zeta2")}
+        pe, npts = np.zeros(1), np.zeros(1)
+        self._ck(self.lib.beom_gpu_diagnostics_all(_dp(h_0), _dp(o["vol"]), _dp(o["ke"]), _dp(pe), _dp(o["enst"]), _dp(o["zeta"]),
+                                                   _dp(o["zeta2"]), _dp(npts)), "diagnostics_all")
+        o["pe"], o["npts"] = float(pe[0]), float(npts[0])
+        return o
+
     def download_pi_s(self):
         out = np.zeros(self.ndeg + 1)
         self._ck(self.lib.beom_gpu_download_pi_s(_dp(out)), "download_pi_s")

@@ -156,6 +156,14 @@ int beom_gpu_download_pi_s(double *pi_s);
  * warp-shuffle trees, block partials added in a fixed order; ncclAllReduce(SUM) over the ranks. */
 int beom_gpu_diagnostics(const double *h_0, double *vol, double *ke, double *pe);
 
+/* The same plus the vorticity integrals of conservation.m:169-211, per layer l over the same points (npts of them):
+ *   enst[l]  = sum of 0.5 pvor^2 hatp          (the script's `enst` = enst[l] / npts: domain-mean potential enstrophy)
+ *   zeta[l]  = sum of (pvor hatp - fcor)        (`rvor` = zeta[l] / npts: domain-mean relative vorticity)
+ *   zeta2[l] = sum of (pvor hatp - fcor)^2      (`rstd`^2 = (zeta2 - zeta^2 / npts) / (npts - 1))
+ * pvor as write_array evaluates it (private_mod.f95:2951-2974, kept in double here, fcor the psi-point field), hatp the mean
+ * thickness of the up to four cells around the psi point that hold a value.  Any pointer may be NULL. */
+int beom_gpu_diagnostics_all(const double *h_0, double *vol, double *ke, double *pe, double *enst, double *zeta, double *zeta2, double *npts);
+
 /* y-slab runs: the vector points this rank holds (owned rows + halo rows: first,count) and owns
  * (own_first, own_count).  beom_gpu_set_window(first, count) declares that the state arrays passed to
  * upload_state / download_state / download_aux from now on hold only points first..first+count-1 of

@@ -84,3 +84,64 @@ def test_conservation_integrals(case_factory, name, nsteps):
     if name == "conservation":  # closed/periodic, unforced: layer volumes are conserved (doc p.4-6)
         np.testing.assert_allclose(vol, vol0, rtol=1e-11)
         assert ke.sum() > 0
+
+
+def vorticity_numpy(hm, hlay, u, v):
+    """conservation.m:169-211 on the vector layout: potential enstrophy, relative vorticity and its square, summed over
+    the vector points (frozen periodic duplicates excluded), with pvor as write_array evaluates it (pm:2951-2974)."""
+    neig = hm.iarray("neig")
+    if neig.shape[0] != 8:
+        neig = neig.T
+    W, SW, S = neig[4], neig[5], neig[6]
+    mk_n, mkpe, mkpi, fcor = (hm.array(k)[0] for k in ("mk_n", "mkpe", "mkpi", "fcor"))
+    dl, uadv = hm.params.dl, hm.params.uadv
+    sub = hm.iarray("subc")
+    n = hlay.shape[1]
+    ok = np.arange(n) > 0
+    if hm.params.xper > 0.5:
+        ok &= sub[0] != sub[0].max()
+    if hm.params.yper > 0.5:
+        ok &= sub[1] != sub[1].max()
+    has = (np.arange(n) > 0).astype(float)  # a neighbour that is a vector point (or a periodic alias of one) holds a value
+    out = {k: np.zeros(hlay.shape[0]) for k in ("enst", "zeta", "zeta2")}
+    for l in range(hlay.shape[0]):
+        h, uu, vv = hlay[l].copy(), u[l].copy(), v[l].copy()
+        h[0] = uu[0] = vv[0] = 0.0
+        zr = ((vv - vv[W]) / dl - (uu - uu[S]) / dl) * mkpe
+        msum = mk_n + mk_n[W] + mk_n[S] + mk_n[SW]
+        with np.errstate(all="ignore"):
+            pv = (fcor + zr * uadv) * mkpi * msum / (h + h[W] + h[SW] + h[S])
+        hatp = (h + h[W] * has[W] + h[S] * has[S] + h[SW] * has[SW]) / (1.0 + has[W] + has[S] + has[SW])
+        z = pv * hatp - fcor
+        good = ok & ~np.isnan(pv)
+        out["enst"][l] = (pv ** 2 * hatp * 0.5)[good].sum()
+        out["zeta"][l] = z[good].sum()
+        out["zeta2"][l] = (z ** 2)[good].sum()
+    return out, float(ok.sum())
+
+
+@pytest.mark.parametrize("name,nsteps", [("conservation", 20), ("unstable_jet", 20), ("sill_exchange3D", 20)])
+def test_vorticity_integrals(case_factory, name, nsteps):
+    """Potential enstrophy and relative vorticity on the device (beom_gpu_diagnostics_all) against the numpy restatement
+    on the downloaded state; sums, so the order of additions differs (rtol 1e-11 of the sum of magnitudes)."""
+    c, d, hm = case_factory(name)
+    orc = Oracle(hm.params, d)
+    h_0 = orc.array("h_0").reshape(hm.array("hlay").shape).copy()
+    orc.close()
+    gm = model.GpuModel(hm.params, hm.fields(), model.default_options(fused=True))
+    gm.upload_state(hm.array("hlay"), hm.array("u"), hm.array("v"))
+    gm.advance(1, nsteps)
+    hl, u, v = gm.download_state()
+    got = gm.diagnostics_all(h_0)
+    vol, ke, pe = gm.diagnostics(h_0)
+    gm.close()
+    want, npts = vorticity_numpy(hm, hl, u, v)
+    assert got["npts"] == npts
+    np.testing.assert_array_equal(got["vol"], vol)
+    np.testing.assert_array_equal(got["ke"], ke)
+    np.testing.assert_allclose(got["enst"], want["enst"], rtol=1e-11)
+    np.testing.assert_allclose(got["zeta2"], want["zeta2"], rtol=1e-11)
+    # the relative vorticity nearly cancels over a closed or periodic domain: compare against the scale of its terms
+    scale = np.sqrt(want["zeta2"] * npts)
+    assert np.all(np.abs(got["zeta"] - want["zeta"]) <= 1e-11 * scale)
+    assert np.all(got["enst"] > 0)
