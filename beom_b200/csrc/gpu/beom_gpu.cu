@@ -90,6 +90,19 @@ struct Ctx {
   double *fnud_tide = nullptr;     // [3][nlay] planes: the step's relaxation targets with the tidal term (fused step only)
   float *rec_f32 = nullptr;        // [nlay] dense float32 planes: one diagnostic record
   float *rec_stage = nullptr;      // vector-layout staging of one layer of a record
+  // asynchronous output records (beom_gpu_records_begin / _wait): two slots of [6][nlay][n] floats, device + page-locked host
+  struct RecSlot {
+    float *dev = nullptr, *host = nullptr;
+    double *mm_dev = nullptr, *mm_host = nullptr;  // [nlay][2] min / max thickness
+    cudaEvent_t ready = nullptr, done = nullptr;
+    bool busy = false, diag = false, used = false;
+    std::vector<double> orph;  // hlay,u,v of the frozen periodic duplicates when the set was begun
+  } rec[2];
+  int rec_head = 0, rec_pending = 0;  // oldest busy slot, number of busy slots
+  float *h0r4 = nullptr;              // [nlay][ndeg] float32 rest thickness (h_0.bin)
+  std::vector<float> h0r4_orph;       // [nlay][orphans]
+  double *mm_partial = nullptr;
+  cudaStream_t copy_stream = nullptr;
   double *diag_h0 = nullptr;       // [nlay] dense h_0 (beom_gpu_diagnostics)
   double *diag_partial = nullptr, *diag_out = nullptr;
   size_t diag_blocks = 0;
@@ -336,6 +349,13 @@ int beom_gpu_finalize(void) {
     if (e) { cudaEventDestroy(e); e = nullptr; }
   if (g.stream) { cudaStreamDestroy(g.stream); g.stream = nullptr; }
   if (g.comm_stream) { cudaStreamDestroy(g.comm_stream); g.comm_stream = nullptr; }
+  if (g.copy_stream) { cudaStreamSynchronize(g.copy_stream); cudaStreamDestroy(g.copy_stream); g.copy_stream = nullptr; }
+  for (auto &r : g.rec) {
+    if (r.host) cudaFreeHost(r.host);
+    if (r.mm_host) cudaFreeHost(r.mm_host);
+    if (r.ready) cudaEventDestroy(r.ready);
+    if (r.done) cudaEventDestroy(r.done);
+  }
   if (g.ev_edge) { cudaEventDestroy(g.ev_edge); g.ev_edge = nullptr; }
   if (g.ev_comm) { cudaEventDestroy(g.ev_comm); g.ev_comm = nullptr; }
   fused_release();
@@ -916,6 +936,117 @@ int beom_gpu_download_diag(float *pvor, float *mont, float *v_cc) {
   CK(cudaGetLastError());
   return 0;
 }
+int beom_gpu_set_rest_thickness(const float *h_0_r4) {
+  if (!g.ready) return fail(-20, "beom_gpu_set_rest_thickness: not initialised");
+  if (!h_0_r4) return fail(-1, "beom_gpu_set_rest_thickness: null argument");
+  int rc;
+  const size_t cnt = (size_t)g.ndeg * g.nlay;
+  if (!g.h0r4 && (rc = dalloc(&g.h0r4, cnt, false))) return rc;
+  CK(cudaMemcpyAsync(g.h0r4, h_0_r4, cnt * sizeof(float), cudaMemcpyHostToDevice, g.stream));
+  CK(cudaStreamSynchronize(g.stream));  // (the caller's array may be pageable and short-lived)
+  const size_t no = g.orphans.size();
+  g.h0r4_orph.resize((size_t)g.nlay * no);
+  for (int l = 0; l < g.nlay; l++)
+    for (size_t k = 0; k < no; k++) g.h0r4_orph[(size_t)l * no + k] = h_0_r4[(size_t)l * g.ndeg + (g.orphans[k] - 1)];
+  return 0;
+}
+
+int beom_gpu_records_begin(int with_diag) {
+  if (!g.ready) return fail(-20, "beom_gpu_records_begin: not initialised");
+  if (!g.h0r4) return fail(-22, "beom_gpu_records_begin: beom_gpu_set_rest_thickness has not been called");
+  if (g.rec_pending >= 2) return fail(-23, "beom_gpu_records_begin: two record sets are in flight already (call beom_gpu_records_wait)");
+  int rc;
+  const int p0 = std::max(g.p_lo, 1), n = g.p_hi - p0 + 1;
+  if (n <= 0) return fail(-24, "beom_gpu_records_begin: this rank holds no vector point");
+  const size_t nl = (size_t)g.nlay, per = nl * (size_t)n, pl = g.plane;
+  const unsigned blocks = (unsigned)((n + 255) / 256);
+  if (!g.copy_stream) CK(cudaStreamCreateWithFlags(&g.copy_stream, cudaStreamNonBlocking));
+  if (!g.mm_partial && (rc = dalloc(&g.mm_partial, (size_t)blocks * nl * 2, false))) return rc;
+  Ctx::RecSlot &r = g.rec[(g.rec_head + g.rec_pending) % 2];
+  if (!r.dev) {
+    if ((rc = dalloc(&r.dev, 6 * per, false)) || (rc = dalloc(&r.mm_dev, 2 * nl, false))) return rc;
+    CK(cudaHostAlloc(&r.host, 6 * per * sizeof(float), cudaHostAllocDefault));
+    CK(cudaHostAlloc(&r.mm_host, 2 * nl * sizeof(double), cudaHostAllocDefault));
+    CK(cudaEventCreateWithFlags(&r.ready, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&r.done, cudaEventDisableTiming));
+  }
+  if (r.used) CK(cudaStreamWaitEvent(g.stream, r.done, 0));  // the previous copy out of this slot's device buffer
+  Dev D = g.D;
+  set_state_pointers(D);
+  k_rec_state<<<blocks, 256, 0, g.stream>>>(D, g.h0r4, g.d_cell, p0, n, g.ndeg, r.dev, g.mm_partial);
+  k_rec_minmax<<<(unsigned)g.nlay, 32, 0, g.stream>>>(g.mm_partial, (int)blocks, r.mm_dev);
+  g.launches += 2;
+  if (with_diag) {
+    if (!g.rec_f32 && ((rc = dalloc(&g.rec_f32, pl * nl)) || (rc = dalloc(&g.rec_stage, (size_t)(g.p_hi - g.p_lo + 1), false)))) return rc;
+    if ((rc = alloc_split_buffers())) return rc;  // wrk1 / wrk2 of the v_cc record live in the split path's rvor / dive planes
+    D = g.D;
+    set_state_pointers(D);
+    const dim3 grid = cell_grid(D, g.nlay, kBlock);
+    auto gather = [&](int which) {
+      for (int l = 0; l < g.nlay; l++) {
+        k_gather<float><<<blocks, 256, 0, g.stream>>>(r.dev + (size_t)which * per + (size_t)l * n, g.rec_f32 + (size_t)l * pl, g.d_cell, p0, n);
+        g.launches++;
+      }
+    };
+    k_rec_pvor<<<grid, kBlock, 0, g.stream>>>(D, g.rec_f32);
+    gather(3);
+    k_rec_mont<<<grid, kBlock, 0, g.stream>>>(D, g.rec_f32);
+    gather(4);
+    k_rec_vort_dive<<<cell_grid(D, g.nlay, kBlock, 2, 2), kBlock, 0, g.stream>>>(D, D.rvor, D.dive);
+    g.launches += 3;
+    if ((rc = sync_fields({{D.rvor, g.nlay}, {D.dive, g.nlay}}))) return rc;
+    k_rec_vcc<<<grid, kBlock, 0, g.stream>>>(D, D.rvor, D.dive, g.rec_f32);
+    g.launches++;
+    gather(5);
+  }
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(r.ready, g.stream));
+  CK(cudaStreamWaitEvent(g.copy_stream, r.ready, 0));
+  CK(cudaMemcpyAsync(r.host, r.dev, (with_diag ? 6 : 3) * per * sizeof(float), cudaMemcpyDeviceToHost, g.copy_stream));
+  CK(cudaMemcpyAsync(r.mm_host, r.mm_dev, 2 * nl * sizeof(double), cudaMemcpyDeviceToHost, g.copy_stream));
+  CK(cudaEventRecord(r.done, g.copy_stream));
+  g.orph.replay();  // the duplicates a sponge moves, as of this step (host side, orphans.h)
+  r.orph = g.orph.val;
+  r.busy = true; r.used = true; r.diag = with_diag != 0;
+  g.rec_pending++;
+  return 0;
+}
+
+int beom_gpu_records_wait(beom_records *out) {
+  if (!g.ready) return fail(-20, "beom_gpu_records_wait: not initialised");
+  if (!out) return fail(-1, "beom_gpu_records_wait: null argument");
+  if (g.rec_pending == 0) return fail(-25, "beom_gpu_records_wait: no record set has been begun");
+  Ctx::RecSlot &r = g.rec[g.rec_head];
+  CK(cudaEventSynchronize(r.done));
+  const int p0 = std::max(g.p_lo, 1), n = g.p_hi - p0 + 1;
+  const size_t nl = (size_t)g.nlay, per = nl * (size_t)n, no = g.orphans.size();
+  // frozen periodic duplicates have no cell: their state lives on the host (same float32 arithmetic as k_rec_state)
+  for (size_t k = 0; k < no; k++) {
+    const int o = g.orphans[k];
+    if (o < p0 || o > g.p_hi) continue;
+    float acc = 0.0f;
+    for (int l = g.nlay - 1; l >= 0; l--) {
+      const double dh = r.orph[((size_t)0 * nl + l) * no + k] - (double)g.h0r4_orph[(size_t)l * no + k];
+      acc = (l == g.nlay - 1) ? (float)dh : (float)(dh + (double)acc);
+      if (!(l == 0 && g.P.rgld > 0.5)) r.host[(size_t)l * n + (o - p0)] = acc;
+      r.host[per + (size_t)l * n + (o - p0)] = (float)r.orph[((size_t)1 * nl + l) * no + k];
+      r.host[2 * per + (size_t)l * n + (o - p0)] = (float)r.orph[((size_t)2 * nl + l) * no + k];
+    }
+  }
+  memset(out, 0, sizeof *out);
+  out->eta = r.host; out->u = r.host + per; out->v = r.host + 2 * per;
+  if (r.diag) { out->pvor = r.host + 3 * per; out->mont = r.host + 4 * per; out->v_cc = r.host + 5 * per; }
+  out->first_point = p0; out->count = n;
+  for (int l = 0; l < g.nlay; l++) {
+    out->hmin[l] = r.mm_host[2 * l]; out->hmax[l] = r.mm_host[2 * l + 1];
+    if (!out->thin_layer && out->hmin[l] < 0.5 * g.P.hmin) out->thin_layer = l + 1;
+  }
+  r.busy = false;
+  g.rec_head = (g.rec_head + 1) % 2;
+  g.rec_pending--;
+  return 0;
+}
+
 int beom_gpu_download_pi_s(double *pi_s) {
   if (!g.ready) return fail(-20, "beom_gpu_download_pi_s: not initialised");
   if (!g.D.pi_s) return fail(-30, "beom_gpu_download_pi_s: rgld = 0, there is no surface pressure");

@@ -61,6 +61,71 @@ __global__ void k_rec_pvor(const __grid_constant__ Dev D, float *__restrict__ ou
   out[L + c] = (float)((D.fcor[c] + zeta * D.uadv) * m_pi(f) * msum / (h[c] + h[c - 1] + h[c - NX - 1] + h[c - NX]));
 }
 
+// ---- the state records of write_array (private_mod.f95:2848-2883) straight in the reference's record layout ----
+// One thread per vector point p = p0 + k of this rank: eta_ = layer thickness minus the float32 rest thickness h_0.bin,
+// cumulated upward from the bottom layer IN FLOAT32 exactly as the reference does (pm:2848-2870; under the rigid lid the
+// top record is pi_s, pm:2871-2875), u___ and v___ rounded to float32.  rec = [3][nlay][n] floats (eta, u, v).
+// The same pass takes the min / max thickness of every layer over the wet points (the report and the `hlay < hmin / 2'
+// halt of write_outputs, pm:2772-2808): one partial pair per block and layer, finished by k_rec_minmax.
+__global__ void k_rec_state(const __grid_constant__ Dev D, const float *__restrict__ h0r4, const int *__restrict__ cell, int p0, int n,
+                            int ndeg, float *__restrict__ rec, double *__restrict__ mm_partial) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int nlay = D.nlay;
+  const int cc = k < n ? cell[p0 + k] : -1;
+  float *eta = rec, *ru = rec + (size_t)nlay * n, *rv = rec + (size_t)2 * nlay * n;
+  const bool wet = cc >= 0 && (D.flags[cc] & F_N);
+  __shared__ double sh[2][8];
+  float acc = 0.0f;
+  for (int l = nlay - 1; l >= 0; l--) {
+    double h = 0.0;
+    if (k < n) {
+      float e = 0.0f, fu = 0.0f, fv = 0.0f;
+      if (cc >= 0) {
+        const size_t c = (size_t)l * D.plane + cc;
+        h = D.hlay[c];
+        const double dh = h - (double)h0r4[(size_t)l * ndeg + (p0 + k - 1)];
+        acc = (l == nlay - 1) ? (float)dh : (float)(dh + (double)acc);
+        e = acc;
+        if (l == 0 && D.rgld > 0.5) e = (float)D.pi_s[cc];
+        fu = (float)D.u[c];
+        fv = (float)D.v[c];
+      }
+      eta[(size_t)l * n + k] = e;
+      ru[(size_t)l * n + k] = fu;
+      rv[(size_t)l * n + k] = fv;
+    }
+    double lo = wet ? h : INFINITY, hi = wet ? h : -INFINITY;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+      hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) { sh[0][w] = lo; sh[1][w] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int i = 1; i < (int)(blockDim.x >> 5); i++) { lo = fmin(lo, sh[0][i]); hi = fmax(hi, sh[1][i]); }
+      mm_partial[((size_t)l * gridDim.x + blockIdx.x) * 2 + 0] = lo;
+      mm_partial[((size_t)l * gridDim.x + blockIdx.x) * 2 + 1] = hi;
+    }
+  }
+}
+__global__ void k_rec_minmax(const double *__restrict__ mm_partial, int per_layer, double *__restrict__ out) {  // one block (32 lanes) per layer
+  const int l = blockIdx.x, lane = threadIdx.x;
+  double lo = INFINITY, hi = -INFINITY;
+  for (int b = lane; b < per_layer; b += 32) {
+    lo = fmin(lo, mm_partial[((size_t)l * per_layer + b) * 2 + 0]);
+    hi = fmax(hi, mm_partial[((size_t)l * per_layer + b) * 2 + 1]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    lo = fmin(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+    hi = fmax(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+  }
+  if (lane == 0) { out[2 * l] = lo; out[2 * l + 1] = hi; }
+}
+
 // ---- conservation integrals (testcases/conservation.m:116-211) over the vector points whose rows this rank owns ----
 // per layer l: q[0] = sum over wet points of hlay, q[1] = 0.5 sum(0.5 (U + U(E))) + 0.5 sum(0.5 (V + V(N))) with
 // U = u^2 * 0.5 (h(W) + h), V = v^2 * 0.5 (h(S) + h) (dry or missing thickness counts as 0); layer 0 also q[2] =

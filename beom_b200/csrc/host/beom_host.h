@@ -48,6 +48,8 @@ void beom_host_counts(const beom_host *h, int *nstp, int *notp, int *n_3d);
  * record to eta_/u___/v___(.bin) (+ pvor/mont/v_cc when diag = 1) and a line to time.txt.  Returns a
  * negative layer number if a wet layer is thinner than 0.5*hmin (private_mod.f95:2798-2808). */
 int beom_host_write_outputs(beom_host *h, double ctim);
+/* the same files, report and halt from records made on the device (beom_gpu_records_begin / _wait) */
+int beom_host_write_records(beom_host *h, double ctim, const beom_records *r);
 /* read_restart_record (private_mod.f95:1299-1344). */
 int beom_host_read_restart(beom_host *h);
 

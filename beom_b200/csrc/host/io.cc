@@ -168,6 +168,42 @@ int beom_host_write_outputs(beom_host *h, double ctim) {
   return 0;
 }
 
+// write_outputs with the records already made on the device (beom_gpu_records_begin / _wait, include/beom_gpu.h): the same
+// files, the same report and the same halt as beom_host_write_outputs, without the double-precision state crossing the bus.
+int beom_host_write_records(beom_host *h, double ctim, const beom_records *r) {
+  const int nlay = h->nlay, ndeg = h->ndeg;
+  const size_t cnt = (size_t)ndeg * nlay;
+  if (h->odir.empty()) { beom_host_set_error("write_outputs: odir is empty"); return -1000; }
+  if (r->first_point != 1 || r->count != ndeg) { beom_host_set_error("write_outputs: the record set does not cover 1..ndeg"); return -1003; }
+  if (!h->out_init) h->irec = 1;
+  bool ok = write_record(h->odir + "eta_.bin", h->out_init, h->irec, r->eta, cnt);
+  ok = ok && write_record(h->odir + "u___.bin", h->out_init, h->irec, r->u, cnt);
+  ok = ok && write_record(h->odir + "v___.bin", h->out_init, h->irec, r->v, cnt);
+  if (r->pvor) {  // pm:2718-2722
+    ok = ok && write_record(h->odir + "pvor.bin", h->out_init, h->irec, r->pvor, cnt);
+    ok = ok && write_record(h->odir + "mont.bin", h->out_init, h->irec, r->mont, cnt);
+    ok = ok && write_record(h->odir + "v_cc.bin", h->out_init, h->irec, r->v_cc, cnt);
+  }
+  if (!ok) { beom_host_set_error("write_array: could not write a record into " + h->odir); return -1001; }
+  {
+    std::FILE *f = std::fopen((h->odir + "time.txt").c_str(), h->out_init ? "a" : "w");
+    if (!f) { beom_host_set_error("write_outputs: cannot open time.txt"); return -1002; }
+    std::fprintf(f, "%s\n", fort_real(ctim).c_str());
+    std::fclose(f);
+  }
+  h->irec += 1;
+  h->out_init = true;
+  h->ctim = ctim;
+  for (int l = 0; l < nlay; l++) std::printf(" min/max h %d = %.15g %.15g\n", l + 1, r->hmin[l], r->hmax[l]);  // pm:2772-2794
+  if (r->thin_layer) {  // pm:2798-2808
+    char b[128];
+    std::snprintf(b, sizeof b, " layer number %d has its thickness < hmin; Calculation halted.", r->thin_layer);
+    beom_host_set_error(std::string("In main, in subroutine write_outputs,") + b);
+    return -r->thin_layer;
+  }
+  return 0;
+}
+
 // Append one diag record (float32, ndeg x nlay) to <var>.bin at the record just written.
 int beom_host_write_diag_record(beom_host *h, const char *var, const float *rec) {
   const size_t cnt = (size_t)h->ndeg * h->nlay;

@@ -6,7 +6,7 @@
 
 #include "host_model.h"
 
-extern "C" int beom_host_write_diag_record(beom_host *h, const char *var, const float *rec);
+extern "C" int beom_host_write_records(beom_host *h, double ctim, const beom_records *r);
 
 namespace {
 int gpu_fail(const char *where, int rc) {
@@ -16,23 +16,30 @@ int gpu_fail(const char *where, int rc) {
   return rc;
 }
 
-int outputs(beom_host *h, double ctim) {
-  int rc = beom_gpu_download_state(h->hlay.data(), h->u.data(), h->v.data());
-  if (rc) return gpu_fail("beom_gpu_download_state", rc);
-  if (h->p.rgld > 0.5 && (rc = beom_gpu_download_pi_s(h->pi_s.data()))) return gpu_fail("beom_gpu_download_pi_s", rc);
-  rc = beom_host_write_outputs(h, ctim);
+// Output is pipelined: at an output step the records are made on the device behind the steps issued so far
+// (beom_gpu_records_begin) and copied out on the library's copy stream while the time loop goes on; they are written --
+// and the thickness report / halt of write_outputs evaluated -- when the next output step (or the end of the run) comes.
+// The files are the reference's, record for record; only the moment the halt is noticed moves by one output interval.
+struct Pending {
+  bool any = false;
+  double ctim = 0.0;
+};
+int finish_outputs(beom_host *h, Pending &pend) {
+  if (!pend.any) return 0;
+  pend.any = false;
+  beom_records r;
+  int rc = beom_gpu_records_wait(&r);
+  if (rc) return gpu_fail("beom_gpu_records_wait", rc);
+  if ((rc = beom_host_write_records(h, pend.ctim, &r))) return rc;
+  std::printf(" ctim = %.15g days; dt_s = %.15g days; record = %d\n", pend.ctim, h->p.dt_s, h->irec - 1);
+  return 0;
+}
+int begin_outputs(beom_host *h, double ctim, Pending &pend) {
+  int rc = finish_outputs(h, pend);
   if (rc) return rc;
-  if (h->p.diag > 0.5) {  // pm:2718-2722
-    const size_t cnt = (size_t)h->ndeg * h->nlay;
-    std::vector<float> pv(cnt), mo(cnt), vc(cnt);
-    if ((rc = beom_gpu_download_diag(pv.data(), mo.data(), vc.data()))) return gpu_fail("beom_gpu_download_diag", rc);
-    if (beom_host_write_diag_record(h, "pvor", pv.data()) || beom_host_write_diag_record(h, "mont", mo.data()) ||
-        beom_host_write_diag_record(h, "v_cc", vc.data())) {
-      beom_host_set_error("write_array: could not write a diag record into " + h->odir);
-      return -1001;
-    }
-  }
-  std::printf(" ctim = %.15g days; dt_s = %.15g days; record = %d\n", ctim, h->p.dt_s, h->irec - 1);
+  if ((rc = beom_gpu_records_begin(h->p.diag > 0.5 ? 1 : 0))) return gpu_fail("beom_gpu_records_begin", rc);
+  pend.any = true;
+  pend.ctim = ctim;
   return 0;
 }
 }  // namespace
@@ -50,7 +57,9 @@ extern "C" int beom_host_run(beom_host *h, const beom_gpu_options *opt, int max_
     std::printf(" *** Restarting from record number %d at time = %.15g\n", h->irec - 1, h->tres);
   }
   if ((rc = beom_gpu_upload_state(h->hlay.data(), h->u.data(), h->v.data()))) return gpu_fail("beom_gpu_upload_state", rc);
-  if (P.rsta < 0.5 && !h->odir.empty() && (rc = outputs(h, 0.0))) return rc;
+  Pending pend;
+  if (!h->odir.empty() && (rc = beom_gpu_set_rest_thickness(h->h_0_r4.data()))) return gpu_fail("beom_gpu_set_rest_thickness", rc);
+  if (P.rsta < 0.5 && !h->odir.empty() && (rc = begin_outputs(h, 0.0, pend))) return rc;
 
   // integrate_time, pm:1840-1919
   std::printf(" dl = %.15g meters.\n dt = %.15g seconds.\n", P.dl, P.dt);
@@ -77,8 +86,9 @@ extern "C" int beom_host_run(beom_host *h, const beom_gpu_options *opt, int max_
     ramp = 1.0;  // pm:1898-1901
     if (P.rsta < 0.5 && ctim < P.dt_r) ramp = ctim / P.dt_r;
     if ((rc = beom_gpu_step(tstp, ctim, ramp, gene, upst ? 1 : 0, 0))) return gpu_fail("beom_gpu_step", rc);
-    if (tstp % h->notp == 0 && !h->odir.empty() && (rc = outputs(h, ctim))) return rc;  // pm:1908-1910
+    if (tstp % h->notp == 0 && !h->odir.empty() && (rc = begin_outputs(h, ctim, pend))) return rc;  // pm:1908-1910
   }
+  if ((rc = finish_outputs(h, pend))) return rc;
   if ((rc = beom_gpu_sync())) return gpu_fail("beom_gpu_sync", rc);
   if ((rc = beom_gpu_download_state(h->hlay.data(), h->u.data(), h->v.data()))) return gpu_fail("beom_gpu_download_state", rc);
   return 0;

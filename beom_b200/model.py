@@ -202,6 +202,27 @@ class GpuModel:
         o["pe"], o["npts"] = float(pe[0]), float(npts[0])
         return o
 
+    def set_rest_thickness(self, h_0_r4):
+        """h_0.bin's content ([nlay][ndeg] float32): needed once before records_begin()."""
+        a = np.ascontiguousarray(h_0_r4, dtype=np.float32).reshape(self.nlay, self.ndeg)
+        self._ck(self.lib.beom_gpu_set_rest_thickness(a.ctypes.data_as(C.POINTER(C.c_float))), "set_rest_thickness")
+
+    def records_begin(self, with_diag=False):
+        """Enqueue the float32 output records of the current state (eta_, u___, v___ [, pvor, mont, v_cc]) and their
+        asynchronous copy to the host; stepping may go on at once."""
+        self._ck(self.lib.beom_gpu_records_begin(1 if with_diag else 0), "records_begin")
+
+    def records_wait(self):
+        """The oldest begun record set: dict of [nlay][count] float32 arrays (copies) + first_point, hmin, hmax, thin_layer."""
+        r = _lib.Records()
+        self._ck(self.lib.beom_gpu_records_wait(C.byref(r)), "records_wait")
+        out = {"first_point": r.first_point, "count": r.count, "thin_layer": r.thin_layer,
+               "hmin": np.array(r.hmin[:self.nlay]), "hmax": np.array(r.hmax[:self.nlay])}
+        for k in ("eta", "u", "v", "pvor", "mont", "v_cc"):
+            ptr = getattr(r, k)
+            out[k] = np.ctypeslib.as_array(ptr, shape=(self.nlay, r.count)).copy() if ptr else None
+        return out
+
     def download_pi_s(self):
         out = np.zeros(self.ndeg + 1)
         self._ck(self.lib.beom_gpu_download_pi_s(_dp(out)), "download_pi_s")

@@ -143,6 +143,29 @@ int beom_gpu_download_aux(double *h_u, double *h_v, double *rs_h, double *dmdx, 
  * float32/double arithmetic; NULL = skip. */
 int beom_gpu_download_diag(float *pvor, float *mont, float *v_cc);
 
+/* The output records of write_outputs / write_array (private_mod.f95:2681-2883) produced ON THE DEVICE and copied
+ * out asynchronously: float32 `eta_' (layer thickness minus the float32 rest thickness of h_0.bin, cumulated upward from the
+ * bottom layer in float32 exactly as pm:2848-2870 does; pi_s on top under the rigid lid), `u___', `v___', with_diag != 0
+ * also `pvor', `mont', `v_cc' (pm:2884-2974), all in the record layout of the files ([nlay][count] floats for the vector
+ * points first_point .. first_point + count - 1; one rank: 1 .. ndeg, i.e. the record itself), plus the min / max
+ * thickness of every layer over the wet points and the `hlay < hmin / 2' verdict of pm:2772-2808.
+ *   beom_gpu_set_rest_thickness   h_0.bin's content ([nlay][ndeg] float32), once, before the first record
+ *   beom_gpu_records_begin        enqueues the record kernels behind the steps issued so far and their device->host copy
+ *                                 into page-locked buffers owned by the library on a copy stream; returns at once, the caller
+ *                                 goes on stepping.  At most two record sets may be in flight.
+ *   beom_gpu_records_wait         blocks until the OLDEST begun set is in host memory; the pointers stay valid until the
+ *                                 next but one beom_gpu_records_begin. */
+typedef struct beom_records {
+  const float *eta, *u, *v;          /* [nlay][count] */
+  const float *pvor, *mont, *v_cc;   /* NULL unless begun with_diag */
+  int first_point, count;
+  double hmin[BEOM_MAXLAY], hmax[BEOM_MAXLAY];  /* over this rank's wet points (+inf / -inf if it has none) */
+  int thin_layer;                    /* 1-based first layer whose thinnest wet point is below hmin / 2, 0 = none */
+} beom_records;
+int beom_gpu_set_rest_thickness(const float *h_0_r4);
+int beom_gpu_records_begin(int with_diag);
+int beom_gpu_records_wait(beom_records *out);
+
 /* Rigid-lid surface pressure pi_s(0:ndeg) (private_mod.f95:91). */
 int beom_gpu_download_pi_s(double *pi_s);
 

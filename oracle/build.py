@@ -1,7 +1,10 @@
 """Build recipe of the CPU checker (TEST INFRASTRUCTURE, see beom_oracle.h):
 
   oracle/libbeom_oracle.so        strict IEEE (-O2 -ffp-contract=off): the parity reference
-  oracle/libbeom_oracle_omp.so    the same source, -O3 -fopenmp: the CPU baseline that bench.py times
+  oracle/libbeom_oracle_omp.so    the same source, -O3 -fopenmp: the CPU baseline that bench.py times (contracts a*b+c into
+                                  FMAs like the reference's own -Ofast build: NOT bit-identical to the strict one)
+  oracle/libbeom_oracle_omp_strict.so  strict IEEE + OpenMP (-O2 -ffp-contract=off -fopenmp): the parallel loops hold no
+                                  reductions, so it returns the strict library's bits; for parity tests at native sizes
 
 There is no oracle/_ref: the reference is Fortran and no Fortran compiler exists in this environment
 (SURVEY.md section 0), so the reference's own sources cannot be compiled here.
@@ -37,6 +40,9 @@ def build_oracle(force: bool = False) -> str:
     omp = os.path.join(ORACLE, "libbeom_oracle_omp.so")
     if force or _newer(omp, deps):
         _run(["gcc", "-O3", "-march=x86-64-v3", "-fopenmp", "-Wall", "-fPIC", "-shared", src, "-o", omp, "-lm"])
+    strict = os.path.join(ORACLE, "libbeom_oracle_omp_strict.so")
+    if force or _newer(strict, deps):
+        _run(["gcc", "-O2", "-ffp-contract=off", "-fopenmp", "-Wall", "-fPIC", "-shared", src, "-o", strict, "-lm"])
     return out
 
 

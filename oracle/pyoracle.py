@@ -11,8 +11,9 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def _load(omp: bool):
-    name = "libbeom_oracle_omp.so" if omp else "libbeom_oracle.so"
+def _load(omp):
+    # omp: False = strict IEEE (the parity reference), "strict" = the same bits with OpenMP, True = the -O3 timing build
+    name = "libbeom_oracle_omp_strict.so" if omp == "strict" else "libbeom_oracle_omp.so" if omp else "libbeom_oracle.so"
     path = os.path.join(HERE, name)
     if not os.path.exists(path):
         raise OSError("%s is not built: run `python -m beom_b200.build`" % path)
@@ -60,7 +61,7 @@ _SHAPES = {  # name -> (planes per point-array as a function of nlay, trailing h
 class Oracle:
     """read_input_data + integrate_time of the reference, on the CPU."""
 
-    def __init__(self, params, idir: str, omp: bool = False):
+    def __init__(self, params, idir: str, omp=False):
         self.lib = _load(omp)
         self.params = params
         self.nlay, self.ndeg = params.nlay, params.ndeg

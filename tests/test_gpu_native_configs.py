@@ -45,7 +45,7 @@ def _record(key, value):
 def _oracle_state(name, hm, d, nsteps):
     key = (name, nsteps)
     if key not in _oracle_cache:
-        orc = Oracle(hm.params, d, omp=True)  # the OpenMP build of the same source: same results, the test stays short
+        orc = Oracle(hm.params, d, omp="strict")  # strict IEEE + OpenMP: the strict oracle's bits (no reductions in its loops)
         orc.advance(1, nsteps)
         _oracle_cache[key] = {k: np.array(orc.array(k), copy=True) for k in ("hlay", "u", "v", "h_u", "h_v")}
         orc.close()
@@ -118,7 +118,7 @@ def test_unstable_jet_long_run_matches_oracle_and_conserves_volume(case_factory)
     gm.upload_state(hl0, u0, v0)
     gm.advance(1, nsteps)
     hl, u, v = gm.download_state()
-    pv = gm.download_diag(("pvor",))[0]
+    pv = gm.download_diag(("pvor",))["pvor"]
     assert gm.path == "fused"
     gm.close()
     # the chaotic case after 1 000 steps: still the oracle's state, bit for bit (strict IEEE on both sides)

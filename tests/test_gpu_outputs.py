@@ -145,3 +145,55 @@ def test_vorticity_integrals(case_factory, name, nsteps):
     scale = np.sqrt(want["zeta2"] * npts)
     assert np.all(np.abs(got["zeta"] - want["zeta"]) <= 1e-11 * scale)
     assert np.all(got["enst"] > 0)
+
+
+@pytest.mark.parametrize("name,fused,diag", [("sill_exchange3D", True, True), ("lock_exchange", True, False), ("conservation", False, True),
+                                             ("stommel1948", True, False)])
+def test_device_side_records_are_the_oracles_and_overlap_the_steps(case_factory, name, fused, diag):
+    """beom_gpu_records_begin / _wait (write_array on the device, pm:2848-2883): two record sets are begun 12 steps apart
+    without waiting in between -- each must be the oracle's float32 record of ITS step (eta_ with the float32 bottom-up
+    accumulation, u___, v___, and the diag records), with the min / max thickness of the report."""
+    c, d, hm = case_factory(name)
+    orc = Oracle(hm.params, d)
+    h0 = orc.array("h_0").reshape(hm.array("hlay").shape)[:, 1:].astype(np.float32)
+    gm = model.GpuModel(hm.params, hm.fields(), model.default_options(fused=fused))
+    gm.set_rest_thickness(h0)
+    gm.upload_state(hm.array("hlay"), hm.array("u"), hm.array("v"))
+    want = []
+    wet = hm.array("mk_n")[0] > 0.5
+    t = 0
+    for nsteps in (10, 12):
+        gm.advance(t + 1, t + nsteps)
+        orc.advance(t + 1, t + nsteps)
+        t += nsteps
+        gm.records_begin(with_diag=diag)
+        w = {k: orc.record(v).copy() for k, v in (("eta", "eta_"), ("u", "u___"), ("v", "v___"))}
+        if diag:
+            w.update({k: orc.record(k).copy() for k in ("pvor", "mont", "v_cc")})
+        hl = orc.array("hlay").reshape(hm.array("hlay").shape)
+        w["hmin"], w["hmax"] = hl[:, wet].min(axis=1), hl[:, wet].max(axis=1)
+        want.append(w)
+    gm.advance(t + 1, t + 3)  # the copies are still owed: the compute stream goes on
+    own = np.ones(c.ndeg, dtype=bool)
+    if hm.params.xper > 0.5 or hm.params.yper > 0.5:
+        sub = hm.iarray("subc")
+        own &= ~(((sub[0] == c.lm + 1) & (hm.params.xper > 0.5)) | ((sub[1] == c.mm + 1) & (hm.params.yper > 0.5)))[1:]
+    for w in want:
+        got = gm.records_wait()
+        assert (got["first_point"], got["count"], got["thin_layer"]) == (1, c.ndeg, 0)
+        for k in ("eta", "u", "v"):  # the state records hold the frozen duplicates too (patched from the host side)
+            a, b = got[k], w[k].reshape(got[k].shape)
+            assert np.array_equal(a, b), "%s record of %s differs at %d entries" % (k, name, (a != b).sum())
+        for k in ("pvor", "mont", "v_cc"):
+            if diag:
+                a, b = got[k], w[k].reshape(got[k].shape)
+                same = (a == b) | (np.isnan(a) & np.isnan(b)) | ~own[None, :]
+                assert same.all(), "%s record of %s differs at %d entries" % (k, name, (~same).sum())
+            else:
+                assert got[k] is None
+        np.testing.assert_array_equal(got["hmin"], w["hmin"])
+        np.testing.assert_array_equal(got["hmax"], w["hmax"])
+    with pytest.raises(RuntimeError):
+        gm.records_wait()  # nothing in flight any more
+    gm.close()
+    orc.close()
