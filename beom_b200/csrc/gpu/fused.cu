@@ -210,13 +210,14 @@ int fused_step(const Dev &in_, const Dev &out, int tstp, bool first_three, cudaS
     rpc = (rows + chunks - 1) / chunks;
     chunks = (rows + rpc - 1) / rpc;
   }
-  a.grid = dim3((unsigned)cfg.strips, (unsigned)chunks, 1);
+  static const bool swap = getenv("BEOM_FUSED_ORDER") && atoi(getenv("BEOM_FUSED_ORDER")) == 1;  // experiment: chunk index fastest
+  a.grid = swap ? dim3((unsigned)chunks, (unsigned)cfg.strips, 1) : dim3((unsigned)cfg.strips, (unsigned)chunks, 1);
   a.block = dim3((unsigned)(cfg.groups * 32 * in.nlay), 1, 1);
   const bool ufirst = (tstp % 2 == 0);
   const StreamTab T = make_streams(in, ufirst);
   a.shmem = fused_smem_bytes(in.nlay, cfg.groups, T, in.has_wind ? cfg.wind_layers : 0);
   a.in = &in; a.out = &out; a.tab = &T; a.open = cfg.open; a.open4 = cfg.open4; a.open4_words = cfg.open4_words;
-  a.groups = cfg.groups; a.rows_per_chunk = rpc; a.wind_layers = cfg.wind_layers;
+  a.groups = cfg.groups; a.rows_per_chunk = rpc; a.wind_layers = cfg.wind_layers | (swap ? 1 << 16 : 0);
   a.stream = s;
   // the lean instantiations assume gene = 1 (tstp >= 4 with g_fb = 1) or gene = 0 (the start-up steps) exactly
   const bool g0 = in.gene == 0.0;  // the start-up steps

@@ -60,9 +60,6 @@ constexpr int kMaxLay = 8;            // layers per CTA (shared-memory exchange,
 #ifndef BEOM_TRYWAIT_HINT
 #define BEOM_TRYWAIT_HINT 20000   // suspend-time hint (ns) of mbarrier.try_wait (the warp sleeps in hardware instead of spinning); 0 = none
 #endif
-#ifndef BEOM_ISSUE_LATE
-#define BEOM_ISSUE_LATE 0
-#endif
 #ifndef BEOM_FUSED_WARPS
 #define BEOM_FUSED_WARPS 16
 #endif
@@ -122,15 +119,9 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
       : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) {
-#ifdef BEOM_BULK_CTA  // experiment: the CTA-local destination form (no cluster rank lookup per copy)
-  asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
-               "r"(bar)
-               : "memory");
-#else
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
                "r"(bar)
                : "memory");
-#endif
 }
 
 // One momentum update: update_u (private_mod.f95:1437-1500) when IS_U, update_v (private_mod.f95:1520-1586)
@@ -250,8 +241,10 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
   unsigned *obits = reinterpret_cast<unsigned *>(wring + kWRings * 4 * kWRow);  // [32]: open-water bit of every 4-row group of the chunk
   double *ring = reinterpret_cast<double *>(smem_raw + sp.ring_off(l));  // input ring of this layer
 
-  const int tile = blockIdx.x * groups + grp;
-  const int xs = D.x_lo + blockIdx.x * groups * kUse - kPad;  // first staged column of the CTA (even)
+  // bit 16 of wind_layers: the grid is (chunks, strips) instead of (strips, chunks) -- which CTAs run side by side in a wave
+  const int bx = ((wind_layers >> 16) & 1) ? blockIdx.y : blockIdx.x, by = ((wind_layers >> 16) & 1) ? blockIdx.x : blockIdx.y;
+  const int tile = bx * groups + grp;
+  const int xs = D.x_lo + bx * groups * kUse - kPad;  // first staged column of the CTA (even)
   const int x = xs + 2 + grp * kUse + lane;                    // lane 0 = first result column - 2
 #ifdef BEOM_DBG_NOSTORE  // timing experiment (tools/ab.sh): every global store predicated off at run time; results are garbage
   const bool col_ok = lane >= kHalo && lane < 32 - kHalo && x <= D.x_hi && D.dt < -1.0;
@@ -260,7 +253,7 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
 #endif
   // rows of this CTA.  rows_per_chunk < 0: the two "edge" chunks of a y-slab (the -rows_per_chunk rows next to each
   // neighbouring rank), which are computed first so that their exchange overlaps the interior rows
-  const int ya = rows_per_chunk > 0 ? D.y_lo + blockIdx.y * rows_per_chunk : (blockIdx.y == 0 ? D.y_lo : D.y_hi + rows_per_chunk + 1);
+  const int ya = rows_per_chunk > 0 ? D.y_lo + by * rows_per_chunk : (by == 0 ? D.y_lo : D.y_hi + rows_per_chunk + 1);
   const int yb = rows_per_chunk > 0 ? min(ya + rows_per_chunk - 1, D.y_hi) : ya - rows_per_chunk - 1;
   const size_t L = (size_t)l * D.plane;
   const bool wind = D.has_wind && ((wind_layers >> l) & 1);
@@ -397,14 +390,6 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
     HN(0, 0) = hn_0;
     __syncwarp();
     if (lane == 0) mbar_arrive(gbar0 + 8 * hslot);  // split-phase: waited for at the end of the row
-#if BEOM_ISSUE_LATE == 1
-    // experiment: the refill of the slots row R - 1 has released is issued here, not at the end of row R - 1 -- a warp that is
-    // ahead of the other column groups of its layer starts its next row instead of waiting for them
-    if (R - 1 >= Rs && R + 1 <= Rend) {
-      mbar_wait(empty0 + 8 * SLOT(1), CT ? (PH == 0 ? bpar ^ 1u : bpar) : (unsigned)(((R - 1 - Rs) >> 2) & 1));
-      issue(R + 1);
-    }
-#endif
 
     // -------------------------------------------------------------------------------- rvor, dive, row R (pm:2388, 2435)
     const double u_0 = LD4(S_U, 0, 0), uE_0 = LD4(S_U, 0, 1), u_m1 = LD4(S_U, 1, 0);
@@ -450,12 +435,6 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
     AT(rv, 0) = rv_0;
     AT(dv, 0) = dv_0;
 
-#if BEOM_ISSUE_LATE == 2
-    if (R - 1 >= Rs && R + 1 <= Rend) {  // experiment: as above, but half a row later
-      mbar_wait(empty0 + 8 * SLOT(1), CT ? (PH == 0 ? bpar ^ 1u : bpar) : (unsigned)(((R - 1 - Rs) >> 2) & 1));
-      issue(R + 1);
-    }
-#endif
     // -------------------------------------------------------------------------------- momentum
     const bool a2 = fw_m2 & (F_ACT | F_GHOST);
     const bool sto2 = col_ok && (!MASKED || (fw_m2 & F_ACT)) && row2_own;
@@ -559,12 +538,10 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
 
     __syncwarp();
     if (lane == 0) mbar_arrive(empty0 + 8 * SLOT(0));  // this warp has finished reading the slots row R + 2 refills
-#if !BEOM_ISSUE_LATE
     if (R + 2 <= Rend) {
       mbar_wait(empty0 + 8 * SLOT(0), bpar);           // ... and so has every other column group of the layer
       issue(R + 2);
     }
-#endif
     off0 += row_bytes;
     off2 += row_bytes;
   };
