@@ -159,6 +159,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--size", type=int, default=8192, help="basin is size x size cells")
     ap.add_argument("--nlay", type=int, default=4)
+    ap.add_argument("--rows", type=int, default=0, help="diagnostic: basin of size x ROWS cells (the shape of one rank's y-slab at N GPUs)")
     ap.add_argument("--split", action="store_true", help="one kernel per reference loop instead of the fused step")
     ap.add_argument("--cpu-sample", type=int, default=2048)
     ap.add_argument("--cpu-steps", type=int, default=120, help="steps of the CPU baseline leg on the sample (about 10-15 s of CPU work on 16 threads)")
@@ -176,8 +177,8 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     n, nlay = args.size, args.nlay
     config = {"workload": "synthetic %dx%dx%d-layer closed flat basin (SURVEY.md 8d): dl=1km, Leith dvis=0.2 every step, "
-                          "generalized forward-backward, wind 0.1cos(pi y/L) Pa, seed 20261018" % (n, n, nlay),
-              "grid": [n, n, nlay], "decomposition": "y-slabs x%d" % args.gpus, "l2": "inputs_exceed_L2",
+                          "generalized forward-backward, wind 0.1cos(pi y/L) Pa, seed 20261018" % (n, args.rows or n, nlay),
+              "grid": [n, args.rows or n, nlay], "decomposition": "y-slabs x%d" % args.gpus, "l2": "inputs_exceed_L2",
               "bytes_per_update_algorithmic": ALGO_BYTES_PER_UPDATE,
               "arithmetic": "fma-contracted (tolerance parity 1e-10)" if args.fma else "strict IEEE, no contraction (bit-exact vs the oracle)"}
 
@@ -251,12 +252,12 @@ def main():
         t0 = time.perf_counter()
         c = None
         if rank == 0:
-            c, blk = make_case(n, nlay, tmp)
+            c, blk = make_case(n, nlay, tmp, mm=(args.rows or None))
             log("[rank 0] inputs written: %.1f s" % (time.perf_counter() - t0))
         if world > 1:
             dist.barrier()
         blk = os.path.join(tmp, "shared_mod_block.f95")
-        nd1 = (n + 1) * (n + 1) + 1
+        nd1 = (n + 1) * ((args.rows or n) + 1) + 1
         opt = model.default_options(fused=not args.split, rank=rank, nranks=world, device=local_rank)
         gm = hl = uu = vv = None
         # read_input_data holds ~25 GB of host arrays for this grid: at most two ranks do it at a time
@@ -291,7 +292,7 @@ def main():
             if world > 1:
                 dist.barrier()
 
-        updates_per_step = float(n) * n * nlay
+        updates_per_step = float(n) * (args.rows or n) * nlay
 
         # ---- device-resident timing: W warm-up steps (incl. the 3 start-up steps), then K timed steps
         gm.upload_state(hl, uu, vv)

@@ -77,7 +77,7 @@ class Records(C.Structure):  # beom_records of include/beom_gpu.h
 GPU_SYMBOLS = [
     "beom_gpu_version", "beom_gpu_abi_version", "beom_gpu_last_error", "beom_gpu_default_options",
     "beom_gpu_init", "beom_gpu_upload_state", "beom_gpu_stress", "beom_gpu_step", "beom_gpu_advance",
-    "beom_gpu_download_state", "beom_gpu_download_aux", "beom_gpu_download_diag", "beom_gpu_download_pi_s",
+    "beom_gpu_download_state", "beom_gpu_download_aux", "beom_gpu_download_diag", "beom_gpu_download_pi_s", "beom_gpu_pi_iterations",
     "beom_gpu_diagnostics", "beom_gpu_diagnostics_all", "beom_gpu_set_rest_thickness", "beom_gpu_records_begin",
     "beom_gpu_records_wait", "beom_gpu_sync", "beom_gpu_mark", "beom_gpu_elapsed_ms", "beom_gpu_launch_count",
     "beom_gpu_path", "beom_gpu_point_range", "beom_gpu_set_window", "beom_gpu_host_alloc", "beom_gpu_host_free", "beom_gpu_comm_unique_id", "beom_gpu_comm_init", "beom_gpu_comm_finalize", "beom_gpu_finalize",
@@ -120,6 +120,7 @@ def bind_gpu(lib: C.CDLL) -> C.CDLL:
     lib.beom_gpu_download_aux.argtypes = [c_double_p] * 5
     lib.beom_gpu_download_diag.argtypes = [c_float_p] * 3
     lib.beom_gpu_download_pi_s.argtypes = [c_double_p]
+    lib.beom_gpu_pi_iterations.argtypes = [C.POINTER(C.c_int)]
     lib.beom_gpu_diagnostics.argtypes = [c_double_p] * 4
     lib.beom_gpu_diagnostics_all.argtypes = [c_double_p] * 8
     lib.beom_gpu_set_rest_thickness.argtypes = [c_float_p]

@@ -18,6 +18,7 @@
 #include "fused.cuh"
 #include "split.cuh"
 #include "diag.cuh"
+#include "rigid.cuh"
 #include "layout.h"
 #include "orphans.h"
 
@@ -110,6 +111,10 @@ struct Ctx {
   long long launches = 0;
   size_t win_first = 0, win_stride = 0;  // host state arrays cover points win_first .. win_first+win_stride-1 per layer
   int n_3d = 1;
+  PiSolve pis;           // rigid lid: the wavefront solver's arrays (rigid.cuh)
+  bool pis_ready = false;
+  int pis_blocks = 0, pis_threads = 0;
+  int *pi_iters = nullptr;  // device: sweeps of the last solve
 };
 Ctx g;
 
@@ -313,9 +318,19 @@ int step_split(int tstp, bool upst, bool first_three) {
     if (first_three) k_centred_flux<<<gridL, kBlock, 0, g.stream>>>(D);
     else k_upstream_flux<<<gridL, kBlock, 0, g.stream>>>(D);
     k_pi_rhs<<<grid1, kBlock, 0, g.stream>>>(D);
-    k_surf_pressure<<<1, 1024, 0, g.stream>>>(D, 1000, 1.e-5, nullptr);
+    static const bool one_cta = getenv("BEOM_PI_ONE_CTA") && atoi(getenv("BEOM_PI_ONE_CTA")) > 0;  // the single-block wavefront (cross-check)
+    if (one_cta || !g.pis_ready) {
+      k_surf_pressure<<<1, 1024, 0, g.stream>>>(D, 1000, 1.e-5, g.pi_iters);
+      g.launches += 1;
+    } else {
+      // every SM: tiles of anti-diagonal wavefronts, several sweeps in flight, the reference's iterates (rigid.cuh)
+      k_pi_begin<<<grid1, kBlock, 0, g.stream>>>(D, g.pis);
+      k_pi_wave<<<(unsigned)g.pis_blocks, (unsigned)g.pis_threads, 0, g.stream>>>(D, g.pis);
+      k_pi_select<<<grid1, kBlock, 0, g.stream>>>(D, g.pis, g.pi_iters);
+      g.launches += 3;
+    }
     k_pi_correct<<<gridL, kBlock, 0, g.stream>>>(D);
-    g.launches += 4;
+    g.launches += 3;
   }
   CK(cudaGetLastError());
   return 0;
@@ -579,6 +594,43 @@ static int init_impl(const beom_params *par, const beom_fields *fld, const beom_
     if ((rc = upload_planes(o1, fld->Ow, 1)) || (rc = upload_planes(o2, fld->Os, 1)) || (rc = upload_planes(o3, fld->Osum_, 1))) return rc;
     if (fld->pi_s && (rc = upload_planes(D.pi_s, fld->pi_s, 1))) return rc;
     D.Ow = o1; D.Os = o2; D.Osum_ = o3;
+    if ((rc = dalloc(&g.pi_iters, (size_t)16))) return rc;
+    {  // the all-SM solver (rigid.cuh): kPiNA - 1 further pi_s arrays, five coefficient planes, per-tile sweep counters
+      PiSolve &S = g.pis;
+      memset(&S, 0, sizeof S);
+      S.X[0] = D.pi_s;
+      for (int k = 1; k < kPiNA; k++)
+        if ((rc = dalloc(&S.X[k], pl))) return rc;
+      double *cE = nullptr, *cN = nullptr, *cW = nullptr, *cS = nullptr;
+      if ((rc = dalloc(&S.c0, pl)) || (rc = dalloc(&cE, pl)) || (rc = dalloc(&cN, pl)) || (rc = dalloc(&cW, pl)) || (rc = dalloc(&cS, pl))) return rc;
+      const int w = D.x_hi - D.x_lo + 1, h = D.y_hi - D.y_lo + 1;
+      S.TI = (w + kPiBx - 1) / kPiBx;
+      S.TJ = (h + kPiBy - 1) / kPiBy;
+      S.maxiters = 1000;   // pm:1717
+      S.tol = 1.e-5;       // pi_tol, pm:1716
+      unsigned long long *mb = nullptr;
+      if ((rc = dalloc(&S.done, (size_t)(S.TI + 2) * (S.TJ + 2))) || (rc = dalloc(&S.count, (size_t)kPiNA)) || (rc = dalloc(&mb, (size_t)kPiNA)) ||
+          (rc = dalloc(&S.decided, (size_t)4)))
+        return rc;
+      S.maxbits = mb;
+      S.final_sweep = S.decided + 1;
+      k_pi_coeff<<<cell_grid(D, 1, kBlock), kBlock, 0, g.stream>>>(D, cE, cN, cW, cS);
+      g.launches++;
+      S.cE = cE; S.cN = cN; S.cW = cW; S.cS = cS;
+      // persistent workers (one warp per tile and sweep): all of them must be resident at once
+      const int ntiles = S.TI * S.TJ;
+#ifdef BEOM_CUDA_EMULATION
+      g.pis_threads = 32 * std::min(ntiles, 32);  // (the emulation runs one block at a time: every worker in one block)
+      g.pis_blocks = 1;
+#else
+      g.pis_threads = 256;
+      int per_sm = 0;
+      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pi_wave, g.pis_threads, 0));
+      const int warps_per_block = g.pis_threads / 32;
+      g.pis_blocks = std::max(1, std::min((ntiles + warps_per_block - 1) / warps_per_block, per_sm * prop.multiProcessorCount));
+#endif
+      g.pis_ready = true;
+    }
   }
 
   // open-boundary segments as dense cells (private_mod.f95:1060-1240, columns 1,4,5,10,13,16)
@@ -1047,6 +1099,13 @@ int beom_gpu_records_wait(beom_records *out) {
   return 0;
 }
 
+int beom_gpu_pi_iterations(int *iters) {
+  if (!g.ready) return fail(-20, "beom_gpu_pi_iterations: not initialised");
+  if (!g.pi_iters) return fail(-30, "beom_gpu_pi_iterations: rgld = 0, there is no surface-pressure solve");
+  CK(cudaMemcpyAsync(iters, g.pi_iters, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  return 0;
+}
 int beom_gpu_download_pi_s(double *pi_s) {
   if (!g.ready) return fail(-20, "beom_gpu_download_pi_s: not initialised");
   if (!g.D.pi_s) return fail(-30, "beom_gpu_download_pi_s: rgld = 0, there is no surface pressure");

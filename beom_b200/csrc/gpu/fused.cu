@@ -159,7 +159,12 @@ int fused_configure(const Dev &D, const beom_params &P, int nmir, int nranks, bo
   if (fused_smem_bytes(D.nlay, groups, T0, wl) > (size_t)max_smem - 1024) return 0;
   cfg.groups = groups;
   cfg.strips = (width + groups * kUse - 1) / (groups * kUse);
-  int chunks = std::max(1, (2 * sms + cfg.strips / 2) / cfg.strips);  // about two CTAs' worth of work per SM
+  // At least two CTAs' worth of work per SM, and chunks of about 256 rows: many short waves instead of two long ones.  Measured
+  // (8192 x 8192 x 4, profiles/r2_chunk_sweep.txt): 1 wave 11.6 ms, 2 waves 10.2, 4 waves 10.1, 8 waves 9.2, 16 waves 8.8, 32 waves
+  // 8.9 -- CTAs that start together stay in step and hit HBM in bursts (all row loads of a wave within the same microsecond);
+  // waves that end at different moments spread the requests out.
+  int chunks = std::max(1, (2 * sms + cfg.strips / 2) / cfg.strips);
+  chunks = std::max(chunks, (rows + 128) / 256);
   if (const char *e = getenv("BEOM_FUSED_CHUNKS")) chunks = std::max(1, atoi(e));  // experiment: y-chunks per strip
   chunks = std::min(chunks, std::max(1, rows / 16));
   chunks = std::max(chunks, (rows + 3839) / 3840);  // the lean kernel keeps a chunk's open-water bitmap in 32 words (32 x 128 rows)
@@ -217,7 +222,8 @@ int fused_step(const Dev &in_, const Dev &out, int tstp, bool first_three, cudaS
   const StreamTab T = make_streams(in, ufirst);
   a.shmem = fused_smem_bytes(in.nlay, cfg.groups, T, in.has_wind ? cfg.wind_layers : 0);
   a.in = &in; a.out = &out; a.tab = &T; a.open = cfg.open; a.open4 = cfg.open4; a.open4_words = cfg.open4_words;
-  a.groups = cfg.groups; a.rows_per_chunk = rpc; a.wind_layers = cfg.wind_layers | (swap ? 1 << 16 : 0);
+  a.groups = cfg.groups; a.rows_per_chunk = rpc; static const int jitter = getenv("BEOM_FUSED_JITTER") ? std::min(4095, std::max(0, atoi(getenv("BEOM_FUSED_JITTER")) / 64)) : 0;  // ns
+  a.wind_layers = cfg.wind_layers | (swap ? 1 << 16 : 0) | (jitter << 17);
   a.stream = s;
   // the lean instantiations assume gene = 1 (tstp >= 4 with g_fb = 1) or gene = 0 (the start-up steps) exactly
   const bool g0 = in.gene == 0.0;  // the start-up steps

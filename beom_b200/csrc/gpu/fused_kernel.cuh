@@ -309,6 +309,17 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  {
+    // bits 17..28 of wind_layers (experiment): CTAs start up to that many x 64 ns apart (a hash of the block index), so that
+    // the CTAs of a wave do not issue their row loads in the same instant
+    const unsigned jit = ((unsigned)wind_layers >> 17) & 0xfffu;
+    if (jit && threadIdx.x == 0) {
+      unsigned hsh = (blockIdx.x * 2654435761u) ^ (blockIdx.y * 40503u + 0x9e3779b9u);
+      hsh ^= hsh >> 15; hsh *= 2246822519u; hsh ^= hsh >> 13;
+      const unsigned ns = (hsh % jit) * 64u;
+      for (unsigned t = 0; t < ns; t += 1000u) __nanosleep(min(1000u, ns - t));
+    }
+  }
   __syncthreads();
   const int R0 = ya - 3, R1 = yb + 2;
   const int Rs = R0 & ~3;  // the row loop starts on a multiple of 4: ring slot = R & 3 = unroll phase

@@ -223,6 +223,12 @@ class GpuModel:
             out[k] = np.ctypeslib.as_array(ptr, shape=(self.nlay, r.count)).copy() if ptr else None
         return out
 
+    def pi_iterations(self) -> int:
+        """Sweeps of the last rigid-lid pressure solve."""
+        n = C.c_int(0)
+        self._ck(self.lib.beom_gpu_pi_iterations(C.byref(n)), "pi_iterations")
+        return int(n.value)
+
     def download_pi_s(self):
         out = np.zeros(self.ndeg + 1)
         self._ck(self.lib.beom_gpu_download_pi_s(_dp(out)), "download_pi_s")

@@ -168,6 +168,8 @@ int beom_gpu_records_wait(beom_records *out);
 
 /* Rigid-lid surface pressure pi_s(0:ndeg) (private_mod.f95:91). */
 int beom_gpu_download_pi_s(double *pi_s);
+/* Sweeps the last surf_pressure solve took (the reference's `iters', private_mod.f95:1756-1803). */
+int beom_gpu_pi_iterations(int *iters);
 
 /* Conservation integrals (testcases/conservation.m:116-211) over the vector points (frozen periodic duplicates
  * excluded, as the script does at :196-201), per layer l:

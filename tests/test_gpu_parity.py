@@ -183,6 +183,26 @@ def test_rigid_lid_bit_exact(case_factory, name, kw, extra):
         assert np.abs(pi_s).max() > 0
 
 
+def test_rigid_lid_wavefront_solver_many_tiles(case_factory):
+    """surf_pressure on every SM (rigid.cuh): 300 x 170 points = 5 x 6 tiles of 64 x 32, up to 15 sweeps in flight -- pi_s, the
+    state and the number of sweeps equal the oracle's lexicographic Gauss-Seidel (pm:1756-1803) bit for bit."""
+    c, d, hm = case_factory("synthetic_basin", small=False, extra=dict(rgld="1.", ocrp="1."), n=300, mm=170, nlay=2)
+    orc = Oracle(hm.params, d)
+    gm = model.GpuModel(hm.params, hm.fields(), model.default_options(fused=True))
+    gm.upload_state(hm.array("hlay"), hm.array("u"), hm.array("v"))
+    iters = []
+    for t in range(1, 7):
+        gm.advance(t, t)
+        iters.append(gm.pi_iterations())
+    orc.advance(1, 6)
+    st = gm.download_state()
+    pi_s = gm.download_pi_s()
+    gm.close()
+    _check_state("rgld_wave", st, orc)
+    assert_same("pi_s", pi_s, orc.array("pi_s")[0])
+    assert np.abs(pi_s).max() > 0 and all(1 <= k <= 1000 for k in iters) and max(iters) > 16  # (more sweeps than rotating arrays)
+
+
 @pytest.mark.parametrize("nlay", [1, 4])
 def test_fma_flavour_within_tolerance(nlay):
     """BEOM_FMA=1 (opt-in): the fused step compiled with FMA contraction, like the reference's own -Ofast build.

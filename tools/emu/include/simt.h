@@ -209,3 +209,19 @@ template <class T> inline T __shfl_down_sync(unsigned, T v, int d) { return emu:
 inline bool __all_sync(unsigned, bool p) { return emu::vote_all(p); }
 inline void __syncwarp() { if (emu::cur_warp) emu::syncwarp(); }
 inline void __syncthreads() { emu::syncthreads(); }
+// inter-warp / inter-CTA communication through global memory (the rigid-lid wavefront solver, rigid.cuh): warps are OS
+// threads here, so the GCC atomics are the real thing
+template <class T> inline T __shfl_sync(unsigned, T v, int src) { return emu::shfl_idx(v, src); }
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
+inline void __nanosleep(unsigned) { std::this_thread::yield(); }
+inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned long long atomicExch(unsigned long long *p, unsigned long long v) { return __atomic_exchange_n(p, v, __ATOMIC_SEQ_CST); }
+inline unsigned long long atomicMax(unsigned long long *p, unsigned long long v) {
+  unsigned long long old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+  while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+  return old;
+}
+template <class T> inline T __ldcg(const T *p) { return *reinterpret_cast<const volatile T *>(p); }
+template <class T> inline T __ldg(const T *p) { return *p; }
+inline long long __double_as_longlong(double d) { long long b; std::memcpy(&b, &d, 8); return b; }
+inline double __longlong_as_double(long long b) { double d; std::memcpy(&d, &b, 8); return d; }
