@@ -254,6 +254,51 @@ int run_stress() {
   return 0;
 }
 
+// surf_pressure's iteration across y-slabs (rigid.cuh).  A sweep of rank r needs the south row of the SAME sweep from rank r-1
+// and the north row of the PREVIOUS sweep from rank r+1, so the ranks work in rounds: rank r runs sweep k in round 2k + r (its
+// neighbours rest in that round), and every round ends with the exchange of one row per neighbour.  Sweeps are done in batches of
+// kPiNA - 1 into rotating arrays; after a batch the per-sweep max-norms are reduced over the ranks and the first sweep that
+// satisfies the reference's stopping rule is final (the later ones of the batch wrote into other arrays).
+int pi_solve_slabs(const Dev &D) {
+  PiSolve &S = g.pis;
+  const int R = g.nranks, r = g.rank, NX = g.NX;
+  const int lo = r > 0 ? r - 1 : -1, hi = r < R - 1 ? r + 1 : -1;
+  const int B = kPiNA - 1;
+  int rc;
+  double *scratch = g.halo_recv[0];                 // (two rows + the reduction buffers: far below the halo capacity)
+  double *red_lo = g.halo_recv[1], *red_hi = g.halo_recv[1] + kPiNA;
+  int fin = 0;
+  for (int b0 = 1; b0 <= S.maxiters && !fin; b0 += B) {
+    const int b1 = std::min(b0 + B - 1, S.maxiters);
+    auto sweep_of = [&](int rank, int t) {  // the sweep `rank' runs in round t (0 = it rests)
+      const int q = t - rank;
+      return (rank >= 0 && rank < R && q % 2 == 0 && q / 2 >= b0 && q / 2 <= b1) ? q / 2 : 0;
+    };
+    for (int t = 2 * b0; t <= 2 * b1 + R - 1; t++) {
+      const int k = sweep_of(r, t), k_lo = sweep_of(lo, t), k_hi = sweep_of(hi, t);
+      if (k) {
+        k_pi_wave<<<(unsigned)g.pis_blocks, (unsigned)g.pis_threads, 0, g.stream>>>(D, S, k, k, 1);
+        g.launches++;
+      }
+      // what this rank wrote in this round goes to both neighbours (a resting rank sends rows nobody looks at)
+      const double *mine = S.X[(k ? k : 0) % kPiNA];
+      double *from_lo = k_lo ? S.X[k_lo % kPiNA] + (size_t)(D.y_lo - 1) * NX : scratch;
+      double *from_hi = k_hi ? S.X[k_hi % kPiNA] + (size_t)(D.y_hi + 1) * NX : scratch + NX;
+      if ((rc = comm_exchange(mine + (size_t)D.y_lo * NX, from_lo, lo, mine + (size_t)D.y_hi * NX, from_hi, hi, (size_t)NX, g.stream, &g_err))) return rc;
+    }
+    for (int it = 0; it < R - 1; it++) {  // max over the ranks of every sweep's max-norm
+      if ((rc = comm_exchange(S.md, red_lo, lo, S.md, red_hi, hi, (size_t)kPiNA, g.stream, &g_err))) return rc;
+      k_pi_max_merge<<<1, 32, 0, g.stream>>>(S.md, red_lo, red_hi, lo >= 0, hi >= 0);
+      g.launches++;
+    }
+    k_pi_verdict<<<1, 32, 0, g.stream>>>(S, b0, b1);
+    g.launches++;
+    CK(cudaMemcpyAsync(&fin, S.final_sweep, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+  }
+  return 0;
+}
+
 // One step of the split path: the reference's call sequence, one kernel per loop.
 int step_split(int tstp, bool upst, bool first_three) {
   int rc = alloc_split_buffers();
@@ -314,23 +359,30 @@ int step_split(int tstp, bool upst, bool first_three) {
     if (g.nmir || g.nranks > 1) sync_fields({{D.u, nl}, {D.v, nl}, {D.h_u, nl}, {D.h_v, nl}});
   }
   if (rgld) {  // pm:2207-2221 / 2292-2314
-    if (g.nranks > 1 || g.nmir) return fail(-30, "rgld = 1 is supported on one GPU, non-periodic domains only");
     if (first_three) k_centred_flux<<<gridL, kBlock, 0, g.stream>>>(D);
     else k_upstream_flux<<<gridL, kBlock, 0, g.stream>>>(D);
+    if (g.nranks > 1 && (rc = sync_fields({{D.h_u, nl}, {D.h_v, nl}}))) return rc;  // the right-hand side reads h_v of the row above
     k_pi_rhs<<<grid1, kBlock, 0, g.stream>>>(D);
     static const bool one_cta = getenv("BEOM_PI_ONE_CTA") && atoi(getenv("BEOM_PI_ONE_CTA")) > 0;  // the single-block wavefront (cross-check)
-    if (one_cta || !g.pis_ready) {
+    if (g.nranks > 1) {
+      k_pi_begin<<<grid1, kBlock, 0, g.stream>>>(D, g.pis);
+      if ((rc = pi_solve_slabs(D))) return rc;
+      k_pi_select<<<grid1, kBlock, 0, g.stream>>>(D, g.pis, g.pi_iters);
+      g.launches += 2;
+      if ((rc = sync_fields({{D.pi_s, 1}}))) return rc;  // the projection reads pi_s of the row below
+    } else if (one_cta || !g.pis_ready) {
       k_surf_pressure<<<1, 1024, 0, g.stream>>>(D, 1000, 1.e-5, g.pi_iters);
       g.launches += 1;
     } else {
       // every SM: tiles of anti-diagonal wavefronts, several sweeps in flight, the reference's iterates (rigid.cuh)
       k_pi_begin<<<grid1, kBlock, 0, g.stream>>>(D, g.pis);
-      k_pi_wave<<<(unsigned)g.pis_blocks, (unsigned)g.pis_threads, 0, g.stream>>>(D, g.pis);
+      k_pi_wave<<<(unsigned)g.pis_blocks, (unsigned)g.pis_threads, 0, g.stream>>>(D, g.pis, 1, g.pis.maxiters, 0);
       k_pi_select<<<grid1, kBlock, 0, g.stream>>>(D, g.pis, g.pi_iters);
       g.launches += 3;
     }
     k_pi_correct<<<gridL, kBlock, 0, g.stream>>>(D);
     g.launches += 3;
+    if (g.nranks > 1 && (rc = sync_fields({{D.u, nl}, {D.v, nl}}))) return rc;  // the projected velocities of the neighbours' rows
   }
   CK(cudaGetLastError());
   return 0;
@@ -586,7 +638,7 @@ static int init_impl(const beom_params *par, const beom_fields *fld, const beom_
     if ((rc = dalloc(&D.tu3d, pl * nl * 2)) || (rc = dalloc(&D.layu, pl * nl)) || (rc = dalloc(&D.taum, pl * 2))) return rc;
 
   if (par->rgld > 0.5) {  // rigid lid: Poisson operators and the start pressure (private_mod.f95:505-563)
-    if (g.nranks > 1 || g.nmir) return fail(-30, "beom_gpu_init: rgld = 1 is supported on one GPU, non-periodic domains only");
+    if (g.nmir || par->xper > 0.5 || par->yper > 0.5) return fail(-30, "beom_gpu_init: rgld = 1 is supported on non-periodic domains only");
     if (!fld->Ow || !fld->Os || !fld->Osum_) return fail(-14, "beom_gpu_init: rgld = 1 needs Ow, Os, Osum_");
     if (nlay != 2) return fail(-14, "beom_gpu_init: the reference's rigid lid is written for two layers (private_mod.f95:1653-1654)");
     double *o1 = nullptr, *o2 = nullptr, *o3 = nullptr;
@@ -610,7 +662,7 @@ static int init_impl(const beom_params *par, const beom_fields *fld, const beom_
       S.tol = 1.e-5;       // pi_tol, pm:1716
       unsigned long long *mb = nullptr;
       if ((rc = dalloc(&S.done, (size_t)(S.TI + 2) * (S.TJ + 2))) || (rc = dalloc(&S.count, (size_t)kPiNA)) || (rc = dalloc(&mb, (size_t)kPiNA)) ||
-          (rc = dalloc(&S.decided, (size_t)4)))
+          (rc = dalloc(&S.decided, (size_t)4)) || (rc = dalloc(&S.md, (size_t)kPiNA)))
         return rc;
       S.maxbits = mb;
       S.final_sweep = S.decided + 1;

@@ -37,6 +37,7 @@ struct PiSolve {
   unsigned long long *maxbits;           // [kPiNA] max |change| of that sweep (bits of a non-negative double)
   int *decided;                          // sweeps 1 .. *decided are complete and were not final
   int *final_sweep;                      // 0 until the final sweep K is known
+  double *md;                            // [kPiNA] y-slab runs: this rank's max |change| per sweep slot (then reduced over the ranks)
   int TI, TJ, maxiters;
   double tol;
 };
@@ -66,7 +67,7 @@ __global__ void k_pi_begin(const __grid_constant__ Dev D, const __grid_constant_
       const int I = i % DW, J = i / DW;
       S.done[i] = (I == 0 || J == 0 || I == DW - 1 || J == S.TJ + 1) ? kPiDoneBorder : 0;
     }
-    for (int i = t; i < kPiNA; i += nt) { S.count[i] = 0; S.maxbits[i] = 0ull; }
+    for (int i = t; i < kPiNA; i += nt) { S.count[i] = 0; S.maxbits[i] = 0ull; S.md[i] = 0.0; }
     if (t == 0) { *S.decided = 0; *S.final_sweep = 0; }
   }
   if (x > D.x_hi || y > D.y_hi) return;
@@ -78,12 +79,15 @@ __global__ void k_pi_begin(const __grid_constant__ Dev D, const __grid_constant_
 
 __device__ __forceinline__ int ld_volatile(const int *p) { return *reinterpret_cast<const volatile int *>(p); }
 
-__global__ void __launch_bounds__(1024) k_pi_wave(const __grid_constant__ Dev D, const __grid_constant__ PiSolve S) {
+// One launch runs sweeps k_first .. k_last.  One rank: 1 .. maxiters with the verdicts taken inside the kernel.  y-slabs
+// (multi != 0): ONE sweep per launch -- the south row of this sweep and the north row of the previous one are the
+// neighbouring ranks' and arrive between launches (beom_gpu.cu, pi_solve_slabs); the sweep's max |change| goes to S.md.
+__global__ void __launch_bounds__(1024) k_pi_wave(const __grid_constant__ Dev D, const __grid_constant__ PiSolve S, int k_first, int k_last, int multi) {
   const int lane = threadIdx.x & 31;
   const int worker = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5), nworkers = (int)((gridDim.x * blockDim.x) >> 5);
   const int ntiles = S.TI * S.TJ, NX = D.NX, DW = S.TI + 2;
   const double rp = 1.0;
-  for (int k = 1; k <= S.maxiters; k++) {
+  for (int k = k_first; k <= k_last; k++) {
     double *__restrict__ Xn = S.X[k % kPiNA];
     const double *__restrict__ Xo = S.X[(k - 1) % kPiNA];
     for (int t = worker; t < ntiles; t += nworkers) {
@@ -92,10 +96,10 @@ __global__ void __launch_bounds__(1024) k_pi_wave(const __grid_constant__ Dev D,
       int fin = 0;
       if (lane == 0) {
         for (;;) {
-          fin = ld_volatile(S.final_sweep);
+          if (!multi) fin = ld_volatile(S.final_sweep);
           if (fin) break;
           if (ld_volatile(dn - 1) >= k && ld_volatile(dn - DW) >= k && ld_volatile(dn + 1) >= k - 1 && ld_volatile(dn + DW) >= k - 1 &&
-              ld_volatile(S.decided) >= k - kPiNA)
+              (multi || ld_volatile(S.decided) >= k - kPiNA))
             break;
           __nanosleep(40);
         }
@@ -144,12 +148,33 @@ __global__ void __launch_bounds__(1024) k_pi_wave(const __grid_constant__ Dev D,
           const double m = __longlong_as_double((long long)atomicExch(S.maxbits + slot, 0ull));
           S.count[slot] = 0;
           __threadfence();
-          if (!(m > S.tol) || k >= S.maxiters) *reinterpret_cast<volatile int *>(S.final_sweep) = k;
+          if (multi) S.md[slot] = m;
+          else if (!(m > S.tol) || k >= S.maxiters) *reinterpret_cast<volatile int *>(S.final_sweep) = k;
           else *reinterpret_cast<volatile int *>(S.decided) = k;
         }
       }
     }
   }
+}
+
+// y-slabs: md = max(md, what the two neighbours hold) -- nranks - 1 rounds of this after a neighbour exchange make every rank
+// hold the maxima over all ranks (the ranks form a line; an allreduce that needs nothing but the halo exchange)
+__global__ void k_pi_max_merge(double *__restrict__ md, const double *__restrict__ from_lo, const double *__restrict__ from_hi, int has_lo, int has_hi) {
+  const int i = threadIdx.x;
+  if (i >= kPiNA) return;
+  double m = md[i];
+  if (has_lo) m = fmax(m, from_lo[i]);
+  if (has_hi) m = fmax(m, from_hi[i]);
+  md[i] = m;
+}
+// y-slabs: the verdict on sweeps b0 .. b1 from their reduced max-norms (pm:1756, 1795-1802); the slots are cleared for the next batch
+__global__ void k_pi_verdict(const __grid_constant__ PiSolve S, int b0, int b1) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int fin = 0;
+  for (int k = b0; k <= b1 && !fin; k++)
+    if (!(S.md[k % kPiNA] > S.tol) || k >= S.maxiters) fin = k;
+  for (int i = 0; i < kPiNA; i++) S.md[i] = 0.0;
+  *S.final_sweep = fin;
 }
 
 // the final sweep's array becomes pi_s (X[0]); iters_out (optional) = number of sweeps, as the reference counts them
@@ -159,7 +184,7 @@ __global__ void k_pi_select(const __grid_constant__ Dev D, const __grid_constant
   if (iters_out && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0 && threadIdx.y == 0) *iters_out = K;
   if (x > D.x_hi || y > D.y_hi || K % kPiNA == 0) return;
   const size_t c = (size_t)y * D.NX + x;
-  if (D.flags[c] & F_ACT) S.X[0][c] = S.X[K % kPiNA][c];
+  if (D.flags[c] & F_ACT) S.X[0][c] = S.X[K % kPiNA][c];  // (y-slabs: the halo rows of pi_s are refreshed by the caller)
 }
 
 }  // namespace beom

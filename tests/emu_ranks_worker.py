@@ -107,8 +107,14 @@ def run_rank(rank):
         for nm, got in zip(("h_u", "h_v", "rs_h", "dmdx", "dmdy"), aux):
             if not np.array_equal(got[:, sl][:, keep], orc.array(nm)[:, sl][:, keep]):
                 bad.append(nm)
+        sweeps = None
+        if hm.params.rgld > 0.5:  # the rigid lid: the surface pressure of the own points and the number of sweeps of the last solve
+            pi_s = gm.download_pi_s()
+            if not np.array_equal(pi_s[sl], orc.array("pi_s")[0][sl]):
+                bad.append("pi_s")
+            sweeps = gm.pi_iterations()
         results[rank] = {"rank": rank, "points": [int(own_first), int(own_first + own_count - 1)], "bad": bad,
-                         "path": lib.beom_gpu_path().decode(), "exchanges": calls[rank]}
+                         "path": lib.beom_gpu_path().decode(), "exchanges": calls[rank], "pi_sweeps": sweeps}
         lib.beom_gpu_finalize()
     except Exception as e:  # noqa: BLE001
         results[rank] = {"rank": rank, "error": repr(e)}

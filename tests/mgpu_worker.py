@@ -23,6 +23,9 @@ def main():
     name, nsteps, fused = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
     if name == "synthetic_basin":
         c = cases.synthetic_basin(n=300, mm=170, nlay=4)
+    elif name == "rigid_lid_basin":  # the rigid lid across y-slabs: surf_pressure in rounds (beom_gpu.cu, pi_solve_slabs)
+        c = cases.synthetic_basin(n=300, mm=170, nlay=2)
+        c.params_text += "rgld       = 1.\nocrp       = 1.\n"
     else:
         from tests.conftest import SMALL
         c = cases.CASES[name](**SMALL.get(name, {}))
@@ -53,6 +56,10 @@ def main():
         want = orc.array(nm)
         if not np.array_equal(got[:, sl][:, keep], want[:, sl][:, keep]):
             bad.append(nm)
+    if hm.params.rgld > 0.5:
+        pi_s = gm.download_pi_s()
+        if not np.array_equal(pi_s[sl], orc.array("pi_s")[0][sl]):
+            bad.append("pi_s")
     path = gm.path
     gm.close()
     dist.barrier()

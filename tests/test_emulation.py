@@ -163,6 +163,8 @@ RANKS = [
     ("conservation", 12, 3, {}, None),
     ("conservation", 12, 2, {"xper": "0."}, None),               # periodic in y only
     ("unstable_jet", 12, 4, {}, None),
+    # the rigid lid across y-slabs: surf_pressure in rounds, batches of 15 sweeps (steps 3 and 4 take 18 and 55)
+    ("synthetic_basin", 4, 3, {"rgld": "1.", "ocrp": "1."}, dict(n=300, mm=170, nlay=2)),
 ]
 
 

@@ -61,7 +61,8 @@ def test_rendezvous_over_gloo():
                                                ("conservation", 12, 1),   # ... and the fused step across the ring
                                                ("unstable_jet", 12, 1),
                                                ("soliton", 12, 0),        # x-periodic slabs
-                                               ("soliton", 12, 1)])       # ... each a torus of its own: fused
+                                               ("soliton", 12, 1),        # ... each a torus of its own: fused
+                                               ("rigid_lid_basin", 4, 0)])  # surf_pressure across the slabs (18 and 55 sweeps in steps 3, 4)
 def test_two_ranks_bit_exact(name, nsteps, fused):
     import torch
     if torch.cuda.device_count() < 2:
