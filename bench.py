@@ -386,7 +386,7 @@ def main():
     achieved = ALGO_BYTES_PER_UPDATE * value / 1.0e9 / world  # per GPU
     traffic = None  # DRAM bytes per launch from the committed ncu capture of this kernel on this grid (not measured live)
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_fused_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_fused_traffic.json")) as f:
             tj = json.load(f)
         if path == "fused" and world == tj["n_gpus"] and [n, n, nlay] == tj["grid"]:
             traffic = tj["dram_bytes_per_launch"]
