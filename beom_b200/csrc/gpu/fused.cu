@@ -163,8 +163,11 @@ int fused_configure(const Dev &D, const beom_params &P, int nmir, int nranks, bo
   // (8192 x 8192 x 4, profiles/r2_chunk_sweep.txt): 1 wave 11.6 ms, 2 waves 10.2, 4 waves 10.1, 8 waves 9.2, 16 waves 8.8, 32 waves
   // 8.9 -- CTAs that start together stay in step and hit HBM in bursts (all row loads of a wave within the same microsecond);
   // waves that end at different moments spread the requests out.
+  // y-slabs of a multi-GPU run are short (1024 rows at 8 GPUs): there at least eight waves, of chunks no shorter than 64 rows
+  // (a chunk runs 8 rows more than it owns: pipeline fill and the 4-row unrolling); 1024 rows: 4 chunks 1.307 ms, 16 chunks 1.243 ms.
   int chunks = std::max(1, (2 * sms + cfg.strips / 2) / cfg.strips);
   chunks = std::max(chunks, (rows + 128) / 256);
+  chunks = std::max(chunks, std::min((8 * sms + cfg.strips - 1) / cfg.strips, rows / 64));
   if (const char *e = getenv("BEOM_FUSED_CHUNKS")) chunks = std::max(1, atoi(e));  // experiment: y-chunks per strip
   chunks = std::min(chunks, std::max(1, rows / 16));
   chunks = std::max(chunks, (rows + 3839) / 3840);  // the lean kernel keeps a chunk's open-water bitmap in 32 words (32 x 128 rows)
