@@ -86,9 +86,9 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
-def make_case(n, nlay, workdir, mm=None):
+def make_case(n, nlay, workdir, mm=None, sponge=False):
     from beom_b200 import cases
-    c = cases.synthetic_basin(n=n, nlay=nlay, mm=mm)
+    c = cases.synthetic_basin(n=n, nlay=nlay, mm=mm, sponge=sponge)
     blk = c.write(workdir)
     return c, blk
 
@@ -101,14 +101,14 @@ def host_cores() -> int:
         return os.cpu_count() or 1
 
 
-def cpu_baseline(sample_n, nlay, steps, tmp, warm=1):
+def cpu_baseline(sample_n, nlay, steps, tmp, warm=1, sponge=False):
     """Times the oracle's OpenMP build (the reference's loops with the reference's `!$OMP PARALLEL DO'
     placement) on a sample_n x sample_n x nlay basin of the same workload, on every host core: torchrun exports
     OMP_NUM_THREADS=1 to its workers, so the thread count is set explicitly, not inherited."""
     from beom_b200 import model
     from oracle.pyoracle import Oracle
     d = os.path.join(tmp, "cpu_sample_%d" % sample_n)
-    c, blk = make_case(sample_n, nlay, d)
+    c, blk = make_case(sample_n, nlay, d, sponge=sponge)
     with open(blk) as f:
         p, idir, _, _ = model.parse_params(f.read())
     cores = host_cores()
@@ -160,6 +160,9 @@ def main():
     ap.add_argument("--size", type=int, default=8192, help="basin is size x size cells")
     ap.add_argument("--nlay", type=int, default=4)
     ap.add_argument("--rows", type=int, default=0, help="diagnostic: basin of size x ROWS cells (the shape of one rank's y-slab at N GPUs)")
+    ap.add_argument("--workload", default="basin", choices=["basin", "sill_like"],
+                    help="basin: BASELINE.json's synthetic basin (the headline); sill_like: the same grid with sill_exchange3D's option set "
+                         "(N/S sponges on eta,u,v + outcropping, no wind): what the specialised sponge instantiation of the fused step delivers")
     ap.add_argument("--split", action="store_true", help="one kernel per reference loop instead of the fused step")
     ap.add_argument("--cpu-sample", type=int, default=2048)
     ap.add_argument("--cpu-steps", type=int, default=120, help="steps of the CPU baseline leg on the sample (about 10-15 s of CPU work on 16 threads)")
@@ -176,8 +179,11 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     n, nlay = args.size, args.nlay
-    config = {"workload": "synthetic %dx%dx%d-layer closed flat basin (SURVEY.md 8d): dl=1km, Leith dvis=0.2 every step, "
-                          "generalized forward-backward, wind 0.1cos(pi y/L) Pa, seed 20261018" % (n, args.rows or n, nlay),
+    sponge = args.workload == "sill_like"
+    config = {"workload": ("synthetic %dx%dx%d-layer closed flat basin (SURVEY.md 8d): dl=1km, Leith dvis=0.2 every step, "
+                           "generalized forward-backward, %s, seed 20261018" % (n, args.rows or n, nlay,
+                           "sill_exchange3D's options: 64-row N/S sponges on eta,u,v (nudg.bin) + outcropping (ocrp=1), no wind" if sponge
+                           else "wind 0.1cos(pi y/L) Pa")),
               "grid": [n, args.rows or n, nlay], "decomposition": "y-slabs x%d" % args.gpus, "l2": "inputs_exceed_L2",
               "bytes_per_update_algorithmic": ALGO_BYTES_PER_UPDATE,
               "arithmetic": "fma-contracted (tolerance parity 1e-10)" if args.fma else "strict IEEE, no contraction (bit-exact vs the oracle)"}
@@ -197,7 +203,7 @@ def main():
             W = max(args.warmup, 0)
             K = max(args.steps, 1)
             # a bounded sample first: it says how long the full grid would take on this box
-            sample = cpu_baseline(args.cpu_sample, nlay, min(K, 20), tmp)
+            sample = cpu_baseline(args.cpu_sample, nlay, min(K, 20), tmp, sponge=sponge)
             est_step = float(n) * n * nlay / sample["value"]
             est_total = est_step * (3 + max(W, 1) + K) + 0.4 * est_step * 20 + 30.0  # + read_input_data + writing the inputs
             try:
@@ -209,7 +215,7 @@ def main():
             full = None
             if n > args.cpu_sample and est_total < args.ref_budget and free_gb > 1.3 * need_gb:
                 log("[reference] full %dx%dx%d grid: estimated %.0f s, %.0f GB of host memory (%.0f GB free)" % (n, n, nlay, est_total, need_gb, free_gb))
-                full = cpu_baseline(n, nlay, K, tmp, warm=max(W, 1))
+                full = cpu_baseline(n, nlay, K, tmp, warm=max(W, 1), sponge=sponge)
             else:
                 log("[reference] the full grid does not fit (estimated %.0f s against a budget of %.0f s; %.0f GB needed, %.0f GB free): "
                     "the %d^2 sample is the arm's value" % (est_total, args.ref_budget, need_gb, free_gb, args.cpu_sample))
@@ -252,7 +258,7 @@ def main():
         t0 = time.perf_counter()
         c = None
         if rank == 0:
-            c, blk = make_case(n, nlay, tmp, mm=(args.rows or None))
+            c, blk = make_case(n, nlay, tmp, mm=(args.rows or None), sponge=sponge)
             log("[rank 0] inputs written: %.1f s" % (time.perf_counter() - t0))
         if world > 1:
             dist.barrier()
@@ -260,9 +266,14 @@ def main():
         nd1 = (n + 1) * ((args.rows or n) + 1) + 1
         opt = model.default_options(fused=not args.split, rank=rank, nranks=world, device=local_rank)
         gm = hl = uu = vv = None
-        # read_input_data holds ~25 GB of host arrays for this grid: at most two ranks do it at a time
-        for turn in range(0, world, 2):
-            if turn <= rank < turn + 2:
+        # read_input_data holds ~25 GB of host arrays for this grid: at most four ranks do it at a time (host memory permitting)
+        try:
+            import psutil
+            par = 4 if psutil.virtual_memory().available > 130 * 2 ** 30 else 2
+        except Exception:
+            par = 2
+        for turn in range(0, world, par):
+            if turn <= rank < turn + par:
                 t0 = time.perf_counter()
                 hm = model.HostModel.from_block(blk)
                 gm = model.GpuModel(hm.params, hm.fields(), opt)
@@ -372,6 +383,7 @@ def main():
                 state_sha = h.hexdigest()
                 log("[rank 0] state checksum over hlay,u,v after %d steps: %s (%.1f s)" % (steps, state_sha, time.perf_counter() - t0))
         path = gm.path
+        variant = gm.fused_variant
         gm.close()
     finally:
         if rank == 0:
@@ -388,7 +400,7 @@ def main():
     try:
         with open(os.path.join(ROOT, "profiles", "r2_fused_traffic.json")) as f:
             tj = json.load(f)
-        if path == "fused" and world == tj["n_gpus"] and [n, n, nlay] == tj["grid"]:
+        if path == "fused" and world == tj["n_gpus"] and [n, args.rows or n, nlay] == tj["grid"] and not sponge:
             traffic = tj["dram_bytes_per_launch"]
     except Exception:
         pass
@@ -400,12 +412,12 @@ def main():
     if not args.no_cpu:
         tmp2 = tempfile.mkdtemp(prefix="beom_cpu_")
         try:
-            cb = cpu_baseline(args.cpu_sample, nlay, args.cpu_steps, tmp2)
+            cb = cpu_baseline(args.cpu_sample, nlay, args.cpu_steps, tmp2, sponge=sponge)
         finally:
             shutil.rmtree(tmp2, ignore_errors=True)
     line = {"metric": "cell_layer_updates_per_s", "value": value, "unit": "cell-layer updates/s", "n_gpus": world, "steps": steps,
             "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": dict(config, path=path), "roofline": roofline, "cpu_baseline": cb,
+            "dtype": "f64", "data": "synthetic", "config": dict(config, path=path, fused_variant=variant), "roofline": roofline, "cpu_baseline": cb,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "state_sha256": state_sha, "state_sha256_nsteps": steps if state_sha else None}
     emit(line)

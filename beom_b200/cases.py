@@ -864,10 +864,12 @@ def wave_sponge(lx: float = 600.0e3, dl: float = 10.0e3, npts: int = 15, dt_s: f
 
 
 def synthetic_basin(n: int = 8192, nlay: int = 4, seed: int = 20261018, dt_s: float = 1.0, wind: bool = True,
-                    mm: int | None = None) -> Case:
+                    mm: int | None = None, sponge: bool = False) -> Case:
     """The throughput workload of BASELINE.json / SURVEY.md section 8(d): an n x n closed flat basin,
     1 km mesh, ``nlay`` layers, Leith viscosity every step, generalized forward-backward, wind stress
-    0.1 cos(pi y / L) Pa, initial surface bump + interface noise.  Not a reference script."""
+    0.1 cos(pi y / L) Pa, initial surface bump + interface noise.  Not a reference script.
+    ``sponge``: the option set of sill_exchange3D on the same grid instead of the wind -- sponges on eta, u, v over the
+    64 southernmost and northernmost rows (nudg.bin, cosine ramp up to 0.02 per step) and outcropping switched on (ocrp = 1)."""
     lm = n
     mm = n if mm is None else mm
     dl = 1000.0
@@ -886,13 +888,22 @@ def synthetic_basin(n: int = 8192, nlay: int = 4, seed: int = 20261018, dt_s: fl
     for k in range(nlay):
         init[:, :, k, 0] += rng.uniform(-0.01, 0.01, size=(lm + 2, mm + 2)).astype(np.float32)
     files = {"init": init}
+    if sponge:
+        wind = False
+        w = max(2, min(64, mm // 4))
+        j = np.arange(mm + 2)
+        dist = np.minimum(j, mm + 1 - j).astype(np.float64)  # rows from the nearest of the two ends
+        coef = np.where(dist < w, 0.01 * (1.0 + np.cos(math.pi * dist / w)), 0.0).astype(np.float32)
+        nudg = np.zeros((lm + 2, mm + 2, 3), dtype=np.float32)
+        nudg[1:-1, :, :] = coef[None, :, None]
+        files["nudg"] = nudg
     if wind:
         taus = np.zeros((lm + 2, mm + 2, 2), dtype=np.float32)
         taus[:, :, 0] = (0.1 * np.cos(math.pi * (ys + 0.5 * mm * dl) / (mm * dl)))[None, :].astype(np.float32)
         files["taus"] = taus
     text = print_params(lm, mm, nlay, ndeg, dl, 198.0, 1.0e-4, rhon, topl, dt_s, dt_s, 0.0, 0.0, 0.0, 0.2, 0.0, 1.0, 10.0, 10.0,
-                        1.0, 1.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, [0, 0], "@DIR@", "@DIR@",
-                        "synthetic %dx%dx%d basin" % (lm, mm, nlay))
+                        1.0, 1.0, 0.0, 1.0 if sponge else 0.0, 0.0, 0.0, 0.0, 0.0, [0, 0], "@DIR@", "@DIR@",
+                        "synthetic %dx%dx%d basin%s" % (lm, mm, nlay, " with N/S sponges and outcropping" if sponge else ""))
     return Case("synthetic_basin", lm, mm, nlay, ndeg, text, files, {})
 
 

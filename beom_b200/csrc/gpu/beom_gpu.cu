@@ -406,6 +406,7 @@ void beom_gpu_default_options(beom_gpu_options *opt) {
   opt->nranks = 1;
 }
 const char *beom_gpu_path(void) { return g.use_fused ? "fused" : "split"; }
+const char *beom_gpu_fused_variant(void) { return g.use_fused ? fused_variant() : "none"; }
 long long beom_gpu_launch_count(void) { return g.launches; }
 
 int beom_gpu_finalize(void) {
@@ -671,16 +672,11 @@ static int init_impl(const beom_params *par, const beom_fields *fld, const beom_
       S.cE = cE; S.cN = cN; S.cW = cW; S.cS = cS;
       // persistent workers (one warp per tile and sweep): all of them must be resident at once
       const int ntiles = S.TI * S.TJ;
-#ifdef BEOM_CUDA_EMULATION
-      g.pis_threads = 32 * std::min(ntiles, 32);  // (the emulation runs one block at a time: every worker in one block)
-      g.pis_blocks = 1;
-#else
       g.pis_threads = 256;
       int per_sm = 0;
-      CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pi_wave, g.pis_threads, 0));
+      CK((cudaError_t)cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pi_wave, g.pis_threads, 0));
       const int warps_per_block = g.pis_threads / 32;
       g.pis_blocks = std::max(1, std::min((ntiles + warps_per_block - 1) / warps_per_block, per_sm * prop.multiProcessorCount));
-#endif
       g.pis_ready = true;
     }
   }

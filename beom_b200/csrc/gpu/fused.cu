@@ -17,9 +17,28 @@ using namespace fusedk;
 
 namespace {
 
+// The specialised instantiations that exist: option set (fused_kernel.cuh FB_*), layers, viscosity, column groups.  Whatever
+// is not listed -- or does not fit the shared memory with its wind streams -- runs the general instantiation.
+struct SpecEntry {
+  int feat, nlay;
+  bool visc;
+  int groups;
+  int (*launch)(const FusedLaunch &, bool ufirst, bool gene0);
+};
+const SpecEntry kSpec[] = {
+    {0, 1, true, kMaxWarps / 1, fused_launch_lean1}, {0, 2, true, kMaxWarps / 2, fused_launch_lean2},
+    {0, 3, true, kMaxWarps / 3, fused_launch_lean3}, {0, 4, true, kMaxWarps / 4, fused_launch_lean4},
+    {FB_NUDG | FB_OCRP, 2, true, 7, fused_launch_spec_3_2_1},            // sill_exchange3D / 2D
+    {FB_NUDG | FB_OCRP, 4, true, 3, fused_launch_spec_3_4_1},            // bench.py --workload sill_like
+    {FB_NUDG, 2, true, 7, fused_launch_spec_1_2_1}, {FB_NUDG, 4, true, 3, fused_launch_spec_1_4_1},
+    {FB_NUDG | FB_OCRP | FB_BDRG, 2, true, 6, fused_launch_spec_7_2_1},  // ... with bottom drag
+    {FB_NUDG | FB_OCRP | FB_BDRG, 4, true, 3, fused_launch_spec_7_4_1},
+    {FB_BDRG, 1, false, 15, fused_launch_spec_4_1_0},                    // stommel1948: wind, linear drag, no viscosity
+};
+
 struct FusedCfg {
   bool ok = false;
-  bool lean = false;  // compile-time specialised instantiation (see fused_configure)
+  const SpecEntry *spec = nullptr;  // compile-time specialised instantiation (see fused_configure), or the general one
   int groups = 1;     // column groups (warps per layer) per CTA
   int strips = 1;     // CTAs along x
   int chunks = 1;     // CTAs along y
@@ -105,6 +124,14 @@ size_t fused_smem_bytes(int nlay, int groups, const StreamTab &T, int wind_layer
 }
 }  // namespace
 
+const char *fused_variant() {
+  static char b[96];
+  if (!cfg.ok) return "none";
+  if (cfg.spec) snprintf(b, sizeof b, "specialised (options %d, %d layers, %d column groups%s)", cfg.spec->feat, cfg.spec->nlay, cfg.spec->groups, cfg.spec->visc ? "" : ", no viscosity");
+  else snprintf(b, sizeof b, "general (%d column groups)", cfg.groups);
+  return b;
+}
+
 void fused_release() {
   if (cfg.open) cudaFree(cfg.open);
   if (cfg.open4) cudaFree(cfg.open4);
@@ -137,12 +164,13 @@ int fused_configure(const Dev &D, const beom_params &P, int nmir, int nranks, bo
   // wind stress reaches only the layers that can hold a share of hsbl
   cfg.wind_layers = 0;
   if (D.has_wind) cfg.wind_layers = (P.ocrp > 0.5) ? ((1 << D.nlay) - 1) : 1;
-  // The specialised instantiation: generalized forward-backward (gene = 1 exactly), Leith viscosity, no
-  // outcropping, sponge, drag, hdot or body force; wind allowed.  Everything else runs the general one.
+  // Specialised instantiations: generalized forward-backward (gene = 1 exactly; the start-up steps run their gene = 0 copy), no
+  // hdot, top drag or body force, an option set and layer count that has been instantiated (kSpec), and its column-group count
+  // must fit the shared memory with the wind streams of this case.  Everything else runs the general instantiation.
   bool bodf0 = true;
   for (int l = 0; l < D.nlay; l++) bodf0 = bodf0 && D.bodf[0][l] == 0.0 && D.bodf[1][l] == 0.0;
-  cfg.lean = cfg.visc && P.g_fb == 1.0 && !(P.ocrp > 0.5) && !D.has_nudg && !D.has_hdot && !D.has_bdrg && !D.has_tdrg && bodf0 &&
-             D.nlay <= 4;
+  const int feat = (D.has_nudg ? FB_NUDG : 0) | (P.ocrp > 0.5 ? FB_OCRP : 0) | (D.has_bdrg ? FB_BDRG : 0);
+  const bool spec_ok = P.g_fb == 1.0 && !D.has_hdot && !D.has_tdrg && bodf0 && !(getenv("BEOM_FUSED_GENERAL") && atoi(getenv("BEOM_FUSED_GENERAL")) > 0);
 
   int dev = 0, sms = 148, max_smem = 227 * 1024;
   cudaGetDevice(&dev);
@@ -152,9 +180,12 @@ int fused_configure(const Dev &D, const beom_params &P, int nmir, int nranks, bo
   if (T0.n > 32) return 0;
   const int width = D.x_hi - D.x_lo + 1, rows = D.y_hi - D.y_lo + 1;
   const int wl = D.has_wind ? cfg.wind_layers : 0;
-  // the lean instantiations have their column-group count compiled in (idle groups on a narrow domain are harmless)
-  int groups = cfg.lean ? kMaxWarps / D.nlay : std::max(1, std::min(kMaxWarps / D.nlay, (width + kUse - 1) / kUse));
-  if (cfg.lean && fused_smem_bytes(D.nlay, groups, T0, wl) > (size_t)max_smem - 1024) cfg.lean = false;
+  cfg.spec = nullptr;
+  if (spec_ok)
+    for (const SpecEntry &e : kSpec)
+      if (e.feat == feat && e.nlay == D.nlay && e.visc == cfg.visc && fused_smem_bytes(D.nlay, e.groups, T0, wl) <= (size_t)max_smem - 1024) cfg.spec = &e;
+  // the specialised instantiations have their column-group count compiled in (idle groups on a narrow domain are harmless)
+  int groups = cfg.spec ? cfg.spec->groups : std::max(1, std::min(kMaxWarps / D.nlay, (width + kUse - 1) / kUse));
   while (groups > 1 && fused_smem_bytes(D.nlay, groups, T0, wl) > (size_t)max_smem - 1024) groups--;
   if (fused_smem_bytes(D.nlay, groups, T0, wl) > (size_t)max_smem - 1024) return 0;
   cfg.groups = groups;
@@ -228,18 +259,22 @@ int fused_step(const Dev &in_, const Dev &out, int tstp, bool first_three, cudaS
   a.groups = cfg.groups; a.rows_per_chunk = rpc; static const int jitter = getenv("BEOM_FUSED_JITTER") ? std::min(4095, std::max(0, atoi(getenv("BEOM_FUSED_JITTER")) / 64)) : 0;  // ns
   a.wind_layers = cfg.wind_layers | (swap ? 1 << 16 : 0) | (jitter << 17);
   a.stream = s;
-  // the lean instantiations assume gene = 1 (tstp >= 4 with g_fb = 1) or gene = 0 (the start-up steps) exactly
+  // the specialised instantiations assume gene = 1 (tstp >= 4 with g_fb = 1) or gene = 0 (the start-up steps) exactly
   const bool g0 = in.gene == 0.0;  // the start-up steps
-  const bool lean = cfg.lean && (in.gene == 1.0 || g0);
+  const bool spec = cfg.spec && (in.gene == 1.0 || g0);
   int rc;
-  if (lean) {
+  if (spec) {
     // BEOM_FMA=1: the copy compiled with FMA contraction (tolerance parity instead of bit-exact parity; off by default)
     static const bool fma = getenv("BEOM_FMA") && atoi(getenv("BEOM_FMA")) > 0;
-    switch (in.nlay) {
-      case 1: rc = (fma && !g0) ? fused_launch_lean1_fma(a, ufirst) : fused_launch_lean1(a, ufirst, g0); break;
-      case 2: rc = (fma && !g0) ? fused_launch_lean2_fma(a, ufirst) : fused_launch_lean2(a, ufirst, g0); break;
-      case 3: rc = (fma && !g0) ? fused_launch_lean3_fma(a, ufirst) : fused_launch_lean3(a, ufirst, g0); break;
-      default: rc = (fma && !g0) ? fused_launch_lean4_fma(a, ufirst) : fused_launch_lean4(a, ufirst, g0); break;
+    if (fma && !g0 && cfg.spec->feat == 0) {
+      switch (in.nlay) {
+        case 1: rc = fused_launch_lean1_fma(a, ufirst); break;
+        case 2: rc = fused_launch_lean2_fma(a, ufirst); break;
+        case 3: rc = fused_launch_lean3_fma(a, ufirst); break;
+        default: rc = fused_launch_lean4_fma(a, ufirst); break;
+      }
+    } else {
+      rc = cfg.spec->launch(a, ufirst, g0);
     }
   } else {
     rc = fused_launch_general(a, ufirst, cfg.visc, in.nlay);

@@ -5,10 +5,10 @@
 #include "fused_kernel.cuh"
 
 namespace beom {
-template <bool UF, bool VI, int NL, bool LEAN, int GROUPS, int FLAVOR = 0, bool G0 = false>
+template <bool UF, bool VI, int NL, int FEAT, int GROUPS, int FLAVOR = 0, bool G0 = false>
 int fused_launch_one(const FusedLaunch &a) {
   static size_t configured = 0;
-  auto kern = fusedk::k_fused_step<UF, VI, NL, LEAN, GROUPS, FLAVOR, G0>;
+  auto kern = fusedk::k_fused_step<UF, VI, NL, FEAT, GROUPS, FLAVOR, G0>;
   if (a.shmem > configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)a.shmem) != cudaSuccess) return -61;
     configured = a.shmem;

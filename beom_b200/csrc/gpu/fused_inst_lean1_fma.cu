@@ -4,6 +4,6 @@
 #include "fused_inst.cuh"
 namespace beom {
 int fused_launch_lean1_fma(const FusedLaunch &a, bool ufirst) {
-  return ufirst ? fused_launch_one<true, true, 1, true, fusedk::kMaxWarps / 1, 1>(a) : fused_launch_one<false, true, 1, true, fusedk::kMaxWarps / 1, 1>(a);
+  return ufirst ? fused_launch_one<true, true, 1, 0, fusedk::kMaxWarps / 1, 1>(a) : fused_launch_one<false, true, 1, 0, fusedk::kMaxWarps / 1, 1>(a);
 }
 }  // namespace beom

@@ -4,6 +4,6 @@
 #include "fused_inst.cuh"
 namespace beom {
 int fused_launch_lean3_fma(const FusedLaunch &a, bool ufirst) {
-  return ufirst ? fused_launch_one<true, true, 3, true, fusedk::kMaxWarps / 3, 1>(a) : fused_launch_one<false, true, 3, true, fusedk::kMaxWarps / 3, 1>(a);
+  return ufirst ? fused_launch_one<true, true, 3, 0, fusedk::kMaxWarps / 3, 1>(a) : fused_launch_one<false, true, 3, 0, fusedk::kMaxWarps / 3, 1>(a);
 }
 }  // namespace beom

@@ -4,7 +4,7 @@
 namespace beom {
 int fused_launch_lean4(const FusedLaunch &a, bool ufirst, bool gene0) {
   constexpr int GR = fusedk::kMaxWarps / 4;
-  if (gene0) return ufirst ? fused_launch_one<true, true, 4, true, GR, 0, true>(a) : fused_launch_one<false, true, 4, true, GR, 0, true>(a);
-  return ufirst ? fused_launch_one<true, true, 4, true, GR>(a) : fused_launch_one<false, true, 4, true, GR>(a);
+  if (gene0) return ufirst ? fused_launch_one<true, true, 4, 0, GR, 0, true>(a) : fused_launch_one<false, true, 4, 0, GR, 0, true>(a);
+  return ufirst ? fused_launch_one<true, true, 4, 0, GR>(a) : fused_launch_one<false, true, 4, 0, GR>(a);
 }
 }  // namespace beom

@@ -4,6 +4,6 @@
 #include "fused_inst.cuh"
 namespace beom {
 int fused_launch_lean4_fma(const FusedLaunch &a, bool ufirst) {
-  return ufirst ? fused_launch_one<true, true, 4, true, fusedk::kMaxWarps / 4, 1>(a) : fused_launch_one<false, true, 4, true, fusedk::kMaxWarps / 4, 1>(a);
+  return ufirst ? fused_launch_one<true, true, 4, 0, fusedk::kMaxWarps / 4, 1>(a) : fused_launch_one<false, true, 4, 0, fusedk::kMaxWarps / 4, 1>(a);
 }
 }  // namespace beom

@@ -91,6 +91,25 @@ struct StreamTab {
 
 __host__ __device__ constexpr int ring_segments(int nstreams) { return 16 + (nstreams - 4) * 2; }
 
+// ---- option sets.  FEAT < 0: the GENERAL instantiation, every option a run-time (warp-uniform) switch, stream slots and
+// column-group count read from the launch arguments.  FEAT >= 0: a SPECIALISED instantiation -- the option set is this
+// compile-time mask, gene is exactly 1 (or exactly 0 in the G0 copy for the start-up steps), there is no hdot, top drag or
+// body force; the stream slots below and the column-group count are compile-time constants, so every shared-memory
+// address of the row code is an immediate.  FEAT == 0 is the bare step of the benchmark workload ("lean").
+constexpr int FB_NUDG = 1;  // sponge: relaxation of hlay, u, v towards fnud (nudg.bin)
+constexpr int FB_OCRP = 2;  // outcropping: Salmon's term in the Montgomery potential, curvature limiter
+constexpr int FB_BDRG = 4;  // bottom drag (tb3d from distribute_stress)
+// slot of a stream in make_streams' order (fused.cu) for a specialised option set
+__host__ __device__ constexpr int spec_slot(int feat, int stream) {
+  const int nudg = (feat & FB_NUDG) ? 6 : 0, bdrg = (feat & FB_BDRG) ? 2 : 0;
+  if (stream < kMandatory) return stream;
+  if (stream >= S_FNN && stream <= S_NUDV) return kMandatory + (stream - S_FNN);
+  if (stream == S_TBX || stream == S_TBY) return kMandatory + nudg + (stream - S_TBX) / 2;  // (S_TBX, S_TUX, S_TBY, S_TUY are interleaved in the enum)
+  if (stream >= S_TTXU && stream <= S_TTYVS) return kMandatory + nudg + bdrg + (stream - S_TTXU);
+  if (stream >= S_TTYU) return kMandatory + nudg + bdrg + 3 + (stream - S_TTYU);
+  return -1;
+}
+
 __device__ __forceinline__ double sel(bool p, double a) { return p ? a : 0.0; }
 __device__ __forceinline__ double shup(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }     // value of lane-1 (west)
 __device__ __forceinline__ double shdn(double v) { return __shfl_down_sync(0xffffffffu, v, 1); }   // value of lane+1 (east)
@@ -134,48 +153,48 @@ struct MomX {  // optional inputs (general instantiation and wind layers)
   double fn = 0.0, nud = 0.0;     // sponge target and rate
   double bodf = 0.0;
 };
-template <bool IS_U, bool VISC, bool MASKED, bool LEAN, bool G0>
+template <bool IS_U, bool VISC, bool MASKED, int FEAT, bool G0>
 __device__ __forceinline__ void momentum(const Dev &D, const bool wind, const double mask, const double hsum, const double m_far,
                                          const double m_here, const double c1, const double c2, const double old, const double h1,
                                          const double h2, const double h3, const double Ph, const double Pf, const double Qf,
                                          const double Qh, const double f_far, const double f_here, const MomX &q, double &vel,
                                          double &flux, double &dmd4) {
+  constexpr bool GEN = FEAT < 0, SPEC = FEAT >= 0;
+  const bool has_bdrg = GEN ? (D.has_bdrg != 0) : ((FEAT & FB_BDRG) != 0);
+  const bool has_tdrg = GEN && D.has_tdrg;
+  const bool has_nudg = GEN ? (D.has_nudg != 0) : ((FEAT & FB_NUDG) != 0);
   const double hcen = hsum * (MASKED ? (mask != 0.0 ? 0.5 : 1.0) : 0.5);
   dmd4 = (m_far - m_here) * D.i_dl * D.grav;
   if (MASKED) dmd4 = sel(mask != 0.0, dmd4);
   double rhsi;
-  if (LEAN && !G0) {  // gene = 1 exactly: dmd4*(1-gene) is an exact zero
+  if (SPEC && !G0) {  // gene = 1 exactly: dmd4*(1-gene) is an exact zero
     rhsi = IS_U ? (c1 + c2) : ((-c1) - c2);
-  } else if (LEAN) {  // gene = 0 exactly (start-up steps): dmd4*(1-gene) = dmd4
+  } else if (SPEC) {  // gene = 0 exactly (start-up steps): dmd4*(1-gene) = dmd4
     rhsi = IS_U ? (dmd4 + c1 + c2) : (dmd4 - c1 - c2);
   } else {
     if (IS_U) rhsi = dmd4 * (1.0 - D.gene) + c1 + c2;
     else      rhsi = dmd4 * (1.0 - D.gene) - c1 - c2;
   }
   double i__h = 0.0;
-  if (wind || (!LEAN && (D.has_bdrg || D.has_tdrg))) i__h = 1.0 / (hcen + 1.0 - (MASKED ? mask : 1.0));
+  if (wind || has_bdrg || has_tdrg) i__h = 1.0 / (hcen + 1.0 - (MASKED ? mask : 1.0));
   if (wind) rhsi = rhsi + 0.5 * (q.tw_a + q.tw_b) * D.ramp * D.i_r0 * i__h;
-  if (!LEAN) {
-    if (D.has_bdrg) rhsi = rhsi - q.tb * D.i_r0 * i__h;
-    if (D.has_tdrg) rhsi = rhsi - q.tu * D.i_r0 * i__h;
-  }
+  if (has_bdrg) rhsi = rhsi - q.tb * D.i_r0 * i__h;
+  if (has_tdrg) rhsi = rhsi - q.tu * D.i_r0 * i__h;
   const double hist = D.del1 * dmd4 + D.del2 * h3 + D.gamm * h2 + D.epsi * h1;
-  if (LEAN && !G0) rhsi = rhsi + hist;  // bodf = 0 and gene = 1 (checked by fused_configure)
-  else if (!LEAN)  rhsi = rhsi + q.bodf + hist * D.gene;  // (LEAN, gene = 0: + 0 + hist*0 changes nothing)
+  if (SPEC && !G0) rhsi = rhsi + hist;  // bodf = 0 and gene = 1 (checked by fused_configure)
+  else if (GEN)    rhsi = rhsi + q.bodf + hist * D.gene;  // (specialised, gene = 0: + 0 + hist*0 changes nothing)
   if (VISC) {
     if (IS_U) rhsi = rhsi + (Ph - Pf) * D.i_dl - (Qf - Qh) * D.i_dl;
     else      rhsi = rhsi + (Ph - Pf) * D.i_dl + (Qf - Qh) * D.i_dl;
   }
   double w = old + (MASKED ? sel(mask != 0.0, rhsi) : rhsi) * D.dt;
-  if (!LEAN) {
-    if (D.has_nudg) {
-      double tgt = q.fn;
-      if (wind) {
-        if (IS_U) tgt = tgt + 0.5 * (q.te_b + q.te_a) * D.i_r1 * D.invf * i__h * D.ramp;
-        else      tgt = tgt - 0.5 * (q.te_b + q.te_a) * D.i_r1 * D.invf * i__h * D.ramp;
-      }
-      w = tgt * q.nud + w * (1.0 - q.nud);
+  if (has_nudg) {
+    double tgt = q.fn;
+    if (wind) {
+      if (IS_U) tgt = tgt + 0.5 * (q.te_b + q.te_a) * D.i_r1 * D.invf * i__h * D.ramp;
+      else      tgt = tgt - 0.5 * (q.te_b + q.te_a) * D.i_r1 * D.invf * i__h * D.ramp;
     }
+    w = tgt * q.nud + w * (1.0 - q.nud);
   }
   vel = w;
   flux = w * (hcen - (w > 0.0 ? f_far : f_here));
@@ -216,12 +235,17 @@ __host__ __device__ inline SmemPlan smem_plan(int nlay, int groups, int n_all, i
 }
 
 // FLAVOR only distinguishes the symbol of the copy compiled with FMA contraction (fused_inst_lean*_fma.cu, BEOM_FMA=1)
-template <bool UFIRST, bool VISC, int NL, bool LEAN, int GROUPS, int FLAVOR = 0, bool G0 = false>
+template <bool UFIRST, bool VISC, int NL, int FEAT, int GROUPS, int FLAVOR = 0, bool G0 = false>
 __global__ void __launch_bounds__(kMaxWarps * 32, 1)
 k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const __grid_constant__ StreamTab T,
              const uint8_t *__restrict__ open, const unsigned *__restrict__ open4, int open4_words, int groups_rt, int rows_per_chunk,
              int wind_layers) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
+  constexpr bool GEN = FEAT < 0, SPEC = FEAT >= 0;
+  static_assert(GEN || (GROUPS > 0 && NL > 0), "a specialised option set has its layer and column-group counts compiled in");
+  const bool has_nudg = GEN ? (D.has_nudg != 0) : ((FEAT & FB_NUDG) != 0);
+  const bool has_bdrg = GEN ? (D.has_bdrg != 0) : ((FEAT & FB_BDRG) != 0);
+  const bool has_tdrg = GEN && D.has_tdrg, has_hdot = GEN && D.has_hdot;
   const int lane = threadIdx.x & 31;
   const int wid = threadIdx.x >> 5;
   const int groups = GROUPS > 0 ? GROUPS : groups_rt;
@@ -269,7 +293,7 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
 #pragma unroll
   for (int i = 0; i < kMaxLay; i++) cb[i] = (i < l) ? (D.rhon[l] - D.rhon[i]) * D.i_rn[l] : 0.0;
   const double kin = 0.25 * D.uadv * D.i_gr;  // private_mod.f95:2381
-  const bool ocrp = !LEAN && D.ocrp > 0.5;
+  const bool ocrp = GEN ? (D.ocrp > 0.5) : ((FEAT & FB_OCRP) != 0);
 
   // ---- producer side: the warps of a layer share the staging; lane j of warp (l, grp) owns stream grp + j*groups ----
   const unsigned full0 = smem_u32(bars + 4 * l);               // [4]: inputs of front row R & 3 have landed (tx)
@@ -346,13 +370,13 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
   const double *sgp = ring + 2 + grp * kUse + lane;
   double *shp = sh_h + (size_t)l * tpad + 1 + tcol;  // + slot*nlay*tpad: this thread's thickness of row slot
   double *wrp = wring + 1 + lane;                     // + (ring*4 + slot)*kWRow
-  const int tt_base = LEAN ? kMandatory : (int)T.slot[S_TTXU];  // wind streams keep their order: TTXU, TTYV, TTYVS
+  const int tt_base = SPEC ? spec_slot(FEAT, S_TTXU) : (int)T.slot[S_TTXU];  // wind streams keep their order: TTXU, TTYV, TTYVS
 
 #define AT(a, age) a[(PH - (age)) & 3]
 #define SLOT(age) (CT ? ((PH - (age)) & 3) : ((R - (age)) & 3))
 #define LD4(s, age, dx) sgp[((s) * 4 + SLOT(age)) * wseg + (dx)]
 #define LD2(slot, dx) sgp[(16 + ((slot)-4) * 2 + (SLOT(0) & 1)) * wseg + (dx)]
-#define LDX(stream, dx) LD2((int)T.slot[stream], dx)
+#define LDX(stream, dx) LD2((SPEC ? spec_slot(FEAT, stream) : (int)T.slot[stream]), dx)
 #define HN(age, dx) shp[SLOT(age) * nlay * tpad + (dx)]
 #define WR(ring_id, age, dx) wrp[((ring_id)*4 + SLOT(age)) * kWRow + (dx)]
 #define SELM(p, a) (MASKED ? sel((p), (a)) : (a))
@@ -377,21 +401,17 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
     const double hu_0 = LD4(S_HU, 0, 0), huE_0 = LD4(S_HU, 0, 1);
     const double hv_p1 = LD4(S_HV, 0, 0), hv_0 = LD4(S_HV, 1, 0);
     double rs_3 = (hu_0 - huE_0) * D.i_dl + (hv_0 - hv_p1) * D.i_dl;
-    if (!LEAN) {
-      if (D.has_hdot) rs_3 = rs_3 + LDX(S_HDOT, 0);
-    }
+    if (has_hdot) rs_3 = rs_3 + LDX(S_HDOT, 0);
     rs_3 = SELM(f_own & F_N, rs_3);
     const double r1 = LD2(S_R1, 0), r2 = LD2(S_R2, 0);
     double rhs_h;
-    if (LEAN && G0) rhs_h = rs_3 * D.dt;  // gene = 0 (start-up steps): the extrapolated term is an exact zero
-    else if (LEAN) rhs_h = (D.c_ab1 * rs_3 - D.c_ab2 * r2 + D.beta * r1) * D.dt;  // gene = 1: the plain term is an exact zero
+    if (SPEC && G0) rhs_h = rs_3 * D.dt;  // gene = 0 (start-up steps): the extrapolated term is an exact zero
+    else if (SPEC) rhs_h = (D.c_ab1 * rs_3 - D.c_ab2 * r2 + D.beta * r1) * D.dt;  // gene = 1: the plain term is an exact zero
     else      rhs_h = (D.c_ab1 * rs_3 - D.c_ab2 * r2 + D.beta * r1) * D.dt * D.gene + rs_3 * D.dt * (1.0 - D.gene);
     double hn_0 = LD2(S_HL, 0) + rhs_h;
-    if (!LEAN) {
-      if (D.has_nudg) {
-        const double fnn_0 = LDX(S_FNN, 0), nudn_0 = LDX(S_NUDN, 0);
-        hn_0 = fnn_0 * nudn_0 + (1.0 - nudn_0) * hn_0;
-      }
+    if (has_nudg) {
+      const double fnn_0 = LDX(S_FNN, 0), nudn_0 = LDX(S_NUDN, 0);
+      hn_0 = fnn_0 * nudn_0 + (1.0 - nudn_0) * hn_0;
     }
     hn_0 = SELM(act, hn_0);
     if (col_ok && row_own && (!MASKED || own)) {
@@ -454,16 +474,14 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
       xu.tw_b = LD2(tt_base, 0); xu.tw_a = LD2(tt_base, -1);
       xv.tw_b = LD2(tt_base + 1, 0); xv.tw_a = LD2(tt_base + 2, 0);
     }
-    if (!LEAN) {
-      if (wind && D.has_nudg) {
-        xu.te_b = LDX(S_TTYU, 0); xu.te_a = LDX(S_TTYU, -1);
-        xv.te_b = LDX(S_TTXV, 0); xv.te_a = LDX(S_TTXVS, 0);
-      }
-      if (D.has_bdrg) { xu.tb = LDX(S_TBX, 0); xv.tb = LDX(S_TBY, 0); }
-      if (D.has_tdrg) { xu.tu = LDX(S_TUX, 0); xv.tu = LDX(S_TUY, 0); }
-      if (D.has_nudg) { xu.fn = LDX(S_FNU, 0); xu.nud = LDX(S_NUDU, 0); xv.fn = LDX(S_FNV, 0); xv.nud = LDX(S_NUDV, 0); }
-      xu.bodf = D.bodf[0][l]; xv.bodf = D.bodf[1][l];
+    if (wind && has_nudg) {
+      xu.te_b = LDX(S_TTYU, 0); xu.te_a = LDX(S_TTYU, -1);
+      xv.te_b = LDX(S_TTXV, 0); xv.te_a = LDX(S_TTXVS, 0);
     }
+    if (has_bdrg) { xu.tb = LDX(S_TBX, 0); xv.tb = LDX(S_TBY, 0); }
+    if (has_tdrg) { xu.tu = LDX(S_TUX, 0); xv.tu = LDX(S_TUY, 0); }
+    if (has_nudg) { xu.fn = LDX(S_FNU, 0); xu.nud = LDX(S_NUDU, 0); xv.fn = LDX(S_FNV, 0); xv.nud = LDX(S_NUDV, 0); }
+    if (GEN) { xu.bodf = D.bodf[0][l]; xv.bodf = D.bodf[1][l]; }
     const double ux1 = LD2(S_DX1, 0), ux2 = LD2(S_DX2, 0), ux3 = LD2(S_DX3, 0);
     const double vy1 = LD2(S_DY1, 0), vy2 = LD2(S_DY2, 0), vy3 = LD2(S_DY3, 0);
     const double mo_m2 = WR(W_MO, 2, 0), P_m2 = VISC ? WR(W_PV, 2, 0) : 0.0, PW_m2 = VISC ? WR(W_PV, 2, -1) : 0.0;
@@ -471,7 +489,7 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
     if (UFIRST) {
       // ---- u at row R-2 (pm:1422-1503) ----
       double un, hun, dm;
-      momentum<true, VISC, MASKED, LEAN, G0>(D, wind, MASKED ? m_u((uint8_t)fw_m2) : 1.0, HN(2, -1) + hn_m2b, WR(W_MO, 2, -1), mo_m2,
+      momentum<true, VISC, MASKED, FEAT, G0>(D, wind, MASKED ? m_u((uint8_t)fw_m2) : 1.0, HN(2, -1) + hn_m2b, WR(W_MO, 2, -1), mo_m2,
                                          AT(Tc, 2), AT(Tc, 1), LD4(S_U, 2, 0), ux1, ux2, ux3, P_m2, PW_m2, AT(Qv, 1),
                                          AT(Qv, 2), WR(W_FX, 2, -1), WR(W_FX, 2, 0), xu, un, hun, dm);
       hun = SELM(a2, hun);
@@ -484,7 +502,7 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
       // ---- v at row R-2 (pm:1505-1591), using the new h_u of rows R-2 and R-3 ----
       const double wc = AT(qp, 2) * (hun + AT(fl, 3));
       double vn, hvn;
-      momentum<false, VISC, MASKED, LEAN, G0>(D, wind, MASKED ? m_v((uint8_t)fw_m2) : 1.0, hn_m2b + HN(3, 0), WR(W_MO, 3, 0), mo_m2, wc,
+      momentum<false, VISC, MASKED, FEAT, G0>(D, wind, MASKED ? m_v((uint8_t)fw_m2) : 1.0, hn_m2b + HN(3, 0), WR(W_MO, 3, 0), mo_m2, wc,
                                           shdn(wc), vold, vy1, vy2, vy3, P_m2, VISC ? WR(W_PV, 3, 0) : 0.0, shdn(AT(Qv, 2)), AT(Qv, 2),
                                           AT(Gy, 3), AT(Gy, 2), xv, vn, hvn, dm);
       if (sto2) {
@@ -498,7 +516,7 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
       const bool a1 = fw_m1 & (F_ACT | F_GHOST);
       const double wc = AT(qp, 1) * (LD4(S_HU, 1, 0) + LD4(S_HU, 2, 0));
       double vn, hvn, dm;
-      momentum<false, VISC, MASKED, LEAN, G0>(D, wind, MASKED ? m_v((uint8_t)fw_m1) : 1.0, hn_m1 + hn_m2b, mo_m2, WR(W_MO, 1, 0), wc,
+      momentum<false, VISC, MASKED, FEAT, G0>(D, wind, MASKED ? m_v((uint8_t)fw_m1) : 1.0, hn_m1 + hn_m2b, mo_m2, WR(W_MO, 1, 0), wc,
                                           shdn(wc), LD4(S_V, 2, 0), vy1, vy2, vy3, P_m1, P_m2, shdn(AT(Qv, 1)), AT(Qv, 1),
                                           AT(Gy, 2), AT(Gy, 1), xv, vn, hvn, dm);
       hvn = SELM(a1, hvn);
@@ -510,7 +528,7 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
       AT(Tc, 1) = AT(qp, 1) * (hvn + shup(hvn));  // Coriolis term of u with the new h_v (pm:1461-1462)
       // ---- u at row R-2 (pm:1422-1503), using the new h_v of rows R-2 and R-1 ----
       double un, hun;
-      momentum<true, VISC, MASKED, LEAN, G0>(D, wind, MASKED ? m_u((uint8_t)fw_m2) : 1.0, HN(2, -1) + hn_m2b, WR(W_MO, 2, -1), mo_m2,
+      momentum<true, VISC, MASKED, FEAT, G0>(D, wind, MASKED ? m_u((uint8_t)fw_m2) : 1.0, HN(2, -1) + hn_m2b, WR(W_MO, 2, -1), mo_m2,
                                          AT(Tc, 2), AT(Tc, 1), LD4(S_U, 2, 0), ux1, ux2, ux3, P_m2, PW_m2, AT(Qv, 1),
                                          AT(Qv, 2), WR(W_FX, 2, -1), WR(W_FX, 2, 0), xu, un, hun, dm);
       if (sto2) {

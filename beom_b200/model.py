@@ -136,6 +136,10 @@ class GpuModel:
     def path(self) -> str:
         return self.lib.beom_gpu_path().decode()
 
+    @property
+    def fused_variant(self) -> str:
+        return self.lib.beom_gpu_fused_variant().decode()
+
     def point_range(self):
         """(first, count, own_first, own_count) of the vector points on this rank."""
         v = [C.c_int() for _ in range(4)]

@@ -212,6 +212,8 @@ int beom_gpu_elapsed_ms(double *ms);
 long long beom_gpu_launch_count(void);
 /* Name of the kernel path in use ("fused" / "split"), for logs. */
 const char *beom_gpu_path(void);
+/* Which instantiation of the fused step runs: "specialised (options <mask>, <n> layers, <g> column groups)", "general (...)", "none". */
+const char *beom_gpu_fused_variant(void);
 
 /* Multi-GPU (one process per GPU).  Rank 0 obtains an id (128 bytes), the host broadcasts it by any
  * means (torch.distributed, MPI, a file), every rank calls comm_init before beom_gpu_init. */

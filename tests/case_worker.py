@@ -34,6 +34,7 @@ with tempfile.TemporaryDirectory() as d:
     state = gm.download_state()
     aux = gm.download_aux()
     path = gm.path
+    variant = gm.fused_variant
     gm.close()
     # cos() of the tidal targets is the one libm-dependent operation: 1e-11 of the field's
     # magnitude there, bit for bit everywhere else
@@ -59,6 +60,6 @@ with tempfile.TemporaryDirectory() as d:
         if (tol == 0.0 and not np.array_equal(got, want)) or err > tol:
             bad.append("%s: %d entries differ, max %.3e of the field's magnitude" % (n, int(np.count_nonzero(got != want)), err))
     moved = float(np.abs(orc.array("u")).max() + np.abs(orc.array("v")).max())
-    print(json.dumps({"case": name, "path": path, "exact": tol == 0.0, "worst": worst, "bad": bad, "moved": moved,
+    print(json.dumps({"case": name, "path": path, "variant": variant, "exact": tol == 0.0, "worst": worst, "bad": bad, "moved": moved,
                       "cell_layers": c.ndeg * c.nlay}))
     sys.exit(1 if bad else 0)

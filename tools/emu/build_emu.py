@@ -108,7 +108,7 @@ def build(outdir: str, sanitize: bool = False, tsan: bool = False) -> str:
     os.makedirs(outdir, exist_ok=True)
     gens, total = [], 0
     units = ["beom_gpu.cu", "fused.cu", "fused_inst_general.cu"] + ["fused_inst_general%d.cu" % k for k in range(5)] + \
-            ["fused_inst_lean%d.cu" % k for k in range(1, 5)]
+            ["fused_inst_lean%d.cu" % k for k in range(1, 5)] + sorted(f for f in os.listdir(GPU_SRC) if f.startswith("fused_inst_spec_"))
     for unit in units + ["fused_inst.cuh", "fused_kernel.cuh"]:
         with open(os.path.join(GPU_SRC, unit)) as f:
             src, n = rewrite_launches(f.read())

@@ -74,7 +74,10 @@ struct emuEvent { std::chrono::steady_clock::time_point t; };
 typedef emuEvent *cudaEvent_t;
 enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaHostAllocDefault = 0 };
 enum cudaMemcpyKind { cudaMemcpyHostToHost, cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
-struct cudaDeviceProp { int major = 10, minor = 0; char name[64] = "cpu-emulation of sm_100a"; };
+// (multiProcessorCount = 1 and one resident block per SM: a persistent kernel sized by the occupancy query -- the rigid-lid
+// solver -- becomes ONE block here, whose warps are concurrent OS threads; blocks run one after the other)
+struct cudaDeviceProp { int major = 10, minor = 0; int multiProcessorCount = 1; char name[64] = "cpu-emulation of sm_100a"; };
+template <class F> inline int cudaOccupancyMaxActiveBlocksPerMultiprocessor(int *n, F, int, size_t) { *n = 1; return 0; }
 
 enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount, cudaDevAttrMaxSharedMemoryPerBlockOptin };
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize };
