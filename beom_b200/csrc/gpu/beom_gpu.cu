@@ -845,10 +845,13 @@ int beom_gpu_step(int tstp, double ctim, double ramp, double gene, int upst, int
       D.fnud = g.fnud_tide;
     }
     const bool obc = g.D.has_nudg && g.P.mcbc < 0.5 && g.obc_any;  // (decided alike on every rank: the exchanges are collective)
-    // BEOM_OVERLAP=1: exchange the edge rows while the interior rows are computed (measured slower than the plain
-    // sequence at 2 GPUs: NCCL's copy kernels displace CTAs of a grid sized for exactly two waves)
-    static const bool want_overlap = getenv("BEOM_OVERLAP") && atoi(getenv("BEOM_OVERLAP")) > 0;
-    const bool overlap = want_overlap && g.nranks > 1 && !obc && (D.y_hi - D.y_lo + 1) >= 4 * G;
+    // The edge rows first, their exchange on the communication stream while the interior rows are computed.  Measured on
+    // 8192 x 8192 x 4 (profiles/r2_bench_n8*.json, r2_bench_n2*.json): 8 GPUs 1.308 ms per step against 1.378 without, 2 GPUs
+    // 4.70 against 4.75.  (Round 1 had it slower: the grid was sized for exactly two waves then, and NCCL's copy CTAs displaced
+    // some of them; with chunks of ~64-256 rows there are eight or more short waves.)  BEOM_OVERLAP=0 switches it off.
+    static const bool want_overlap = !(getenv("BEOM_OVERLAP") && atoi(getenv("BEOM_OVERLAP")) == 0);
+    // (not with periodic images: they mirror every owned row, so they can only be refreshed once the interior rows are done)
+    const bool overlap = want_overlap && g.nranks > 1 && !obc && g.nmir == 0 && (D.y_hi - D.y_lo + 1) >= 4 * G;
     if (overlap) {
       // y-slabs: the G rows next to each neighbour first, then their exchange on the communication stream while the
       // rows in between are computed (the interior reads time level n only, the exchange touches halo rows of n+1)

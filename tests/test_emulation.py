@@ -463,11 +463,12 @@ def test_no_race_between_warps_under_threadsanitizer(emu_so, tmp_path_factory):
     shutil.rmtree(os.path.dirname(so), ignore_errors=True)
 
 
-def test_halo_overlap_variant_on_emulated_ranks(emu_so):
-    """BEOM_OVERLAP=1 (off by default): the G rows next to each neighbour first, their exchange while
-    the rows in between are computed -- three launches per step instead of one; the result must not change."""
+@pytest.mark.parametrize("overlap", ["1", "0"])
+def test_halo_overlap_variant_on_emulated_ranks(emu_so, overlap):
+    """The default on several ranks: the G rows next to each neighbour first, their exchange while the rows
+    in between are computed -- three launches per step instead of one; BEOM_OVERLAP=0 is the plain sequence.  Same result."""
     cmd = [sys.executable, os.path.join(ROOT, "tests", "emu_ranks_worker.py"), emu_so, "synthetic_basin", "9", "2", "{}",
            json.dumps(dict(n=60, mm=90, nlay=2)), "1"]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=dict(os.environ, BEOM_OVERLAP="1"))
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=dict(os.environ, BEOM_OVERLAP=overlap))
     res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
     assert r.returncode == 0 and all(not k["bad"] and k["path"] == "fused" for k in res["ranks"]), res
