@@ -30,6 +30,16 @@ module beom_gpu_mod
   end type beom_params
 
 ! struct beom_fields: addresses of the module arrays of private_mod.f95:27-93 (c_loc of element 0).
+  integer, parameter, public :: BEOM_MAXLAY = 16
+  ! one set of output records in page-locked host memory (beom_gpu_records_wait)
+  type, bind(C), public :: beom_records
+    type(c_ptr) :: eta, u, v            ! real(c_float) (count, nlay)
+    type(c_ptr) :: pvor, mont, v_cc     ! c_null_ptr unless begun with_diag
+    integer(c_int) :: first_point, count
+    real(c_double) :: hmin(BEOM_MAXLAY), hmax(BEOM_MAXLAY)
+    integer(c_int) :: thin_layer        ! first layer thinner than hmin / 2 somewhere wet, 0 = none (private_mod.f95:2798-2808)
+  end type beom_records
+
   type, bind(C), public :: beom_fields
     type(c_ptr) :: neig, subc
     type(c_ptr) :: mk_u, mk_v, mk_n, mkpe, mkpi
@@ -106,6 +116,41 @@ module beom_gpu_mod
       import :: c_double, c_int
       real(c_double), intent(in) :: h_0(*)
       real(c_double), intent(inout) :: vol(*), ke(*), pe(*)
+      integer(c_int) :: rc
+    end function
+
+    ! the same plus potential enstrophy and relative vorticity (conservation.m:169-211): enst, zeta, zeta2 (nlay each), npts(1)
+    function beom_gpu_diagnostics_all(h_0, vol, ke, pe, enst, zeta, zeta2, npts) bind(C, name = 'beom_gpu_diagnostics_all') result(rc)
+      import :: c_double, c_int
+      real(c_double), intent(in) :: h_0(*)
+      real(c_double), intent(inout) :: vol(*), ke(*), pe(*), enst(*), zeta(*), zeta2(*), npts(*)
+      integer(c_int) :: rc
+    end function
+
+    ! write_array's records made on the device and copied out asynchronously (private_mod.f95:2817-2974):
+    !   call beom_gpu_set_rest_thickness(h_0 as written to h_0.bin)          once
+    !   rc = beom_gpu_records_begin(with_diag)                                at an output step; returns at once
+    !   rc = beom_gpu_records_wait(rec)                                        before writing: c_f_pointer(rec%eta, ior4, (/ndeg, nlay/)) ...
+    function beom_gpu_set_rest_thickness(h_0_r4) bind(C, name = 'beom_gpu_set_rest_thickness') result(rc)
+      import :: c_float, c_int
+      real(c_float), intent(in) :: h_0_r4(*)
+      integer(c_int) :: rc
+    end function
+    function beom_gpu_records_begin(with_diag) bind(C, name = 'beom_gpu_records_begin') result(rc)
+      import :: c_int
+      integer(c_int), value :: with_diag
+      integer(c_int) :: rc
+    end function
+    function beom_gpu_records_wait(rec) bind(C, name = 'beom_gpu_records_wait') result(rc)
+      import :: beom_records, c_int
+      type(beom_records), intent(out) :: rec
+      integer(c_int) :: rc
+    end function
+
+    ! sweeps of the last surf_pressure solve (the reference's `iters', private_mod.f95:1756-1803)
+    function beom_gpu_pi_iterations(iters) bind(C, name = 'beom_gpu_pi_iterations') result(rc)
+      import :: c_int
+      integer(c_int), intent(out) :: iters
       integer(c_int) :: rc
     end function
 
