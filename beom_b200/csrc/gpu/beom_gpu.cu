@@ -311,30 +311,30 @@ int step_split(int tstp, bool upst, bool first_three) {
   if (first_three) {  // pm:2166-2177
     k_centred_flux<<<gridL, kBlock, 0, g.stream>>>(D);
     g.launches++;
-    sync_fields({{D.h_u, nl}, {D.h_v, nl}});
+    if ((rc = sync_fields({{D.h_u, nl}, {D.h_v, nl}}))) return rc;
   } else if (rgld) {  // pm:2237-2257
     k_upstream_flux<<<gridL, kBlock, 0, g.stream>>>(D);
     g.launches++;
-    sync_fields({{D.h_u, nl}, {D.h_v, nl}});
+    if ((rc = sync_fields({{D.h_u, nl}, {D.h_v, nl}}))) return rc;
   }
   k_update_h<<<grid1, kBlock, 0, g.stream>>>(D);  // pm:2181 / 2259
   g.launches++;
   if (rgld) { k_rgld_correct<<<grid1, kBlock, 0, g.stream>>>(D); g.launches++; }
-  sync_fields({{D.hlay, nl}, {(g.nranks > 1 || g.torus) ? D.rs_new : nullptr, nl}});
+  if ((rc = sync_fields({{D.hlay, nl}, {(g.nranks > 1 || g.torus) ? D.rs_new : nullptr, nl}}))) return rc;
   g.rs_o = (g.rs_o + 1) % 3;
 
   k_diag<<<gridL, kBlock, 0, g.stream>>>(D);  // pm:2187 / 2266
   g.launches++;
-  if (g.nmir || g.nranks > 1) sync_fields({{D.mont, nl}, {D.rvor, nl}, {D.pvor, nl}, {D.dive, nl}, {D.d2hx, nl}, {D.d2hy, nl}});
+  if (((g.nmir || g.nranks > 1) && (rc = sync_fields({{D.mont, nl}, {D.rvor, nl}, {D.pvor, nl}, {D.dive, nl}, {D.d2hx, nl}, {D.d2hy, nl}}))) return rc;
   if (first_three || (g.P.dvis > 1.e-3 && upst) || g.P.svis > 0) {  // pm:2188 / 2268-2270
     k_visc<<<gridL, kBlock, 0, g.stream>>>(D);
     g.launches++;
-    if (g.nmir || g.nranks > 1) sync_fields({{D.v_cc, nl}, {D.v_ll, nl}});
+    if (((g.nmir || g.nranks > 1) && (rc = sync_fields({{D.v_cc, nl}, {D.v_ll, nl}}))) return rc;
     if (g.P.svis > 0.0) {
-      if (g.nmir || g.nranks > 1) sync_fields({{D.delu, nl}, {D.delv, nl}});
+      if (((g.nmir || g.nranks > 1) && (rc = sync_fields({{D.delu, nl}, {D.delv, nl}}))) return rc;
       k_biharm<<<gridL, kBlock, 0, g.stream>>>(D);
       g.launches++;
-      if (g.nmir || g.nranks > 1) sync_fields({{D.UU4, nl}, {D.VV4, nl}});
+      if (((g.nmir || g.nranks > 1) && (rc = sync_fields({{D.UU4, nl}, {D.VV4, nl}}))) return rc;
     }
   }
   for (int pass = 0; pass < 2; pass++) {  // pm:2193-2199 / 2276-2282
@@ -342,11 +342,11 @@ int step_split(int tstp, bool upst, bool first_three) {
     if (do_u) {
       k_update_u<<<gridL, kBlock, 0, g.stream>>>(D);
       g.launches++;
-      sync_fields({{D.u, nl}, {D.h_u, nl}, {(g.nranks > 1 || g.torus) ? D.dx_new : nullptr, nl}});
+      if ((rc = sync_fields({{D.u, nl}, {D.h_u, nl}, {(g.nranks > 1 || g.torus) ? D.dx_new : nullptr, nl}}))) return rc;
     } else {
       k_update_v<<<gridL, kBlock, 0, g.stream>>>(D);
       g.launches++;
-      sync_fields({{D.v, nl}, {D.h_v, nl}, {(g.nranks > 1 || g.torus) ? D.dy_new : nullptr, nl}});
+      if ((rc = sync_fields({{D.v, nl}, {D.h_v, nl}, {(g.nranks > 1 || g.torus) ? D.dy_new : nullptr, nl}}))) return rc;
     }
   }
   g.dx_o = (g.dx_o + 1) % 4;
@@ -356,7 +356,7 @@ int step_split(int tstp, bool upst, bool first_three) {
       k_obc<<<(g.nseg + 63) / 64, 64, 0, g.stream>>>(D, g.d_seg, g.nseg, pass);
       g.launches++;
     }
-    if (g.nmir || g.nranks > 1) sync_fields({{D.u, nl}, {D.v, nl}, {D.h_u, nl}, {D.h_v, nl}});
+    if (((g.nmir || g.nranks > 1) && (rc = sync_fields({{D.u, nl}, {D.v, nl}, {D.h_u, nl}, {D.h_v, nl}}))) return rc;
   }
   if (rgld) {  // pm:2207-2221 / 2292-2314
     if (first_three) k_centred_flux<<<gridL, kBlock, 0, g.stream>>>(D);
@@ -805,7 +805,8 @@ int beom_gpu_upload_state(const double *hlay, const double *u, const double *v) 
     }
   // halo rows come straight from the caller's arrays: no exchange here (upload is not a collective) -- except across the
   // seam of a y-periodic slab chain, whose images are another rank's rows (every rank uploads, so the ring closes)
-  for (int f = 0; f < 3; f++) sync_fields({{g.st[f][0], g.nlay}}, g.ring);
+  for (int f = 0; f < 3; f++)
+    if (int rc = sync_fields({{g.st[f][0], g.nlay}}, g.ring)) return rc;
   const size_t no = g.orphans.size();
   for (int f = 0; f < 3; f++)
     for (int l = 0; l < g.nlay; l++)
