@@ -325,16 +325,16 @@ int step_split(int tstp, bool upst, bool first_three) {
 
   k_diag<<<gridL, kBlock, 0, g.stream>>>(D);  // pm:2187 / 2266
   g.launches++;
-  if (((g.nmir || g.nranks > 1) && (rc = sync_fields({{D.mont, nl}, {D.rvor, nl}, {D.pvor, nl}, {D.dive, nl}, {D.d2hx, nl}, {D.d2hy, nl}}))) return rc;
+  if ((g.nmir || g.nranks > 1) && (rc = sync_fields({{D.mont, nl}, {D.rvor, nl}, {D.pvor, nl}, {D.dive, nl}, {D.d2hx, nl}, {D.d2hy, nl}}))) return rc;
   if (first_three || (g.P.dvis > 1.e-3 && upst) || g.P.svis > 0) {  // pm:2188 / 2268-2270
     k_visc<<<gridL, kBlock, 0, g.stream>>>(D);
     g.launches++;
-    if (((g.nmir || g.nranks > 1) && (rc = sync_fields({{D.v_cc, nl}, {D.v_ll, nl}}))) return rc;
+    if ((g.nmir || g.nranks > 1) && (rc = sync_fields({{D.v_cc, nl}, {D.v_ll, nl}}))) return rc;
     if (g.P.svis > 0.0) {
-      if (((g.nmir || g.nranks > 1) && (rc = sync_fields({{D.delu, nl}, {D.delv, nl}}))) return rc;
+      if ((g.nmir || g.nranks > 1) && (rc = sync_fields({{D.delu, nl}, {D.delv, nl}}))) return rc;
       k_biharm<<<gridL, kBlock, 0, g.stream>>>(D);
       g.launches++;
-      if (((g.nmir || g.nranks > 1) && (rc = sync_fields({{D.UU4, nl}, {D.VV4, nl}}))) return rc;
+      if ((g.nmir || g.nranks > 1) && (rc = sync_fields({{D.UU4, nl}, {D.VV4, nl}}))) return rc;
     }
   }
   for (int pass = 0; pass < 2; pass++) {  // pm:2193-2199 / 2276-2282
@@ -356,7 +356,7 @@ int step_split(int tstp, bool upst, bool first_three) {
       k_obc<<<(g.nseg + 63) / 64, 64, 0, g.stream>>>(D, g.d_seg, g.nseg, pass);
       g.launches++;
     }
-    if (((g.nmir || g.nranks > 1) && (rc = sync_fields({{D.u, nl}, {D.v, nl}, {D.h_u, nl}, {D.h_v, nl}}))) return rc;
+    if ((g.nmir || g.nranks > 1) && (rc = sync_fields({{D.u, nl}, {D.v, nl}, {D.h_u, nl}, {D.h_v, nl}}))) return rc;
   }
   if (rgld) {  // pm:2207-2221 / 2292-2314
     if (first_three) k_centred_flux<<<gridL, kBlock, 0, g.stream>>>(D);
