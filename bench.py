@@ -266,33 +266,58 @@ def main():
         nd1 = (n + 1) * ((args.rows or n) + 1) + 1
         opt = model.default_options(fused=not args.split, rank=rank, nranks=world, device=local_rank)
         gm = hl = uu = vv = None
-        # read_input_data holds ~25 GB of host arrays for this grid: at most four ranks do it at a time (host memory permitting)
-        try:
-            import psutil
-            par = 4 if psutil.virtual_memory().available > 130 * 2 ** 30 else 2
-        except Exception:
-            par = 2
-        for turn in range(0, world, par):
-            if turn <= rank < turn + par:
-                t0 = time.perf_counter()
-                hm = model.HostModel.from_block(blk)
-                gm = model.GpuModel(hm.params, hm.fields(), opt)
-                first, count, own_first, own_count = gm.point_range()
-                if world > 1:
-                    gm.set_window(first, count)
-                else:
-                    first, count = 0, nd1
-                hl = gm.pinned((nlay, count)); uu = gm.pinned((nlay, count)); vv = gm.pinned((nlay, count))
-                hl[:] = hm.array("hlay")[:, first:first + count]
-                uu[:] = hm.array("u")[:, first:first + count]
-                vv[:] = hm.array("v")[:, first:first + count]
-                # grid row of every own point: the state checksum below is taken row by row, which makes it independent
-                # of how the rows are dealt out to ranks
-                own_rows = np.array(hm.iarray("subc")[1][own_first:own_first + own_count], copy=True)
-                hm.close()
-                log("[rank %d] read_input_data + beom_gpu_init: %.1f s" % (rank, time.perf_counter() - t0))
+        init_how = None
+        # read_input_data's grid-shaped work on the device (beom_gpu_init_grids): the raw files are memory-mapped and handed over
+        t0 = time.perf_counter()
+        with open(blk) as f:
+            params, idir, _, _ = model.parse_params(f.read())
+        if not os.environ.get("BEOM_HOST_INIT"):
+            gm = model.GpuModel.from_grids(params, idir, opt)
+        if gm is not None:
+            init_how = "device (beom_gpu_init_grids)"
+            first, count, own_first, own_count = gm.point_range()
             if world > 1:
-                dist.barrier()
+                gm.set_window(first, count)
+                w_first = first
+            else:
+                w_first, count = 0, nd1
+            hl = gm.pinned((nlay, count)); uu = gm.pinned((nlay, count)); vv = gm.pinned((nlay, count))
+            gm.download_state((hl, uu, vv))  # the initial state the e2e leg uploads again from host memory
+            sj = gm.download_subc()[1]
+            own_rows = np.array(sj[own_first - first:own_first - first + own_count], copy=True)
+            first = w_first
+            log("[rank %d] beom_gpu_init_grids (device-side read_input_data) + initial state to the host: %.1f s" % (rank, time.perf_counter() - t0))
+        else:
+            init_how = "host (read_input_data + beom_gpu_init)"
+            # read_input_data holds ~25 GB of host arrays for this grid: at most four ranks do it at a time (host memory permitting)
+            try:
+                import psutil
+                par = 4 if psutil.virtual_memory().available > 130 * 2 ** 30 else 2
+            except Exception:
+                par = 2
+            for turn in range(0, world, par):
+                if turn <= rank < turn + par:
+                    t0 = time.perf_counter()
+                    hm = model.HostModel.from_block(blk)
+                    gm = model.GpuModel(hm.params, hm.fields(), opt)
+                    first, count, own_first, own_count = gm.point_range()
+                    if world > 1:
+                        gm.set_window(first, count)
+                    else:
+                        first, count = 0, nd1
+                    hl = gm.pinned((nlay, count)); uu = gm.pinned((nlay, count)); vv = gm.pinned((nlay, count))
+                    hl[:] = hm.array("hlay")[:, first:first + count]
+                    uu[:] = hm.array("u")[:, first:first + count]
+                    vv[:] = hm.array("v")[:, first:first + count]
+                    # grid row of every own point: the state checksum below is taken row by row, which makes it independent
+                    # of how the rows are dealt out to ranks
+                    own_rows = np.array(hm.iarray("subc")[1][own_first:own_first + own_count], copy=True)
+                    hm.close()
+                    log("[rank %d] read_input_data + beom_gpu_init: %.1f s" % (rank, time.perf_counter() - t0))
+                if world > 1:
+                    dist.barrier()
+        if world > 1:
+            dist.barrier()
         if rank == 0:
             for f in os.listdir(tmp):
                 if f.endswith(".bin"):
@@ -417,7 +442,7 @@ def main():
             shutil.rmtree(tmp2, ignore_errors=True)
     line = {"metric": "cell_layer_updates_per_s", "value": value, "unit": "cell-layer updates/s", "n_gpus": world, "steps": steps,
             "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": dict(config, path=path, fused_variant=variant), "roofline": roofline, "cpu_baseline": cb,
+            "dtype": "f64", "data": "synthetic", "config": dict(config, path=path, fused_variant=variant, init=init_how), "roofline": roofline, "cpu_baseline": cb,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "state_sha256": state_sha, "state_sha256_nsteps": steps if state_sha else None}
     emit(line)

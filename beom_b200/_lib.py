@@ -74,9 +74,14 @@ class Records(C.Structure):  # beom_records of include/beom_gpu.h
     ]
 
 
+class Grids(C.Structure):  # beom_grids of include/beom_gpu.h: the raw input files (float32), NULL = absent
+    _fields_ = [(k, C.POINTER(C.c_float)) for k in ("h_bo", "init", "nudg", "taus", "fcor", "hdot", "bodf")] + \
+               [("has_tide", C.c_int32), ("has_h_to", C.c_int32)]
+
+
 GPU_SYMBOLS = [
     "beom_gpu_version", "beom_gpu_abi_version", "beom_gpu_last_error", "beom_gpu_default_options",
-    "beom_gpu_init", "beom_gpu_upload_state", "beom_gpu_stress", "beom_gpu_step", "beom_gpu_advance",
+    "beom_gpu_init", "beom_gpu_init_grids", "beom_gpu_download_subc", "beom_gpu_debug_static", "beom_gpu_upload_state", "beom_gpu_stress", "beom_gpu_step", "beom_gpu_advance",
     "beom_gpu_download_state", "beom_gpu_download_aux", "beom_gpu_download_diag", "beom_gpu_download_pi_s", "beom_gpu_pi_iterations",
     "beom_gpu_diagnostics", "beom_gpu_diagnostics_all", "beom_gpu_set_rest_thickness", "beom_gpu_records_begin",
     "beom_gpu_records_wait", "beom_gpu_sync", "beom_gpu_mark", "beom_gpu_elapsed_ms", "beom_gpu_launch_count",
@@ -121,6 +126,9 @@ def bind_gpu(lib: C.CDLL) -> C.CDLL:
     lib.beom_gpu_download_diag.argtypes = [c_float_p] * 3
     lib.beom_gpu_download_pi_s.argtypes = [c_double_p]
     lib.beom_gpu_pi_iterations.argtypes = [C.POINTER(C.c_int)]
+    lib.beom_gpu_init_grids.argtypes = [C.POINTER(Params), C.POINTER(Grids), C.POINTER(Options)]
+    lib.beom_gpu_download_subc.argtypes = [C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+    lib.beom_gpu_debug_static.argtypes = [C.c_char_p, C.c_int, c_double_p]
     lib.beom_gpu_diagnostics.argtypes = [c_double_p] * 4
     lib.beom_gpu_diagnostics_all.argtypes = [c_double_p] * 8
     lib.beom_gpu_set_rest_thickness.argtypes = [c_float_p]

@@ -19,6 +19,7 @@
 #include "split.cuh"
 #include "diag.cuh"
 #include "rigid.cuh"
+#include "gridinit.cuh"
 #include "layout.h"
 #include "orphans.h"
 
@@ -442,15 +443,12 @@ int beom_gpu_init(const beom_params *par, const beom_fields *fld, const beom_gpu
   }
   return rc;
 }
-static int init_impl(const beom_params *par, const beom_fields *fld, const beom_gpu_options *opt_in) {
-  if (!par || !fld) return fail(-1, "beom_gpu_init: null argument");
+// device, streams and events: common to beom_gpu_init and beom_gpu_init_grids
+static int init_prologue(const beom_params *par, const beom_gpu_options *opt_in, cudaDeviceProp *prop_out) {
   beom_gpu_options opt;
   if (opt_in) opt = *opt_in;
   else beom_gpu_default_options(&opt);
-  if (!fld->neig || !fld->subc || !fld->mk_u || !fld->mk_v || !fld->mk_n || !fld->mkpe || !fld->mkpi || !fld->fcor || !fld->h_th)
-    return fail(-2, "beom_gpu_init: a required static field is NULL");
   if (par->nlay < 1 || par->nlay > BEOM_MAXLAY) return fail(-3, "beom_gpu_init: nlay out of range");
-  if (fld->nudg && !fld->fnud) return fail(-4, "beom_gpu_init: nudg given without fnud");
 
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -465,6 +463,7 @@ static int init_impl(const beom_params *par, const beom_fields *fld, const beom_
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, dev));
   if (prop.major != 10) return fail(-11, "beom_gpu_init: device %d is sm_%d%d; kernels are built for sm_100a only", dev, prop.major, prop.minor);
+  if (prop_out) *prop_out = prop;
 
   g.P = *par;
   g.opt = opt;
@@ -481,6 +480,20 @@ static int init_impl(const beom_params *par, const beom_fields *fld, const beom_
   }
   CK(cudaEventCreate(&g.ev[0]));
   CK(cudaEventCreate(&g.ev[1]));
+  return 0;
+}
+static int init_tail(double invf, double w_ti, const double *bodf);
+
+static int init_impl(const beom_params *par, const beom_fields *fld, const beom_gpu_options *opt_in) {
+  if (!par || !fld) return fail(-1, "beom_gpu_init: null argument");
+  if (!fld->neig || !fld->subc || !fld->mk_u || !fld->mk_v || !fld->mk_n || !fld->mkpe || !fld->mkpi || !fld->fcor || !fld->h_th)
+    return fail(-2, "beom_gpu_init: a required static field is NULL");
+  if (fld->nudg && !fld->fnud) return fail(-4, "beom_gpu_init: nudg given without fnud");
+  cudaDeviceProp prop = cudaDeviceProp();
+  {
+    const int rc0 = init_prologue(par, opt_in, &prop);
+    if (rc0) return rc0;
+  }
 
   const int lm = g.lm, mm = g.mm, nlay = g.nlay, ndeg = g.ndeg;
   const size_t nd1 = (size_t)ndeg + 1;
@@ -710,9 +723,20 @@ static int init_impl(const beom_params *par, const beom_fields *fld, const beom_
     }
   }
 
+  return init_tail(fld->invf, fld->w_ti, fld->bodf);
+}
+
+// state buffers, exchange buffers, the scalars of the Dev template, the fused step: common to both ways of initialising
+static int init_tail(double invf, double w_ti, const double *bodf) {
+  const beom_params *par = &g.P;
+  const beom_gpu_options &opt = g.opt;
+  Dev &D = g.D;
+  const int nlay = g.nlay;
+  const size_t pl = g.plane, nl = (size_t)nlay, nd1 = (size_t)g.ndeg + 1;
+  int rc;
   // state
   for (int f = 0; f < 5; f++)
-    if ((rc = dalloc(&g.st[f][0], pl * nl))) return rc;
+    if (!g.st[f][0] && (rc = dalloc(&g.st[f][0], pl * nl))) return rc;
   for (auto &p : g.rs)
     if ((rc = dalloc(&p, pl * nl))) return rc;
   for (auto &p : g.dx)
@@ -737,7 +761,7 @@ static int init_impl(const beom_params *par, const beom_fields *fld, const beom_
   }
 
   // scalars and constants, evaluated like the reference does
-  D.invf = fld->invf; D.w_ti = fld->w_ti;
+  D.invf = invf; D.w_ti = w_ti;
   D.dl = par->dl; D.dt = par->dt; D.grav = par->grav;
   D.i_dl = 1.0 / par->dl; D.i_gr = 1.0 / par->grav; D.i_r0 = 1.0 / par->rho0; D.i_r1 = 1.0 / par->rhon[0];
   D.uadv = par->uadv; D.ocrp = par->ocrp; D.qdrg = par->qdrg; D.rgld = par->rgld;
@@ -752,8 +776,8 @@ static int init_impl(const beom_params *par, const beom_fields *fld, const beom_
   for (int l = 0; l < nlay; l++) {
     D.rhon[l] = par->rhon[l];
     D.i_rn[l] = 1.0 / par->rhon[l];
-    D.bodf[0][l] = fld->bodf ? fld->bodf[l] : 0.0;
-    D.bodf[1][l] = fld->bodf ? fld->bodf[(size_t)nlay + l] : 0.0;
+    D.bodf[0][l] = bodf ? bodf[l] : 0.0;
+    D.bodf[1][l] = bodf ? bodf[(size_t)nlay + l] : 0.0;
   }
   D.bstress_thr = (par->variant == BEOM_VARIANT_1D ? 0.0 : 2.0) * par->hsal;
   D.variant = par->variant; D.nsal = par->nsal;
@@ -780,6 +804,325 @@ static int init_impl(const beom_params *par, const beom_fields *fld, const beom_
   g_err.clear();
   return 0;
 }
+
+}  // extern "C"
+namespace {
+__global__ void k_flags_as_double(const uint8_t *f, double *out, size_t n) {
+  const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n) out[k] = (double)f[k];
+}
+int download_planes_fwd(double *dst, const double *dense, int nplanes);
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------------
+// beom_gpu_init_grids: read_input_data's grid-shaped work on the device (gridinit.cuh).  The caller hands over the raw
+// contents of the input files; masks, vector numbering, rest thickness, relaxation targets, forcing planes and the initial
+// state are built straight in the dense layout of this rank, with the reference's arithmetic.  Returns
+// BEOM_GRIDS_UNSUPPORTED (and says why in the error string) for what still needs the host path: periodic domains, the rigid
+// lid, the 1d/3d/plume variants, tides, h_to, restarts, and sponges with the open-boundary copy switched on (mcbc < 0.5: the
+// segment table of index_boundary_points is built on the host).
+// ---------------------------------------------------------------------------------------------------------------------
+static int init_grids_impl(const beom_params *par, const beom_grids *gr, const beom_gpu_options *opt_in) {
+  if (!par || !gr) return fail(-1, "beom_gpu_init_grids: null argument");
+  const char *why = nullptr;
+  if (par->xper > 0.5 || par->yper > 0.5) why = "periodic domain";
+  else if (par->rgld > 0.5) why = "rigid lid";
+  else if (par->variant != BEOM_VARIANT_STANDARD) why = "1d / 3d / plume variant";
+  else if (par->topt > 0.5 || gr->has_h_to) why = "h_to.bin";
+  else if (gr->has_tide) why = "tide.bin";
+  else if (par->rsta > 0.5) why = "restart";
+  else if (gr->nudg && par->mcbc < 0.5) why = "sponge with the open-boundary copy (mcbc < 0.5)";
+  if (why) {
+    fail(BEOM_GRIDS_UNSUPPORTED, "beom_gpu_init_grids: %s is initialised on the host (read_input_data + beom_gpu_init)", why);
+    return BEOM_GRIDS_UNSUPPORTED;
+  }
+  cudaDeviceProp prop = cudaDeviceProp();
+  int rc;
+  if ((rc = init_prologue(par, opt_in, &prop))) return rc;
+  const int lm = g.lm, mm = g.mm, nlay = g.nlay, ndeg = g.ndeg;
+  const size_t nd1 = (size_t)ndeg + 1, nl = (size_t)nlay;
+
+  // y-slab and dense layout of this rank: the same rules as analyse_layout (layout.h) on a non-periodic domain
+  {
+    const int rows = mm + 1, base = rows / g.nranks, rem = rows % g.nranks;
+    g.j0 = 1 + g.rank * base + std::min(g.rank, rem);
+    g.j1 = g.j0 + base + (g.rank < rem ? 1 : 0) - 1;
+    if (g.j1 < g.j0) return fail(-5, "beom_gpu_init: more ranks than grid rows");
+  }
+  g.NX = ((lm + GX0 + 34) + 15) / 16 * 16;
+  g.NY = (g.j1 - g.j0 + 1) + 2 * G;
+  g.plane = (size_t)g.NX * g.NY;
+  if (g.plane > 0x7fffffffull) return fail(-6, "beom_gpu_init: plane too large for 32-bit cell offsets");
+  const int j_off = G - g.j0;
+  const size_t pl = g.plane;
+  g.torus = false; g.ring = false; g.nmir = 0;
+  g.halo = halo_rows(g.rank, g.nranks, false, G, G + (g.j1 - g.j0));
+  g.orph = Orphans();
+  g.orph.nlay = nlay;
+  g.orphans.clear();
+  g.cell_of_point.clear();
+
+  // the raw files on the device (released again at the end)
+  std::vector<void *> raw;
+  auto put = [&](const float *src, size_t count, const float **dst) -> int {
+    *dst = nullptr;
+    if (!src) return 0;
+    float *d = nullptr;
+    CK(cudaMalloc(&d, count * sizeof(float)));
+    raw.push_back(d);
+    CK(cudaMemcpyAsync(d, src, count * sizeof(float), cudaMemcpyHostToDevice, g.stream));
+    *dst = d;
+    return 0;
+  };
+  struct Release {
+    std::vector<void *> &v;
+    ~Release() { for (void *q : v) cudaFree(q); }
+  } release{raw};
+  GridIn A;
+  memset(&A, 0, sizeof A);
+  A.lm = lm; A.mm = mm; A.nlay = nlay; A.NX = g.NX; A.NY = g.NY; A.j_off = j_off;
+  A.jlo = std::max(g.j0 - G, 0); A.jhi = std::min(g.j1 + G, mm + 1);
+  A.hdry = par->hdry;
+  A.flat = (par->cext * par->cext) / par->grav;
+  A.tauw[0] = par->tauw[0]; A.tauw[1] = par->tauw[1]; A.f0 = par->f0;
+  for (int l = 0; l < nlay; l++) A.topl[l] = par->topl[l];
+  const size_t gp = (size_t)(lm + 2) * (mm + 2);
+  if ((rc = put(gr->h_bo, gp, &A.h_bo)) || (rc = put(gr->init, gp * nl * 3, &A.init)) || (rc = put(gr->nudg, gp * 3, &A.nudg)) ||
+      (rc = put(gr->taus, gp * 2, &A.taus)) || (rc = put(gr->fcor, gp, &A.fcor)) || (rc = put(gr->hdot, gp * nl, &A.hdot)))
+    return rc;
+
+  // ---- index_grid_points (pm:567-764): points per row, their prefix sum, the depth extremes (pm:134-135)
+  int *d_rowcnt = nullptr, *d_rowoff = nullptr;
+  double *d_rowmm = nullptr;
+  if ((rc = dalloc(&d_rowcnt, (size_t)mm + 3, false)) || (rc = dalloc(&d_rowoff, (size_t)mm + 3, false)) || (rc = dalloc(&d_rowmm, 2 * ((size_t)mm + 2), false))) return rc;
+  k_gi_row_counts<<<(unsigned)(mm + 2), 256, 0, g.stream>>>(A, d_rowcnt, d_rowmm, d_rowmm + (mm + 2));
+  g.launches++;
+  std::vector<int> rowcnt(mm + 2), rowoff(mm + 3, 0);
+  std::vector<double> rowmm(2 * ((size_t)mm + 2));
+  CK(cudaMemcpyAsync(rowcnt.data(), d_rowcnt, sizeof(int) * (mm + 2), cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaMemcpyAsync(rowmm.data(), d_rowmm, sizeof(double) * rowmm.size(), cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  double dmin = INFINITY, dmax = 0.0;
+  for (int j = 0; j <= mm + 1; j++) {
+    rowoff[j + 1] = rowoff[j] + rowcnt[j];
+    dmin = std::min(dmin, rowmm[j]);
+    dmax = std::max(dmax, rowmm[(size_t)(mm + 2) + j]);
+  }
+  if (rowoff[mm + 2] != ndeg) return fail(-15, " wrong input parameter! Please set ndeg = %d inside file shared_mod.f95.", rowoff[mm + 2]);
+  if (par->ocrp < 0.5 && nlay > 1) {  // pm:137-152
+    if (par->topl[nlay - 1] * dmax + 10.0 * par->hmin >= dmin) return fail(-16, " Please modify topl so that bathymetry is contained within lower layer.");
+  } else if (par->ocrp < 0.5 && nlay == 1) {
+    if (dmin <= 10.0 * par->hmin) return fail(-16, " Please adjust h_bo or hmin so that min(h_bo) > 10. * hmin.");
+  }
+  A.dmax = dmax;
+  CK(cudaMemcpyAsync(d_rowoff, rowoff.data(), sizeof(int) * (mm + 3), cudaMemcpyHostToDevice, g.stream));
+  g.p_lo = 1 + rowoff[A.jlo]; g.p_hi = rowoff[A.jhi + 1];
+  if (g.p_hi < g.p_lo) return fail(-8, "beom_gpu_init: no grid points on rank %d", g.rank);
+  g.own_first = 1 + rowoff[g.j0]; g.own_last = rowoff[g.j1 + 1];
+  if (g.own_last < g.own_first) { g.own_first = 0; g.own_last = -1; }
+
+  // ---- Dev template, flags, cell map, h_th
+  Dev &D = g.D;
+  memset(&D, 0, sizeof D);
+  D.NX = g.NX; D.NY = g.NY; D.plane = pl;
+  D.x_lo = 1 + GX0; D.x_hi = lm + 1 + GX0;
+  D.y_lo = G; D.y_hi = G + (g.j1 - g.j0);
+  D.i_off = GX0; D.j_off = j_off;
+  D.lm = lm; D.mm = mm; D.nlay = nlay;
+  if ((rc = dalloc(&g.flags, pl)) || (rc = dalloc(&g.d_cell, nd1, false))) return rc;
+  CK(cudaMemsetAsync(g.d_cell, 0xff, sizeof(int) * nd1, g.stream));  // -1: not held on this rank
+  D.flags = g.flags;
+  double *h_th = nullptr, *fcor = nullptr;
+  if ((rc = dalloc(&h_th, pl)) || (rc = dalloc(&fcor, pl))) return rc;
+  k_gi_index<<<(unsigned)(A.jhi - A.jlo + 1), 256, 0, g.stream>>>(A, d_rowoff, g.d_cell, g.flags, h_th);
+  g.launches++;
+  D.h_th = h_th; D.fcor = fcor;
+  const int nloc = g.p_hi - g.p_lo + 1;
+  g.stage_elems = (size_t)nloc * nlay * 3;
+  if ((rc = dalloc(&g.stage, g.stage_elems, false))) return rc;
+
+  // ---- rest thickness (pm:154-183)
+  if ((rc = dalloc(&g.diag_h0, pl * nl))) return rc;
+  const unsigned cb = (unsigned)((pl + 255) / 256);
+  if (par->ocrp < 0.5) {
+    k_gi_h0_stack<<<cb, 256, 0, g.stream>>>(A, g.flags, h_th, g.diag_h0, pl);
+  } else {
+    RestSolver S;
+    memset(&S, 0, sizeof S);
+    S.nlay = nlay; S.nsal = par->nsal; S.itmx = par->itmx;
+    S.hsal = par->hsal; S.thre = par->tole; S.sor = par->sor; S.dmax = dmax;
+    for (int l = 0; l < nlay; l++) { S.rho[l] = par->rhon[l]; S.topl[l] = par->topl[l]; }
+    S.prepare();
+    int *d_bad = nullptr, bad = -1;
+    if ((rc = dalloc(&d_bad, (size_t)4, false))) return rc;
+    CK(cudaMemcpyAsync(d_bad, &bad, sizeof(int), cudaMemcpyHostToDevice, g.stream));
+    k_gi_h0_newton<<<(unsigned)((pl + 127) / 128), 128, 0, g.stream>>>(S, g.flags, h_th, g.diag_h0, pl, d_bad);
+    CK(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, g.stream));
+    CK(cudaStreamSynchronize(g.stream));
+    if (bad >= 0) return fail(-17, " calculation of h_layers did not converge, tolerance (meters) was %g, at cell %d", S.thre, bad);
+  }
+  g.launches++;
+
+  // ---- forcing files and the initial state (pm:198-216, 840-964)
+  for (int f = 0; f < 3; f++)
+    if ((rc = dalloc(&g.st[f][0], pl * nl))) return rc;
+  GridOut O;
+  memset(&O, 0, sizeof O);
+  O.plane = pl; O.flags = g.flags; O.h_0 = g.diag_h0;
+  O.hlay = g.st[0][0]; O.u = g.st[1][0]; O.v = g.st[2][0];
+  O.fcor = fcor;
+  O.set_state = 1;
+  double *tmp = nullptr;
+  if (A.nudg) {
+    if ((rc = dalloc(&tmp, pl * 3))) return rc;
+    O.nudg = tmp;
+    if ((rc = dalloc(&tmp, pl * nl * 3))) return rc;
+    O.fnud = tmp;
+  }
+  const bool tauw_live = std::fabs(par->tauw[0]) > 1.e-7 || std::fabs(par->tauw[1]) > 1.e-7;
+  if (A.taus || tauw_live) {
+    if ((rc = dalloc(&tmp, pl * 2))) return rc;
+    O.taus = tmp;
+  }
+  if (A.hdot) {
+    if ((rc = dalloc(&tmp, pl * nl))) return rc;
+    O.hdot = tmp;
+  }
+  unsigned *d_any = nullptr, any = 0;
+  if ((rc = dalloc(&d_any, (size_t)4))) return rc;
+  O.any = d_any;
+  k_gi_forcing<<<dim3((unsigned)((g.NX + 127) / 128), (unsigned)g.NY), 128, 0, g.stream>>>(A, O);
+  g.launches++;
+  CK(cudaMemcpyAsync(&any, d_any, sizeof(unsigned), cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  CK(cudaGetLastError());
+  D.has_nudg = (any & 2u) ? 1 : 0;
+  if (D.has_nudg) { D.nudg = O.nudg; D.fnud = O.fnud; }
+  D.has_tide = 0;
+  D.has_hdot = (any & 8u) ? 1 : 0;
+  if (D.has_hdot) D.hdot = O.hdot;
+  g.any_taus = (any & 4u) != 0;
+  D.has_wind = g.any_taus;
+  D.has_bdrg = par->bdrg > 1.e-7;
+  D.has_tdrg = par->tdrg > 1.e-7;
+  if (D.has_wind) {
+    D.taus = O.taus;
+    if ((rc = dalloc(&D.tt3d, pl * nl * 2)) || (rc = dalloc(&D.layt, pl * nl))) return rc;
+  }
+  if (D.has_bdrg)
+    if ((rc = dalloc(&D.tb3d, pl * nl * 2)) || (rc = dalloc(&D.layb, pl * nl)) || (rc = dalloc(&D.taub, pl * 2))) return rc;
+  if (D.has_tdrg)
+    if ((rc = dalloc(&D.tu3d, pl * nl * 2)) || (rc = dalloc(&D.layu, pl * nl)) || (rc = dalloc(&D.taum, pl * 2))) return rc;
+  g.nseg = 0;
+  g.obc_any = false;
+
+  // invf = 1 / mean(fcor(0:ndeg)) (pm:223-229): a sum in vector order, so it is taken on the host from what the vector holds
+  double invf;
+  {
+    double acc = 0.0;
+    if (!gr->fcor) {
+      for (size_t q = 0; q < nd1; q++) acc += par->f0;
+    } else {
+      const float *f = gr->fcor, *hb = gr->h_bo;
+      float mean = 0.0f;
+      for (size_t k = 0; k < gp; k++) mean = mean + f[k];
+      acc += (double)(mean / (float)gp);  // fcor(0)
+      auto depth = [&](int i, int j) -> double {
+        if (i < 1 || i > lm || j < 1 || j > mm) return 0.0;
+        if (!hb) return A.flat;
+        const double d = (double)hb[(size_t)j * (lm + 2) + i];
+        return d < par->hdry ? 0.0 : d;
+      };
+      auto wet = [&](int i, int j) { return depth(i, j) > par->hdry; };
+      for (int j = 0; j <= mm + 1; j++)
+        for (int i = 0; i <= lm + 1; i++) {
+          if (!(wet(i, j) || wet(i - 1, j) || wet(i, j - 1) || wet(i - 1, j - 1))) continue;
+          const size_t k0 = (size_t)j * (lm + 2) + i;
+          if (i > 0 && j > 0) {
+            float t = f[k0] * 0.25f;
+            t = t + f[k0 - 1] * 0.25f;
+            t = t + f[k0 - (lm + 2)] * 0.25f;
+            t = t + f[k0 - (lm + 2) - 1] * 0.25f;
+            acc += (double)t;
+          } else {
+            acc += (double)f[k0];
+          }
+        }
+    }
+    invf = acc / (double)nd1;
+    invf = std::fabs(invf) > 1.25e-5 ? 1.0 / invf : 0.0;
+  }
+  std::vector<double> bodf((size_t)nlay * 2, 0.0);
+  if (gr->bodf)
+    for (size_t k = 0; k < (size_t)nlay * 2; k++) bodf[k] = (double)gr->bodf[k];
+
+  if ((rc = init_tail(invf, 0.0, gr->bodf ? bodf.data() : nullptr))) return rc;
+
+  // h_0.bin's content for the output records (pm:185-194)
+  if ((rc = dalloc(&g.h0r4, (size_t)ndeg * nl))) return rc;
+  {
+    const int p0 = std::max(g.p_lo, 1), n = g.p_hi - p0 + 1;
+    k_gi_h0r4<<<(unsigned)((n + 255) / 256), 256, 0, g.stream>>>(g.diag_h0, pl, g.d_cell, p0, n, ndeg, nlay, g.h0r4);
+    g.launches++;
+  }
+  g.h0r4_orph.clear();
+  CK(cudaStreamSynchronize(g.stream));
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int beom_gpu_init_grids(const beom_params *par, const beom_grids *gr, const beom_gpu_options *opt_in) {
+  if (g.ready) beom_gpu_finalize();
+  const int rc = init_grids_impl(par, gr, opt_in);
+  if (rc) {
+    const std::string keep = g_err;
+    beom_gpu_finalize();
+    g_err = keep;
+  }
+  return rc;
+}
+
+// grid coordinates (i, j) of the vector points first .. first + count - 1 this rank holds (beom_gpu_point_range)
+extern "C" int beom_gpu_download_subc(int32_t *si, int32_t *sj) {
+  if (!g.ready) return fail(-20, "beom_gpu_download_subc: not initialised");
+  const int n = g.p_hi - g.p_lo + 1;
+  int *d = reinterpret_cast<int *>(g.stage);  // (3 nlay n doubles: room for 2 n ints)
+  k_gi_subc<<<(unsigned)((n + 255) / 256), 256, 0, g.stream>>>(g.d_cell, g.p_lo, n, g.NX, g.D.j_off, d, d + n);
+  g.launches++;
+  CK(cudaMemcpyAsync(si, d, sizeof(int) * n, cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaMemcpyAsync(sj, d + n, sizeof(int) * n, cudaMemcpyDeviceToHost, g.stream));
+  CK(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
+// A static plane in the reference's vector layout (tests: the device-side initialisation against read_input_data):
+// name = fcor | h_th | nudg | fnud | taus | hdot | h_0 | flags (the flag byte as a double), index = plane within the array
+extern "C" int beom_gpu_debug_static(const char *name, int index, double *out) {
+  if (!g.ready) return fail(-20, "beom_gpu_debug_static: not initialised");
+  const std::string nm = name ? name : "";
+  const Dev &D = g.D;
+  const double *base = nm == "fcor" ? D.fcor : nm == "h_th" ? D.h_th : nm == "nudg" ? D.nudg : nm == "fnud" ? D.fnud : nm == "taus" ? D.taus
+                       : nm == "hdot" ? D.hdot : nm == "h_0" ? g.diag_h0 : nullptr;
+  const int n = g.p_hi - g.p_lo + 1;
+  const size_t keep_first = g.win_first, keep_stride = g.win_stride;
+  g.win_first = 0; g.win_stride = (size_t)g.ndeg + 1;
+  int rc = 0;
+  if (nm == "flags") {
+    double *tmp = nullptr;
+    if ((rc = dalloc(&tmp, g.plane, false))) return rc;
+    k_flags_as_double<<<(unsigned)((g.plane + 255) / 256), 256, 0, g.stream>>>(g.flags, tmp, g.plane);
+    rc = download_planes_fwd(out, tmp, 1);
+  } else if (!base) {
+    rc = fail(-26, "beom_gpu_debug_static: no such plane (%s)", nm.c_str());
+  } else {
+    rc = download_planes_fwd(out, base + (size_t)index * g.plane, 1);
+  }
+  g.win_first = keep_first; g.win_stride = keep_stride;
+  (void)n;
+  return rc;
+}
+
+extern "C" {
 
 int beom_gpu_upload_state(const double *hlay, const double *u, const double *v) {
   if (!g.ready) return fail(-20, "beom_gpu_upload_state: not initialised");
@@ -952,6 +1295,12 @@ static int download_planes(double *dst, const double *dense, int nplanes) {
   }
   return 0;
 }
+
+}  // extern "C"
+namespace {
+int download_planes_fwd(double *dst, const double *dense, int nplanes) { return download_planes(dst, dense, nplanes); }
+}  // namespace
+extern "C" {
 
 int beom_gpu_download_state(double *hlay, double *u, double *v) {
   if (!g.ready) return fail(-20, "beom_gpu_download_state: not initialised");
@@ -1178,8 +1527,9 @@ int beom_gpu_diagnostics_all(const double *h_0, double *vol, double *ke, double 
   const dim3 block(256, 1, 1);
   const dim3 grid((unsigned)((std::max(np, 1) + 255) / 256), (unsigned)g.nlay, 1);
   const size_t per_layer = (size_t)grid.x;
-  if (!g.diag_h0) {
-    if ((rc = dalloc(&g.diag_h0, pl * nl)) || (rc = dalloc(&g.diag_partial, kNQ * per_layer * nl)) || (rc = dalloc(&g.diag_out, kNQ * nl + 1))) return rc;
+  if (!g.diag_h0 && (rc = dalloc(&g.diag_h0, pl * nl))) return rc;
+  if (!g.diag_partial) {
+    if ((rc = dalloc(&g.diag_partial, kNQ * per_layer * nl)) || (rc = dalloc(&g.diag_out, kNQ * nl + 1))) return rc;
     g.diag_blocks = per_layer;
   }
   if (h_0) {  // rest thickness h_0(0:ndeg, nlay), reference layout; static, but cheap enough to refresh per call

@@ -128,6 +128,50 @@ class GpuModel:
         if rc:
             raise RuntimeError("beom_gpu_init: %s" % _lib.gpu_error())
 
+    GRID_FILES = ("h_bo", "init", "nudg", "taus", "fcor", "hdot", "bodf")
+
+    @classmethod
+    def from_grids(cls, params: Params, idir: str, options: Options | None = None):
+        """read_input_data's grid-shaped work on the device (beom_gpu_init_grids): the raw files of ``idir`` are memory-mapped
+        and handed over as they are; masks, vector numbering, rest thickness, targets, forcing and the initial state are
+        built in HBM.  Returns None when the case needs the host path (periodic, rigid lid, tides, ...): the caller then uses
+        HostModel + GpuModel(...) + upload_state as before."""
+        self = cls.__new__(cls)
+        self.lib = _lib.gpu_lib()
+        self.params = params
+        self.nlay, self.ndeg = params.nlay, params.ndeg
+        self.opt = options or default_options()
+        gr = _lib.Grids()
+        keep = []
+        for k in cls.GRID_FILES:
+            path = os.path.join(idir, k + ".bin")
+            if os.path.exists(path):
+                a = np.memmap(path, dtype="<f4", mode="r")
+                keep.append(a)
+                setattr(gr, k, C.cast(a.ctypes.data, C.POINTER(C.c_float)))
+        gr.has_tide = int(os.path.exists(os.path.join(idir, "tide.bin")))
+        gr.has_h_to = int(os.path.exists(os.path.join(idir, "h_to.bin")))
+        rc = self.lib.beom_gpu_init_grids(C.byref(params), C.byref(gr), C.byref(self.opt))
+        del keep
+        if rc == 1:  # BEOM_GRIDS_UNSUPPORTED
+            return None
+        if rc:
+            raise RuntimeError("beom_gpu_init_grids: %s" % _lib.gpu_error())
+        return self
+
+    def download_subc(self):
+        """Grid coordinates (i, j) of the vector points this rank holds (point_range: first .. first + count - 1)."""
+        first, count, _, _ = self.point_range()
+        si, sj = np.zeros(count, dtype=np.int32), np.zeros(count, dtype=np.int32)
+        self._ck(self.lib.beom_gpu_download_subc(si.ctypes.data_as(C.POINTER(C.c_int32)), sj.ctypes.data_as(C.POINTER(C.c_int32))), "download_subc")
+        return si, sj
+
+    def debug_static(self, name: str, index: int = 0):
+        """A static plane in the reference's vector layout (0:ndeg) -- for checks of the device-side initialisation."""
+        out = np.zeros(self.ndeg + 1)
+        self._ck(self.lib.beom_gpu_debug_static(name.encode(), index, _dp(out)), "debug_static")
+        return out
+
     def _ck(self, rc, what):
         if rc:
             raise RuntimeError("%s: %s" % (what, _lib.gpu_error()))

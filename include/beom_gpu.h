@@ -166,6 +166,32 @@ int beom_gpu_set_rest_thickness(const float *h_0_r4);
 int beom_gpu_records_begin(int with_diag);
 int beom_gpu_records_wait(beom_records *out);
 
+/* Initialisation from the raw input files with read_input_data's grid-shaped work done ON THE DEVICE (private_mod.f95:105-250:
+ * the masks and the vector numbering of index_grid_points as a prefix sum, the rest thickness -- layers stacked from the bottom or
+ * the per-column Newton solve of get_equilibrium_thickness_h_0 --, the relaxation targets, forcing planes and the initial state
+ * of read_input_file), written straight into the dense planes with the reference's arithmetic; replaces read_input_data +
+ * beom_gpu_init + beom_gpu_upload_state for the cases it covers.  The arrays hold the files' contents as they are on disk
+ * (little-endian float32, Fortran order, no record markers; NULL = file absent).  par carries the derived values of
+ * shared_mod.f95 (dt, hsal, ...) and ndeg.  Returns 0, a negative error, or BEOM_GRIDS_UNSUPPORTED for what is initialised on
+ * the host: periodic domains, the rigid lid, the 1d/3d/plume variants, tide.bin, h_to.bin, restarts, sponges with mcbc < 0.5. */
+typedef struct beom_grids {
+  const float *h_bo;   /* (0:lm+1, 0:mm+1) */
+  const float *init;   /* (0:lm+1, 0:mm+1, nlay, 3) */
+  const float *nudg;   /* (0:lm+1, 0:mm+1, 3) */
+  const float *taus;   /* (0:lm+1, 0:mm+1, 2) */
+  const float *fcor;   /* (0:lm+1, 0:mm+1) */
+  const float *hdot;   /* (0:lm+1, 0:mm+1, nlay) */
+  const float *bodf;   /* (nlay, 2) */
+  int32_t has_tide, has_h_to;  /* files that exist but are not handled here */
+} beom_grids;
+#define BEOM_GRIDS_UNSUPPORTED 1
+int beom_gpu_init_grids(const beom_params *par, const beom_grids *grids, const beom_gpu_options *opt);
+/* Grid coordinates (i, j) of the vector points this rank holds (beom_gpu_point_range: first .. first + count - 1). */
+int beom_gpu_download_subc(int32_t *si, int32_t *sj);
+/* A static plane in the reference's vector layout (0:ndeg), for checks: name = "fcor", "h_th", "nudg", "fnud", "taus", "hdot",
+ * "h_0", "flags" (the flag byte: masks mk_n = 1, mk_u = 2, mk_v = 4, mkpe = 8, mkpi = 16, vector point = 32); index = plane. */
+int beom_gpu_debug_static(const char *name, int index, double *out);
+
 /* Rigid-lid surface pressure pi_s(0:ndeg) (private_mod.f95:91). */
 int beom_gpu_download_pi_s(double *pi_s);
 /* Sweeps the last surf_pressure solve took (the reference's `iters', private_mod.f95:1756-1803). */

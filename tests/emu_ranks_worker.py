@@ -53,11 +53,25 @@ def make_exchange(rank):
     return EXCH(exchange)
 
 
+GRID_INIT = bool(os.environ.get("BEOM_GRID_INIT"))  # initialise every rank on the "device" from the raw files (beom_gpu_init_grids)
+
+
 class EmuRank(model.GpuModel):
-    def __init__(self, lib, params, fields, options):
+    def __init__(self, lib, params, fields, options, idir=None):
         self.lib, self.params, self.opt = lib, params, options
         self.nlay, self.ndeg = params.nlay, params.ndeg
-        self._ck(lib.beom_gpu_init(C.byref(params), C.byref(fields), C.byref(options)), "beom_gpu_init")
+        if idir is None:
+            self._ck(lib.beom_gpu_init(C.byref(params), C.byref(fields), C.byref(options)), "beom_gpu_init")
+            return
+        gr = _lib.Grids()
+        self._keep = []
+        for k in model.GpuModel.GRID_FILES:
+            path = os.path.join(idir, k + ".bin")
+            if os.path.exists(path):
+                a = np.fromfile(path, dtype="<f4")
+                self._keep.append(a)
+                setattr(gr, k, a.ctypes.data_as(C.POINTER(C.c_float)))
+        self._ck(lib.beom_gpu_init_grids(C.byref(params), C.byref(gr), C.byref(options)), "beom_gpu_init_grids")
 
     def _ck(self, rc, what):
         if rc:
@@ -89,9 +103,10 @@ def run_rank(rank):
         opt = model.Options()
         lib.beom_gpu_default_options(C.byref(opt))
         opt.fused, opt.rank, opt.nranks, opt.device = fused, rank, nranks, 0
-        gm = EmuRank(lib, hm.params, hm.fields(), opt)
+        gm = EmuRank(lib, hm.params, hm.fields(), opt, idir=work if GRID_INIT else None)
         first, count, own_first, own_count = gm.point_range()
-        gm.upload_state(hm.array("hlay"), hm.array("u"), hm.array("v"))
+        if not GRID_INIT:
+            gm.upload_state(hm.array("hlay"), hm.array("u"), hm.array("v"))
         gm.advance(1, nsteps)
         state = gm.download_state()
         aux = gm.download_aux()

@@ -34,9 +34,12 @@ def main():
     hm = model.HostModel.from_block(blk)
     orc = Oracle(hm.params, d)
     orc.advance(1, nsteps)
-    gm = model.GpuModel(hm.params, hm.fields(), model.default_options(fused=bool(fused), rank=rank, nranks=world, device=local))
+    opt = model.default_options(fused=bool(fused), rank=rank, nranks=world, device=local)
+    gm = model.GpuModel.from_grids(hm.params, d, opt) if len(sys.argv) > 4 and sys.argv[4] == "grids" else None  # device-side init
+    if gm is None:
+        gm = model.GpuModel(hm.params, hm.fields(), opt)
+        gm.upload_state(hm.array("hlay"), hm.array("u"), hm.array("v"))
     first, count, own_first, own_count = gm.point_range()
-    gm.upload_state(hm.array("hlay"), hm.array("u"), hm.array("v"))
     gm.advance(1, nsteps)
     hl, u, v = gm.download_state()
     aux = gm.download_aux()

@@ -463,6 +463,21 @@ def test_no_race_between_warps_under_threadsanitizer(emu_so, tmp_path_factory):
     shutil.rmtree(os.path.dirname(so), ignore_errors=True)
 
 
+def test_device_side_initialisation_on_the_emulation(emu_so):
+    """beom_gpu_init_grids (gridinit.cuh: index_grid_points as a prefix sum, the rest thickness incl. the Newton solve, the forcing
+    files) against the host's read_input_data on every case it covers, and the refusals (tests/test_grid_init.py re-run with the
+    emulated library); then every rank of a y-slab run initialised that way."""
+    env = dict(os.environ, BEOM_TEST_EMU=emu_so)
+    cmd = [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_grid_init.py"), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=1200, cwd=ROOT, env=env)
+    assert r.returncode == 0 and " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
+    for spec in (["synthetic_basin", "9", "3", "{}", json.dumps(dict(n=60, mm=90, nlay=4)), "1"], ["sill_exchange3D", "12", "2", "{}", "null", "1"]):
+        cmd = [sys.executable, os.path.join(ROOT, "tests", "emu_ranks_worker.py"), emu_so] + spec
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=dict(os.environ, BEOM_GRID_INIT="1"))
+        res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+        assert r.returncode == 0 and all(not k["bad"] and k["path"] == "fused" for k in res["ranks"]), res
+
+
 @pytest.mark.parametrize("overlap", ["1", "0"])
 def test_halo_overlap_variant_on_emulated_ranks(emu_so, overlap):
     """The default on several ranks: the G rows next to each neighbour first, their exchange while the rows

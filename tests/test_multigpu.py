@@ -56,19 +56,22 @@ def test_rendezvous_over_gloo():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,nsteps,fused", [("synthetic_basin", 12, 1), ("synthetic_basin", 9, 0), ("sill_exchange3D", 12, 1),
-                                               ("conservation", 12, 0),   # y-periodic: ring-closed exchange
-                                               ("conservation", 12, 1),   # ... and the fused step across the ring
-                                               ("unstable_jet", 12, 1),
-                                               ("soliton", 12, 0),        # x-periodic slabs
-                                               ("soliton", 12, 1),        # ... each a torus of its own: fused
-                                               ("rigid_lid_basin", 4, 0)])  # surf_pressure across the slabs (18 and 55 sweeps in steps 3, 4)
-def test_two_ranks_bit_exact(name, nsteps, fused):
+@pytest.mark.parametrize("name,nsteps,fused,how", [
+    ("synthetic_basin", 12, 1, ""), ("synthetic_basin", 9, 0, ""), ("sill_exchange3D", 12, 1, ""),
+    ("conservation", 12, 0, ""),      # y-periodic: ring-closed exchange
+    ("conservation", 12, 1, ""),      # ... and the fused step across the ring
+    ("unstable_jet", 12, 1, ""),
+    ("soliton", 12, 0, ""),           # x-periodic slabs
+    ("soliton", 12, 1, ""),           # ... each a torus of its own: fused
+    ("rigid_lid_basin", 4, 0, ""),    # surf_pressure across the slabs (18 and 55 sweeps in steps 3, 4)
+    ("synthetic_basin", 12, 1, "grids"),  # every rank initialised on the device from the raw files (beom_gpu_init_grids)
+    ("sill_exchange3D", 12, 1, "grids")])
+def test_two_ranks_bit_exact(name, nsteps, fused, how):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", str(29500 + os.getpid() % 400), os.path.join(ROOT, "tests", "mgpu_worker.py"), name, str(nsteps), str(fused)]
+           "--master-port", str(29500 + os.getpid() % 400), os.path.join(ROOT, "tests", "mgpu_worker.py"), name, str(nsteps), str(fused)] + ([how] if how else [])
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert r.stdout.count("bit-identical") == 2, r.stdout

@@ -44,7 +44,7 @@ def _split_top(s: str) -> list[str]:
 
 
 # kernels whose threads cooperate (shuffles, votes, barriers, mbarriers): launched through the SIMT emulator
-SIMT = {"kern", "k_open_rows", "k_conservation", "k_sum_partials", "k_surf_pressure", "k_rec_state", "k_rec_minmax", "k_pi_wave"}
+SIMT = {"kern", "k_open_rows", "k_conservation", "k_sum_partials", "k_surf_pressure", "k_rec_state", "k_rec_minmax", "k_pi_wave", "k_gi_row_counts", "k_gi_index"}
 
 
 def rewrite_launches(text: str) -> tuple[str, int]:

@@ -117,6 +117,18 @@ inline bool vote_all(bool p) {
     if (((part >> l) & 1u) && !w.buf[g & 1][l]) return false;
   return true;
 }
+inline unsigned vote_ballot(bool p) {
+  Warp &w = warp();
+  const unsigned g = w.gen;
+  unsigned part = 0;
+  for (int l = 0; l < 32; l++)
+    if (!w.done[l]) part |= 1u << l;
+  warp_collect(w, p ? 1u : 0u);
+  unsigned b = 0;
+  for (int l = 0; l < 32; l++)
+    if (((part >> l) & 1u) && w.buf[g & 1][l]) b |= 1u << l;
+  return b;
+}
 inline void syncwarp() { warp_collect(warp(), 0); }
 inline void syncthreads() {
   Warp &w = warp();
@@ -207,6 +219,14 @@ template <class T> inline T __shfl_xor_sync(unsigned, T v, int m) { return emu::
 template <class T> inline T __shfl_up_sync(unsigned, T v, int d) { return emu::shfl_idx(v, emu::warp().cur - d); }
 template <class T> inline T __shfl_down_sync(unsigned, T v, int d) { return emu::shfl_idx(v, emu::warp().cur + d); }
 inline bool __all_sync(unsigned, bool p) { return emu::vote_all(p); }
+inline unsigned __ballot_sync(unsigned, bool p) { return emu::vote_ballot(p); }
+inline int __popc(unsigned v) { return __builtin_popcount(v); }
+inline unsigned atomicOr(unsigned *p, unsigned v) { return __atomic_fetch_or(p, v, __ATOMIC_SEQ_CST); }
+inline int atomicMax(int *p, int v) {
+  int old = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+  while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {}
+  return old;
+}
 inline void __syncwarp() { if (emu::cur_warp) emu::syncwarp(); }
 inline void __syncthreads() { emu::syncthreads(); }
 // inter-warp / inter-CTA communication through global memory (the rigid-lid wavefront solver, rigid.cuh): warps are OS
