@@ -75,8 +75,8 @@ class Records(C.Structure):  # beom_records of include/beom_gpu.h
 
 
 class Grids(C.Structure):  # beom_grids of include/beom_gpu.h: the raw input files (float32), NULL = absent
-    _fields_ = [(k, C.POINTER(C.c_float)) for k in ("h_bo", "init", "nudg", "taus", "fcor", "hdot", "bodf")] + \
-               [("has_tide", C.c_int32), ("has_h_to", C.c_int32)]
+    _fields_ = [(k, C.POINTER(C.c_float)) for k in ("h_bo", "init", "nudg", "taus", "fcor", "hdot", "bodf", "tide")] + \
+               [("has_h_to", C.c_int32)]
 
 
 GPU_SYMBOLS = [

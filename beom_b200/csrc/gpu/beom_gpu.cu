@@ -829,7 +829,7 @@ static int init_grids_impl(const beom_params *par, const beom_grids *gr, const b
   else if (par->rgld > 0.5) why = "rigid lid";
   else if (par->variant != BEOM_VARIANT_STANDARD) why = "1d / 3d / plume variant";
   else if (par->topt > 0.5 || gr->has_h_to) why = "h_to.bin";
-  else if (gr->has_tide) why = "tide.bin";
+  else if (gr->tide && !gr->nudg) why = "tide.bin without nudg.bin";
   else if (par->rsta > 0.5) why = "restart";
   else if (gr->nudg && par->mcbc < 0.5) why = "sponge with the open-boundary copy (mcbc < 0.5)";
   if (why) {
@@ -888,7 +888,8 @@ static int init_grids_impl(const beom_params *par, const beom_grids *gr, const b
   for (int l = 0; l < nlay; l++) A.topl[l] = par->topl[l];
   const size_t gp = (size_t)(lm + 2) * (mm + 2);
   if ((rc = put(gr->h_bo, gp, &A.h_bo)) || (rc = put(gr->init, gp * nl * 3, &A.init)) || (rc = put(gr->nudg, gp * 3, &A.nudg)) ||
-      (rc = put(gr->taus, gp * 2, &A.taus)) || (rc = put(gr->fcor, gp, &A.fcor)) || (rc = put(gr->hdot, gp * nl, &A.hdot)))
+      (rc = put(gr->taus, gp * 2, &A.taus)) || (rc = put(gr->fcor, gp, &A.fcor)) || (rc = put(gr->hdot, gp * nl, &A.hdot)) ||
+      (rc = put(gr->tide, gp * 6, &A.tide)))
     return rc;
 
   // ---- index_grid_points (pm:567-764): points per row, their prefix sum, the depth extremes (pm:134-135)
@@ -988,6 +989,11 @@ static int init_grids_impl(const beom_params *par, const beom_grids *gr, const b
     if ((rc = dalloc(&tmp, pl * nl))) return rc;
     O.hdot = tmp;
   }
+  const double w_ti = gr->tide ? (double)gr->tide[0] : 0.0;  // tide(1,1,0,0,1) is the frequency (pm:951-964)
+  if (A.tide && w_ti != 0.0) {
+    if ((rc = dalloc(&tmp, pl * 6))) return rc;
+    O.tide = tmp;
+  }
   unsigned *d_any = nullptr, any = 0;
   if ((rc = dalloc(&d_any, (size_t)4))) return rc;
   O.any = d_any;
@@ -998,7 +1004,8 @@ static int init_grids_impl(const beom_params *par, const beom_grids *gr, const b
   CK(cudaGetLastError());
   D.has_nudg = (any & 2u) ? 1 : 0;
   if (D.has_nudg) { D.nudg = O.nudg; D.fnud = O.fnud; }
-  D.has_tide = 0;
+  D.has_tide = (O.tide && D.has_nudg) ? 1 : 0;
+  if (D.has_tide) D.tide = O.tide;
   D.has_hdot = (any & 8u) ? 1 : 0;
   if (D.has_hdot) D.hdot = O.hdot;
   g.any_taus = (any & 4u) != 0;
@@ -1056,7 +1063,7 @@ static int init_grids_impl(const beom_params *par, const beom_grids *gr, const b
   if (gr->bodf)
     for (size_t k = 0; k < (size_t)nlay * 2; k++) bodf[k] = (double)gr->bodf[k];
 
-  if ((rc = init_tail(invf, 0.0, gr->bodf ? bodf.data() : nullptr))) return rc;
+  if ((rc = init_tail(invf, w_ti, gr->bodf ? bodf.data() : nullptr))) return rc;
 
   // h_0.bin's content for the output records (pm:185-194)
   if ((rc = dalloc(&g.h0r4, (size_t)ndeg * nl))) return rc;

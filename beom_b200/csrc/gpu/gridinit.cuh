@@ -18,7 +18,7 @@ struct GridIn {
   int jlo, jhi;               // grid rows held (owned + halo rows, clipped to 0 .. mm+1)
   double hdry, flat;          // dry threshold; default depth cext**2/grav (private_mod.f95:119-121)
   const float *h_bo;          // raw files (device copies), Fortran order (0:lm+1, 0:mm+1, ...); null = absent
-  const float *init, *nudg, *taus, *fcor, *hdot;
+  const float *init, *nudg, *taus, *fcor, *hdot, *tide;
   double tauw[2], f0, dmax;
   double topl[BEOM_MAXLAY];
 };
@@ -147,6 +147,7 @@ struct GridOut {
   double *taus;                      // [2] or null
   double *fcor;                      // [1]
   double *hdot;                      // [nlay] or null
+  double *tide;                      // [3][2] (amplitude, phase of eta, u, v) or null
   unsigned *any;                     // bit 0: nudg live (> 1e-9), 1: nudg non-zero, 2: |taus| > 1e-7, 3: hdot non-zero
   int set_state;                     // rsta < 0.5: init.bin is the initial state too
 };
@@ -211,6 +212,10 @@ __global__ void k_gi_forcing(const __grid_constant__ GridIn A, const __grid_cons
       O.hdot[(size_t)l * pl + c] = hd;
       if (hd != 0.0) any |= 8u;
     }
+  }
+  if (A.tide && O.tide) {  // pm:951-964: tide(2, 1, 0:lm+1, 0:mm+1, 3), amplitude and phase de-interleaved into planes
+    for (int c3 = 0; c3 < 3; c3++)
+      for (int a = 0; a < 2; a++) O.tide[((size_t)c3 * 2 + a) * pl + c] = (double)A.tide[((size_t)c3 * gp + k0) * 2 + a];
   }
   if (any) atomicOr(O.any, any);
 }

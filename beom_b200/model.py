@@ -128,7 +128,7 @@ class GpuModel:
         if rc:
             raise RuntimeError("beom_gpu_init: %s" % _lib.gpu_error())
 
-    GRID_FILES = ("h_bo", "init", "nudg", "taus", "fcor", "hdot", "bodf")
+    GRID_FILES = ("h_bo", "init", "nudg", "taus", "fcor", "hdot", "bodf", "tide")
 
     @classmethod
     def from_grids(cls, params: Params, idir: str, options: Options | None = None):
@@ -149,7 +149,6 @@ class GpuModel:
                 a = np.memmap(path, dtype="<f4", mode="r")
                 keep.append(a)
                 setattr(gr, k, C.cast(a.ctypes.data, C.POINTER(C.c_float)))
-        gr.has_tide = int(os.path.exists(os.path.join(idir, "tide.bin")))
         gr.has_h_to = int(os.path.exists(os.path.join(idir, "h_to.bin")))
         rc = self.lib.beom_gpu_init_grids(C.byref(params), C.byref(gr), C.byref(self.opt))
         del keep

@@ -173,7 +173,7 @@ int beom_gpu_records_wait(beom_records *out);
  * beom_gpu_init + beom_gpu_upload_state for the cases it covers.  The arrays hold the files' contents as they are on disk
  * (little-endian float32, Fortran order, no record markers; NULL = file absent).  par carries the derived values of
  * shared_mod.f95 (dt, hsal, ...) and ndeg.  Returns 0, a negative error, or BEOM_GRIDS_UNSUPPORTED for what is initialised on
- * the host: periodic domains, the rigid lid, the 1d/3d/plume variants, tide.bin, h_to.bin, restarts, sponges with mcbc < 0.5. */
+ * the host: periodic domains, the rigid lid, the 1d/3d/plume variants, h_to.bin, restarts, sponges with mcbc < 0.5. */
 typedef struct beom_grids {
   const float *h_bo;   /* (0:lm+1, 0:mm+1) */
   const float *init;   /* (0:lm+1, 0:mm+1, nlay, 3) */
@@ -182,7 +182,8 @@ typedef struct beom_grids {
   const float *fcor;   /* (0:lm+1, 0:mm+1) */
   const float *hdot;   /* (0:lm+1, 0:mm+1, nlay) */
   const float *bodf;   /* (nlay, 2) */
-  int32_t has_tide, has_h_to;  /* files that exist but are not handled here */
+  const float *tide;   /* (2, 1, 0:lm+1, 0:mm+1, 3) */
+  int32_t has_h_to;    /* h_to.bin exists (not handled here) */
 } beom_grids;
 #define BEOM_GRIDS_UNSUPPORTED 1
 int beom_gpu_init_grids(const beom_params *par, const beom_grids *grids, const beom_gpu_options *opt);

@@ -21,11 +21,14 @@ COVERED = [
     ("sill_exchange2D", None, {}),
     ("carrier_beach", None, {}),                                           # one outcropping layer, sloping beach
     ("outcrop_seamount", None, {}),                                        # five layers, most of them grounded
+    ("wave_sponge", None, {}),                                             # sponges on four sides (mcbc = 1)
+    ("sill_exchange2Dtides", None, {}),                                    # tide.bin: amplitude / phase planes, w_ti
+    ("tide_ridge", None, {}),                                              # seven layers, tide.bin, dt_r ramp
     ("random_coast", None, {}),                                            # random coastline: every mask combination
     ("option_basin", dict(hdot=True, sponge=False, wind=True), {}),        # hdot.bin, island
     ("option_basin", dict(bodf=True, sponge=False, wind=False), {}),       # bodf.bin
 ]
-REFUSED = [("conservation", None, {}), ("soliton", None, {}), ("tide_ridge", None, {}), ("mixed_open_bc", None, {}),
+REFUSED = [("conservation", None, {}), ("soliton", None, {}), ("baines_ridge", None, {}), ("mixed_open_bc", None, {}),
            ("lock_exchange", None, {"rgld": "1."})]
 
 
@@ -78,7 +81,7 @@ def test_device_side_initialisation_equals_read_input_data(case_factory, name, k
     assert gh.fused_variant == variant
     gh.close()
     for nm, a, b in zip(("hlay", "u", "v"), got, want):
-        assert np.array_equal(a, b), nm
+        assert np.array_equal(a, b), nm  # (tides: the same libm cos on both sides, so also exact)
     assert np.abs(got[1]).max() + np.abs(got[2]).max() > 0 or name in ("carrier_beach",)
 
 
