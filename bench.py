@@ -275,6 +275,7 @@ def main():
             gm = model.GpuModel.from_grids(params, idir, opt)
         if gm is not None:
             init_how = "device (beom_gpu_init_grids)"
+            t_init = time.perf_counter() - t0
             first, count, own_first, own_count = gm.point_range()
             if world > 1:
                 gm.set_window(first, count)
@@ -286,7 +287,8 @@ def main():
             sj = gm.download_subc()[1]
             own_rows = np.array(sj[own_first - first:own_first - first + own_count], copy=True)
             first = w_first
-            log("[rank %d] beom_gpu_init_grids (device-side read_input_data) + initial state to the host: %.1f s" % (rank, time.perf_counter() - t0))
+            log("[rank %d] beom_gpu_init_grids (device-side read_input_data): %.1f s; page-locked host arrays + initial state to the host "
+                "(for the e2e leg): %.1f s" % (rank, t_init, time.perf_counter() - t0 - t_init))
         else:
             init_how = "host (read_input_data + beom_gpu_init)"
             # read_input_data holds ~25 GB of host arrays for this grid: at most four ranks do it at a time (host memory permitting)
