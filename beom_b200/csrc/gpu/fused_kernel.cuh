@@ -236,7 +236,8 @@ __host__ __device__ inline SmemPlan smem_plan(int nlay, int groups, int n_all, i
 
 // FLAVOR only distinguishes the symbol of the copy compiled with FMA contraction (fused_inst_lean*_fma.cu, BEOM_FMA=1)
 template <bool UFIRST, bool VISC, int NL, int FEAT, int GROUPS, int FLAVOR = 0, bool G0 = false>
-__global__ void __launch_bounds__(kMaxWarps * 32, 1)
+// (a specialised instantiation knows its block size: fewer than 16 warps leave each thread more than 128 registers)
+__global__ void __launch_bounds__((FEAT >= 0 && NL > 0 && GROUPS > 0) ? NL * GROUPS * 32 : kMaxWarps * 32, 1)
 k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const __grid_constant__ StreamTab T,
              const uint8_t *__restrict__ open, const unsigned *__restrict__ open4, int open4_words, int groups_rt, int rows_per_chunk,
              int wind_layers) {
