@@ -27,7 +27,7 @@ struct SpecEntry {
 };
 const SpecEntry kSpec[] = {
     {0, 1, true, kMaxWarps / 1, fused_launch_lean1}, {0, 2, true, kMaxWarps / 2, fused_launch_lean2},
-    {0, 3, true, kMaxWarps / 3, fused_launch_lean3}, {0, 4, true, kMaxWarps / 4, fused_launch_lean4},
+    {0, 3, true, kMaxWarps / 3, fused_launch_lean3}, {0, 4, true, BEOM_LEAN4_GROUPS, fused_launch_lean4},
     {FB_NUDG | FB_OCRP, 2, true, 7, fused_launch_spec_3_2_1},            // sill_exchange3D / 2D
     {FB_NUDG | FB_OCRP, 4, true, 3, fused_launch_spec_3_4_1},            // bench.py --workload sill_like
     {FB_NUDG, 2, true, 7, fused_launch_spec_1_2_1}, {FB_NUDG, 4, true, 3, fused_launch_spec_1_4_1},

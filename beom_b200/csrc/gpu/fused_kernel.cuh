@@ -63,6 +63,9 @@ constexpr int kMaxLay = 8;            // layers per CTA (shared-memory exchange,
 #ifndef BEOM_FUSED_WARPS
 #define BEOM_FUSED_WARPS 16
 #endif
+#ifndef BEOM_LEAN4_GROUPS
+#define BEOM_LEAN4_GROUPS (BEOM_FUSED_WARPS / 4)  // column groups of the 4-layer bare step (experiment: 3 = 12 warps at 168 registers)
+#endif
 constexpr int kMaxWarps = BEOM_FUSED_WARPS;  // warps per CTA: 16 -> <= 128 registers per thread, 12 -> <= 168
 constexpr int kPad = 4;               // staged columns on each side of a CTA's result columns (16-byte aligned rows)
 __host__ __device__ constexpr int seg_doubles(int groups) { return groups * kUse + 2 * kPad; }  // one staged row segment
