@@ -81,7 +81,7 @@ class Grids(C.Structure):  # beom_grids of include/beom_gpu.h: the raw input fil
 
 GPU_SYMBOLS = [
     "beom_gpu_version", "beom_gpu_abi_version", "beom_gpu_last_error", "beom_gpu_default_options",
-    "beom_gpu_init", "beom_gpu_init_grids", "beom_gpu_download_subc", "beom_gpu_debug_static", "beom_gpu_upload_state", "beom_gpu_stress", "beom_gpu_step", "beom_gpu_advance",
+    "beom_gpu_init", "beom_gpu_init_grids", "beom_gpu_download_subc", "beom_gpu_download_grid_files", "beom_gpu_debug_static", "beom_gpu_upload_state", "beom_gpu_stress", "beom_gpu_step", "beom_gpu_advance",
     "beom_gpu_download_state", "beom_gpu_download_aux", "beom_gpu_download_diag", "beom_gpu_download_pi_s", "beom_gpu_pi_iterations",
     "beom_gpu_diagnostics", "beom_gpu_diagnostics_all", "beom_gpu_set_rest_thickness", "beom_gpu_records_begin",
     "beom_gpu_records_wait", "beom_gpu_sync", "beom_gpu_mark", "beom_gpu_elapsed_ms", "beom_gpu_launch_count",

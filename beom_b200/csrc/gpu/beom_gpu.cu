@@ -1102,6 +1102,27 @@ extern "C" int beom_gpu_download_subc(int32_t *si, int32_t *sj) {
   return 0;
 }
 
+// grid.bin's records (posc, mk_n, mk_u, mk_v, mkpi: 5 x ndeg int32, pm:732-749) and h_0.bin's (float32 [nlay][ndeg], pm:185-194)
+// for a host driver that initialised on the device (one rank)
+extern "C" int beom_gpu_download_grid_files(int32_t *grid5, float *h_0_r4) {
+  if (!g.ready) return fail(-20, "beom_gpu_download_grid_files: not initialised");
+  if (g.nranks > 1 || g.p_lo != 1 || g.p_hi != g.ndeg) return fail(-27, "beom_gpu_download_grid_files: one rank holding every point only");
+  const int n = g.ndeg;
+  if (grid5) {
+    int *d = nullptr, rc;
+    if ((rc = dalloc(&d, (size_t)5 * n, false))) return rc;
+    k_gi_grid_record<<<(unsigned)((n + 255) / 256), 256, 0, g.stream>>>(g.d_cell, g.flags, 1, n, g.NX, g.D.j_off, g.lm, d);
+    g.launches++;
+    CK(cudaMemcpyAsync(grid5, d, sizeof(int) * 5 * (size_t)n, cudaMemcpyDeviceToHost, g.stream));
+  }
+  if (h_0_r4) {
+    if (!g.h0r4) return fail(-22, "beom_gpu_download_grid_files: no rest thickness on the device");
+    CK(cudaMemcpyAsync(h_0_r4, g.h0r4, sizeof(float) * (size_t)n * g.nlay, cudaMemcpyDeviceToHost, g.stream));
+  }
+  CK(cudaStreamSynchronize(g.stream));
+  return 0;
+}
+
 // A static plane in the reference's vector layout (tests: the device-side initialisation against read_input_data):
 // name = fcor | h_th | nudg | fnud | taus | hdot | h_0 | flags (the flag byte as a double), index = plane within the array
 extern "C" int beom_gpu_debug_static(const char *name, int index, double *out) {

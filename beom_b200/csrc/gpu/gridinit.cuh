@@ -236,5 +236,20 @@ __global__ void k_gi_subc(const int *__restrict__ cell, int p0, int n, int NX, i
   sj[k] = cc >= 0 ? cc / NX - j_off : 0;
 }
 
+// grid.bin's five records (pm:732-749): posc = i + 1 + j (lm + 2) and the masks mk_n, mk_u, mk_v, mkpi as integers, per vector point
+__global__ void k_gi_grid_record(const int *__restrict__ cell, const uint8_t *__restrict__ flags, int p0, int n, int NX, int j_off, int lm,
+                                 int *__restrict__ out /* [5][n] */) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int cc = cell[p0 + k];
+  const uint8_t f = cc >= 0 ? flags[cc] : 0;
+  const int i = cc >= 0 ? cc % NX - GX0 : 0, j = cc >= 0 ? cc / NX - j_off : 0;
+  out[k] = i + 1 + j * (lm + 2);
+  out[n + k] = (f & F_N) ? 1 : 0;
+  out[2 * n + k] = (f & F_U) ? 1 : 0;
+  out[3 * n + k] = (f & F_V) ? 1 : 0;
+  out[4 * n + k] = (f & F_PI) ? 1 : 0;
+}
+
 }  // namespace beom
 #endif

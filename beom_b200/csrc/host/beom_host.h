@@ -31,6 +31,11 @@ int beom_host_last_error(char *buf, int len);
 /* read_input_data (private_mod.f95:105-250) up to and including save_metadata; writes grid.bin,
  * h_0.bin and param_basin.txt into odir when odir is non-empty.  Does NOT touch the GPU. */
 beom_host *beom_host_create(const beom_params *par, const char *idir, const char *odir, const char *desc);
+/* The same with read_input_data's grid-shaped work done on the device (beom_gpu_init_grids, include/beom_gpu.h): the input
+ * files are memory-mapped and handed to the GPU library, which is left initialised with the initial state in place; the host
+ * object keeps no big array (beom_host_array returns NULL for them).  Cases the device path does not cover (periodic domains,
+ * the rigid lid, ...) fall back to beom_host_create.  beom_host_run works on either kind. */
+beom_host *beom_host_create_on_device(const beom_params *par, const char *idir, const char *odir, const char *desc, const beom_gpu_options *opt);
 void beom_host_destroy(beom_host *h);
 
 /* Reference-layout arrays (see include/beom_gpu.h).  Names: neig subc posc segm (int32);

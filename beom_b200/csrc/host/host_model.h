@@ -45,6 +45,10 @@ struct beom_host {
   bool out_init = false;
   int irec = 0;
   std::vector<float> h_0_r4;  // h_0.bin as written (private_mod.f95:185-194), read back by write_array
+  // read_input_data was done on the device (beom_gpu_init_grids): the big vectors above stay empty, the GPU library is
+  // initialised and holds the initial state already
+  bool device_init = false;
+  std::vector<int32_t> grid5;  // grid.bin's five records as the device made them
 };
 
 void beom_host_set_error(const std::string &s);

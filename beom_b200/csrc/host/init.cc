@@ -540,6 +540,103 @@ beom_host *beom_host_create(const beom_params *par, const char *idir, const char
   return nullptr;
 }
 
+namespace {
+// a read-only mapping of <idir><keyw>.bin, or {nullptr, 0} if the file does not exist (private_mod.f95:775-776)
+struct Mapped {
+  const float *p = nullptr;
+  size_t bytes = 0;
+  void *base = nullptr;
+};
+}  // namespace
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+namespace {
+Mapped map_file(const std::string &dir, const char *keyw, size_t n) {
+  Mapped m;
+  const std::string path = dir + keyw + ".bin";
+  const int fd = ::open(path.c_str(), O_RDONLY);
+  if (fd < 0) return m;
+  struct stat st;
+  if (::fstat(fd, &st) != 0 || (size_t)st.st_size < n * sizeof(float)) {
+    ::close(fd);
+    throw Fail{" could not open/read file " + std::string(keyw) + ".bin from directory " + dir};
+  }
+  void *b = ::mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+  ::close(fd);
+  if (b == MAP_FAILED) throw Fail{" could not map file " + std::string(keyw) + ".bin from directory " + dir};
+  m.base = b; m.bytes = (size_t)st.st_size; m.p = static_cast<const float *>(b);
+  return m;
+}
+}  // namespace
+
+beom_host *beom_host_create_on_device(const beom_params *par, const char *idir, const char *odir, const char *desc, const beom_gpu_options *opt) {
+  beom_host *h = new beom_host();
+  std::vector<Mapped> maps;
+  auto unmap = [&]() { for (auto &m : maps) if (m.base) ::munmap(m.base, m.bytes); maps.clear(); };
+  try {
+    h->p = *par;
+    h->lm = par->lm; h->mm = par->mm; h->nlay = par->nlay; h->ndeg = par->ndeg;
+    h->nd1 = (size_t)par->ndeg + 1;
+    auto slash = [](const char *s) {
+      std::string r = s ? s : "";
+      if (!r.empty() && r.back() != '/') r.push_back('/');
+      return r;
+    };
+    h->idir = slash(idir);
+    h->odir = slash(odir);
+    h->desc = desc ? desc : "";
+    if (par->nlay < 1 || par->nlay > BEOM_MAXLAY) throw Fail{" nlay must be within 1..16."};
+    check_consistency_options(h->p);
+    const size_t gp = (size_t)(h->lm + 2) * (h->mm + 2), nl = (size_t)h->nlay;
+    beom_grids gr;
+    std::memset(&gr, 0, sizeof gr);
+    auto get = [&](const char *k, size_t n) { maps.push_back(map_file(h->idir, k, n)); return maps.back().p; };
+    gr.h_bo = get("h_bo", gp); gr.init = get("init", gp * nl * 3); gr.nudg = get("nudg", gp * 3); gr.taus = get("taus", gp * 2);
+    gr.fcor = get("fcor", gp); gr.hdot = get("hdot", gp * nl); gr.bodf = get("bodf", nl * 2); gr.tide = get("tide", gp * 6);
+    {
+      struct stat st;
+      gr.has_h_to = ::stat((h->idir + "h_to.bin").c_str(), &st) == 0;
+    }
+    const int rc = beom_gpu_init_grids(&h->p, &gr, opt);
+    unmap();
+    if (rc == BEOM_GRIDS_UNSUPPORTED) {  // the host path serves it
+      delete h;
+      return beom_host_create(par, idir, odir, desc);
+    }
+    if (rc) {
+      char b[1024];
+      beom_gpu_last_error(b, sizeof b);
+      throw Fail{std::string(" ") + b};
+    }
+    h->device_init = true;
+    const double dtd8 = h->p.dt / 24.0 / 3600.0;  // pm:1853-1856
+    h->nstp = (int)nint(h->p.dt_s / dtd8);
+    h->notp = std::max((int)nint(h->p.dt_o / dtd8), 1);
+    h->n_3d = std::max((int)nint(h->p.dt3d / dtd8), 1);
+    if (!h->odir.empty()) {
+      h->grid5.resize((size_t)5 * h->ndeg);
+      h->h_0_r4.resize((size_t)h->ndeg * nl);
+      if (beom_gpu_download_grid_files(h->grid5.data(), h->h_0_r4.data())) {
+        char b[1024];
+        beom_gpu_last_error(b, sizeof b);
+        throw Fail{std::string(" ") + b};
+      }
+      if (!beom_host_write_grid_files(h)) throw Fail{" could not write grid.bin / h_0.bin into " + h->odir};
+      if (!beom_host_save_metadata(h)) throw Fail{" could not write param_basin.txt into " + h->odir};
+    }
+    return h;
+  } catch (const Fail &e) {
+    beom_host_set_error("In main, in subroutine read_input_data," + e.msg);
+  } catch (const std::exception &e) {
+    beom_host_set_error(std::string("In main, in subroutine read_input_data, ") + e.what());
+  }
+  unmap();
+  delete h;
+  return nullptr;
+}
+
 void beom_host_destroy(beom_host *h) { delete h; }
 
 double *beom_host_array(beom_host *h, const char *name) {

@@ -67,8 +67,13 @@ bool beom_host_write_grid_files(beom_host *h) {
       for (size_t p = 0; p < nd; p++) rec[p] = (int32_t)std::lround(m[p + 1]);
       return std::fwrite(rec.data(), 4, nd, f) == nd;
     };
-    bool ok = std::fwrite(h->posc.data() + 1, 4, nd, f) == nd;
-    ok = ok && put(h->mk_n.data()) && put(h->mk_u.data()) && put(h->mk_v.data()) && put(h->mkpi.data());
+    bool ok;
+    if (h->device_init) {  // the five records as the device made them (beom_gpu_download_grid_files)
+      ok = std::fwrite(h->grid5.data(), 4, 5 * nd, f) == 5 * nd;
+    } else {
+      ok = std::fwrite(h->posc.data() + 1, 4, nd, f) == nd;
+      ok = ok && put(h->mk_n.data()) && put(h->mk_u.data()) && put(h->mk_v.data()) && put(h->mkpi.data());
+    }
     std::fclose(f);
     if (!ok) return false;
   }

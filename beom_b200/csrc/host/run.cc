@@ -46,17 +46,22 @@ int begin_outputs(beom_host *h, double ctim, Pending &pend) {
 
 extern "C" int beom_host_run(beom_host *h, const beom_gpu_options *opt, int max_steps) {
   const beom_params &P = h->p;
-  beom_fields fld;
-  beom_host_fields(h, &fld);
-  int rc = beom_gpu_init(&P, &fld, opt);
-  if (rc) return gpu_fail("beom_gpu_init", rc);
+  int rc = 0;
+  if (!h->device_init) {
+    beom_fields fld;
+    beom_host_fields(h, &fld);
+    rc = beom_gpu_init(&P, &fld, opt);
+    if (rc) return gpu_fail("beom_gpu_init", rc);
+  } else {
+    std::printf(" read_input_data: on the device (beom_gpu_init_grids)\n");
+  }
 
   std::printf(" lm = %d\n mm = %d\n", h->lm, h->mm);  // pm:233-234
   if (P.rsta > 0.5) {                                  // pm:236-243
     if ((rc = beom_host_read_restart(h))) return rc;
     std::printf(" *** Restarting from record number %d at time = %.15g\n", h->irec - 1, h->tres);
   }
-  if ((rc = beom_gpu_upload_state(h->hlay.data(), h->u.data(), h->v.data()))) return gpu_fail("beom_gpu_upload_state", rc);
+  if (!h->device_init && (rc = beom_gpu_upload_state(h->hlay.data(), h->u.data(), h->v.data()))) return gpu_fail("beom_gpu_upload_state", rc);
   Pending pend;
   if (!h->odir.empty() && (rc = beom_gpu_set_rest_thickness(h->h_0_r4.data()))) return gpu_fail("beom_gpu_set_rest_thickness", rc);
   if (P.rsta < 0.5 && !h->odir.empty() && (rc = begin_outputs(h, 0.0, pend))) return rc;
@@ -90,6 +95,9 @@ extern "C" int beom_host_run(beom_host *h, const beom_gpu_options *opt, int max_
   }
   if ((rc = finish_outputs(h, pend))) return rc;
   if ((rc = beom_gpu_sync())) return gpu_fail("beom_gpu_sync", rc);
+  if (h->device_init) {  // the final state for callers that look at the host arrays
+    h->hlay.resize(h->nd1 * (size_t)h->nlay); h->u.resize(h->hlay.size()); h->v.resize(h->hlay.size());
+  }
   if ((rc = beom_gpu_download_state(h->hlay.data(), h->u.data(), h->v.data()))) return gpu_fail("beom_gpu_download_state", rc);
   return 0;
 }

@@ -189,6 +189,9 @@ typedef struct beom_grids {
 int beom_gpu_init_grids(const beom_params *par, const beom_grids *grids, const beom_gpu_options *opt);
 /* Grid coordinates (i, j) of the vector points this rank holds (beom_gpu_point_range: first .. first + count - 1). */
 int beom_gpu_download_subc(int32_t *si, int32_t *sj);
+/* After beom_gpu_init_grids on one rank: grid.bin's five records (posc, mk_n, mk_u, mk_v, mkpi; 5 x ndeg int32, private_mod.f95:732-749)
+ * and h_0.bin's content (float32 [nlay][ndeg], :185-194), so that a host driver can write its metadata files; either may be NULL. */
+int beom_gpu_download_grid_files(int32_t *grid5, float *h_0_r4);
 /* A static plane in the reference's vector layout (0:ndeg), for checks: name = "fcor", "h_th", "nudg", "fnud", "taus", "hdot",
  * "h_0", "flags" (the flag byte: masks mk_n = 1, mk_u = 2, mk_v = 4, mkpe = 8, mkpi = 16, vector point = 32); index = plane. */
 int beom_gpu_debug_static(const char *name, int index, double *out);

@@ -241,6 +241,34 @@ def test_the_executable_end_to_end_on_the_emulation(emu_so, tmp_path, name, dt_o
             assert same.all(), (name, var, k, int((~same).sum()))
 
 
+@pytest.mark.parametrize("name", ["sill_exchange3D", "stommel1948", "sill_exchange2Dtides"])
+def test_the_executable_initialised_on_the_device_writes_the_same_files(emu_so, tmp_path, name):
+    """beom_run initialises on the device where beom_gpu_init_grids covers the case (csrc/host/init.cc: beom_host_create_on_device):
+    every file it leaves behind -- grid.bin, h_0.bin, param_basin.txt, the records, time.txt -- must be byte for byte what the run
+    initialised by the host's read_input_data (--host-init) writes."""
+    import re
+    from beom_b200 import cases
+    from tests.conftest import SMALL
+    outs = {}
+    for how in ("device", "host"):
+        d = tmp_path / how
+        d.mkdir()
+        c = cases.CASES[name](**SMALL.get(name, {}))
+        c.params_text = re.sub(r"diag       = \S+", "diag       = 1.", c.params_text)
+        blk = c.write(str(d))
+        exe = os.path.join(ROOT, "beom_b200", "lib", "beom_run")
+        r = subprocess.run([exe, blk, "--steps", "40"] + (["--host-init"] if how == "host" else []), capture_output=True, text=True, timeout=600,
+                           env=dict(os.environ, LD_PRELOAD=emu_so), cwd=str(d))
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        assert ("read_input_data: on the device" in r.stdout) == (how == "device"), r.stdout[:600]
+        outs[how] = {f: open(os.path.join(d, f), "rb").read() for f in sorted(os.listdir(d))
+                     if f in ("grid.bin", "h_0.bin", "eta_.bin", "u___.bin", "v___.bin", "pvor.bin", "mont.bin", "v_cc.bin", "time.txt")}
+        assert "grid.bin" in outs[how] and "eta_.bin" in outs[how] and len(outs[how]["eta_.bin"]) > 0
+    assert outs["device"].keys() == outs["host"].keys()
+    for f in outs["host"]:
+        assert outs["device"][f] == outs["host"][f], f
+
+
 def test_restart_continues_the_record_files_on_the_emulation(emu_so, tmp_path):
     """rsta = 1 (private_mod.f95:236-243, 1299-1420): a second beom_run picks the state up from the last float32 record,
     keeps counting time from there and appends its records.  The oracle, started from the same float32-rounded state,
