@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <initializer_list>
 #include <string>
 #include <vector>
@@ -20,6 +21,7 @@
 #include "diag.cuh"
 #include "rigid.cuh"
 #include "gridinit.cuh"
+#include "grid_index.h"
 #include "layout.h"
 #include "orphans.h"
 
@@ -484,26 +486,41 @@ static int init_prologue(const beom_params *par, const beom_gpu_options *opt_in,
 }
 static int init_tail(double invf, double w_ti, const double *bodf);
 
-static int init_impl(const beom_params *par, const beom_fields *fld, const beom_gpu_options *opt_in) {
-  if (!par || !fld) return fail(-1, "beom_gpu_init: null argument");
-  if (!fld->neig || !fld->subc || !fld->mk_u || !fld->mk_v || !fld->mk_n || !fld->mkpe || !fld->mkpi || !fld->fcor || !fld->h_th)
-    return fail(-2, "beom_gpu_init: a required static field is NULL");
-  if (fld->nudg && !fld->fnud) return fail(-4, "beom_gpu_init: nudg given without fnud");
-  cudaDeviceProp prop = cudaDeviceProp();
-  {
-    const int rc0 = init_prologue(par, opt_in, &prop);
-    if (rc0) return rc0;
+// open-boundary segments as dense cells (private_mod.f95:1060-1240; segm is [18][nseg]: columns 1-3 the face point and its (i, j),
+// 4 / 5 zonal / meridional, 10-12 the wet cell, 13-15 the interior normal-velocity point, 16-18 the interior cell); cell_of(p, i, j) = the
+// dense cell of vector point p at grid point (i, j), or < 0.  A rank keeps the segments whose wet or face point lies in its rows.
+static int build_segments(const int32_t *segm, int nseg, bool flag_nudging, const std::function<int(int, int, int)> &cell_of) {
+  g.nseg = 0;
+  g.obc_any = segm && nseg > 0 && flag_nudging;
+  if (!g.obc_any) return 0;
+  std::vector<SegDev> segs;
+  for (int s = 0; s < nseg; s++) {
+    auto col = [&](int cidx) { return segm[(size_t)(cidx - 1) * nseg + s]; };
+    if (col(10) < 1 || col(12) < g.j0 || col(12) > g.j1)
+      if (col(1) < 1 || col(3) < g.j0 || col(3) > g.j1) continue;
+    SegDev sd;
+    sd.zonal = col(4); sd.merid = col(5);
+    sd.c_face = cell_of(col(1), col(2), col(3)); sd.c_wet = cell_of(col(10), col(11), col(12));
+    sd.c_norm = cell_of(col(13), col(14), col(15)); sd.c_int = cell_of(col(16), col(17), col(18));
+    if (sd.c_face < 0 || sd.c_wet < 0 || sd.c_norm < 0 || sd.c_int < 0) {
+      if (g.P.mcbc < 0.5) return fail(-12, "beom_gpu_init: open-boundary segment %d touches a cell outside the grid", s + 1);
+      continue;
+    }
+    segs.push_back(sd);
   }
+  g.nseg = (int)segs.size();
+  if (g.nseg) {
+    int rc;
+    if ((rc = dalloc(&g.d_seg, (size_t)g.nseg, false))) return rc;
+    CK(cudaMemcpy(g.d_seg, segs.data(), sizeof(SegDev) * g.nseg, cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
 
-  const int lm = g.lm, mm = g.mm, nlay = g.nlay, ndeg = g.ndeg;
-  const size_t nd1 = (size_t)ndeg + 1;
-  const int32_t *sj = fld->subc + nd1;
-
-  // dense layout of this rank: slab rows, cell map, flags, periodic images, duplicates (layout.h)
-  Layout lay;
-  if (analyse_layout(lay, lm, mm, ndeg, par->xper > 0.5, par->yper > 0.5, g.rank, g.nranks, fld->subc, fld->neig, fld->mk_n, fld->mk_u,
-                     fld->mk_v, fld->mkpe, fld->mkpi))
-    return fail(lay.rc, "%s", lay.error.c_str());
+// what analyse_layout (layout.h) found becomes this rank's context: slab rows, plane geometry, cell map, flags, mirror lists, duplicates
+static int adopt_layout(const Layout &lay, const int32_t *sj) {
+  const int nlay = g.nlay;
+  const size_t nd1 = (size_t)g.ndeg + 1;
   g.j0 = lay.j0; g.j1 = lay.j1;
   g.NX = lay.NX; g.NY = lay.NY; g.plane = lay.plane;
   g.p_lo = lay.p_lo; g.p_hi = lay.p_hi;
@@ -515,7 +532,6 @@ static int init_impl(const beom_params *par, const beom_fields *fld, const beom_
   g.own_first = 0; g.own_last = -1;
   for (int p = g.p_lo; p <= g.p_hi; p++)
     if (sj[p] >= g.j0 && sj[p] <= g.j1) { if (!g.own_first) g.own_first = p; g.own_last = p; }
-  const int j_off = lay.j_off;  // Y = j + j_off
   const std::vector<uint8_t> &hflags = lay.flags;
   int rc;
   g.nmir = (int)lay.mdst.size();
@@ -536,6 +552,32 @@ static int init_impl(const beom_params *par, const beom_fields *fld, const beom_
   const int nloc = g.p_hi - g.p_lo + 1;
   g.stage_elems = (size_t)nloc * nlay * 3;
   if ((rc = dalloc(&g.stage, g.stage_elems, false))) return rc;
+  return 0;
+}
+
+static int init_impl(const beom_params *par, const beom_fields *fld, const beom_gpu_options *opt_in) {
+  if (!par || !fld) return fail(-1, "beom_gpu_init: null argument");
+  if (!fld->neig || !fld->subc || !fld->mk_u || !fld->mk_v || !fld->mk_n || !fld->mkpe || !fld->mkpi || !fld->fcor || !fld->h_th)
+    return fail(-2, "beom_gpu_init: a required static field is NULL");
+  if (fld->nudg && !fld->fnud) return fail(-4, "beom_gpu_init: nudg given without fnud");
+  cudaDeviceProp prop = cudaDeviceProp();
+  {
+    const int rc0 = init_prologue(par, opt_in, &prop);
+    if (rc0) return rc0;
+  }
+
+  const int lm = g.lm, mm = g.mm, nlay = g.nlay, ndeg = g.ndeg;
+  const size_t nd1 = (size_t)ndeg + 1;
+  const int32_t *sj = fld->subc + nd1;
+
+  // dense layout of this rank: slab rows, cell map, flags, periodic images, duplicates (layout.h)
+  Layout lay;
+  if (analyse_layout(lay, lm, mm, ndeg, par->xper > 0.5, par->yper > 0.5, g.rank, g.nranks, fld->subc, fld->neig, fld->mk_n, fld->mk_u,
+                     fld->mk_v, fld->mkpe, fld->mkpi))
+    return fail(lay.rc, "%s", lay.error.c_str());
+  int rc;
+  if ((rc = adopt_layout(lay, sj))) return rc;
+  const int j_off = lay.j_off;  // Y = j + j_off
 
   // ---- Dev template ----
   Dev &D = g.D;
@@ -694,34 +736,8 @@ static int init_impl(const beom_params *par, const beom_fields *fld, const beom_
     }
   }
 
-  // open-boundary segments as dense cells (private_mod.f95:1060-1240, columns 1,4,5,10,13,16)
-  g.nseg = 0;
-  g.obc_any = fld->segm && fld->nseg > 0 && fld->flag_nudging;
-  if (fld->segm && fld->nseg > 0 && fld->flag_nudging) {
-    std::vector<SegDev> segs;
-    for (int s = 0; s < fld->nseg; s++) {
-      auto col = [&](int cidx) { return fld->segm[(size_t)(cidx - 1) * fld->nseg + s]; };
-      const int pw = col(10);
-      if (pw < 1 || sj[pw] < g.j0 || sj[pw] > g.j1) {
-        const int pf = col(1);
-        if (pf < 1 || sj[pf] < g.j0 || sj[pf] > g.j1) continue;
-      }
-      SegDev sd;
-      sd.zonal = col(4); sd.merid = col(5);
-      auto cell = [&](int p) { return (p >= 1 && p <= ndeg) ? g.cell_of_point[p] : -1; };
-      sd.c_face = cell(col(1)); sd.c_wet = cell(col(10)); sd.c_norm = cell(col(13)); sd.c_int = cell(col(16));
-      if (sd.c_face < 0 || sd.c_wet < 0 || sd.c_norm < 0 || sd.c_int < 0) {
-        if (par->mcbc < 0.5) return fail(-12, "beom_gpu_init: open-boundary segment %d touches a cell outside the grid", s + 1);
-        continue;
-      }
-      segs.push_back(sd);
-    }
-    g.nseg = (int)segs.size();
-    if (g.nseg) {
-      if ((rc = dalloc(&g.d_seg, (size_t)g.nseg, false))) return rc;
-      CK(cudaMemcpy(g.d_seg, segs.data(), sizeof(SegDev) * g.nseg, cudaMemcpyHostToDevice));
-    }
-  }
+  rc = build_segments(fld->segm, fld->nseg, fld->flag_nudging != 0, [&](int p, int, int) { return (p >= 1 && p <= ndeg) ? g.cell_of_point[p] : -1; });
+  if (rc) return rc;
 
   return init_tail(fld->invf, fld->w_ti, fld->bodf);
 }
@@ -818,20 +834,18 @@ int download_planes_fwd(double *dst, const double *dense, int nplanes);
 // beom_gpu_init_grids: read_input_data's grid-shaped work on the device (gridinit.cuh).  The caller hands over the raw
 // contents of the input files; masks, vector numbering, rest thickness, relaxation targets, forcing planes and the initial
 // state are built straight in the dense layout of this rank, with the reference's arithmetic.  Returns
-// BEOM_GRIDS_UNSUPPORTED (and says why in the error string) for what still needs the host path: periodic domains, the rigid
-// lid, the 1d/3d/plume variants, tides, h_to, restarts, and sponges with the open-boundary copy switched on (mcbc < 0.5: the
-// segment table of index_boundary_points is built on the host).
+// BEOM_GRIDS_UNSUPPORTED (and says why in the error string) for what still needs the host path: the rigid lid, the 1d/3d/plume
+// variants, h_to, restarts.  Periodic aliases, the layout analysis and the open-boundary segment table are host work here too
+// (grid_index.h, layout.h), from the depth grid; everything plane-shaped is device work.
 // ---------------------------------------------------------------------------------------------------------------------
 static int init_grids_impl(const beom_params *par, const beom_grids *gr, const beom_gpu_options *opt_in) {
   if (!par || !gr) return fail(-1, "beom_gpu_init_grids: null argument");
   const char *why = nullptr;
-  if (par->xper > 0.5 || par->yper > 0.5) why = "periodic domain";
-  else if (par->rgld > 0.5) why = "rigid lid";
+  if (par->rgld > 0.5) why = "rigid lid";
   else if (par->variant != BEOM_VARIANT_STANDARD) why = "1d / 3d / plume variant";
   else if (par->topt > 0.5 || gr->has_h_to) why = "h_to.bin";
   else if (gr->tide && !gr->nudg) why = "tide.bin without nudg.bin";
   else if (par->rsta > 0.5) why = "restart";
-  else if (gr->nudg && par->mcbc < 0.5) why = "sponge with the open-boundary copy (mcbc < 0.5)";
   if (why) {
     fail(BEOM_GRIDS_UNSUPPORTED, "beom_gpu_init_grids: %s is initialised on the host (read_input_data + beom_gpu_init)", why);
     return BEOM_GRIDS_UNSUPPORTED;
@@ -842,25 +856,55 @@ static int init_grids_impl(const beom_params *par, const beom_grids *gr, const b
   const int lm = g.lm, mm = g.mm, nlay = g.nlay, ndeg = g.ndeg;
   const size_t nd1 = (size_t)ndeg + 1, nl = (size_t)nlay;
 
-  // y-slab and dense layout of this rank: the same rules as analyse_layout (layout.h) on a non-periodic domain
-  {
-    const int rows = mm + 1, base = rows / g.nranks, rem = rows % g.nranks;
-    g.j0 = 1 + g.rank * base + std::min(g.rank, rem);
-    g.j1 = g.j0 + base + (g.rank < rem ? 1 : 0) - 1;
-    if (g.j1 < g.j0) return fail(-5, "beom_gpu_init: more ranks than grid rows");
+  const bool periodic = par->xper > 0.5 || par->yper > 0.5;
+  const double flat_depth = (par->cext * par->cext) / par->grav;
+  auto host_depth = [&](int i, int j) -> double {  // the depth of cell (i, j) as read_input_data sees it (pm:119-121, 827-839)
+    if (i < 1 || i > lm || j < 1 || j > mm) return 0.0;
+    if (!gr->h_bo) return flat_depth;
+    const double d = (double)gr->h_bo[(size_t)j * (lm + 2) + i];
+    return d < par->hdry ? 0.0 : d;
+  };
+  std::vector<int32_t> h_subc;  // periodic domains: the grid coordinates of the vector points (for the duplicates' host-side state)
+  int j_off;
+  if (!periodic) {
+    // y-slab and dense layout of this rank: the same rules as analyse_layout (layout.h) on a non-periodic domain
+    {
+      const int rows = mm + 1, base = rows / g.nranks, rem = rows % g.nranks;
+      g.j0 = 1 + g.rank * base + std::min(g.rank, rem);
+      g.j1 = g.j0 + base + (g.rank < rem ? 1 : 0) - 1;
+      if (g.j1 < g.j0) return fail(-5, "beom_gpu_init: more ranks than grid rows");
+    }
+    g.NX = ((lm + GX0 + 34) + 15) / 16 * 16;
+    g.NY = (g.j1 - g.j0 + 1) + 2 * G;
+    g.plane = (size_t)g.NX * g.NY;
+    if (g.plane > 0x7fffffffull) return fail(-6, "beom_gpu_init: plane too large for 32-bit cell offsets");
+    j_off = G - g.j0;
+    g.torus = false; g.ring = false; g.nmir = 0;
+    g.halo = halo_rows(g.rank, g.nranks, false, G, G + (g.j1 - g.j0));
+    g.orph = Orphans();
+    g.orph.nlay = nlay;
+    g.orphans.clear();
+    g.cell_of_point.clear();
+  } else {
+    // Periodic domains: the aliases of index_grid_points (pm:614-685) decide which cells are images of which and which points are
+    // displaced duplicates -- the analysis of the neighbour table beom_gpu_init runs (layout.h).  The table is built here on the
+    // host from the depth grid (grid_index.h, the host driver's own source) and analysed the same way; the planes are then filled
+    // on the device like on any other domain.
+    std::vector<int32_t> neig(nd1 * 8, 0), posc(nd1, 0);
+    h_subc.assign(nd1 * 2, 0);
+    std::vector<double> mk[5];
+    for (auto &m : mk) m.assign(nd1, 0.0);
+    const int count = index_grid_points_core(lm, mm, ndeg, par->hdry, par->xper > 0.5, par->yper > 0.5, host_depth, neig.data(), h_subc.data(),
+                                             posc.data(), mk[0].data(), mk[1].data(), mk[2].data(), mk[3].data(), mk[4].data());
+    if (count != ndeg) return fail(-15, " wrong input parameter! Please set ndeg = %d inside file shared_mod.f95.", count);
+    Layout lay;
+    if (analyse_layout(lay, lm, mm, ndeg, par->xper > 0.5, par->yper > 0.5, g.rank, g.nranks, h_subc.data(), neig.data(), mk[2].data(), mk[0].data(),
+                       mk[1].data(), mk[3].data(), mk[4].data()))
+      return fail(lay.rc, "%s", lay.error.c_str());
+    if ((rc = adopt_layout(lay, h_subc.data() + nd1))) return rc;
+    j_off = lay.j_off;
   }
-  g.NX = ((lm + GX0 + 34) + 15) / 16 * 16;
-  g.NY = (g.j1 - g.j0 + 1) + 2 * G;
-  g.plane = (size_t)g.NX * g.NY;
-  if (g.plane > 0x7fffffffull) return fail(-6, "beom_gpu_init: plane too large for 32-bit cell offsets");
-  const int j_off = G - g.j0;
   const size_t pl = g.plane;
-  g.torus = false; g.ring = false; g.nmir = 0;
-  g.halo = halo_rows(g.rank, g.nranks, false, G, G + (g.j1 - g.j0));
-  g.orph = Orphans();
-  g.orph.nlay = nlay;
-  g.orphans.clear();
-  g.cell_of_point.clear();
 
   // the raw files on the device (released again at the end)
   std::vector<void *> raw;
@@ -883,7 +927,7 @@ static int init_grids_impl(const beom_params *par, const beom_grids *gr, const b
   A.lm = lm; A.mm = mm; A.nlay = nlay; A.NX = g.NX; A.NY = g.NY; A.j_off = j_off;
   A.jlo = std::max(g.j0 - G, 0); A.jhi = std::min(g.j1 + G, mm + 1);
   A.hdry = par->hdry;
-  A.flat = (par->cext * par->cext) / par->grav;
+  A.flat = flat_depth;
   A.tauw[0] = par->tauw[0]; A.tauw[1] = par->tauw[1]; A.f0 = par->f0;
   for (int l = 0; l < nlay; l++) A.topl[l] = par->topl[l];
   const size_t gp = (size_t)(lm + 2) * (mm + 2);
@@ -916,11 +960,13 @@ static int init_grids_impl(const beom_params *par, const beom_grids *gr, const b
     if (dmin <= 10.0 * par->hmin) return fail(-16, " Please adjust h_bo or hmin so that min(h_bo) > 10. * hmin.");
   }
   A.dmax = dmax;
-  CK(cudaMemcpyAsync(d_rowoff, rowoff.data(), sizeof(int) * (mm + 3), cudaMemcpyHostToDevice, g.stream));
-  g.p_lo = 1 + rowoff[A.jlo]; g.p_hi = rowoff[A.jhi + 1];
-  if (g.p_hi < g.p_lo) return fail(-8, "beom_gpu_init: no grid points on rank %d", g.rank);
-  g.own_first = 1 + rowoff[g.j0]; g.own_last = rowoff[g.j1 + 1];
-  if (g.own_last < g.own_first) { g.own_first = 0; g.own_last = -1; }
+  if (!periodic) {
+    CK(cudaMemcpyAsync(d_rowoff, rowoff.data(), sizeof(int) * (mm + 3), cudaMemcpyHostToDevice, g.stream));
+    g.p_lo = 1 + rowoff[A.jlo]; g.p_hi = rowoff[A.jhi + 1];
+    if (g.p_hi < g.p_lo) return fail(-8, "beom_gpu_init: no grid points on rank %d", g.rank);
+    g.own_first = 1 + rowoff[g.j0]; g.own_last = rowoff[g.j1 + 1];
+    if (g.own_last < g.own_first) { g.own_first = 0; g.own_last = -1; }
+  }
 
   // ---- Dev template, flags, cell map, h_th
   Dev &D = g.D;
@@ -930,17 +976,21 @@ static int init_grids_impl(const beom_params *par, const beom_grids *gr, const b
   D.y_lo = G; D.y_hi = G + (g.j1 - g.j0);
   D.i_off = GX0; D.j_off = j_off;
   D.lm = lm; D.mm = mm; D.nlay = nlay;
-  if ((rc = dalloc(&g.flags, pl)) || (rc = dalloc(&g.d_cell, nd1, false))) return rc;
-  CK(cudaMemsetAsync(g.d_cell, 0xff, sizeof(int) * nd1, g.stream));  // -1: not held on this rank
-  D.flags = g.flags;
   double *h_th = nullptr, *fcor = nullptr;
   if ((rc = dalloc(&h_th, pl)) || (rc = dalloc(&fcor, pl))) return rc;
-  k_gi_index<<<(unsigned)(A.jhi - A.jlo + 1), 256, 0, g.stream>>>(A, d_rowoff, g.d_cell, g.flags, h_th);
+  if (!periodic) {
+    if ((rc = dalloc(&g.flags, pl)) || (rc = dalloc(&g.d_cell, nd1, false))) return rc;
+    CK(cudaMemsetAsync(g.d_cell, 0xff, sizeof(int) * nd1, g.stream));  // -1: not held on this rank
+    k_gi_index<<<(unsigned)(A.jhi - A.jlo + 1), 256, 0, g.stream>>>(A, d_rowoff, g.d_cell, g.flags, h_th);
+    const int nloc = g.p_hi - g.p_lo + 1;
+    g.stage_elems = (size_t)nloc * nlay * 3;
+    if ((rc = dalloc(&g.stage, g.stage_elems, false))) return rc;
+  } else {  // (flags, cell map and staging buffer: adopt_layout)
+    k_gi_hth<<<dim3((unsigned)((g.NX + 127) / 128), (unsigned)g.NY), 128, 0, g.stream>>>(A, g.flags, h_th);
+  }
   g.launches++;
+  D.flags = g.flags;
   D.h_th = h_th; D.fcor = fcor;
-  const int nloc = g.p_hi - g.p_lo + 1;
-  g.stage_elems = (size_t)nloc * nlay * 3;
-  if ((rc = dalloc(&g.stage, g.stage_elems, false))) return rc;
 
   // ---- rest thickness (pm:154-183)
   if ((rc = dalloc(&g.diag_h0, pl * nl))) return rc;
@@ -1022,6 +1072,22 @@ static int init_grids_impl(const beom_params *par, const beom_grids *gr, const b
     if ((rc = dalloc(&D.tu3d, pl * nl * 2)) || (rc = dalloc(&D.layu, pl * nl)) || (rc = dalloc(&D.taum, pl * 2))) return rc;
   g.nseg = 0;
   g.obc_any = false;
+  if (gr->nudg && (any & 1u)) {  // flag_nudging: the nudged open-boundary faces (index_boundary_points, pm:1060-1240; O(N) pass on the host)
+    std::vector<int32_t> segm;
+    const int nseg = index_boundary_points_core(lm, mm, par->hdry, par->xper > 0.5, par->yper > 0.5, host_depth, gr->nudg, segm);
+    if (nseg == 0) return fail(-18, " the nudged open boundary segments could not be identified.");
+    const int NX = g.NX;
+    if (periodic) rc = build_segments(segm.data(), nseg, true, [&](int p, int, int) { return (p >= 1 && p <= ndeg) ? g.cell_of_point[p] : -1; });
+    else rc = build_segments(segm.data(), nseg, true, [&](int p, int i, int j) {
+      return (p >= 1 && j >= g.j0 - G && j <= g.j1 + G) ? (j + j_off) * NX + (i + GX0) : -1;
+    });
+    if (rc) return rc;
+  }
+  if (g.torus) {  // the fused step reads the statics at its (recomputed) halo cells: periodic images on this rank
+    if ((rc = sync_fields({{fcor, 1}, {h_th, 1}}, false))) return rc;
+    if (D.has_nudg && ((rc = sync_fields({{const_cast<double *>(D.nudg), 3}}, false)) || (rc = sync_fields({{const_cast<double *>(D.fnud), 3 * nlay}}, false)))) return rc;
+    if (D.has_hdot && (rc = sync_fields({{const_cast<double *>(D.hdot), nlay}}, false))) return rc;
+  }
 
   // invf = 1 / mean(fcor(0:ndeg)) (pm:223-229): a sum in vector order, so it is taken on the host from what the vector holds
   double invf;
@@ -1063,7 +1129,67 @@ static int init_grids_impl(const beom_params *par, const beom_grids *gr, const b
   if (gr->bodf)
     for (size_t k = 0; k < (size_t)nlay * 2; k++) bodf[k] = (double)gr->bodf[k];
 
+  // Displaced periodic duplicates (orphans.h) have no cell: their state and, where a sponge covers them, the data of their
+  // relaxation recurrence are kept on the host -- the same statements as k_gi_forcing, for those few points (their masks are 0)
+  if (!g.orphans.empty()) {
+    Orphans &O = g.orph;
+    const size_t no = O.n;
+    const int lm2 = lm + 2;
+    const int32_t *si = h_subc.data(), *sj = h_subc.data() + nd1;
+    O.nud.assign(3 * no, 0.0);
+    std::vector<double> ofn(3 * nl * no, 0.0), otide(gr->tide ? 6 * no : 0, 0.0);
+    bool uv = false;
+    for (size_t k = 0; k < no; k++) {
+      const int i = si[g.orphans[k]], j = sj[g.orphans[k]];
+      const size_t k0 = (size_t)j * lm2 + i;
+      if (gr->nudg) {
+        const float *n0 = gr->nudg, *n1 = gr->nudg + gp, *n2 = gr->nudg + 2 * gp;
+        double nu = 0.0, nv = 0.0;
+        if (i >= 1 && n1[k0 - 1] > 1.e-9f && n1[k0] > 1.e-9f) nu = (double)n1[k0] * 0.5 + (double)n1[k0 - 1] * 0.5;
+        if (j >= 1 && n2[k0 - lm2] > 1.e-9f && n2[k0] > 1.e-9f) nv = (double)n2[k0] * 0.5 + (double)n2[k0 - lm2] * 0.5;
+        O.nud[k] = (double)n0[k0]; O.nud[no + k] = nu; O.nud[2 * no + k] = nv;
+        for (int f = 0; f < 3; f++) {
+          O.live = O.live || O.nud[(size_t)f * no + k] != 0.0;
+          uv = uv || (f > 0 && O.nud[(size_t)f * no + k] != 0.0);
+        }
+      }
+      for (int l = 0; l < nlay; l++) {
+        double hl = 0.0 * 0.0, fn = hl, fu = 0.0, fv = 0.0;  // h_0 * mk_n with mk_n = 0 (pm:198-200)
+        if (gr->init) {
+          double t = hl + (double)gr->init[((size_t)0 * nl + l) * gp + k0];
+          if (l < nlay - 1) t = t - (double)gr->init[((size_t)0 * nl + l + 1) * gp + k0];
+          fn = t * 0.0;
+          fu = (double)gr->init[((size_t)1 * nl + l) * gp + k0];
+          fv = (double)gr->init[((size_t)2 * nl + l) * gp + k0];
+          hl = fn * 0.0;
+        }
+        O.val[((size_t)0 * nl + l) * no + k] = hl;
+        O.val[((size_t)1 * nl + l) * no + k] = fu;
+        O.val[((size_t)2 * nl + l) * no + k] = fv;
+        ofn[((size_t)0 * nl + l) * no + k] = fn; ofn[((size_t)1 * nl + l) * no + k] = fu; ofn[((size_t)2 * nl + l) * no + k] = fv;
+      }
+      if (gr->tide)
+        for (int c3 = 0; c3 < 3; c3++)
+          for (int a = 0; a < 2; a++) otide[((size_t)c3 * no + k) * 2 + a] = (double)gr->tide[((size_t)c3 * gp + k0) * 2 + a];
+    }
+    if (O.live) {
+      if (uv && D.has_wind && invf != 0.0)
+        return fail(-9, "beom_gpu_init: unsupported periodic connectivity (a velocity sponge over the duplicate row/column under wind stress: the Ekman term of its target, private_mod.f95:1449-1452)");
+      O.fnud = ofn;
+      O.has_tide = D.has_tide != 0;
+      O.w_ti = w_ti;
+      if (O.has_tide) O.tide = otide;
+    } else {
+      O.nud.clear();
+    }
+    O.forget();
+  }
+
   if ((rc = init_tail(invf, w_ti, gr->bodf ? bodf.data() : nullptr))) return rc;
+  if (periodic) {  // images of the initial state (across the seam of a y-periodic slab chain they are another rank's rows)
+    for (int f = 0; f < 3; f++)
+      if ((rc = sync_fields({{g.st[f][0], nlay}}, g.ring))) return rc;
+  }
 
   // h_0.bin's content for the output records (pm:185-194)
   if ((rc = dalloc(&g.h0r4, (size_t)ndeg * nl))) return rc;

@@ -3,8 +3,9 @@
 // (:154-183: layers stacked from the bottom, or the per-column Newton solve of get_equilibrium_thickness_h_0, :309-502),
 // and read_input_file's conversions of the raw float32 input grids (:840-964) -- written straight into the dense planes
 // of this rank, with the reference's operations in the reference's order (the host restatement init.cc produces the same
-// bits: tests/test_grid_init.py).  Non-periodic domains; what it does not cover makes beom_gpu_init_grids say so and the
-// caller falls back to read_input_data + beom_gpu_init.
+// bits: tests/test_grid_init.py).  On periodic domains the numbering, the flags and the image lists come from the host's layout
+// analysis instead of k_gi_index; what is not covered at all makes beom_gpu_init_grids say so and the caller falls back to
+// read_input_data + beom_gpu_init.
 #ifndef BEOM_GRIDINIT_CUH
 #define BEOM_GRIDINIT_CUH
 #include "dev.cuh"
@@ -108,11 +109,19 @@ __global__ void k_gi_index(const __grid_constant__ GridIn A, const int *__restri
   }
 }
 
+// periodic domains (the cell map and the flags come from the host's layout analysis): h_th of the vector points' cells (pm:753-757)
+__global__ void k_gi_hth(const __grid_constant__ GridIn A, const uint8_t *__restrict__ flags, double *__restrict__ h_th) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= A.NX) return;
+  const size_t c = (size_t)y * A.NX + x;
+  if (flags[c] & F_ACT) h_th[c] = gi_depth(A, x - GX0, y - A.j_off);
+}
+
 // rest thickness without outcropping: layers stacked from the bottom (pm:154-175); h_0 stays 0 at dry points
 __global__ void k_gi_h0_stack(const __grid_constant__ GridIn A, const uint8_t *__restrict__ flags, const double *__restrict__ h_th,
                               double *__restrict__ h_0, size_t plane) {
   const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= plane || !(flags[c] & F_N)) return;
+  if (c >= plane || (flags[c] & (F_ACT | F_N)) != (F_ACT | F_N)) return;  // wet vector points (not their periodic images)
   const double depth = h_th[c];
   for (int l = A.nlay - 1; l >= 0; l--) {
     const double above = l > 0 ? A.dmax * A.topl[l] : 0.0;
@@ -127,7 +136,7 @@ __global__ void k_gi_h0_stack(const __grid_constant__ GridIn A, const uint8_t *_
 __global__ void k_gi_h0_newton(const __grid_constant__ RestSolver S, const uint8_t *__restrict__ flags, const double *__restrict__ h_th,
                                double *__restrict__ h_0, size_t plane, int *__restrict__ bad) {
   const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= plane || !(flags[c] & F_N)) return;
+  if (c >= plane || (flags[c] & (F_ACT | F_N)) != (F_ACT | F_N)) return;  // wet vector points (not their periodic images)
   double col[BEOM_MAXLAY];
   if (!S.column(h_th[c], col)) {
     atomicMax(bad, (int)c);

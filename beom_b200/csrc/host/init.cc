@@ -13,6 +13,7 @@
 #include <limits>
 
 #include "host_model.h"
+#include "../gpu/grid_index.h"
 #include "../gpu/rest_solver.h"
 
 namespace {
@@ -54,86 +55,15 @@ inline long nint(double x) { return (long)(x >= 0 ? std::floor(x + 0.5) : -std::
 // index_grid_points (private_mod.f95:567-764)
 // ------------------------------------------------------------------------------------------------
 void index_grid_points(beom_host *h) {
-  const int lm = h->lm, mm = h->mm;
-  const double hdry = h->p.hdry;
   const Grid2<double> &H = h->h2d;
-  Grid2<unsigned char> wet;
-  wet.reset(-1, lm + 2, -1, mm + 2, 0);
-  for (int j = -1; j <= mm + 2; j++)
-    for (int i = -1; i <= lm + 2; i++) wet(i, j) = H(i, j) > hdry;
-  // a grid point enters the vector if it carries an eta, u, v or psi point that touches water
-  auto carries = [&](int i, int j) { return wet(i, j) || wet(i - 1, j) || wet(i, j - 1) || wet(i - 1, j - 1); };
-
-  Grid2<int32_t> alias;  // "indc": which vector entry a neighbour reference resolves to
-  alias.reset(-1, lm + 2, -1, mm + 2, 0);
-  int count = 0;
-  for (int j = 0; j <= mm + 1; j++)
-    for (int i = 0; i <= lm + 1; i++)
-      if (carries(i, j)) alias(i, j) = ++count;
+  const int count = beom::index_grid_points_core(h->lm, h->mm, h->ndeg, h->p.hdry, h->p.xper > 0.5, h->p.yper > 0.5,
+                                                 [&](int i, int j) { return H(i, j); }, h->neig.data(), h->subc.data(), h->posc.data(),
+                                                 h->mk_u.data(), h->mk_v.data(), h->mk_n.data(), h->mkpe.data(), h->mkpi.data());
   if (count != h->ndeg) {
     char b[160];
     std::snprintf(b, sizeof b, " wrong input parameter! Please set ndeg = %d inside file shared_mod.f95.", count);
     throw Fail{b};
   }
-
-  if (h->p.xper > 0.5) {  // pm:614-640
-    for (int j = 1; j <= mm; j++) {
-      const bool both = wet(1, j) && wet(lm, j);
-      if (both) {
-        alias(0, j) = alias(lm, j);
-        alias(lm + 1, j) = alias(1, j);
-        h->mk_u[alias(1, j)] = 1.0;
-      }
-      if (j > 1 && wet(1, j - 1) && wet(1, j) && wet(lm, j - 1) && wet(lm, j)) h->mkpe[alias(1, j)] = 1.0;
-      if (j == mm && both) {
-        alias(0, mm + 1) = alias(lm, mm + 1);
-        alias(lm + 1, mm + 1) = alias(1, mm + 1);
-      }
-    }
-  }
-  if (h->p.yper > 0.5) {  // pm:642-668
-    for (int i = 1; i <= lm; i++) {
-      const bool both = wet(i, 1) && wet(i, mm);
-      if (both) {
-        alias(i, 0) = alias(i, mm);
-        alias(i, mm + 1) = alias(i, 1);
-        h->mk_v[alias(i, 1)] = 1.0;
-      }
-      if (i > 1 && wet(i - 1, 1) && wet(i, 1) && wet(i - 1, mm) && wet(i, mm)) h->mkpe[alias(i, 1)] = 1.0;
-      if (i == lm && both) {
-        alias(lm + 1, 0) = alias(lm + 1, mm);
-        alias(lm + 1, mm + 1) = alias(lm + 1, 1);
-      }
-    }
-  }
-  if (h->p.xper > 0.5 && h->p.yper > 0.5) {  // pm:672-685
-    if (wet(1, 1) && wet(lm, 1) && wet(1, mm)) {
-      alias(0, 0) = alias(lm, mm);
-      h->mkpe[alias(1, 1)] = 1.0;
-      alias(0, mm + 1) = alias(lm, 1);
-    }
-    if (wet(lm, mm) && wet(1, mm) && wet(lm, 1)) {
-      alias(lm + 1, 0) = alias(1, mm);
-      alias(lm + 1, mm + 1) = alias(1, 1);
-    }
-  }
-
-  static const int di[8] = {1, 1, 0, -1, -1, -1, 0, 1}, dj[8] = {0, 1, 1, 1, 0, -1, -1, -1};
-  int p = 0;
-  for (int j = 0; j <= mm + 1; j++)  // pm:692-730
-    for (int i = 0; i <= lm + 1; i++) {
-      if (!carries(i, j)) continue;
-      ++p;
-      if (wet(i, j)) h->mk_n[p] = 1.0;
-      if (wet(i - 1, j) && wet(i, j)) h->mk_u[p] = 1.0;
-      if (wet(i, j - 1) && wet(i, j)) h->mk_v[p] = 1.0;
-      if (wet(i - 1, j - 1) && wet(i, j - 1) && wet(i - 1, j) && wet(i, j)) h->mkpe[p] = 1.0;
-      h->mkpi[p] = 1.0;  // carries() already says one of the four cells is wet (pm:712-714)
-      h->posc[p] = i + 1 + j * (lm + 2);
-      h->subc[p] = i;
-      h->subc[h->nd1 + p] = j;
-      for (int k = 0; k < 8; k++) h->neig[(size_t)p * 8 + k] = alias(i + di[k], j + dj[k]);
-    }
   for (size_t q = 0; q < h->nd1; q++) h->h_th[q] = H(h->subc[q], h->subc[h->nd1 + q]);  // pm:753-757
 }
 
@@ -210,53 +140,10 @@ void rest_thickness(beom_host *h) {
 // index_boundary_points (private_mod.f95:1060-1240): one entry per nudged open-boundary face
 // ------------------------------------------------------------------------------------------------
 void index_boundary_points(beom_host *h, const std::vector<float> &nf) {
-  const int lm = h->lm, mm = h->mm;
-  const double hdry = h->p.hdry;
-  const float tiny4 = std::numeric_limits<float>::min();
   const Grid2<double> &H = h->h2d;
-  Grid2<int32_t> own;
-  own.reset(-1, lm + 2, -1, mm + 2, 0);
-  {
-    int c = 0;
-    for (int j = 0; j <= mm + 1; j++)
-      for (int i = 0; i <= lm + 1; i++)
-        if (H(i, j) > hdry || H(i - 1, j) > hdry || H(i, j - 1) > hdry || H(i - 1, j - 1) > hdry) own(i, j) = ++c;
-  }
-  auto coef = [&](int i, int j, int comp) -> float {  // comp: 1 eta, 2 u, 3 v
-    if (i < 0 || i > lm + 1 || j < 0 || j > mm + 1) return 0.0f;
-    return nf[((size_t)(comp - 1) * (mm + 2) + j) * (lm + 2) + i];
-  };
-  struct Seg { int32_t c[18]; };
-  std::vector<Seg> segs;
-  auto push = [&](int i, int j, bool zonal, int sign, int di, int dj, int wi, int wj, int ni, int nj, int ci, int cj) {
-    Seg s;
-    std::memset(&s, 0, sizeof s);
-    s.c[0] = own(i, j); s.c[1] = i; s.c[2] = j;
-    s.c[zonal ? 3 : 4] = 1;
-    s.c[5] = sign;
-    s.c[6] = own(di, dj); s.c[7] = di; s.c[8] = dj;      // the dry cell
-    s.c[9] = own(wi, wj); s.c[10] = wi; s.c[11] = wj;    // the wet cell
-    s.c[12] = own(ni, nj); s.c[13] = ni; s.c[14] = nj;   // interior normal-velocity point
-    s.c[15] = own(ci, cj); s.c[16] = ci; s.c[17] = cj;   // interior cell
-    segs.push_back(s);
-  };
-  for (int j = 0; j <= mm + 1; j++)
-    for (int i = 0; i <= lm + 1; i++) {
-      const bool here = H(i, j) > hdry, west = H(i - 1, j) > hdry, south = H(i, j - 1) > hdry;
-      if (here && !west && coef(i, j, 2) > tiny4 && coef(i - 1, j, 2) > tiny4 && h->p.xper < 0.5)
-        push(i, j, true, 1, i - 1, j, i, j, i + 1, j, i + 1, j);
-      if (!here && west && coef(i - 1, j, 2) > tiny4 && coef(i, j, 2) > tiny4 && h->p.xper < 0.5)
-        push(i, j, true, -1, i, j, i - 1, j, i - 1, j, i - 2, j);
-      if (here && !south && coef(i, j, 3) > tiny4 && coef(i, j - 1, 3) > tiny4 && h->p.yper < 0.5)
-        push(i, j, false, 1, i, j - 1, i, j, i, j + 1, i, j + 1);
-      if (!here && south && coef(i, j - 1, 3) > tiny4 && coef(i, j, 3) > tiny4 && h->p.yper < 0.5)
-        push(i, j, false, -1, i, j, i, j - 1, i, j - 1, i, j - 2);
-    }
-  if (segs.empty()) throw Fail{" the nudged open boundary segments could not be identified."};
-  h->nseg = (int)segs.size();
-  h->segm.assign((size_t)h->nseg * 18, 0);
-  for (int s = 0; s < h->nseg; s++)
-    for (int c = 0; c < 18; c++) h->segm[(size_t)c * h->nseg + s] = segs[(size_t)s].c[c];
+  h->nseg = beom::index_boundary_points_core(h->lm, h->mm, h->p.hdry, h->p.xper > 0.5, h->p.yper > 0.5, [&](int i, int j) { return H(i, j); },
+                                             nf.data(), h->segm);
+  if (h->nseg == 0) throw Fail{" the nudged open boundary segments could not be identified."};
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -172,8 +172,11 @@ int beom_gpu_records_wait(beom_records *out);
  * of read_input_file), written straight into the dense planes with the reference's arithmetic; replaces read_input_data +
  * beom_gpu_init + beom_gpu_upload_state for the cases it covers.  The arrays hold the files' contents as they are on disk
  * (little-endian float32, Fortran order, no record markers; NULL = file absent).  par carries the derived values of
- * shared_mod.f95 (dt, hsal, ...) and ndeg.  Returns 0, a negative error, or BEOM_GRIDS_UNSUPPORTED for what is initialised on
- * the host: periodic domains, the rigid lid, the 1d/3d/plume variants, h_to.bin, restarts, sponges with mcbc < 0.5. */
+ * shared_mod.f95 (dt, hsal, ...) and ndeg.  Periodic domains and sponges with the open-boundary copy are covered as well: their
+ * irregular part -- the aliases of index_grid_points, the layout analysis beom_gpu_init runs on the neighbour table, the segment
+ * table of index_boundary_points -- is done on the host from the depth grid (the host driver's own source, grid_index.h), the planes
+ * are filled on the device.  Returns 0, a negative error, or BEOM_GRIDS_UNSUPPORTED for what is initialised on the host: the rigid
+ * lid, the 1d/3d/plume variants, h_to.bin, restarts. */
 typedef struct beom_grids {
   const float *h_bo;   /* (0:lm+1, 0:mm+1) */
   const float *init;   /* (0:lm+1, 0:mm+1, nlay, 3) */

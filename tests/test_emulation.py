@@ -499,7 +499,9 @@ def test_device_side_initialisation_on_the_emulation(emu_so):
     cmd = [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_grid_init.py"), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=1200, cwd=ROOT, env=env)
     assert r.returncode == 0 and " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
-    for spec in (["synthetic_basin", "9", "3", "{}", json.dumps(dict(n=60, mm=90, nlay=4)), "1"], ["sill_exchange3D", "12", "2", "{}", "null", "1"]):
+    for spec in (["synthetic_basin", "9", "3", "{}", json.dumps(dict(n=60, mm=90, nlay=4)), "1"], ["sill_exchange3D", "12", "2", "{}", "null", "1"],
+                 ["conservation", "12", "3", "{}", "null", "1"],                     # ring-closed y-periodic slabs
+                 ["wave_sponge", "12", "4", json.dumps({"mcbc": "0."}), "null", "1"]):  # open-boundary segments spread over the ranks
         cmd = [sys.executable, os.path.join(ROOT, "tests", "emu_ranks_worker.py"), emu_so] + spec
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=dict(os.environ, BEOM_GRID_INIT="1"))
         res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
