@@ -1232,7 +1232,8 @@ extern "C" int beom_gpu_download_subc(int32_t *si, int32_t *sj) {
 // for a host driver that initialised on the device (one rank)
 extern "C" int beom_gpu_download_grid_files(int32_t *grid5, float *h_0_r4) {
   if (!g.ready) return fail(-20, "beom_gpu_download_grid_files: not initialised");
-  if (g.nranks > 1 || g.p_lo != 1 || g.p_hi != g.ndeg) return fail(-27, "beom_gpu_download_grid_files: one rank holding every point only");
+  if (g.nranks > 1 || g.p_lo != 1 || g.p_hi != g.ndeg || !g.orphans.empty())
+    return fail(-27, "beom_gpu_download_grid_files: one rank holding every point in a cell only (no displaced periodic duplicates)");
   const int n = g.ndeg;
   if (grid5) {
     int *d = nullptr, rc;

@@ -459,6 +459,9 @@ Mapped map_file(const std::string &dir, const char *keyw, size_t n) {
 }  // namespace
 
 beom_host *beom_host_create_on_device(const beom_params *par, const char *idir, const char *odir, const char *desc, const beom_gpu_options *opt) {
+  // periodic domains: grid.bin lists the displaced duplicate points too, which have no cell on the device -- those (small) cases keep
+  // the host's read_input_data
+  if (par->xper > 0.5 || par->yper > 0.5) return beom_host_create(par, idir, odir, desc);
   beom_host *h = new beom_host();
   std::vector<Mapped> maps;
   auto unmap = [&]() { for (auto &m : maps) if (m.base) ::munmap(m.base, m.bytes); maps.clear(); };
