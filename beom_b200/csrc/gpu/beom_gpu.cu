@@ -404,7 +404,7 @@ int beom_gpu_last_error(char *buf, int len) {
 void beom_gpu_default_options(beom_gpu_options *opt) {
   memset(opt, 0, sizeof *opt);
   opt->device = -1;
-  opt->fused = 1;
+  opt->fused = 2;  // by size
   opt->rank = 0;
   opt->nranks = 1;
 }
@@ -805,7 +805,10 @@ static int init_tail(double invf, double w_ti, const double *bodf) {
   }
 
   g.use_fused = false;
-  if (opt.fused) {
+  // fused = 2 (the default): small grids are latency bound and one kernel per loop over every SM beats one CTA marching through
+  // a strip (sill_exchange3D 0.028 against 0.093 ms per step, stommel1948 0.032 against 0.063)
+  const double cell_layers = (double)(D.x_hi - D.x_lo + 1) * (double)(D.y_hi - D.y_lo + 1) * (double)nlay;
+  if (opt.fused == 1 || (opt.fused == 2 && cell_layers >= 250000.0)) {
     // periodic images that are not a complete single-rank torus (incl. the ring of a y-periodic slab chain): split path
     rc = fused_configure(g.D, g.P, g.torus ? 0 : g.nmir + (g.ring ? 1 : 0), g.nranks, &g.use_fused);
     if (rc) return rc;

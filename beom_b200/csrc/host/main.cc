@@ -1,5 +1,5 @@
 // main.cc -- the executable form of main.f95:26-37: errc/errm initialised, run(), quit().
-// usage: beom_run <shared_mod.f95 | parameter block> [--steps N] [--split] [--variant 0..3] [--host-init]
+// usage: beom_run <shared_mod.f95 | parameter block> [--steps N] [--split | --fused] [--variant 0..3] [--host-init]
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -8,7 +8,7 @@
 
 int main(int argc, char **argv) {
   if (argc < 2) {
-    std::fprintf(stderr, "usage: %s <shared_mod.f95> [--steps N] [--split] [--variant k] [--host-init]\n", argv[0]);
+    std::fprintf(stderr, "usage: %s <shared_mod.f95> [--steps N] [--split | --fused] [--variant k] [--host-init]\n", argv[0]);
     return 2;
   }
   beom_params par;
@@ -25,6 +25,7 @@ int main(int argc, char **argv) {
   for (int a = 2; a < argc; a++) {
     if (!std::strcmp(argv[a], "--steps") && a + 1 < argc) steps = std::atoi(argv[++a]);
     else if (!std::strcmp(argv[a], "--split")) opt.fused = 0;
+    else if (!std::strcmp(argv[a], "--fused")) opt.fused = 1;  // (default: by size, include/beom_gpu.h)
     else if (!std::strcmp(argv[a], "--variant") && a + 1 < argc) par.variant = std::atoi(argv[++a]);
     else if (!std::strcmp(argv[a], "--host-init")) host_init = true;
   }

@@ -95,7 +95,10 @@ typedef struct beom_fields {
 typedef struct beom_gpu_options {
   int32_t device;        /* CUDA device ordinal; -1 = current/LOCAL_RANK              */
   int32_t fused;         /* 1 = fused single-pass step where the case allows, 0 = one  */
-                         /*     kernel per reference loop (always available)           */
+                         /*     kernel per reference loop (always available), 2 = by   */
+                         /*     size (the default): the fused step from 250 000        */
+                         /*     cell-layers per rank on, below that the split path,    */
+                         /*     which is quicker on latency-bound grids  */
   int32_t rank, nranks;  /* y-slab decomposition; nranks = 1 for a single GPU          */
   int32_t strict;        /* reserved (kernels are always built -fmad=false)            */
   int32_t reserved_[3];

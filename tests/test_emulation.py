@@ -257,7 +257,7 @@ def test_the_executable_initialised_on_the_device_writes_the_same_files(emu_so, 
         c.params_text = re.sub(r"diag       = \S+", "diag       = 1.", c.params_text)
         blk = c.write(str(d))
         exe = os.path.join(ROOT, "beom_b200", "lib", "beom_run")
-        r = subprocess.run([exe, blk, "--steps", "40"] + (["--host-init"] if how == "host" else []), capture_output=True, text=True, timeout=600,
+        r = subprocess.run([exe, blk, "--steps", "40", "--fused"] + (["--host-init"] if how == "host" else []), capture_output=True, text=True, timeout=600,
                            env=dict(os.environ, LD_PRELOAD=emu_so), cwd=str(d))
         assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
         assert ("read_input_data: on the device" in r.stdout) == (how == "device"), r.stdout[:600]
@@ -485,7 +485,7 @@ def test_no_race_between_warps_under_threadsanitizer(emu_so, tmp_path_factory):
                            cases.conservation(dl=30.0e3))):                              # torus
         d = str(tmp_path_factory.mktemp("tsan_case%d" % k))
         blk = c.write(d)
-        r = subprocess.run([exe, blk, "--steps", "5"], capture_output=True, text=True, timeout=1500, env=env, cwd=d)
+        r = subprocess.run([exe, blk, "--steps", "5", "--fused"], capture_output=True, text=True, timeout=1500, env=env, cwd=d)
         assert r.returncode == 0 and "record = 1" in r.stdout, r.stdout[-800:] + r.stderr[-2000:]
         assert "ThreadSanitizer" not in r.stderr, r.stderr[:6000]
     shutil.rmtree(os.path.dirname(so), ignore_errors=True)
