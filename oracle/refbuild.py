@@ -1,0 +1,194 @@
+"""oracle/_ref: the reference itself, built here without a Fortran compiler (TEST INFRASTRUCTURE ONLY).
+
+BEOM is configured at compile time: a user pastes the parameter block a test-case script prints into
+``shared_mod.f95`` and rebuilds.  ``build_case`` does exactly that for one parameter block:
+
+1. reads ``/root/reference/shared_mod.f95`` and sets the values of the user-modifiable section from the block
+   (the three parameters ``private_mod.f95`` uses but the shipped ``shared_mod.f95`` never declares -- ``svis``,
+   ``tdrg``, ``topt`` -- are declared next to their neighbours, as a user of this fork must do to compile it at all);
+2. translates that text + ``/root/reference/private_mod.f95`` (or one of the 1d / 3d / plume variants) +
+   ``/root/reference/main.f95`` to C++ with oracle/f95c (a language translator, not a restatement: it has no notion
+   of what the statements mean);
+3. compiles the result with ``g++ -O2 -ffp-contract=off`` (strict IEEE, the oracle's own convention) into
+   ``oracle/_ref/<hash>/beom_ref`` and, with ``omp=True``, ``-O3 -fopenmp`` using the reference's own PARALLEL DO directives.
+
+Nothing is copied from the reference into the repository: translated sources and binaries live under ``oracle/_ref/``
+(git-ignored).  ``/root/reference`` exists only in the development container; on the GPU box the prebuilt binaries of
+``oracle/_ref/`` travel with the snapshot and ``build_case`` returns them without looking at the sources.
+
+``run_case`` runs the binary (the reference's ``run()``: read_input_data + integrate_time + its own output files) and
+returns the harness's raw dump of every module array at STOP (``ref_dump.bin``, written by the translated program's
+epilogue -- the one thing the harness adds) as numpy arrays in the reference's own shapes.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("BEOM_REFERENCE_DIR", "/root/reference")
+OUT = os.path.join(HERE, "_ref")
+VARIANT_FILES = {0: "private_mod.f95", 1: "private_mod1d.f95", 3: "private_mod3d.f95", 4: "private_modplumenew.f95"}
+UNDECLARED = ("svis", "tdrg", "topt")  # used by private_mod.f95, absent from the shipped shared_mod.f95
+
+
+def reference_available() -> bool:
+    return os.path.exists(os.path.join(REF, "private_mod.f95"))
+
+
+def parse_block(block: str) -> dict:
+    """'name = value' lines of a print_params block -> {name: value text}."""
+    vals = {}
+    for line in block.splitlines():
+        line = line.strip()
+        if not line or line.startswith("!"):
+            continue
+        m = re.match(r"^([a-z_0-9]+)\s*(?:\(\s*nlay\s*\))?\s*=\s*(.*?)\s*$", line, re.I)
+        if not m:
+            raise ValueError("parameter block line %r" % line)
+        vals[m.group(1).lower()] = m.group(2)
+    return vals
+
+
+def shared_mod_text(block: str) -> str:
+    """The reference's shared_mod.f95 with the block's values in its user-modifiable section."""
+    vals = parse_block(block)
+    src = open(os.path.join(REF, "shared_mod.f95")).read().split("\n")
+    begin = next(i for i, s in enumerate(src) if "BEGINNING OF USER-MODIFIABLE SECTION" in s)
+    end = next(i for i, s in enumerate(src) if "END OF USER-MODIFIABLE SECTION" in s)
+    seen = set()
+    pat = re.compile(r"^(\s*)([a-z_0-9]+)(\s*\(\s*nlay\s*\))?(\s*=\s*)", re.I)
+    last_real = None
+    for i in range(begin, end):
+        m = pat.match(src[i])
+        if not m or src[i].lstrip().startswith("!"):
+            continue
+        name = m.group(2).lower()
+        if name == "mcbc":
+            last_real = i
+        if name in vals:
+            seen.add(name)
+            code, q = [], None  # the statement part of the line (comment stripped, quotes respected)
+            for ch in src[i]:
+                if q:
+                    q = None if ch == q else q
+                elif ch in "'\"":
+                    q = ch
+                elif ch == "!":
+                    break
+                code.append(ch)
+            cont = "".join(code).rstrip().endswith("&")
+            src[i] = "%s%s%s%s%s%s" % (m.group(1), m.group(2), m.group(3) or "", m.group(4), vals[name],
+                                       ", &" if cont else "")
+    if last_real is None:
+        raise ValueError("shared_mod.f95: user section not recognised")
+    extra = [n for n in UNDECLARED]
+    lines = []
+    for n in extra:
+        lines.append("    %-10s = %s, &" % (n, vals.get(n, "0.")))
+        seen.add(n)
+    src[last_real:last_real] = lines
+    missing = sorted(set(vals) - seen - {"plum"})
+    if missing:
+        raise ValueError("parameter block names with no slot in shared_mod.f95: %s" % missing)
+    return "\n".join(src)
+
+
+def _translate(block: str, variant: int) -> str:
+    sys.path.insert(0, os.path.join(HERE, "f95c"))
+    try:
+        import f95c
+    finally:
+        sys.path.pop(0)
+    pm = os.path.join(REF, VARIANT_FILES[variant])
+    srcs = [(shared_mod_text(block), os.path.join(REF, "shared_mod.f95"), False),
+            (open(pm).read(), pm, True),
+            (open(os.path.join(REF, "main.f95")).read(), os.path.join(REF, "main.f95"), False)]
+    return f95c.translate(srcs)
+
+
+def case_key(block: str, variant: int, omp: bool) -> str:
+    # idir / odir are part of the compiled text, like in the reference
+    h = hashlib.sha256()
+    h.update(block.encode())
+    h.update(b"|%d|%d" % (variant, int(omp)))
+    for f in ("f95c/f95c.py", "f95c/f95rt.h"):
+        with open(os.path.join(HERE, f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
+def build_case(block: str, variant: int = 0, omp: bool = False, name: str | None = None) -> str:
+    """-> path of the binary.  ``name`` gives the binary a stable directory (bench); else it is keyed by content."""
+    key = name or case_key(block, variant, omp)
+    d = os.path.join(OUT, key)
+    exe = os.path.join(d, "beom_ref")
+    stamp = os.path.join(d, "stamp")
+    want = case_key(block, variant, omp)
+    if os.path.exists(exe) and os.path.exists(stamp) and open(stamp).read().strip() == want:
+        return exe
+    if not reference_available():
+        if os.path.exists(exe) and name:
+            return exe  # prebuilt, travelled with the snapshot
+        raise FileNotFoundError("the reference sources (%s) are not here and %s is not prebuilt" % (REF, exe))
+    os.makedirs(d, exist_ok=True)
+    cpp = os.path.join(d, "beom_ref.cpp")
+    with open(cpp, "w") as f:
+        f.write(_translate(block, variant))
+    flags = ["-std=c++17", "-I", os.path.join(HERE, "f95c"), "-ffp-contract=off", "-fno-fast-math", "-w"]
+    flags += ["-O3", "-march=x86-64-v3", "-fopenmp"] if omp else ["-O2"]
+    r = subprocess.run(["g++"] + flags + [cpp, "-o", exe], capture_output=True, text=True)
+    if r.returncode:
+        raise RuntimeError("g++ failed on the translated reference:\n" + r.stderr[-4000:])
+    with open(stamp, "w") as f:
+        f.write(want)
+    return exe
+
+
+_DT = {1: np.int32, 2: np.bool_, 4: np.float32, 8: np.float64}
+
+
+def read_dump(path: str) -> dict:
+    """ref_dump.bin -> {name: array in the reference's shape (Fortran order; index 0 = the declared lower bound)}."""
+    out = {}
+    with open(path, "rb") as f:
+        data = f.read()
+    pos = 0
+    while pos < len(data):
+        name = data[pos:pos + 32].split(b"\0", 1)[0].decode()
+        pos += 32
+        ty, rank = np.frombuffer(data, np.int32, 2, pos)
+        pos += 8
+        lo = np.frombuffer(data, np.int64, rank, pos)
+        pos += 8 * rank
+        ext = np.frombuffer(data, np.int64, rank, pos)
+        pos += 8 * rank
+        n = int(np.prod(ext)) if rank else 1
+        dt = np.dtype(_DT[int(ty)])
+        a = np.frombuffer(data, dt, n, pos)
+        pos += n * dt.itemsize
+        out[name] = a.reshape(tuple(int(e) for e in ext), order="F") if rank else a[0]
+        out[name + "__lb"] = tuple(int(x) for x in lo)
+    return out
+
+
+def run_case(exe: str, odir: str, threads: int | None = None, timeout: float = 3600.0):
+    """Run the translated reference (its directories are compiled in); -> (dump dict, stdout)."""
+    env = dict(os.environ)
+    if threads:
+        env["OMP_NUM_THREADS"] = str(threads)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=timeout, env=env)
+    if r.returncode:
+        raise RuntimeError("the translated reference stopped with code %d:\n%s\n%s" % (r.returncode, r.stdout[-2000:],
+                                                                                    r.stderr[-2000:]))
+    return read_dump(os.path.join(odir, "ref_dump.bin")), r.stdout
+
+
+if __name__ == "__main__":
+    blk = open(sys.argv[1]).read()
+    print(build_case(blk, int(sys.argv[2]) if len(sys.argv) > 2 else 0))
