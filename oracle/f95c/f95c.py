@@ -705,8 +705,9 @@ class Scope:
 
 
 class Emitter:
-    def __init__(self, unit: Unit):
+    def __init__(self, unit: Unit, uninit=None):
         self.u = unit
+        self.uninit = dict(uninit or {})
         self.out = []
         self.scope = Scope(unit, None)
         self.ind = 0
@@ -906,7 +907,7 @@ class Emitter:
                 return "((int)(%s))" % x
             return "f_nint(%s)" % x
         if name in ("abs", "max", "min", "sqrt", "cos", "sin", "exp", "mod", "sign", "aimag", "trim", "len_trim",
-                    "adjustl", "tiny", "huge"):
+                    "adjustl", "tiny", "huge", "floor", "ceiling", "log", "tanh", "atan"):
             return "f_%s(%s)" % (name, ", ".join(self.ex(a, lv) for a in pos))
         if name == "present":
             return "(%s__p != nullptr)" % cname(pos[0][1])
@@ -1036,7 +1037,9 @@ class Emitter:
             if s.init is not None:
                 self.w("%s%s%s %s = %s;" % (st, const, s.ctype, n, self.ex(s.init)))
             else:
-                self.w("%s%s %s = %s;" % (st, s.ctype, n, "0" if s.ftype != "c8" else "0.0"))
+                # Fortran leaves an unassigned local undefined; here it is 0 unless the caller names the value it is to hold
+                v0 = self.uninit.get(s.name) if self.scope.proc is not None else None
+                self.w("%s%s %s = %s;" % (st, s.ctype, n, v0 or ("0" if s.ftype != "c8" else "0.0")))
             return
         b = self.bounds(s.dims)
         if b is None:  # allocatable
@@ -1398,9 +1401,9 @@ class Emitter:
         # the harness's state dump + STOP
         self.w("void f95_stop() {")
         self.ind += 1
-        self.w("Dump d(%s);" % dump_path_expr)
+        self.w("Dump dump__(%s);" % dump_path_expr)
         for name in u.dump_names:
-            self.w('d.put("%s", %s);' % (name, cname(name)))
+            self.w('dump__.put("%s", %s);' % (name, cname(name)))
         self.w("std::fflush(nullptr);")
         self.w("std::exit(errc != 0 ? 1 : 0);")
         self.ind -= 1
@@ -1421,12 +1424,14 @@ class Emitter:
         return "\n".join(self.out) + "\n"
 
 
-def translate(sources, dump_path_expr='f_cat(f_trim(odir), std::string("ref_dump.bin"))'):
-    """sources: [(text, file name, dump its module variables?)] in dependency order -> C++ text."""
+def translate(sources, dump_path_expr='f_cat(f_trim(odir), std::string("ref_dump.bin"))', uninit=None):
+    """sources: [(text, file name, dump its module variables?)] in dependency order -> C++ text.
+    uninit: {local name: C++ literal} -- the value a local that the source reads before assigning it holds on entry
+    (undefined in Fortran; 0 here unless named)."""
     u = Unit()
     for text, fname, dump in sources:
         u.parse_file(text, fname, dump)
-    return Emitter(u).translate(dump_path_expr)
+    return Emitter(u, uninit).translate(dump_path_expr)
 
 
 if __name__ == "__main__":

@@ -206,6 +206,16 @@ inline float f_sin(float x) { return std::sin(x); }
 inline double f_sin(double x) { return std::sin(x); }
 inline float f_exp(float x) { return std::exp(x); }
 inline double f_exp(double x) { return std::exp(x); }
+inline int f_floor(double x) { return static_cast<int>(std::floor(x)); }
+inline int f_floor(float x) { return static_cast<int>(std::floor(x)); }
+inline int f_ceiling(double x) { return static_cast<int>(std::ceil(x)); }
+inline int f_ceiling(float x) { return static_cast<int>(std::ceil(x)); }
+inline float f_log(float x) { return std::log(x); }
+inline double f_log(double x) { return std::log(x); }
+inline float f_tanh(float x) { return std::tanh(x); }
+inline double f_tanh(double x) { return std::tanh(x); }
+inline float f_atan(float x) { return std::atan(x); }
+inline double f_atan(double x) { return std::atan(x); }
 inline int f_nint(double x) { return static_cast<int>(std::lround(x)); }
 inline int f_nint(float x) { return static_cast<int>(std::lroundf(x)); }
 template <class A, class C>

@@ -33,7 +33,11 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.environ.get("BEOM_REFERENCE_DIR", "/root/reference")
 OUT = os.path.join(HERE, "_ref")
-VARIANT_FILES = {0: "private_mod.f95", 1: "private_mod1d.f95", 3: "private_mod3d.f95", 4: "private_modplumenew.f95"}
+VARIANT_FILES = {0: "private_mod.f95", 1: "private_mod1d.f95", 2: "private_mod3d.f95", 3: "private_modplumenew.f95"}  # beom_gpu.h: BEOM_VARIANT_*
+# private_modplumenew.f95 reads its local Lnud (:1643, :1666) before the only assignment to it (:1645, inside the
+# branch the first read guards): undefined in Fortran.  The oracle takes the assigned value, 5000 m, throughout
+# (oracle/README.md); the translated build is given the same value for the unassigned local so that the two can be compared.
+UNINIT = {3: {"lnud": "5000."}}
 UNDECLARED = ("svis", "tdrg", "topt")  # used by private_mod.f95, absent from the shipped shared_mod.f95
 
 
@@ -55,7 +59,7 @@ def parse_block(block: str) -> dict:
     return vals
 
 
-def shared_mod_text(block: str) -> str:
+def shared_mod_text(block: str, variant: int = 0) -> str:
     """The reference's shared_mod.f95 with the block's values in its user-modifiable section."""
     vals = parse_block(block)
     src = open(os.path.join(REF, "shared_mod.f95")).read().split("\n")
@@ -87,7 +91,7 @@ def shared_mod_text(block: str) -> str:
                                        ", &" if cont else "")
     if last_real is None:
         raise ValueError("shared_mod.f95: user section not recognised")
-    extra = [n for n in UNDECLARED]
+    extra = list(UNDECLARED) + (["plum"] if variant == 3 else [])  # private_modplumenew.f95 also uses plum
     lines = []
     for n in extra:
         lines.append("    %-10s = %s, &" % (n, vals.get(n, "0.")))
@@ -106,10 +110,10 @@ def _translate(block: str, variant: int) -> str:
     finally:
         sys.path.pop(0)
     pm = os.path.join(REF, VARIANT_FILES[variant])
-    srcs = [(shared_mod_text(block), os.path.join(REF, "shared_mod.f95"), False),
+    srcs = [(shared_mod_text(block, variant), os.path.join(REF, "shared_mod.f95"), False),
             (open(pm).read(), pm, True),
             (open(os.path.join(REF, "main.f95")).read(), os.path.join(REF, "main.f95"), False)]
-    return f95c.translate(srcs)
+    return f95c.translate(srcs, uninit=UNINIT.get(variant))
 
 
 def case_key(block: str, variant: int, omp: bool) -> str:

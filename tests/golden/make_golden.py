@@ -1,12 +1,17 @@
-"""Regenerates tests/golden/*.npz from the CPU oracle (oracle/beom_oracle.c).
+"""Regenerates tests/golden/*.npz -- outputs of THE REFERENCE ITSELF, run in the development container.
 
-The reference ships no expected arrays, and it cannot be compiled here (no
-Fortran compiler), so these vectors are NOT outputs of the reference: they freeze the oracle's own
-results after it was pinned against the reference's analytical checks (tests/test_oracle_pins.py), and
-give the GPU tests a fixture that does not depend on running the oracle.
+The reference ships no expected arrays and there is no Fortran compiler here, so the reference's
+own sources (/root/reference/{shared_mod,private_mod,main}.f95, read where they lie) are translated to C++ by
+oracle/f95c (a language translator without any knowledge of the model), compiled with g++ in strict IEEE mode and run
+on the inputs of each test-case script (oracle/refbuild.py).  Every vector below is what that program left in its module
+arrays after ``nsteps`` time steps (its raw double-precision state, dumped at STOP) and the last record of the
+``eta_.bin`` it wrote.  The hand-written oracle reproduces all of them bit for bit
+(tests/test_oracle_pins.py::test_oracle_reproduces_the_reference_vectors runs wherever the fixtures are, also without
+/root/reference; tests/test_reference_pin.py re-runs the translated reference and compares every module array).
 
-    python tests/golden/make_golden.py
-"""
+    python tests/golden/make_golden.py [--all]          (needs /root/reference)
+
+``run(name)`` is the oracle's side of the same computation (used by the tests)."""
 import os
 import sys
 import tempfile
@@ -39,9 +44,11 @@ GOLDEN = {
     "tide_ridge": (dict(lm=200), 60),
     "wave_sponge": (dict(dl=20.0e3), 60),
 }
+KEYS = ("hlay", "u", "v", "h_u", "h_v")
 
 
 def run(name):
+    """The oracle's vectors for one case."""
     kw, nsteps = GOLDEN[name]
     c = cases.CASES[name](**kw)
     with tempfile.TemporaryDirectory() as d:
@@ -49,9 +56,29 @@ def run(name):
         hm = model.HostModel.from_block(blk)
         orc = Oracle(hm.params, d)
         orc.advance(1, nsteps)
-        out = {k: orc.array(k).copy() for k in ("hlay", "u", "v", "h_u", "h_v")}
+        out = {k: orc.array(k).copy() for k in KEYS}
         out["nsteps"] = np.array(nsteps)
         out["eta_record"] = orc.record("eta_")
+        return out
+
+
+def run_reference(name):
+    """The same vectors from the translated reference (development container only)."""
+    from oracle import refbuild, refcheck
+
+    kw, nsteps = GOLDEN[name]
+    c = cases.CASES[name](**kw)
+    with tempfile.TemporaryDirectory(prefix="g_") as d:
+        blk = c.write(d)
+        text = open(blk).read()
+        p, _, _, _ = model.parse_params(text)
+        text = refcheck.block_for_steps(text, nsteps, p.dt)
+        p, _, odir, _ = model.parse_params(text)
+        dump, _ = refbuild.run_case(refbuild.build_case(text), odir)
+        out = {k: np.ascontiguousarray(dump[k].T) for k in KEYS}  # (0:ndeg, nlay) -> [nlay][0:ndeg]
+        out["nsteps"] = np.array(nsteps)
+        out["eta_record"] = refcheck.read_records(os.path.join(odir, "eta_.bin"), p.ndeg, p.nlay)[-1].copy()
+        out["source"] = np.array("translated reference (oracle/f95c), g++ -O2 -ffp-contract=off")
         return out
 
 
@@ -60,5 +87,8 @@ if __name__ == "__main__":
         path = os.path.join(HERE, name + ".npz")
         if os.path.exists(path) and "--all" not in sys.argv:
             continue  # frozen: only missing vectors are made (--all regenerates everything)
-        np.savez_compressed(path, **run(name))
-        print("wrote", name)
+        ref = run_reference(name)
+        mine = run(name)
+        same = all(np.array_equal(ref[k], mine[k]) for k in KEYS + ("eta_record",))
+        np.savez_compressed(path, **ref)
+        print("wrote %-24s (reference output; the oracle %s)" % (name, "agrees bit for bit" if same else "DIFFERS"))

@@ -1,7 +1,9 @@
-"""What pins the CPU oracle.  The reference has no golden vectors; its correctness references are the
+"""What pins the CPU oracle.  The reference holds no golden vectors of its own; its correctness references are the
 analytical solutions inside its test scripts and the conservation property its documentation states
-(SURVEY.md section 8c).  The oracle must reproduce those, and must keep reproducing its own frozen
-outputs (tests/golden, made by tests/golden/make_golden.py)."""
+(SURVEY.md section 8c): the oracle must reproduce those.  Since round 2 it must also reproduce, bit for bit, outputs of
+the reference itself -- tests/golden/*.npz, made by running the reference's own sources (translated to C++ by
+oracle/f95c, no Fortran compiler exists here) in the development container; tests/test_reference_pin.py re-runs that
+program where /root/reference is present and compares every module array."""
 import os
 import tempfile
 
@@ -283,7 +285,11 @@ def test_two_dimensional_sill_cases_run_and_keep_their_layers(name):
 @pytest.mark.parametrize("name", ["stommel1948", "lock_exchange", "unstable_jet", "sill_exchange3D", "conservation", "soliton",
                                   "baines_ridge", "carrier_beach", "upwelling_seaward_wind", "mixed_open_bc", "morel_upwelling",
                                   "outcrop_seamount", "sill_exchange2D", "sill_exchange2Dtides", "tide_ridge", "wave_sponge"])
-def test_oracle_reproduces_its_golden_vectors(name):
+def test_oracle_reproduces_the_reference_vectors(name):
+    """tests/golden/*.npz are outputs of the reference itself (its own sources translated to C++ by oracle/f95c and run in
+    the development container, tests/golden/make_golden.py): the double-precision state after N steps and the last
+    record of the eta_.bin it wrote.  The oracle must reproduce them bit for bit -- this runs wherever the fixtures are,
+    /root/reference or not."""
     import importlib.util
     spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLD, "make_golden.py"))
     mg = importlib.util.module_from_spec(spec)
