@@ -133,6 +133,34 @@ def cpu_baseline(sample_n, nlay, steps, tmp, warm=1, sponge=False):
             "grid": [sample_n, sample_n, nlay], "seconds": dt, "init_seconds": t_init}
 
 
+def translated_reference_leg(sample_n, nlay, steps, tmp, warm=1):
+    """The reference ITSELF on the sample: its own Fortran sources translated to C++ by oracle/f95c (no Fortran compiler
+    exists here or on the GPU boxes), compiled -O3 -fopenmp with the reference's own PARALLEL DO directives in the
+    development container (oracle/_ref/bench_<n>x<nlay>, travels with the snapshot).  Bit-identical to the port above
+    (tests/test_reference_pin.py) and slower than it (array descriptors instead of hand-hoisted pointers), which is why the
+    port stays the arm's value; this leg shows what the untouched reference code does on the same cores."""
+    from oracle import refbuild
+    exe = refbuild.prebuilt("bench_%dx%d" % (sample_n, nlay))
+    if exe is None:
+        return None
+    d = os.path.join(tmp, "ref_translated_%d" % sample_n)
+    c, blk = make_case(sample_n, nlay, d)
+    cores = host_cores()
+    try:
+        r = refbuild.time_case(exe, refbuild.named_block(c), d, steps, max(warm, 1), cores)
+    except Exception as err:  # reported, never fatal for the arm
+        log("[reference] translated reference leg failed: %s" % err)
+        return None
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+    ups = float(sample_n) * sample_n * nlay / r["seconds_per_step"]
+    return {"value": ups, "unit": "cell-layer updates/s", "cores": cores, "kind": "reference",
+            "sample": "%dx%dx%d basin of the same workload, %d generalized-FB steps after %d warm-up steps: the reference's own "
+                      "shared_mod/private_mod/main.f95 translated statement by statement to C++ (oracle/f95c), g++ -O3 -fopenmp "
+                      "-ffp-contract=off, %d threads" % (sample_n, sample_n, nlay, steps, r["warmup_steps"], cores),
+            "grid": [sample_n, sample_n, nlay], "seconds_per_step": r["seconds_per_step"], "seconds_total": r["seconds_total"]}
+
+
 def emit(line: dict) -> None:
     """The ONE JSON line of the contract, on the real stdout (see _quiet_stdout)."""
     os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
@@ -219,6 +247,7 @@ def main():
             else:
                 log("[reference] the full grid does not fit (estimated %.0f s against a budget of %.0f s; %.0f GB needed, %.0f GB free): "
                     "the %d^2 sample is the arm's value" % (est_total, args.ref_budget, need_gb, free_gb, args.cpu_sample))
+            translated = None if sponge else translated_reference_leg(args.cpu_sample, nlay, min(K, 20), tmp, warm=max(W, 1))
         finally:
             shutil.rmtree(tmp, ignore_errors=True)
         cb = full or sample
@@ -231,7 +260,7 @@ def main():
         line = {"impl": "reference", "metric": "cell_layer_updates_per_s", "value": cb["value"], "unit": "cell-layer updates/s",
                 "n_gpus": args.gpus, "steps": K, "warmup": W, "ms_per_step": ms, "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
-                "cpu_baseline": cb, "sample_leg": sample if full else None, "gpu_launches": 0,
+                "cpu_baseline": cb, "sample_leg": sample if full else None, "reference_translated": translated, "gpu_launches": 0,
                 "e2e": {"value": cb["value"], "unit": "cell-layer updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         emit(line)
         return 0

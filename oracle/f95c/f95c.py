@@ -705,9 +705,11 @@ class Scope:
 
 
 class Emitter:
-    def __init__(self, unit: Unit, uninit=None):
+    def __init__(self, unit: Unit, uninit=None, env_params=(), trace=()):
         self.u = unit
         self.uninit = dict(uninit or {})
+        self.env_params = set(env_params)  # module scalars / strings a run may override through F95_<NAME> (harness)
+        self.trace = set(trace)            # procedures whose entries are time-stamped (harness)
         self.out = []
         self.scope = Scope(unit, None)
         self.ind = 0
@@ -1028,14 +1030,20 @@ class Emitter:
             if s.rank:
                 raise FError("character arrays are outside the subset (%s)" % s.name)
             if s.init is not None:
-                self.w("%sFStr %s(%s, %s);" % (st, n, ln, self.ex(s.init)))
+                init = self.ex(s.init)
+                if self.scope.proc is None and s.name in self.env_params:
+                    init = 'env_str("F95_%s", %s)' % (s.name.upper(), init)
+                self.w("%sFStr %s(%s, %s);" % (st, n, ln, init))
             else:
                 self.w("%sFStr %s(%s);" % (st, n, ln))
             return
         if s.rank == 0:
             const = "const " if "parameter" in s.attrs else ""
             if s.init is not None:
-                self.w("%s%s%s %s = %s;" % (st, const, s.ctype, n, self.ex(s.init)))
+                init = self.ex(s.init)
+                if self.scope.proc is None and s.name in self.env_params:
+                    init = 'env_num("F95_%s", %s)' % (s.name.upper(), init)
+                self.w("%s%s%s %s = %s;" % (st, const, s.ctype, n, init))
             else:
                 # Fortran leaves an unassigned local undefined; here it is 0 unless the caller names the value it is to hold
                 v0 = self.uninit.get(s.name) if self.scope.proc is not None else None
@@ -1369,6 +1377,8 @@ class Emitter:
                 self.w("%s %s__r = 0;" % (s.ctype, cname(name)))
                 continue
             self.declare(s, static="save" in s.attrs or "parameter" in s.attrs or s.init is not None)
+        if p.name in self.trace:
+            self.w('trace_mark("%s");' % p.name)
         self.block(p.body)
         if p.kind == "function":
             self.w("return %s__r;" % cname(p.name))
@@ -1401,9 +1411,14 @@ class Emitter:
         # the harness's state dump + STOP
         self.w("void f95_stop() {")
         self.ind += 1
+        if self.trace:
+            self.w('trace_mark("stop");')
+            self.w('trace_write(f_cat(f_trim(odir), std::string("ref_trace.txt")));')
+        self.w("if (!std::getenv(\"F95_NO_DUMP\")) {")
         self.w("Dump dump__(%s);" % dump_path_expr)
         for name in u.dump_names:
             self.w('dump__.put("%s", %s);' % (name, cname(name)))
+        self.w("}")
         self.w("std::fflush(nullptr);")
         self.w("std::exit(errc != 0 ? 1 : 0);")
         self.ind -= 1
@@ -1424,14 +1439,18 @@ class Emitter:
         return "\n".join(self.out) + "\n"
 
 
-def translate(sources, dump_path_expr='f_cat(f_trim(odir), std::string("ref_dump.bin"))', uninit=None):
+def translate(sources, dump_path_expr='f_cat(f_trim(odir), std::string("ref_dump.bin"))', uninit=None, env_params=(),
+              trace=()):
     """sources: [(text, file name, dump its module variables?)] in dependency order -> C++ text.
     uninit: {local name: C++ literal} -- the value a local that the source reads before assigning it holds on entry
-    (undefined in Fortran; 0 here unless named)."""
+    (undefined in Fortran; 0 here unless named).
+    env_params: module parameters / strings whose compiled-in value a run may replace through the environment variable
+    F95_<NAME> (the timing harness sets the directories and the run length that way; the pin builds use none).
+    trace: procedures whose entries are time-stamped into <odir>/ref_trace.txt (timing harness)."""
     u = Unit()
     for text, fname, dump in sources:
         u.parse_file(text, fname, dump)
-    return Emitter(u, uninit).translate(dump_path_expr)
+    return Emitter(u, uninit, env_params, trace).translate(dump_path_expr)
 
 
 if __name__ == "__main__":

@@ -24,7 +24,9 @@
 #include <map>
 #include <string>
 #include <sys/stat.h>
+#include <time.h>
 #include <type_traits>
+#include <vector>
 
 namespace f95 {
 
@@ -467,6 +469,39 @@ struct ListIn {
     }
     void end() {}
 };
+
+// ---------------------------------------------------------------- harness knobs (timing runs only)
+inline double env_num(const char* name, double compiled) {
+    const char* v = std::getenv(name);
+    return v ? std::atof(v) : compiled;
+}
+inline std::string env_str(const char* name, const std::string& compiled) {
+    const char* v = std::getenv(name);
+    return v ? std::string(v) : compiled;
+}
+struct TraceLog {
+    std::string names;
+    std::vector<double> t;
+    std::vector<int> id;
+};
+inline TraceLog& trace_log() {
+    static TraceLog l;
+    return l;
+}
+inline void trace_mark(const char* name) {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    auto& l = trace_log();
+    l.t.push_back(ts.tv_sec + 1e-9 * ts.tv_nsec);
+    l.id.push_back(name[0] == 's' && name[1] == 't' && name[2] == 'o' ? 1 : 0);
+}
+inline void trace_write(const std::string& path) {
+    FILE* f = std::fopen(rtrim(path).c_str(), "w");
+    if (!f) return;
+    auto& l = trace_log();
+    for (size_t k = 0; k < l.t.size(); ++k) std::fprintf(f, "%d %.9f\n", l.id[k], l.t[k]);
+    std::fclose(f);
+}
 
 // ---------------------------------------------------------------- the harness's state dump
 // Not part of the reference: at STOP the driver writes every module array in raw form so that a test can compare

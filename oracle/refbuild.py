@@ -103,7 +103,7 @@ def shared_mod_text(block: str, variant: int = 0) -> str:
     return "\n".join(src)
 
 
-def _translate(block: str, variant: int) -> str:
+def _translate(block: str, variant: int, timing: bool = False) -> str:
     sys.path.insert(0, os.path.join(HERE, "f95c"))
     try:
         import f95c
@@ -113,27 +113,30 @@ def _translate(block: str, variant: int) -> str:
     srcs = [(shared_mod_text(block, variant), os.path.join(REF, "shared_mod.f95"), False),
             (open(pm).read(), pm, True),
             (open(os.path.join(REF, "main.f95")).read(), os.path.join(REF, "main.f95"), False)]
+    if timing:  # bench.py --impl reference: directories and run length come from the environment, steps are time-stamped
+        return f95c.translate(srcs, uninit=UNINIT.get(variant), env_params=("idir", "odir", "dt_s", "dt_o"),
+                              trace=("gener_forward_backward",))
     return f95c.translate(srcs, uninit=UNINIT.get(variant))
 
 
-def case_key(block: str, variant: int, omp: bool) -> str:
+def case_key(block: str, variant: int, omp: bool, timing: bool = False) -> str:
     # idir / odir are part of the compiled text, like in the reference
     h = hashlib.sha256()
     h.update(block.encode())
-    h.update(b"|%d|%d" % (variant, int(omp)))
+    h.update(b"|%d|%d|%d" % (variant, int(omp), int(timing)))
     for f in ("f95c/f95c.py", "f95c/f95rt.h"):
         with open(os.path.join(HERE, f), "rb") as fh:
             h.update(fh.read())
     return h.hexdigest()[:16]
 
 
-def build_case(block: str, variant: int = 0, omp: bool = False, name: str | None = None) -> str:
+def build_case(block: str, variant: int = 0, omp: bool = False, name: str | None = None, timing: bool = False) -> str:
     """-> path of the binary.  ``name`` gives the binary a stable directory (bench); else it is keyed by content."""
-    key = name or case_key(block, variant, omp)
-    d = os.path.join(OUT, key)
+    # named builds travel to the GPU box; content-keyed ones (the pin tests') are a local cache (.gpurunignore)
+    d = os.path.join(OUT, name) if name else os.path.join(OUT, "cache", case_key(block, variant, omp, timing))
     exe = os.path.join(d, "beom_ref")
     stamp = os.path.join(d, "stamp")
-    want = case_key(block, variant, omp)
+    want = case_key(block, variant, omp, timing)
     if os.path.exists(exe) and os.path.exists(stamp) and open(stamp).read().strip() == want:
         return exe
     if not reference_available():
@@ -143,7 +146,7 @@ def build_case(block: str, variant: int = 0, omp: bool = False, name: str | None
     os.makedirs(d, exist_ok=True)
     cpp = os.path.join(d, "beom_ref.cpp")
     with open(cpp, "w") as f:
-        f.write(_translate(block, variant))
+        f.write(_translate(block, variant, timing))
     flags = ["-std=c++17", "-I", os.path.join(HERE, "f95c"), "-ffp-contract=off", "-fno-fast-math", "-w"]
     flags += ["-O3", "-march=x86-64-v3", "-fopenmp"] if omp else ["-O2"]
     r = subprocess.run(["g++"] + flags + [cpp, "-o", exe], capture_output=True, text=True)
@@ -196,3 +199,63 @@ def run_case(exe: str, odir: str, threads: int | None = None, timeout: float = 3
 if __name__ == "__main__":
     blk = open(sys.argv[1]).read()
     print(build_case(blk, int(sys.argv[2]) if len(sys.argv) > 2 else 0))
+
+
+# ------------------------------------------------------------------------------------------------ timing builds
+# bench.py --impl reference and __graft_entry__.smoke() use binaries built HERE (development container) under fixed names,
+# because the GPU box has no /root/reference: the grid size, layer count and every switch are compiled in (as in the
+# reference); the directories and the run length come from the environment (F95_IDIR, F95_ODIR, F95_DT_S, F95_DT_O).
+
+def named_block(case) -> str:
+    """The parameter block of a generated case with a placeholder directory (the run sets the real one)."""
+    return case.params_text.replace("@DIR@", "/tmp/")
+
+
+def time_case(exe: str, block: str, workdir: str, steps: int, warm: int, threads: int, dump: bool = False):
+    """Run a timing build for 3 + warm + steps + 1 time steps in ``workdir`` (inputs already written there) and return
+    the seconds per generalized forward-backward step, from the time stamps the harness takes at the entries of
+    gener_forward_backward (private_mod.f95:2225) -- read_input_data, the three start-up steps and the warm-up steps
+    are outside the timed span, the reference's own per-record output (one record after the last step) too."""
+    import time
+
+    from beom_b200 import model
+
+    p, _, _, _ = model.parse_params(block)
+    dtd8 = p.dt / 24.0 / 3600.0
+    nstp = 3 + warm + steps + 1
+    val = "%.9e" % (nstp * dtd8)
+    d = workdir if workdir.endswith("/") else workdir + "/"
+    env = dict(os.environ, F95_IDIR=d, F95_ODIR=d, F95_DT_S=val, F95_DT_O=val, OMP_NUM_THREADS=str(threads))
+    if not dump:
+        env["F95_NO_DUMP"] = "1"
+    t0 = time.perf_counter()
+    r = subprocess.run([exe], env=env, capture_output=True, text=True)
+    total = time.perf_counter() - t0
+    if r.returncode:
+        raise RuntimeError("translated reference: exit code %d\n%s" % (r.returncode, (r.stdout + r.stderr)[-2000:]))
+    marks = np.loadtxt(os.path.join(d, "ref_trace.txt"))
+    ts = marks[:, 1]
+    if len(ts) < warm + steps + 1:
+        raise RuntimeError("translated reference: %d step marks, expected %d" % (len(ts), warm + steps + 2))
+    per_step = float(ts[warm + steps] - ts[warm]) / steps  # mark k = entry of time step 4 + k
+    return {"seconds_per_step": per_step, "seconds_total": total, "seconds_before_first_gfb_step": float(ts[0] - (ts[-1] - total)),
+            "steps": steps, "warmup_steps": 3 + warm, "threads": threads}
+
+
+def build_named(name: str, case, omp: bool):
+    return build_case(named_block(case), omp=omp, name=name, timing=True)
+
+
+def build_prebuilt():
+    """What travels to the GPU box: the bench sample (2048 x 2048 x 4 basin, OpenMP) and the smoke case (40 x 25 x 2)."""
+    from beom_b200 import cases
+
+    out = {}
+    out["bench_2048x4"] = build_named("bench_2048x4", cases.synthetic_basin(n=2048, nlay=4), omp=True)
+    out["smoke_40x25x2"] = build_named("smoke_40x25x2", cases.synthetic_basin(n=40, mm=25, nlay=2), omp=False)
+    return out
+
+
+def prebuilt(name: str):
+    exe = os.path.join(OUT, name, "beom_ref")
+    return exe if os.path.exists(exe) else None

@@ -80,9 +80,14 @@ def test_bit_exact_synthetic_basin(case_factory, fused, nlay):
     assert_same("dmdy", dmdy, orc.array("dmdy"))
 
 
-@pytest.mark.parametrize("name", ["stommel1948", "lock_exchange", "unstable_jet", "sill_exchange3D", "conservation"])
+@pytest.mark.parametrize("name", ["stommel1948", "lock_exchange", "unstable_jet", "sill_exchange3D", "conservation", "soliton",
+                                  "baines_ridge", "carrier_beach", "upwelling_seaward_wind", "mixed_open_bc", "morel_upwelling",
+                                  "outcrop_seamount", "sill_exchange2D", "sill_exchange2Dtides", "tide_ridge", "wave_sponge"])
 def test_golden_vectors(case_factory, name):
-    """The committed fixtures (tests/golden, frozen oracle outputs) without running the oracle."""
+    """The CUDA path against outputs of THE REFERENCE ITSELF, without running any checker: tests/golden/*.npz is the state the
+    reference's own sources (translated to C++ by oracle/f95c, tests/golden/make_golden.py) left after N steps of each of its
+    sixteen test-case scripts.  Bit for bit -- except the two tidal cases, where the device's cos() may differ from glibc's
+    in the last place (1e-11, as everywhere tides are compared)."""
     import os
     from tests.golden.make_golden import GOLDEN
     kw, nsteps = GOLDEN[name]
@@ -93,6 +98,10 @@ def test_golden_vectors(case_factory, name):
     gm.advance(1, nsteps)
     hl, u, v = gm.download_state()
     gm.close()
+    if name in ("sill_exchange2Dtides", "tide_ridge"):
+        for k, got in (("hlay", hl), ("u", u), ("v", v)):
+            assert np.max(np.abs(got - want[k])) <= 1e-11 * max(1.0, np.max(np.abs(want[k]))), k
+        return
     assert_same("hlay", hl, want["hlay"])
     assert_same("u", u, want["u"])
     assert_same("v", v, want["v"])
