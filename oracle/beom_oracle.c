@@ -8,7 +8,10 @@
  * Build: gcc -O2 -ffp-contract=off (strict IEEE double; no FMA contraction, no reassociation).
  * With -fopenmp the same `ipnt' loops the reference parallelises are parallel (bench cpu_baseline).
  *
- * PARITY UNPINNED: no golden vectors exist in the reference and it cannot be built here.
+ * PARITY PINNED (round 2): the reference holds no golden vectors and no Fortran compiler exists here, but its own
+ * sources, translated to C++ by oracle/f95c and run in the development container (oracle/_ref), leave every module
+ * array bit-identical to this restatement on all 16 reference scripts, 24 option / variant cases and the three variant
+ * files (tests/test_reference_pin.py); tests/golden holds outputs of that program.  See oracle/README.md.
  *
  * Conventions fixed by this restatement where Fortran leaves latitude:
  *   - SUM() intrinsics are evaluated sequentially in array order;

@@ -5,9 +5,10 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
  * this library; nothing under beom_b200/ does.
  *
- * PARITY UNPINNED: the reference ships no golden vectors and cannot be compiled in this environment
- * (no Fortran compiler), see oracle/README.md.  What pins the oracle is listed there (analytical
- * solutions of the reference's own test scripts and its documented conservation property).
+ * PARITY PINNED (round 2) against the reference itself: its Fortran sources are translated to C++ by oracle/f95c
+ * (no Fortran compiler exists here), built into oracle/_ref and compared with this restatement bit for bit on every
+ * module array (tests/test_reference_pin.py, oracle/README.md); the analytical solutions of the reference's test scripts
+ * and its documented conservation property (tests/test_oracle_pins.py) are kept as a second, independent pin.
  */
 #ifndef BEOM_ORACLE_H
 #define BEOM_ORACLE_H

@@ -58,6 +58,9 @@ PAIRS += [
     ("variant-plume-off", "sponge_basin", dict(nlay=3), 60, dict(plum="0."), 3),
     ("variant-plume-on", "sponge_basin", dict(nlay=3), 60, dict(plum="1."), 3),
 ]
+# the four named configs of BASELINE.json at the sizes their scripts ship with (ndeg 6 464 / 322 / 54 136 / 63 252), 200 steps:
+# what tests/test_gpu_native_configs.py compares the CUDA path with
+PAIRS += [("native-" + n, n, {}, 200, {}, 0) for n in ("stommel1948", "lock_exchange", "unstable_jet", "sill_exchange3D")]
 IDS = [p[0] for p in PAIRS]
 
 
