@@ -705,8 +705,10 @@ class Scope:
 
 
 class Emitter:
-    def __init__(self, unit: Unit, uninit=None, env_params=(), trace=()):
+    def __init__(self, unit: Unit, uninit=None, env_params=(), trace=(), externs=(), hooks_include=None):
         self.u = unit
+        self.externs = set(externs)          # procedures defined in C++ by hooks_include (the drop-in build's binding)
+        self.hooks_include = hooks_include   # included inside namespace ref after the module variables
         self.uninit = dict(uninit or {})
         self.env_params = set(env_params)  # module scalars / strings a run may override through F95_<NAME> (harness)
         self.trace = set(trace)            # procedures whose entries are time-stamped (harness)
@@ -1189,6 +1191,9 @@ class Emitter:
 
     def s_call(self, st):
         _, where, name, args = st
+        if name in self.externs:
+            self.w("%s(%s);" % (cname(name), ", ".join(self.ex(a) for a in args)))
+            return
         self.w("%s(%s);" % (cname(name), ", ".join(self.call_args(name, args))))
 
     def s_exit(self, st):
@@ -1405,6 +1410,8 @@ class Emitter:
             self.scope = Scope(u, p)
             self.w(self.signature(p) + ";")
         self.scope = Scope(u, None)
+        if self.hooks_include:
+            self.w('#include "%s"' % self.hooks_include)
         self.w()
         for name in u.proc_order:
             self.procedure(u.procs[name])
@@ -1440,17 +1447,19 @@ class Emitter:
 
 
 def translate(sources, dump_path_expr='f_cat(f_trim(odir), std::string("ref_dump.bin"))', uninit=None, env_params=(),
-              trace=()):
+              trace=(), externs=(), hooks_include=None):
     """sources: [(text, file name, dump its module variables?)] in dependency order -> C++ text.
     uninit: {local name: C++ literal} -- the value a local that the source reads before assigning it holds on entry
     (undefined in Fortran; 0 here unless named).
     env_params: module parameters / strings whose compiled-in value a run may replace through the environment variable
     F95_<NAME> (the timing harness sets the directories and the run length that way; the pin builds use none).
-    trace: procedures whose entries are time-stamped into <odir>/ref_trace.txt (timing harness)."""
+    trace: procedures whose entries are time-stamped into <odir>/ref_trace.txt (timing harness).
+    externs / hooks_include: procedure names the source CALLs that are defined in C++ by the named header, which is included
+    after the module variables (the drop-in build: the reference driving libbeom_gpu.so through its C ABI)."""
     u = Unit()
     for text, fname, dump in sources:
         u.parse_file(text, fname, dump)
-    return Emitter(u, uninit, env_params, trace).translate(dump_path_expr)
+    return Emitter(u, uninit, env_params, trace, externs, hooks_include).translate(dump_path_expr)
 
 
 if __name__ == "__main__":

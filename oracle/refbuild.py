@@ -246,16 +246,128 @@ def build_named(name: str, case, omp: bool):
     return build_case(named_block(case), omp=omp, name=name, timing=True)
 
 
+# cases of tests/test_gpu_dropin.py: name -> (generator, kwargs, steps)
+DROPIN_CASES = {
+    "lock_exchange": ("lock_exchange", {}, 200),                                  # native size, two layers, Leith
+    "sill_exchange3D": ("sill_exchange3D", dict(lx=6.0e3, ly=100.0e3), 80),       # sponges, outcropping, open-boundary segments
+    "stommel1948": ("stommel1948", dict(dl=250.0e3), 120),                        # wind, linear drag, beta plane, no viscosity
+    "basin": ("synthetic_basin", dict(n=300, mm=170, nlay=4), 40),                # the bench workload, small
+}
+
+
 def build_prebuilt():
-    """What travels to the GPU box: the bench sample (2048 x 2048 x 4 basin, OpenMP) and the smoke case (40 x 25 x 2)."""
+    """What travels to the GPU box: the bench sample (2048 x 2048 x 4 basin, OpenMP), the smoke case (40 x 25 x 2), and for
+    every DROPIN_CASES entry the pure translated reference and its drop-in flavour linked against libbeom_gpu.so."""
+    from concurrent.futures import ThreadPoolExecutor
+
     from beom_b200 import cases
 
-    out = {}
-    out["bench_2048x4"] = build_named("bench_2048x4", cases.synthetic_basin(n=2048, nlay=4), omp=True)
-    out["smoke_40x25x2"] = build_named("smoke_40x25x2", cases.synthetic_basin(n=40, mm=25, nlay=2), omp=False)
-    return out
+    root = os.path.dirname(HERE)
+    jobs = {"bench_2048x4": lambda: build_named("bench_2048x4", cases.synthetic_basin(n=2048, nlay=4), omp=True),
+            "smoke_40x25x2": lambda: build_named("smoke_40x25x2", cases.synthetic_basin(n=40, mm=25, nlay=2), omp=False)}
+    for name, (gen, kw, _) in DROPIN_CASES.items():
+        blk = named_block(cases.CASES[gen](**kw))
+        jobs["pure_" + name] = (lambda b=blk, n=name: build_case(b, name="pure_" + n, timing=True))
+        jobs["dropin_" + name] = (lambda b=blk, n=name: build_dropin(
+            b, os.path.join(root, "beom_b200", "lib"), "beom_gpu", name="dropin_" + n, rpath="$ORIGIN/../../../beom_b200/lib"))
+    with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as ex:
+        futs = {k: ex.submit(f) for k, f in jobs.items()}
+        return {k: f.result() for k, f in futs.items()}
 
 
 def prebuilt(name: str):
     exe = os.path.join(OUT, name, "beom_ref")
     return exe if os.path.exists(exe) else None
+
+
+# ------------------------------------------------------------------------------------------------ the drop-in flavour
+# The reference's own program with the edits of INTEGRATION.md section 2 applied to its text (in memory, at build time):
+# its read_input_data, time loop and output routines stay, the step routines are replaced one for one by calls into the
+# C ABI of include/beom_gpu.h (oracle/f95c/dropin_hooks.h holds the C++ twin of the Fortran binding lines).
+
+DROPIN_EXTERNS = ("gpu_setup", "gpu_stress", "gpu_step", "gpu_download", "gpu_finalize")
+
+
+def _sub_once(pattern, repl, text, count=1, where=""):
+    new, n = re.subn(pattern, repl, text, flags=re.I | re.M)
+    if n != count:
+        raise ValueError("drop-in edit %r: %d matches, expected %d" % (where or pattern, n, count))
+    return new
+
+
+def dropin_sources(block: str):
+    """-> the (text, file, dump) list of the translator with INTEGRATION.md's edits applied to private_mod.f95 / main.f95."""
+    pm = open(os.path.join(REF, "private_mod.f95")).read()
+    mainf = open(os.path.join(REF, "main.f95")).read()
+    # end of read_input_data (private_mod.f95:238)
+    pm = _sub_once(r"^(\s*)if \( rsta > 0\.5_rw \) call read_restart_record\s*$",
+                   r"\g<0>\n\1call gpu_setup()", pm, where="gpu_setup")
+    a = pm.lower().index("subroutine integrate_time")
+    b = pm.lower().index("end subroutine integrate_time")
+    body = pm[a:b]
+    body = _sub_once(r"call distribute_stress\(\)", "call gpu_stress()", body, 2, "distribute_stress")
+    body = _sub_once(r"call first_three_timesteps\( tstp \)", "call gpu_step( tstp, ctim, ramp, gene, .true., 1 )", body, 3,
+                     "first_three_timesteps")
+    body = _sub_once(r"call gener_forward_backward\( tstp, upst \)", "call gpu_step( tstp, ctim, ramp, gene, upst, 0 )", body, 1,
+                     "gener_forward_backward")
+    body = _sub_once(r"^(\s*)call write_outputs\(\)\s*$", r"\1call gpu_download()\n\g<0>", body, 1, "write_outputs")
+    pm = pm[:a] + body + pm[b:]
+    mainf = _sub_once(r"^(\s*)call quit\(\)", r"\1call gpu_finalize()\n\g<0>", mainf, 1, "gpu_finalize")
+    return [(shared_mod_text(block, 0), os.path.join(REF, "shared_mod.f95"), False),
+            (pm, os.path.join(REF, "private_mod.f95") + " (+ INTEGRATION.md edits)", True),
+            (mainf, os.path.join(REF, "main.f95") + " (+ INTEGRATION.md edits)", False)]
+
+
+def build_dropin(block: str, libdir: str, libname: str = "beom_gpu", name: str | None = None, rpath: str | None = None) -> str:
+    """The drop-in flavour for one parameter block, linked against ``lib<libname>.so`` in ``libdir`` (libbeom_gpu.so for a
+    B200, the emulated library of tools/emu for the CPU suite).  Directories and run length come from the environment
+    (F95_IDIR, F95_ODIR, F95_DT_S, F95_DT_O), like the timing builds."""
+    sys.path.insert(0, os.path.join(HERE, "f95c"))
+    try:
+        import f95c
+    finally:
+        sys.path.pop(0)
+    h = hashlib.sha256()
+    h.update(("dropin|" + block + "|" + libdir + "|" + libname).encode())
+    for f in ("f95c/f95c.py", "f95c/f95rt.h", "f95c/dropin_hooks.h", "../include/beom_gpu.h"):
+        with open(os.path.join(HERE, f), "rb") as fh:
+            h.update(fh.read())
+    want = h.hexdigest()[:16]
+    d = os.path.join(OUT, name) if name else os.path.join(OUT, "cache", "dropin_" + want)
+    exe, stamp = os.path.join(d, "beom_ref"), os.path.join(d, "stamp")
+    if os.path.exists(exe) and os.path.exists(stamp) and open(stamp).read().strip() == want:
+        return exe
+    if not reference_available():
+        if os.path.exists(exe) and name:
+            return exe
+        raise FileNotFoundError("the reference sources (%s) are not here and %s is not prebuilt" % (REF, exe))
+    os.makedirs(d, exist_ok=True)
+    cpp = os.path.join(d, "beom_ref.cpp")
+    with open(cpp, "w") as f:
+        f.write(f95c.translate(dropin_sources(block), env_params=("idir", "odir", "dt_s", "dt_o"), externs=DROPIN_EXTERNS,
+                               hooks_include="dropin_hooks.h"))
+    inc = os.path.join(os.path.dirname(HERE), "include")
+    cmd = ["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fno-fast-math", "-w", "-I", os.path.join(HERE, "f95c"), "-I", inc,
+           cpp, "-o", exe, "-L", libdir, "-l" + libname, "-Wl,-rpath," + (rpath or libdir)]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode:
+        raise RuntimeError("g++ failed on the drop-in build:\n" + r.stderr[-4000:])
+    with open(stamp, "w") as f:
+        f.write(want)
+    return exe
+
+
+def run_with_env(exe: str, workdir: str, block: str, nsteps: int, extra_env=None, timeout: float = 1800.0):
+    """Run a build whose directories / run length come from the environment for ``nsteps`` steps (one record after the
+    last); -> (dump, stdout)."""
+    from beom_b200 import model
+
+    p, _, _, _ = model.parse_params(block)
+    val = "%.9e" % (nsteps * (p.dt / 24.0 / 3600.0))
+    d = workdir if workdir.endswith("/") else workdir + "/"
+    env = dict(os.environ, F95_IDIR=d, F95_ODIR=d, F95_DT_S=val, F95_DT_O=val)
+    env.update(extra_env or {})
+    r = subprocess.run([exe], env=env, capture_output=True, text=True, timeout=timeout)
+    if r.returncode:
+        raise RuntimeError("exit code %d:\n%s\n%s" % (r.returncode, r.stdout[-3000:], r.stderr[-3000:]))
+    return read_dump(os.path.join(d, "ref_dump.bin")), r.stdout

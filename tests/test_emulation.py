@@ -387,6 +387,32 @@ def test_open_boundaries_after_the_emulated_fused_step(emu_so, name, nsteps):
     run(emu_so, name, nsteps, {"mcbc": "0."}, fused=1, path="fused")
 
 
+@pytest.mark.parametrize("name,fused", [("lock_exchange", 1), ("sill_exchange3D", 1), ("sill_exchange3D", 0), ("stommel1948", 1)])
+def test_reference_program_drives_the_library_through_the_c_abi(emu_so, name, fused):
+    """The drop-in boundary, executed (tests/test_gpu_dropin.py is the same comparison on a B200): the reference's own program
+    -- its read_input_data, time loop, write_outputs, translated from /root/reference by oracle/f95c -- with the edits of
+    INTEGRATION.md section 2 applied to its text, linked here against the EMULATED library, writes byte-identical output
+    files to the pure reference and leaves a bit-identical state."""
+    import shutil
+    import tempfile
+    from oracle import refbuild
+    from tests.test_gpu_dropin import check_pair, run_pair
+    from beom_b200 import cases
+    if not refbuild.reference_available():
+        pytest.skip("needs the reference's sources (/root/reference)")
+    gen, kw, _ = refbuild.DROPIN_CASES[name]
+    blk = refbuild.named_block(cases.CASES[gen](**kw))
+    libname = os.path.basename(emu_so)[3:-3]
+    exe_pure = refbuild.build_case(blk, timing=True)
+    exe_dropin = refbuild.build_dropin(blk, os.path.dirname(emu_so), libname)
+    root = tempfile.mkdtemp(prefix="di", dir="/tmp")
+    try:
+        out = run_pair(name, exe_pure, exe_dropin, fused, root)
+        check_pair(out)
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
 def test_gpu_test_modules_on_the_emulation(emu_so):
     """The GPU tests themselves, re-run with the emulated library swapped in (tests/conftest.py, BEOM_TEST_EMU): the ones
     whose kernels nothing above reaches -- the rigid lid (hyperplane Gauss-Seidel with __syncthreads and shuffle
