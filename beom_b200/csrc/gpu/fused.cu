@@ -201,7 +201,10 @@ int fused_configure(const Dev &D, const beom_params &P, int nmir, int nranks, bo
   chunks = std::max(chunks, std::min((8 * sms + cfg.strips - 1) / cfg.strips, rows / 64));
   if (const char *e = getenv("BEOM_FUSED_CHUNKS")) chunks = std::max(1, atoi(e));  // experiment: y-chunks per strip
   chunks = std::min(chunks, std::max(1, rows / 16));
-  chunks = std::max(chunks, (rows + 3839) / 3840);  // the lean kernel keeps a chunk's open-water bitmap in 32 words (32 x 128 rows)
+  {  // the kernel keeps a chunk's open-water bitmap in kOWords words of 32 four-row groups (a chunk visits 8 rows more than it owns)
+    const int max_rows = kOWords * 128 - 256;
+    chunks = std::max(chunks, (rows + max_rows - 1) / max_rows);
+  }
   cfg.rows_per_chunk = (rows + chunks - 1) / chunks;
   cfg.chunks = (rows + cfg.rows_per_chunk - 1) / cfg.rows_per_chunk;
   {

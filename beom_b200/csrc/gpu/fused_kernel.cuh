@@ -69,7 +69,17 @@ constexpr int kMaxLay = 8;            // layers per CTA (shared-memory exchange,
 constexpr int kMaxWarps = BEOM_FUSED_WARPS;  // warps per CTA: 16 -> <= 128 registers per thread, 12 -> <= 168
 constexpr int kPad = 4;               // staged columns on each side of a CTA's result columns (16-byte aligned rows)
 __host__ __device__ constexpr int seg_doubles(int groups) { return groups * kUse + 2 * kPad; }  // one staged row segment
-constexpr int kWRow = 34;             // per-warp state ring: 32 lanes + 1 pad column on each side
+#ifndef BEOM_WROW
+#define BEOM_WROW 34
+#endif
+#ifndef BEOM_OWORDS
+#define BEOM_OWORDS 32
+#endif
+#ifndef BEOM_MIN_CTAS
+#define BEOM_MIN_CTAS 1   // experiment: 2 = two CTAs of <= 256 threads per SM (needs <= 113 KB of shared memory per CTA)
+#endif
+constexpr int kWRow = BEOM_WROW;      // per-warp state ring: 32 lanes + 1 pad column on the west side (33; 34 = padded on both)
+constexpr int kOWords = BEOM_OWORDS;  // words of a chunk's open-water bitmap kept in shared memory (one bit per 4-row group)
 constexpr int kWRings = 3;            // mo, P, F
 
 // ---- raw-input streams: one 36-double row segment per (field, row), staged by TMA bulk copies ----
@@ -226,7 +236,7 @@ __host__ __device__ inline SmemPlan smem_plan(int nlay, int groups, int n_all, i
   o += (size_t)(8 * nlay + 2 * groups) * 8;           // full[nlay][4], empty[nlay][4], gbar[groups][2]
   o = (o + 15) & ~(size_t)15;
   p.off_wring = o;
-  o += (size_t)nlay * groups * (kWRings * 4 * kWRow * 8 + 128);  // per-warp state rings + open-water bitmap (32 words)
+  o += (size_t)nlay * groups * (kWRings * 4 * kWRow * 8 + kOWords * 4);  // per-warp state rings + open-water bitmap
   o = (o + 127) & ~(size_t)127;
   p.off_ring = o;
   p.seg_bytes = (size_t)seg_doubles(groups) * 8;
@@ -240,7 +250,8 @@ __host__ __device__ inline SmemPlan smem_plan(int nlay, int groups, int n_all, i
 // FLAVOR only distinguishes the symbol of the copy compiled with FMA contraction (fused_inst_lean*_fma.cu, BEOM_FMA=1)
 template <bool UFIRST, bool VISC, int NL, int FEAT, int GROUPS, int FLAVOR = 0, bool G0 = false>
 // (a specialised instantiation knows its block size: fewer than 16 warps leave each thread more than 128 registers)
-__global__ void __launch_bounds__((FEAT >= 0 && NL > 0 && GROUPS > 0) ? NL * GROUPS * 32 : kMaxWarps * 32, 1)
+__global__ void __launch_bounds__((FEAT >= 0 && NL > 0 && GROUPS > 0) ? NL * GROUPS * 32 : kMaxWarps * 32,
+                                  (FEAT >= 0 && NL > 0 && GROUPS > 0 && NL * GROUPS * 32 <= 256) ? BEOM_MIN_CTAS : 1)
 k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const __grid_constant__ StreamTab T,
              const uint8_t *__restrict__ open, const unsigned *__restrict__ open4, int open4_words, int groups_rt, int rows_per_chunk,
              int wind_layers) {
@@ -265,7 +276,7 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
   const SmemPlan sp = smem_plan(nlay, groups, T.n, T.n_nowind, D.has_wind ? wind_layers : 0);
   double *sh_h = reinterpret_cast<double *>(smem_raw);
   unsigned long long *bars = reinterpret_cast<unsigned long long *>(smem_raw + sp.off_bars);
-  double *wring = reinterpret_cast<double *>(smem_raw + sp.off_wring) + (size_t)wid * (kWRings * 4 * kWRow + 16);
+  double *wring = reinterpret_cast<double *>(smem_raw + sp.off_wring) + (size_t)wid * (kWRings * 4 * kWRow + kOWords / 2);
   unsigned *obits = reinterpret_cast<unsigned *>(wring + kWRings * 4 * kWRow);  // [32]: open-water bit of every 4-row group of the chunk
   double *ring = reinterpret_cast<double *>(smem_raw + sp.ring_off(l));  // input ring of this layer
 
@@ -599,7 +610,7 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
     // open-water bit of every 4-row group of the chunk, kept in shared memory: word k covers groups 32k .. 32k+31
     // past the first (a global load per group would sit on the critical path of every group)
     const int w0 = Rs >> 7;
-    obits[lane] = (w0 + lane < open4_words) ? open4[(size_t)tile * open4_words + w0 + lane] : 0u;
+    if (lane < kOWords) obits[lane] = (w0 + lane < open4_words) ? open4[(size_t)tile * open4_words + w0 + lane] : 0u;
     __syncwarp();
 #pragma unroll 1
     for (int R = Rs; R <= R1; R += 4) {
