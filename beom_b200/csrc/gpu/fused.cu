@@ -42,11 +42,11 @@ struct FusedCfg {
   int groups = 1;     // column groups (warps per layer) per CTA
   int strips = 1;     // CTAs along x
   int chunks = 1;     // CTAs along y
-  int rows_per_chunk = 1;
+  int rows_per_chunk = 1;  // packed: see chunk_rows()
   bool visc = false;    // Leith viscosity recomputed every step
   int wind_layers = 0;  // bit l set: tt3d of layer l may be non-zero
   uint8_t *open = nullptr;  // [tiles][NY]: bit 0 = rows R-2..R open water on the tile's 32 columns, bit 1 = the same for R..R+3
-  unsigned *open4 = nullptr;  // [tiles][open4_words]: bit g of the row-group bitmap = bit 1 of open[4g]
+  unsigned *open4 = nullptr;  // [tiles][4][open4_words]: bit g of the row-group bitmap of residue r = bit 1 of open[4g + r]
   int open4_words = 0;
 } cfg;
 
@@ -72,15 +72,28 @@ __global__ void k_open_groups(uint8_t *__restrict__ open, int NY, int ntiles) {
   if (all) o[R] |= 2;  // bit 1 is read by nobody in this kernel
 }
 
+// one bitmap per residue of the group's first row mod 4 (a chunk's groups start at its own first row): bit g of
+// open4[tile][res] says rows 4g + res - 2 .. 4g + res + 3 are open water on the tile's 32 columns
 __global__ void k_open_bits(const uint8_t *__restrict__ open, unsigned *__restrict__ open4, int NY, int nwords) {
-  const int w = blockIdx.x * blockDim.x + threadIdx.x, tile = blockIdx.y;
+  const int w = blockIdx.x * blockDim.x + threadIdx.x, tile = blockIdx.y, res = blockIdx.z;
   if (w >= nwords) return;
   unsigned bits = 0;
   for (int b = 0; b < 32; b++) {
-    const int R = (w * 32 + b) * 4;
+    const int R = (w * 32 + b) * 4 + res;
     if (R < NY && (open[(size_t)tile * NY + R] & 2)) bits |= 1u << b;
   }
-  open4[(size_t)tile * nwords + w] = bits;
+  open4[((size_t)tile * 4 + res) * nwords + w] = bits;
+}
+
+// Rows of the y-chunks of a strip.  A chunk runs its rows + 5 (3 of pipeline lead-in, 2 of tail) in groups of 4, so chunks of
+// 4k + 3 rows waste nothing: `rows` are cut into `chunks` pieces of base or base + 4 rows, base = 3 mod 4 (the first `nbig` get
+// the 4 more; the last one also takes the 0..3 rows that are left).  Returns the kernel's argument: base | nbig << 16.
+int chunk_rows(int rows, int chunks) {
+  const int q = rows / chunks;
+  if (chunks <= 1 || q < 7) return rows;  // one piece (the last chunk takes everything that is left)
+  const int base = ((q - 3) & ~3) + 3;
+  const int nbig = (rows - base * chunks) / 4;
+  return base | (nbig << 16);
 }
 
 // Stream table for one step: where each staged row segment comes from (pointers follow the state
@@ -205,16 +218,19 @@ int fused_configure(const Dev &D, const beom_params &P, int nmir, int nranks, bo
     const int max_rows = kOWords * 128 - 256;
     chunks = std::max(chunks, (rows + max_rows - 1) / max_rows);
   }
-  cfg.rows_per_chunk = (rows + chunks - 1) / chunks;
-  cfg.chunks = (rows + cfg.rows_per_chunk - 1) / cfg.rows_per_chunk;
+  {
+    const int rpc = (rows + chunks - 1) / chunks;
+    cfg.chunks = (rows + rpc - 1) / rpc;
+    cfg.rows_per_chunk = chunk_rows(rows, cfg.chunks);
+  }
   {
     const int ntiles = cfg.strips * groups;
     if (cudaMalloc(&cfg.open, (size_t)ntiles * D.NY) != cudaSuccess) return -62;
     k_open_rows<<<dim3((unsigned)ntiles, (unsigned)((D.NY + 7) / 8)), dim3(32, 8)>>>(D.flags, cfg.open, D.NX, D.NY, D.x_lo);
     k_open_groups<<<dim3((unsigned)((D.NY + 127) / 128), (unsigned)ntiles), 128>>>(cfg.open, D.NY, ntiles);
     cfg.open4_words = (D.NY + 127) / 128;
-    if (cudaMalloc(&cfg.open4, (size_t)ntiles * cfg.open4_words * sizeof(unsigned)) != cudaSuccess) return -62;
-    k_open_bits<<<dim3((unsigned)((cfg.open4_words + 63) / 64), (unsigned)ntiles), 64>>>(cfg.open, cfg.open4, D.NY, cfg.open4_words);
+    if (cudaMalloc(&cfg.open4, (size_t)ntiles * 4 * cfg.open4_words * sizeof(unsigned)) != cudaSuccess) return -62;
+    k_open_bits<<<dim3((unsigned)((cfg.open4_words + 63) / 64), (unsigned)ntiles, 4), 64>>>(cfg.open, cfg.open4, D.NY, cfg.open4_words);
     if (cudaDeviceSynchronize() != cudaSuccess) return -63;
   }
   cfg.ok = true;
@@ -251,6 +267,7 @@ int fused_step(const Dev &in_, const Dev &out, int tstp, bool first_three, cudaS
     chunks = std::max(1, std::min(cfg.chunks, rows / 16));
     rpc = (rows + chunks - 1) / chunks;
     chunks = (rows + rpc - 1) / rpc;
+    rpc = chunk_rows(rows, chunks);
   }
   static const bool swap = getenv("BEOM_FUSED_ORDER") && atoi(getenv("BEOM_FUSED_ORDER")) == 1;  // experiment: chunk index fastest
   a.grid = swap ? dim3((unsigned)chunks, (unsigned)cfg.strips, 1) : dim3((unsigned)cfg.strips, (unsigned)chunks, 1);

@@ -81,6 +81,9 @@ __host__ __device__ constexpr int seg_doubles(int groups) { return groups * kUse
 constexpr int kWRow = BEOM_WROW;      // per-warp state ring: 32 lanes + 1 pad column on the west side (33; 34 = padded on both)
 constexpr int kOWords = BEOM_OWORDS;  // words of a chunk's open-water bitmap kept in shared memory (one bit per 4-row group)
 constexpr int kWRings = 3;            // mo, P, F
+#ifndef BEOM_L2_AHEAD
+#define BEOM_L2_AHEAD 0   // rows of L2 prefetch ahead of the staging copies (0 = none)
+#endif
 
 // ---- raw-input streams: one 36-double row segment per (field, row), staged by TMA bulk copies ----
 enum {
@@ -154,6 +157,12 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void *src, unsigned
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
                "r"(bar)
                : "memory");
+}
+
+// L2 prefetch of a row segment the CTA stages BEOM_L2_AHEAD rows later (no destination, no completion to wait for).  An
+// experiment (build switch, off): measured SLOWER the further ahead it reaches (profiles/r2_l2_prefetch_ab.txt)
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 
 // One momentum update: update_u (private_mod.f95:1437-1500) when IS_U, update_v (private_mod.f95:1520-1586)
@@ -292,8 +301,11 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
 #endif
   // rows of this CTA.  rows_per_chunk < 0: the two "edge" chunks of a y-slab (the -rows_per_chunk rows next to each
   // neighbouring rank), which are computed first so that their exchange overlaps the interior rows
-  const int ya = rows_per_chunk > 0 ? D.y_lo + by * rows_per_chunk : (by == 0 ? D.y_lo : D.y_hi + rows_per_chunk + 1);
-  const int yb = rows_per_chunk > 0 ? min(ya + rows_per_chunk - 1, D.y_hi) : ya - rows_per_chunk - 1;
+  // (rows_per_chunk > 0: base | nbig << 16 -- chunks of base rows, the first nbig of base + 4, the last one up to y_hi; fused.cu)
+  const int rpc = rows_per_chunk & 0xffff, nbig = rows_per_chunk >> 16;
+  const int nchunks = (int)(((wind_layers >> 16) & 1) ? gridDim.x : gridDim.y);
+  const int ya = rows_per_chunk > 0 ? D.y_lo + by * rpc + 4 * min(by, nbig) : (by == 0 ? D.y_lo : D.y_hi + rows_per_chunk + 1);
+  const int yb = rows_per_chunk > 0 ? (by == nchunks - 1 ? D.y_hi : ya + rpc + (by < nbig ? 4 : 0) - 1) : ya - rows_per_chunk - 1;
   const size_t L = (size_t)l * D.plane;
   const bool wind = D.has_wind && ((wind_layers >> l) & 1);
   const int nstr = wind ? T.n : T.n_nowind;
@@ -361,17 +373,23 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
   }
   __syncthreads();
   const int R0 = ya - 3, R1 = yb + 2;
-  const int Rs = R0 & ~3;  // the row loop starts on a multiple of 4: ring slot = R & 3 = unroll phase
-  const int Rend = R1 | 3;  // last row the loop visits (the unrolled loop works in groups of 4)
+  // The row loop works in groups of 4 rows from R0 on: ring slot = (R - R0) & 3 = unroll phase.  (It used to start on a
+  // multiple of 4, which cost every chunk 3 rows of alignment on average; the host now picks chunks of 4k + 3 rows, whose
+  // rows + 5 of pipeline lead-in and tail are whole groups.)
+  const int Rend = R0 + ((R1 - R0) | 3);  // last row the loop visits
   const size_t row_bytes = (size_t)NX * 8;
-  auto issue = [&](int Rt) {  // stage this warp's share of the inputs of front row Rt
-    const unsigned bar = full0 + 8 * (Rt & 3);
+  auto issue = [&](int Rt, int slot) {  // stage this warp's share of the inputs of front row Rt (slot = (Rt - R0) & 3)
+    const unsigned bar = full0 + 8 * slot;
     if (lane == 0) mbar_expect_tx(bar, my_bytes);
-    if (my_on) bulk_g2s(my_dst + (unsigned)(Rt & my_mask) * segb, my_src + (size_t)min(max(Rt - my_lag, 0), NY - 1) * row_bytes, segb, bar);
+    if (my_on) bulk_g2s(my_dst + (unsigned)(slot & my_mask) * segb, my_src + (size_t)min(max(Rt - my_lag, 0), NY - 1) * row_bytes, segb, bar);
+    if (BEOM_L2_AHEAD > 0 && my_on && Rt + BEOM_L2_AHEAD <= Rend)
+      bulk_prefetch_l2(my_src + (size_t)min(max(Rt + BEOM_L2_AHEAD - my_lag, 0), NY - 1) * row_bytes, segb);
   };
-  issue(Rs);
-  issue(Rs + 1);
-  size_t off0 = ((size_t)Rs * NX + x) * 8;                   // only dereferenced for rows this chunk owns
+  issue(R0, 0);
+  issue(R0 + 1, 1);
+  for (int k = 2; k < BEOM_L2_AHEAD; k++)  // rows the first two issues do not reach
+    if (my_on && R0 + k <= Rend) bulk_prefetch_l2(my_src + (size_t)min(max(R0 + k - my_lag, 0), NY - 1) * row_bytes, segb);
+  size_t off0 = ((size_t)R0 * NX + x) * 8;                   // only dereferenced for rows this chunk owns
   size_t off2 = off0 - 2 * row_bytes;
 
   // ---- values carried from earlier rows: X[(phase - age) & 3] is X of row R - age ----
@@ -388,7 +406,7 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
   const int tt_base = SPEC ? spec_slot(FEAT, S_TTXU) : (int)T.slot[S_TTXU];  // wind streams keep their order: TTXU, TTYV, TTYVS
 
 #define AT(a, age) a[(PH - (age)) & 3]
-#define SLOT(age) (CT ? ((PH - (age)) & 3) : ((R - (age)) & 3))
+#define SLOT(age) ((PH - (age)) & 3)
 #define LD4(s, age, dx) sgp[((s) * 4 + SLOT(age)) * wseg + (dx)]
 #define LD2(slot, dx) sgp[(16 + ((slot)-4) * 2 + (SLOT(0) & 1)) * wseg + (dx)]
 #define LDX(stream, dx) LD2((SPEC ? spec_slot(FEAT, stream) : (int)T.slot[stream]), dx)
@@ -397,15 +415,14 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
 #define SELM(p, a) (MASKED ? sel((p), (a)) : (a))
 #define MKN(f) (MASKED ? m_n(f) : 1.0)
   enum { W_MO = 0, W_PV = 1, W_FX = 2 };
-  // One row of the pipeline.  PH = phase of the carried rings; CT: the ring slot is the compile-time phase.
+  // One row of the pipeline.  PH = phase of the carried rings = ring slot of the row, (R - R0) & 3.
   // MASKED = false is the open-water fast path: every mask of the three rows in flight is 1 on all 32 lanes,
   // so no select is needed.
-  auto row = [&](auto ph_tag, auto ct_tag, auto masked_tag, const int R, const unsigned f_own, const unsigned fw_0, const unsigned bpar) {
+  auto row = [&](auto ph_tag, auto masked_tag, const int R, const unsigned f_own, const unsigned fw_0, const unsigned bpar) {
     constexpr int PH = decltype(ph_tag)::value;
-    constexpr bool CT = decltype(ct_tag)::value;
     constexpr bool MASKED = decltype(masked_tag)::value;
     const int hslot = SLOT(0) & 1;
-    const unsigned hpar = CT ? ((PH >> 1) & 1) : ((R >> 1) & 1);
+    constexpr unsigned hpar = (PH >> 1) & 1;
     mbar_wait(full0 + 8 * SLOT(0), bpar);  // staged inputs of front row R have landed
     const bool act = f_own & (F_ACT | F_GHOST);  // evaluated (ghost cells: like the cell they mirror) ...
     const bool own = f_own & F_ACT;              // ... and stored
@@ -584,7 +601,7 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
     if (lane == 0) mbar_arrive(empty0 + 8 * SLOT(0));  // this warp has finished reading the slots row R + 2 refills
     if (R + 2 <= Rend) {
       mbar_wait(empty0 + 8 * SLOT(0), bpar);           // ... and so has every other column group of the layer
-      issue(R + 2);
+      issue(R + 2, (PH + 2) & 3);
     }
     off0 += row_bytes;
     off2 += row_bytes;
@@ -608,29 +625,31 @@ k_fused_step(const __grid_constant__ Dev D, const __grid_constant__ Dev O, const
   {
     unsigned bpar = 0;
     // open-water bit of every 4-row group of the chunk, kept in shared memory: word k covers groups 32k .. 32k+31
-    // past the first (a global load per group would sit on the critical path of every group)
-    const int w0 = Rs >> 7;
-    if (lane < kOWords) obits[lane] = (w0 + lane < open4_words) ? open4[(size_t)tile * open4_words + w0 + lane] : 0u;
+    // past the first (a global load per group would sit on the critical path of every group).  The groups of this chunk are
+    // the rows congruent to R0 mod 4: open4 holds one bitmap per residue, bit (R >> 2) of it says rows R-2 .. R+3 are open
+    const int w0 = R0 >> 7;
+    const unsigned *o4 = open4 + ((size_t)tile * 4 + (R0 & 3)) * open4_words;  // [tile][residue][word]
+    if (lane < kOWords) obits[lane] = (w0 + lane < open4_words) ? o4[w0 + lane] : 0u;
     __syncwarp();
 #pragma unroll 1
-    for (int R = Rs; R <= R1; R += 4) {
+    for (int R = R0; R <= R1; R += 4) {
       const unsigned o = obits[(R >> 7) - w0] >> ((R >> 2) & 31);
       if (o & 1) {  // rows R-2 .. R+3 are open water on all 32 columns
-        row(ic<0>{}, Tt{}, Ft{}, R, kAllMasks, kAllMasks, bpar);
-        row(ic<1>{}, Tt{}, Ft{}, R + 1, kAllMasks, kAllMasks, bpar);
-        row(ic<2>{}, Tt{}, Ft{}, R + 2, kAllMasks, kAllMasks, bpar);
-        row(ic<3>{}, Tt{}, Ft{}, R + 3, kAllMasks, kAllMasks, bpar);
+        row(ic<0>{}, Ft{}, R, kAllMasks, kAllMasks, bpar);
+        row(ic<1>{}, Ft{}, R + 1, kAllMasks, kAllMasks, bpar);
+        row(ic<2>{}, Ft{}, R + 2, kAllMasks, kAllMasks, bpar);
+        row(ic<3>{}, Ft{}, R + 3, kAllMasks, kAllMasks, bpar);
         fw_m1 = fw_m2 = kAllMasks;
       } else {
         const unsigned f0 = flags_of(R), f1 = flags_of(R + 1), f2 = flags_of(R + 2), f3 = flags_of(R + 3);
         const unsigned e0 = widen(f0), e1 = widen(f1), e2 = widen(f2), e3 = widen(f3);
-        row(ic<0>{}, Tt{}, Tt{}, R, f0, e0, bpar);
+        row(ic<0>{}, Tt{}, R, f0, e0, bpar);
         fw_m2 = fw_m1; fw_m1 = e0;
-        row(ic<1>{}, Tt{}, Tt{}, R + 1, f1, e1, bpar);
+        row(ic<1>{}, Tt{}, R + 1, f1, e1, bpar);
         fw_m2 = fw_m1; fw_m1 = e1;
-        row(ic<2>{}, Tt{}, Tt{}, R + 2, f2, e2, bpar);
+        row(ic<2>{}, Tt{}, R + 2, f2, e2, bpar);
         fw_m2 = fw_m1; fw_m1 = e2;
-        row(ic<3>{}, Tt{}, Tt{}, R + 3, f3, e3, bpar);
+        row(ic<3>{}, Tt{}, R + 3, f3, e3, bpar);
         fw_m2 = fw_m1; fw_m1 = e3;
       }
       bpar ^= 1;

@@ -81,6 +81,7 @@ inline void mbar_expect_tx(unsigned bar, unsigned bytes) { emu::mbar_expect_tx(b
 inline void mbar_arrive(unsigned bar) { emu::mbar_arrive(bar); }
 inline void mbar_wait(unsigned bar, unsigned parity) { emu::mbar_wait(bar, parity); }
 inline void bulk_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar) { emu::bulk_g2s(dst, src, bytes, bar); }
+inline void bulk_prefetch_l2(const void *, unsigned) {}  // a cache hint: nothing to emulate
 
 """
 
