@@ -2,8 +2,10 @@
 // sequencing (first_three_timesteps / gener_forward_backward, private_mod.f95:2151-2316).
 // sm_100a only; no CPU path exists in this library.
 #include <cuda_runtime.h>
+#include <sched.h>
 
 #include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -1737,9 +1739,60 @@ int beom_gpu_set_window(int first, int count) {
   return 0;
 }
 
+}  // extern "C"
+namespace {
+// CPUs of the NUMA node the current device hangs off (sysfs: the PCI function's numa_node, the node's cpulist); false if the
+// machine does not say (one node, a VM, no sysfs)
+bool device_node_cpus(cpu_set_t *set) {
+  int dev = 0;
+  char bus[32] = {0};
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetPCIBusId(bus, (int)sizeof bus, dev) != cudaSuccess) return false;
+  for (char *c = bus; *c; c++) *c = (char)tolower((unsigned char)*c);
+  char path[128];
+  snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+  FILE *f = fopen(path, "r");
+  if (!f) return false;
+  int node = -1;
+  const int got = fscanf(f, "%d", &node);
+  fclose(f);
+  if (got != 1 || node < 0) return false;
+  snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+  if (!(f = fopen(path, "r"))) return false;
+  CPU_ZERO(set);
+  int a, b, n = 0;
+  while (fscanf(f, "%d", &a) == 1) {  // "0-31,64-95"
+    b = a;
+    int ch = fgetc(f);
+    if (ch == '-') {
+      if (fscanf(f, "%d", &b) != 1) break;
+      ch = fgetc(f);
+    }
+    for (int c = a; c <= b && c < CPU_SETSIZE; c++) { CPU_SET(c, set); n++; }
+    if (ch != ',') break;
+  }
+  fclose(f);
+  return n > 0;
+}
+}  // namespace
+extern "C" {
+
+// The pages are allocated (and pinned) by the calling thread inside cudaHostAlloc, on the node of the CPU it runs on: run it on
+// the device's own node for the duration of the call, so that with one process per GPU on a two-socket host every rank's
+// boundary copies stay on its socket (the aggregate copy rate of 8 ranks was 120 GB/s against 50 GB/s for one, profiles/
+// r2_bench_n8.json).  BEOM_HOST_NUMA=0 switches it off.
 void *beom_gpu_host_alloc(size_t bytes) {
   void *p = nullptr;
-  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) { fail(-50, "cudaHostAlloc(%zu) failed", bytes); return nullptr; }
+  cpu_set_t old_set, node_set;
+  static const bool want = !(getenv("BEOM_HOST_NUMA") && atoi(getenv("BEOM_HOST_NUMA")) == 0);
+  bool moved = false;
+  if (want && sched_getaffinity(0, sizeof old_set, &old_set) == 0 && device_node_cpus(&node_set)) {
+    cpu_set_t both;
+    CPU_AND(&both, &old_set, &node_set);  // never widen what the caller was given
+    if (CPU_COUNT(&both) > 0) moved = sched_setaffinity(0, sizeof both, &both) == 0;
+  }
+  const cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocDefault);
+  if (moved) sched_setaffinity(0, sizeof old_set, &old_set);
+  if (e != cudaSuccess) { fail(-50, "cudaHostAlloc(%zu) failed", bytes); return nullptr; }
   return p;
 }
 void beom_gpu_host_free(void *p) { if (p) cudaFreeHost(p); }

@@ -233,7 +233,8 @@ int beom_gpu_point_range(int *first, int *count, int *own_first, int *own_count)
 int beom_gpu_set_window(int first, int count);
 
 /* Page-locked host memory for state arrays that cross the boundary every output interval (the
- * Fortran side maps it with c_f_pointer); plain malloc'ed arrays work too, only slower. */
+ * Fortran side maps it with c_f_pointer); plain malloc'ed arrays work too, only slower.  The pages are placed on the NUMA
+ * node of the current device (sysfs; BEOM_HOST_NUMA=0 switches that off): call it after beom_gpu_init / cudaSetDevice. */
 void *beom_gpu_host_alloc(size_t bytes);
 void  beom_gpu_host_free(void *p);
 
