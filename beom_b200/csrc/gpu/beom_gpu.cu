@@ -1778,8 +1778,9 @@ extern "C" {
 
 // The pages are allocated (and pinned) by the calling thread inside cudaHostAlloc, on the node of the CPU it runs on: run it on
 // the device's own node for the duration of the call, so that with one process per GPU on a two-socket host every rank's
-// boundary copies stay on its socket (the aggregate copy rate of 8 ranks was 120 GB/s against 50 GB/s for one, profiles/
-// r2_bench_n8.json).  BEOM_HOST_NUMA=0 switches it off.
+// boundary copies stay on its socket.  (The B200 boxes of this pool are single-node VMs whose sysfs reports numa_node = -1, so
+// there it does nothing -- profiles/r2_topology_4gpu.txt, same end-to-end time with and without, r2_bench_n4*.json; the
+// aggregate host<->device rate of 4-8 ranks, 85-120 GB/s against 50 GB/s for one, is the VM's.)  BEOM_HOST_NUMA=0 switches it off.
 void *beom_gpu_host_alloc(size_t bytes) {
   void *p = nullptr;
   cpu_set_t old_set, node_set;
