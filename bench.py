@@ -46,17 +46,58 @@ def measured_peak_gbs():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock + throttle reasons during the timed region (B200_PROFILING.md's clocks line).  NVML is polled in this process
+    every 10 ms (a timed region of 20 steps lasts 0.2 s: `nvidia-smi -lms 100` through a pipe often delivered nothing in that
+    time); nvidia-smi is the fallback when pynvml is missing."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index: int):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag, self.proc = index, [], False, None
+        self.index, self.samples, self.stop_flag, self.proc, self.how = index, [], False, None, None
+        self.nvml = self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # torch's device index follows CUDA_VISIBLE_DEVICES; NVML's does not
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = index
+            if vis:
+                ent = [v.strip() for v in vis.split(",") if v.strip()]
+                if index < len(ent) and ent[index].isdigit():
+                    phys = int(ent[index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml, self.how = pynvml, "nvml"
+        except Exception:
+            self.nvml = None
+
+    def _poll_nvml(self):
+        n = self.nvml
+        bits = [(getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8), "hw_slowdown"),
+                (getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40), "hw_thermal_slowdown"),
+                (getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), "sw_thermal_slowdown"),
+                (getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4), "sw_power_cap")]
+        smax = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+        while not self.stop_flag:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                try:
+                    r = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append([str(sm), str(smax)] + ["Active" if (r & b) else "Not Active" for b, _ in bits])
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def run(self):
         try:
+            if self.nvml is not None:
+                self._poll_nvml()
+                return
+            self.how = "nvidia-smi"
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -71,19 +112,20 @@ class ClockSampler(threading.Thread):
         self.stop_flag = True
         if self.proc:
             self.proc.terminate()
+        if self.nvml is not None and self.is_alive():
+            self.join(timeout=1.0)
         sm, smax, reasons = [], 0.0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        for s in list(self.samples):
             try:
                 sm.append(float(s[0]))
                 smax = max(smax, float(s[1]))
-                for n, v in zip(names, s[2:6]):
+                for n, v in zip(self.NAMES, s[2:6]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
             except Exception:
                 continue
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": self.how}
 
 
 def make_case(n, nlay, workdir, mm=None, sponge=False):
