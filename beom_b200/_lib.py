@@ -84,7 +84,7 @@ GPU_SYMBOLS = [
     "beom_gpu_init", "beom_gpu_init_grids", "beom_gpu_download_subc", "beom_gpu_download_grid_files", "beom_gpu_debug_static", "beom_gpu_upload_state", "beom_gpu_stress", "beom_gpu_step", "beom_gpu_advance",
     "beom_gpu_download_state", "beom_gpu_download_aux", "beom_gpu_download_diag", "beom_gpu_download_pi_s", "beom_gpu_pi_iterations",
     "beom_gpu_diagnostics", "beom_gpu_diagnostics_all", "beom_gpu_set_rest_thickness", "beom_gpu_records_begin",
-    "beom_gpu_records_wait", "beom_gpu_sync", "beom_gpu_mark", "beom_gpu_elapsed_ms", "beom_gpu_launch_count",
+    "beom_gpu_records_wait", "beom_gpu_sync", "beom_gpu_mark", "beom_gpu_elapsed_ms", "beom_gpu_launch_count", "beom_gpu_graph_launch_count",
     "beom_gpu_path", "beom_gpu_fused_variant", "beom_gpu_point_range", "beom_gpu_set_window", "beom_gpu_host_alloc", "beom_gpu_host_free", "beom_gpu_comm_unique_id", "beom_gpu_comm_init", "beom_gpu_comm_finalize", "beom_gpu_finalize",
 ]
 
@@ -137,6 +137,7 @@ def bind_gpu(lib: C.CDLL) -> C.CDLL:
     lib.beom_gpu_mark.argtypes = [C.c_int]
     lib.beom_gpu_elapsed_ms.argtypes = [c_double_p]
     lib.beom_gpu_launch_count.restype = C.c_longlong
+    lib.beom_gpu_graph_launch_count.restype = C.c_longlong
     lib.beom_gpu_fused_variant.restype = C.c_char_p
     lib.beom_gpu_point_range.argtypes = [C.POINTER(C.c_int)] * 4
     lib.beom_gpu_set_window.argtypes = [C.c_int, C.c_int]

@@ -13,6 +13,7 @@
 #include <cstring>
 #include <functional>
 #include <initializer_list>
+#include <map>
 #include <string>
 #include <vector>
 
@@ -114,6 +115,18 @@ struct Ctx {
   size_t diag_blocks = 0;
   cudaEvent_t ev[2] = {nullptr, nullptr};
   long long launches = 0;
+  // CUDA graphs of whole steps for latency-bound grids (step_graphed): one executable graph per phase of the rotating buffers
+  struct StepGraph {
+    cudaGraphExec_t exec = nullptr;
+    long long launches = 0;            // kernel nodes
+    int cur = 0, rs_o = 0, dx_o = 0, dy_o = 0;  // the rotating indices after the step
+    bool stress_done = false;
+  };
+  std::map<unsigned, StepGraph> graphs;
+  bool graphs_on = false;      // decided at init (one rank, no tides, no rigid lid, a latency-bound grid; BEOM_GRAPH overrides)
+  double graph_gene = -1.0;    // the gene the graphs were captured with
+  int direct_steps = 0;        // steady steps launched directly since the last upload (the first ones are never captured)
+  long long graph_launches = 0;
   size_t win_first = 0, win_stride = 0;  // host state arrays cover points win_first .. win_first+win_stride-1 per layer
   int n_3d = 1;
   PiSolve pis;           // rigid lid: the wavefront solver's arrays (rigid.cuh)
@@ -122,6 +135,7 @@ struct Ctx {
   int *pi_iters = nullptr;  // device: sweeps of the last solve
 };
 Ctx g;
+void drop_graphs_fwd();  // (defined next to step_graphed)
 
 // Device allocation.  Large planes are staggered: allocation k starts (k mod 8) x 2 MiB + (k mod 5) x 4 KiB into its
 // block, so that the ~90 row streams the fused step reads and writes at the same time do not all sit at the same
@@ -416,6 +430,7 @@ long long beom_gpu_launch_count(void) { return g.launches; }
 
 int beom_gpu_finalize(void) {
   if (g.stream) cudaStreamSynchronize(g.stream);
+  drop_graphs_fwd();
   for (void *p : g.allocs) cudaFree(p);
   g.allocs.clear();
   for (auto &e : g.ev)
@@ -817,6 +832,15 @@ static int init_tail(double invf, double w_ti, const double *bodf) {
     if (g.use_fused)
       for (int f = 0; f < 5; f++)
         if ((rc = dalloc(&g.st[f][1], pl * nl))) return rc;
+  }
+  {
+    // whole steps as CUDA graphs where the step is launch bound (step_graphed): the same size rule as the kernel path
+    const char *e = getenv("BEOM_GRAPH");
+    const bool want = e ? atoi(e) > 0 : cell_layers < 250000.0;
+    g.graphs_on = want && g.nranks == 1 && !D.has_tide && !(par->rgld > 0.5);
+    g.graph_gene = -1.0;
+    g.direct_steps = 0;
+    g.graph_launches = 0;
   }
   CK(cudaStreamSynchronize(g.stream));
   g.win_first = 0;
@@ -1295,6 +1319,8 @@ int beom_gpu_upload_state(const double *hlay, const double *u, const double *v) 
   for (auto p : g.dy) CK(cudaMemsetAsync(p, 0, pl * nl * sizeof(double), g.stream));
   g.rs_o = g.dx_o = g.dy_o = 0;
   g.stress_const_done = false;
+  drop_graphs_fwd();  // (captured with the stress state and buffer phases of the run so far)
+  g.direct_steps = 0;
   // one H2D copy per field (all layers), then scatter into the dense planes
   const int n = g.p_hi - g.p_lo + 1;
   for (int f = 0; f < 3; f++) {
@@ -1325,10 +1351,11 @@ int beom_gpu_stress(void) {
   return run_stress();
 }
 
-int beom_gpu_step(int tstp, double ctim, double ramp, double gene, int upst, int first_three) {
-  if (!g.ready) return fail(-20, "beom_gpu_step: not initialised");
-  g.D.ctim = ctim; g.D.ramp = ramp; g.D.gene = gene;
-  g.orph.record(ctim, ramp);
+}  // extern "C"
+namespace {
+
+// One step, launched kernel by kernel on g.stream (g.D.ctim / ramp / gene already set).
+int step_direct(int tstp, int upst, int first_three) {
   if (g.use_fused && fused_supports(first_three != 0, upst != 0)) {
     Dev D = g.D;
     set_state_pointers(D);
@@ -1406,6 +1433,89 @@ int beom_gpu_step(int tstp, double ctim, double ramp, double gene, int upst, int
   return step_split(tstp, upst != 0, first_three != 0);
 }
 
+void drop_graphs() {
+  for (auto &kv : g.graphs)
+    if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  g.graphs.clear();
+}
+void drop_graphs_fwd() { drop_graphs(); }
+
+// One step (with distribute_stress in front of it when `with_stress'), as ONE graph launch where the step is launch bound.
+// The reference's small configurations (322 .. 63 252 points) take 5-9 kernels of a few microseconds per step; what varies
+// from step to step in their arguments is only which of the rotating buffers is which (state double buffer, rs_h / dmdx /
+// dmdy rings, u-first or v-first): a period of 12 steps.  So each phase is captured once -- the very launch sequence of
+// step_direct, recorded instead of run -- and replayed from then on.  Not captured: the start-up steps, the first two steady
+// steps after an upload (allocations and function attributes happen there), steps with ramp != 1 or tides (ctim and ramp are
+// kernel arguments), the rigid lid, more than one rank.  A capture that fails switches the graphs off; the step then runs
+// directly, as before.  BEOM_GRAPH=0 / 1 overrides the size rule.
+int step_graphed(int tstp, double ctim, double ramp, double gene, int upst, int first_three, bool with_stress) {
+  g.D.ctim = ctim; g.D.ramp = ramp; g.D.gene = gene;
+  g.orph.record(ctim, ramp);
+  int rc;
+  const bool steady = !first_three && ramp == 1.0;
+  if (!(g.graphs_on && steady && g.direct_steps >= 2)) {
+    if (with_stress && (rc = run_stress())) return rc;
+    rc = step_direct(tstp, upst, first_three);
+    if (!rc && steady) g.direct_steps++;
+    return rc;
+  }
+  if (gene != g.graph_gene) {
+    drop_graphs();
+    g.graph_gene = gene;
+  }
+  const unsigned key = (with_stress ? 1u : 0u) | (upst ? 2u : 0u) | ((unsigned)(tstp & 1) << 2) | ((unsigned)g.cur << 3) |
+                       ((unsigned)g.rs_o << 4) | ((unsigned)g.dx_o << 6) | ((unsigned)g.dy_o << 8);
+  auto it = g.graphs.find(key);
+  if (it == g.graphs.end()) {
+    const int cur = g.cur, rs = g.rs_o, dx = g.dx_o, dy = g.dy_o;
+    const bool sd = g.stress_const_done;
+    const long long l0 = g.launches;
+    cudaGraph_t graph = nullptr;
+    Ctx::StepGraph sg;
+    bool bad = cudaStreamBeginCapture(g.stream, cudaStreamCaptureModeRelaxed) != cudaSuccess;
+    if (!bad) {
+      rc = with_stress ? run_stress() : 0;
+      if (!rc) rc = step_direct(tstp, upst, 0);
+      const cudaError_t e = cudaStreamEndCapture(g.stream, &graph);
+      bad = rc != 0 || e != cudaSuccess || !graph;
+    }
+    if (!bad) bad = cudaGraphInstantiate(&sg.exec, graph, 0) != cudaSuccess;
+    if (graph) cudaGraphDestroy(graph);
+    if (bad) {  // nothing has run: put the indices back and do this step (and all later ones) directly
+      cudaGetLastError();
+      g.cur = cur; g.rs_o = rs; g.dx_o = dx; g.dy_o = dy;
+      g.stress_const_done = sd;
+      g.launches = l0;
+      g.graphs_on = false;
+      drop_graphs();
+      if (with_stress && (rc = run_stress())) return rc;
+      return step_direct(tstp, upst, 0);
+    }
+    sg.launches = g.launches - l0;
+    sg.cur = g.cur; sg.rs_o = g.rs_o; sg.dx_o = g.dx_o; sg.dy_o = g.dy_o;
+    sg.stress_done = g.stress_const_done;
+    g.launches = l0;
+    it = g.graphs.emplace(key, sg).first;
+  }
+  const Ctx::StepGraph &sg = it->second;
+  CK(cudaGraphLaunch(sg.exec, g.stream));
+  g.cur = sg.cur; g.rs_o = sg.rs_o; g.dx_o = sg.dx_o; g.dy_o = sg.dy_o;
+  g.stress_const_done = sg.stress_done;
+  g.launches += sg.launches;
+  g.graph_launches++;
+  return 0;
+}
+
+}  // namespace
+extern "C" {
+
+int beom_gpu_step(int tstp, double ctim, double ramp, double gene, int upst, int first_three) {
+  if (!g.ready) return fail(-20, "beom_gpu_step: not initialised");
+  return step_graphed(tstp, ctim, ramp, gene, upst, first_three, false);
+}
+
+long long beom_gpu_graph_launch_count(void) { return g.graph_launches; }
+
 int beom_gpu_advance(int tstp0, int tstp1, double tres) {
   if (!g.ready) return fail(-20, "beom_gpu_advance: not initialised");
   const beom_params &P = g.P;
@@ -1431,10 +1541,10 @@ int beom_gpu_advance(int tstp0, int tstp1, double tres) {
         gene = P.g_fb;
         if (gene > 0.5 && P.rgld > 0.5) gene = 0.0;
       }
-      if (upst && (rc = run_stress())) return rc;
       ramp = 1.0;
       if (P.rsta < 0.5 && ctim < P.dt_r) ramp = ctim / P.dt_r;
-      if ((rc = beom_gpu_step(tstp, ctim, ramp, gene, upst ? 1 : 0, 0))) return rc;
+      // distribute_stress (pm:1895, before the ramp is set: it does not use it) + the step, one graph launch where that pays
+      if ((rc = step_graphed(tstp, ctim, ramp, gene, upst ? 1 : 0, 0, upst))) return rc;
     }
   }
   return 0;

@@ -292,6 +292,10 @@ class GpuModel:
     def launch_count(self) -> int:
         return int(self.lib.beom_gpu_launch_count())
 
+    def graph_launch_count(self) -> int:
+        """Steps that ran as one CUDA-graph launch (beom_gpu_graph_launch_count)."""
+        return int(self.lib.beom_gpu_graph_launch_count())
+
     def pinned(self, shape) -> np.ndarray:
         """A float64 array in page-locked host memory (beom_gpu_host_alloc); freed at close()."""
         n = int(np.prod(shape))

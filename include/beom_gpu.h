@@ -247,6 +247,9 @@ int beom_gpu_mark(int which);
 int beom_gpu_elapsed_ms(double *ms);
 /* Number of kernel launches issued by this library since init. */
 long long beom_gpu_launch_count(void);
+/* Steps that ran as one CUDA-graph launch instead of kernel by kernel (latency-bound grids on one rank, steady steps: the launch
+ * sequence of each buffer phase is captured once and replayed; BEOM_GRAPH=0 / 1 overrides the size rule).  Diagnostic. */
+long long beom_gpu_graph_launch_count(void);
 /* Name of the kernel path in use ("fused" / "split"), for logs. */
 const char *beom_gpu_path(void);
 /* Which instantiation of the fused step runs: "specialised (options <mask>, <n> layers, <g> column groups)", "general (...)", "none". */

@@ -35,6 +35,7 @@ with tempfile.TemporaryDirectory() as d:
     aux = gm.download_aux()
     path = gm.path
     variant = gm.fused_variant
+    graph_steps = gm.graph_launch_count()  # steps that ran as one CUDA-graph launch (latency-bound grids)
     gm.close()
     # cos() of the tidal targets is the one libm-dependent operation: 1e-11 of the field's
     # magnitude there, bit for bit everywhere else
@@ -61,5 +62,5 @@ with tempfile.TemporaryDirectory() as d:
             bad.append("%s: %d entries differ, max %.3e of the field's magnitude" % (n, int(np.count_nonzero(got != want)), err))
     moved = float(np.abs(orc.array("u")).max() + np.abs(orc.array("v")).max())
     print(json.dumps({"case": name, "path": path, "variant": variant, "exact": tol == 0.0, "worst": worst, "bad": bad, "moved": moved,
-                      "cell_layers": c.ndeg * c.nlay}))
+                      "cell_layers": c.ndeg * c.nlay, "graph_steps": graph_steps}))
     sys.exit(1 if bad else 0)

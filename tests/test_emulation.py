@@ -543,3 +543,34 @@ def test_halo_overlap_variant_on_emulated_ranks(emu_so, overlap):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=dict(os.environ, BEOM_OVERLAP=overlap))
     res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
     assert r.returncode == 0 and all(not k["bad"] and k["path"] == "fused" for k in res["ranks"]), res
+
+
+# ---- whole steps as CUDA graphs on latency-bound grids (beom_gpu.cu: step_graphed).  The emulation records the launches of a
+# capture with their arguments as they were when issued and replays them in order, which is what a graph launch does: what is
+# checked here is the library's bookkeeping -- one graph per phase of the rotating buffers (period 12), the indices after a
+# replayed step, what may and may not be captured -- not CUDA's.
+GRAPH_CASES = [("lock_exchange", 45, {}, 0, 40), ("stommel1948", 45, {}, 0, 40), ("soliton", 40, {}, 0, 35),
+               ("sill_exchange3D", 45, {"bdrg": "2.e-3", "qdrg": "1."}, 0, 40),   # distribute_stress in front of every step
+               ("sill_exchange3D", 45, {"dt3d": "0.002"}, 0, 40),                  # n_3d = 2: upst alternates
+               ("baines_ridge", 40, {"mcbc": "0."}, 0, 35),                        # periodic images + the open-boundary copy
+               ("lock_exchange", 40, {}, 1, 35), ("baines_ridge", 36, {"mcbc": "0."}, 1, 31),  # the fused step
+               ("upwelling_seaward_wind", 30, {}, 0, 0),                           # dt_r ramp: ramp is a kernel argument
+               ("tide_ridge", 30, {}, 0, 0)]                                       # tides: so is ctim
+for _n, _s, _e, _f, _g in GRAPH_CASES:
+    job(_n, _s, _e, fused=_f)
+
+
+@pytest.mark.parametrize("name,nsteps,extra,fused,graph_steps", GRAPH_CASES,
+                         ids=["%s-%s-%d" % (n, "fused" if f else "split", i) for i, (n, _, _, f, _) in enumerate(GRAPH_CASES)])
+def test_steps_replayed_from_graphs_are_the_same_steps(emu_so, name, nsteps, extra, fused, graph_steps):
+    res = run(emu_so, name, nsteps, extra, fused=fused, path="fused" if fused else "split")
+    assert res["graph_steps"] == graph_steps, res  # all steady steps but the first two (0: never steady / not eligible)
+
+
+@pytest.mark.parametrize("env", [{"BEOM_EMU_NO_CAPTURE": "1"}, {"BEOM_GRAPH": "0"}], ids=["capture-refused", "switched-off"])
+def test_step_graphs_fall_back_to_direct_launches(emu_so, env):
+    """A capture that fails switches the graphs off for good; the step that was being captured runs directly, nothing runs twice."""
+    cmd = _cmd(emu_so, "sill_exchange3D", 30, {"bdrg": "2.e-3", "qdrg": "1."}, None, 0, 0)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=dict(os.environ, **env))
+    res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    assert r.returncode == 0 and not res["bad"] and res["worst"] == 0.0 and res["graph_steps"] == 0, res

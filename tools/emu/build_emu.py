@@ -63,12 +63,13 @@ def rewrite_launches(text: str) -> tuple[str, int]:
         assert text[a0] == "(", text[k - 40:k + 80]
         a1 = _match(text, a0, "(", ")")
         assert text[a1 + 1] == ";", text[k - 40:a1 + 10]
-        call = "%s%s" % (name, text[a0:a1 + 1])
+        # the arguments are evaluated and copied when the launch is issued, as CUDA does (a launch recorded into a graph runs later)
+        body = "[_k = %s, _t = std::make_tuple%s]() { std::apply(_k, _t); }" % (name, text[a0:a1 + 1])
         if name.split("<")[0] in SIMT:
             shmem = cfg[2] if len(cfg) > 2 else "0"
-            out += text[pos:b] + "emu::launch_simt(dim3(%s), dim3(%s), (size_t)(%s), [&]() { %s; })" % (cfg[0], cfg[1], shmem, call)
+            out += text[pos:b] + "emu::launch_simt_c(dim3(%s), dim3(%s), (size_t)(%s), %s)" % (cfg[0], cfg[1], shmem, body)
         else:
-            out += text[pos:b] + "emu::launch(dim3(%s), dim3(%s), [&]() { %s; })" % (cfg[0], cfg[1], call)
+            out += text[pos:b] + "emu::launch(dim3(%s), dim3(%s), %s)" % (cfg[0], cfg[1], body)
         pos = a1 + 1
         n += 1
 

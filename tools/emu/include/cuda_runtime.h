@@ -18,6 +18,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <tuple>
+#include <vector>
 
 #define BEOM_CUDA_EMULATION 1
 #define __global__
@@ -36,8 +39,22 @@ namespace emu {
 struct Idx { unsigned x, y, z; };
 extern thread_local Idx block_idx, thread_idx;
 extern thread_local dim3 block_dim, grid_dim;
+// A stream capture in progress (cudaStreamBeginCapture below): launches are recorded, not run.  One capture at a time, streams
+// are not told apart (the library captures on its compute stream only).
+struct Graph { std::vector<std::function<void()>> nodes; };
+inline Graph *capturing = nullptr;
+template <class F>
+void run_grid(dim3 grid, dim3 block, const F &body);
 template <class F>
 void launch(dim3 grid, dim3 block, F &&body) {
+  if (capturing) {
+    capturing->nodes.push_back([grid, block, body]() { run_grid(grid, block, body); });
+    return;
+  }
+  run_grid(grid, block, body);
+}
+template <class F>
+void run_grid(dim3 grid, dim3 block, const F &body) {
   grid_dim = grid;
   block_dim = block;
   for (unsigned bz = 0; bz < grid.z; bz++)
@@ -62,6 +79,15 @@ void launch(dim3 grid, dim3 block, F &&body) {
 #define gridDim (emu::grid_dim)
 
 #include "simt.h"  // shuffles, votes, __syncwarp, __syncthreads, mbarriers: only inside emu::launch_simt
+namespace emu {
+inline void launch_simt_c(dim3 grid, dim3 block, size_t shmem, std::function<void()> body) {
+  if (capturing) {
+    capturing->nodes.push_back([grid, block, shmem, body]() { launch_simt(grid, block, shmem, body); });
+    return;
+  }
+  launch_simt(grid, block, shmem, body);
+}
+}  // namespace emu
 template <class T> inline void __stcs(T *p, T v) { *p = v; }
 using std::max;
 using std::min;
@@ -83,6 +109,11 @@ enum cudaDeviceAttr { cudaDevAttrMultiProcessorCount, cudaDevAttrMaxSharedMemory
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize, cudaFuncAttributePreferredSharedMemoryCarveout };
 enum { cudaSharedmemCarveoutMaxShared = 100 };
 inline cudaError_t cudaGetDevice(int *d) { *d = 0; return cudaSuccess; }
+// CUDA graphs: a capture records the launches (with their arguments as they were when issued) instead of running them, a graph
+// launch runs them in order.  BEOM_EMU_NO_CAPTURE=1 makes the capture fail, which is how the library's fallback is tested.
+typedef emu::Graph *cudaGraph_t;
+typedef emu::Graph *cudaGraphExec_t;
+enum cudaStreamCaptureMode { cudaStreamCaptureModeGlobal = 0, cudaStreamCaptureModeThreadLocal = 1, cudaStreamCaptureModeRelaxed = 2 };
 inline cudaError_t cudaDeviceGetPCIBusId(char *b, int n, int) { if (n > 0) b[0] = 0; return cudaErrorEmulation; }  // no PCI device: no NUMA placement
 inline cudaError_t cudaDeviceGetAttribute(int *v, cudaDeviceAttr a, int) { *v = a == cudaDevAttrMultiProcessorCount ? 148 : 227 * 1024; return cudaSuccess; }
 template <class F> inline cudaError_t cudaFuncSetAttribute(F, cudaFuncAttribute, int) { return cudaSuccess; }
@@ -94,6 +125,24 @@ inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t *s, unsigned) { *s = n
 inline cudaError_t cudaStreamCreateWithPriority(cudaStream_t *s, unsigned, int) { *s = nullptr; return cudaSuccess; }
 inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
 inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaStreamBeginCapture(cudaStream_t, cudaStreamCaptureMode) {
+  if (emu::capturing || (getenv("BEOM_EMU_NO_CAPTURE") && atoi(getenv("BEOM_EMU_NO_CAPTURE")) > 0)) return cudaErrorEmulation;
+  emu::capturing = new emu::Graph;
+  return cudaSuccess;
+}
+inline cudaError_t cudaStreamEndCapture(cudaStream_t, cudaGraph_t *g) {
+  *g = emu::capturing;
+  emu::capturing = nullptr;
+  return *g ? cudaSuccess : cudaErrorEmulation;
+}
+inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t *e, cudaGraph_t g, unsigned long long = 0) { *e = new emu::Graph(*g); return cudaSuccess; }
+inline cudaError_t cudaGraphDestroy(cudaGraph_t g) { delete g; return cudaSuccess; }
+inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t e) { delete e; return cudaSuccess; }
+inline cudaError_t cudaGraphLaunch(cudaGraphExec_t e, cudaStream_t) {
+  if (emu::capturing) return cudaErrorEmulation;
+  for (auto &n : e->nodes) n();
+  return cudaSuccess;
+}
 inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 inline cudaError_t cudaEventCreate(cudaEvent_t *e) { *e = new emuEvent(); return cudaSuccess; }
 inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t *e, unsigned) { return cudaEventCreate(e); }
@@ -116,6 +165,6 @@ inline cudaError_t cudaFree(void *p) { std::free(p); return cudaSuccess; }
 template <class T> inline cudaError_t cudaHostAlloc(T **p, size_t n, unsigned) { return cudaMalloc(p, n); }
 inline cudaError_t cudaFreeHost(void *p) { std::free(p); return cudaSuccess; }
 inline cudaError_t cudaMemcpy(void *d, const void *s, size_t n, cudaMemcpyKind) { std::memcpy(d, s, n); return cudaSuccess; }
-inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind k, cudaStream_t = nullptr) { return cudaMemcpy(d, s, n, k); }
+inline cudaError_t cudaMemcpyAsync(void *d, const void *s, size_t n, cudaMemcpyKind k, cudaStream_t = nullptr) { return emu::capturing ? cudaErrorEmulation : cudaMemcpy(d, s, n, k); }  // (not recordable here)
 inline cudaError_t cudaMemset(void *d, int v, size_t n) { std::memset(d, v, n); return cudaSuccess; }
-inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t = nullptr) { return cudaMemset(d, v, n); }
+inline cudaError_t cudaMemsetAsync(void *d, int v, size_t n, cudaStream_t = nullptr) { return emu::capturing ? cudaErrorEmulation : cudaMemset(d, v, n); }
