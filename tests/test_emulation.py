@@ -74,7 +74,7 @@ def run(emu_so, name, nsteps, extra=None, kwargs=None, variant=0, fused=0, path=
         todo = [j for j in JOBS if _key(*j) not in _done] or [(name, nsteps, extra, kwargs, variant, fused)]
         if k not in {_key(*j) for j in todo}:
             todo.append((name, nsteps, extra, kwargs, variant, fused))
-        with ThreadPoolExecutor(max_workers=max(4, min(8, os.cpu_count() or 4))) as pool:
+        with ThreadPoolExecutor(max_workers=max(4, min(16, os.cpu_count() or 4))) as pool:
             for kk, r in pool.map(lambda j: _run_one(emu_so, j), todo):
                 _done[kk] = r
     r = _done[k]

@@ -78,12 +78,19 @@ def _prepare(spec, root):
     text = open(blk).read()
     p, _, _, _ = model.parse_params(text, variant)
     text = refcheck.block_for_steps(text, nsteps, p.dt)
-    return text, refbuild.build_case(text, variant)
+    exe = refbuild.build_case(text, variant)
+    # ... and run it here, next to the other cases' compiles and runs (the native-size sill run alone takes a minute)
+    _, _, odir, _ = model.parse_params(text, variant)
+    try:
+        ran = refbuild.run_case(exe, odir, threads=1)
+    except Exception as err:  # reported by the case's own test
+        ran = err
+    return text, exe, ran
 
 
 @pytest.fixture(scope="module")
 def built(tmp_path_factory):
-    """All translated references of this module, compiled side by side (g++ -O2 takes about six seconds per case)."""
+    """All translated references of this module, compiled and run side by side (g++ -O2 takes about six seconds per case)."""
     import tempfile
 
     root = tempfile.mkdtemp(prefix="rp", dir="/tmp")
@@ -108,9 +115,11 @@ def test_oracle_equals_the_translated_reference(built, spec):
     got = built[pid]
     if isinstance(got, Exception):
         raise got
-    text, exe = got
+    text, exe, ran = got
+    if isinstance(ran, Exception):
+        raise ran
     p, idir, odir, _ = model.parse_params(text, variant)
-    dump, _ = refbuild.run_case(exe, odir)
+    dump, _ = ran
     orc = Oracle(p, idir)
     orc.advance(1, nsteps)
     rows = refcheck.compare(dump, orc) + refcheck.compare_files(odir, orc, diag=p.diag > 0.5)
