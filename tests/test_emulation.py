@@ -36,7 +36,48 @@ def emu_so(tmp_path_factory):
     pool = ThreadPoolExecutor(max_workers=2)
     _sanitizer_builds["asan"] = pool.submit(mod.build, str(tmp_path_factory.mktemp("emu_asan")), True, False)
     _sanitizer_builds["tsan"] = pool.submit(mod.build, str(tmp_path_factory.mktemp("emu_tsan")), False, True)
-    return so
+    # the one-command tests of this module (EARLY, filled next to each of them) start now, three at a time, beside the
+    # emulation jobs; the tests pick their results up (_sp_run) -- a few minutes of single-threaded runs that would
+    # otherwise follow one another
+    early_pool = ThreadPoolExecutor(max_workers=3)
+    for argv, env in EARLY:
+        cmd = [a.replace("@EMU@", so) for a in argv]
+        env = {k: v.replace("@EMU@", so) for k, v in env.items()}
+        _early_futs[_ekey(cmd, env)] = early_pool.submit(subprocess.run, cmd, capture_output=True, text=True, timeout=1500, cwd=ROOT,
+                                                         env=dict(os.environ, **env))
+    yield so
+    early_pool.shutdown(wait=False, cancel_futures=True)
+
+
+EARLY = []        # (argv with "@EMU@" for the emulated library's path, environment additions)
+_early_futs = {}
+
+
+def _ekey(cmd, env):
+    return json.dumps([list(cmd), sorted((env or {}).items())])
+
+
+def early(argv, env=None):
+    EARLY.append((list(argv), dict(env or {})))
+
+
+def _sp_run(cmd, env=None, timeout=900):
+    """subprocess.run of a command of this module: the result of its early start if it had one (same argv, same environment)."""
+    fut = _early_futs.pop(_ekey(cmd, env), None)
+    if fut is not None:
+        return fut.result()
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT, env=dict(os.environ, **(env or {})))
+
+
+def _ranks_cmd(emu_so, name, nsteps, nranks, extra=None, kwargs=None, fused=None):
+    cmd = [sys.executable, os.path.join(ROOT, "tests", "emu_ranks_worker.py"), emu_so, name, str(nsteps), str(nranks)]
+    if extra is not None or kwargs is not None or fused is not None:
+        cmd.append(json.dumps(extra if extra is not None else {}))
+    if kwargs is not None or fused is not None:
+        cmd.append(json.dumps(kwargs))
+    if fused is not None:
+        cmd.append(str(fused))
+    return cmd
 
 
 def _cmd(emu_so, name, nsteps, extra, kwargs, variant, fused):
@@ -168,15 +209,16 @@ RANKS = [
 ]
 
 
+for _r in RANKS:
+    early(_ranks_cmd("@EMU@", _r[0], _r[1], _r[2], _r[3], _r[4]))
+
+
 @pytest.mark.parametrize("name,nsteps,nranks,extra,kwargs", RANKS, ids=["%s-%d%s" % (r[0], r[2], "-" + "".join(r[3]) if r[3] else "") for r in RANKS])
 def test_y_slab_ranks_on_the_emulated_split_path(emu_so, name, nsteps, nranks, extra, kwargs):
     """One emulated library instance per rank (own file, own globals, own thread); the packed halo exchange goes through
     a callback that pairs the messages like NCCL.  Every rank's own slab -- periodic duplicates included -- must equal the
     oracle bit for bit, and the own ranges must tile 1..ndeg (output records are their concatenation)."""
-    cmd = [sys.executable, os.path.join(ROOT, "tests", "emu_ranks_worker.py"), emu_so, name, str(nsteps), str(nranks), json.dumps(extra)]
-    if kwargs is not None:
-        cmd.append(json.dumps(kwargs))
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    r = _sp_run(_ranks_cmd(emu_so, name, nsteps, nranks, extra, kwargs))
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert lines, r.stdout[-2000:] + r.stderr[-2000:]
     res = json.loads(lines[-1])
@@ -187,9 +229,11 @@ def test_y_slab_ranks_on_the_emulated_split_path(emu_so, name, nsteps, nranks, e
     assert res["moved"] > 0
 
 
+early(_ranks_cmd("@EMU@", "baines_ridge", 5, 2))
+
+
 def test_ranks_that_cannot_hold_the_seam_fail_loudly(emu_so):
-    cmd = [sys.executable, os.path.join(ROOT, "tests", "emu_ranks_worker.py"), emu_so, "baines_ridge", "5", "2"]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    r = _sp_run(_ranks_cmd(emu_so, "baines_ridge", 5, 2))
     assert r.returncode == 1 and "rows per rank" in r.stdout
 
 
@@ -413,16 +457,18 @@ def test_reference_program_drives_the_library_through_the_c_abi(emu_so, name, fu
         shutil.rmtree(root, ignore_errors=True)
 
 
+_GPU_MODULES_CMD = [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), os.path.join(ROOT, "tests", "test_gpu_outputs.py"),
+                    "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider", "-k", "rigid_lid or conservation_integrals or diagnostic_records or biharmonic"]
+early(_GPU_MODULES_CMD, {"BEOM_TEST_EMU": "@EMU@"})
+
+
 def test_gpu_test_modules_on_the_emulation(emu_so):
     """The GPU tests themselves, re-run with the emulated library swapped in (tests/conftest.py, BEOM_TEST_EMU): the ones
     whose kernels nothing above reaches -- the rigid lid (hyperplane Gauss-Seidel with __syncthreads and shuffle
     reductions), the biharmonic viscosity, the float32 diagnostic records and the conservation integrals (warp-shuffle
     reductions).  The whole of tests/test_gpu_parity.py and tests/test_gpu_outputs.py passes this way too (about five
     minutes; `BEOM_TEST_EMU=<libbeom_gpu_emu.so> pytest tests/test_gpu_parity.py tests/test_gpu_outputs.py -m gpu`)."""
-    env = dict(os.environ, BEOM_TEST_EMU=emu_so)
-    cmd = [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), os.path.join(ROOT, "tests", "test_gpu_outputs.py"),
-           "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider", "-k", "rigid_lid or conservation_integrals or diagnostic_records or biharmonic"]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=1200, cwd=ROOT, env=env)
+    r = _sp_run(_GPU_MODULES_CMD, {"BEOM_TEST_EMU": emu_so}, timeout=1200)
     assert r.returncode == 0 and " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
 
 
@@ -436,15 +482,17 @@ RANKS_FUSED = [("synthetic_basin", 9, 2, dict(n=60, mm=40, nlay=2), {}),
                ("sill_exchange3D", 12, 3, None, {"mcbc": "0."})]
 
 
+for _r in RANKS_FUSED:
+    early(_ranks_cmd("@EMU@", _r[0], _r[1], _r[2], _r[4], _r[3], 1))
+
+
 @pytest.mark.parametrize("name,nsteps,nranks,kwargs,extra", RANKS_FUSED,
                          ids=["%s-%d%s" % (r[0], r[2], "-obc" if r[4] else "") for r in RANKS_FUSED])
 def test_y_slab_ranks_on_the_emulated_fused_step(emu_so, name, nsteps, nranks, kwargs, extra):
     """The fused step on y-slabs: one packed exchange of the 8 new fields' four boundary rows per step, the deep halo
     recomputed locally -- every rank's slab bit-identical to the oracle.  With no_gradient_obc
     (mcbc = 0) the exchange runs before the open-boundary copy and once more, for u, v, h_u, h_v, after it."""
-    cmd = [sys.executable, os.path.join(ROOT, "tests", "emu_ranks_worker.py"), emu_so, name, str(nsteps), str(nranks), json.dumps(extra),
-           json.dumps(kwargs), "1"]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    r = _sp_run(_ranks_cmd(emu_so, name, nsteps, nranks, extra, kwargs, 1))
     lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
     assert lines, r.stdout[-2000:] + r.stderr[-2000:]
     res = json.loads(lines[-1])
@@ -517,30 +565,36 @@ def test_no_race_between_warps_under_threadsanitizer(emu_so, tmp_path_factory):
     shutil.rmtree(os.path.dirname(so), ignore_errors=True)
 
 
+_GRID_INIT_CMD = [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_grid_init.py"), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"]
+_GRID_INIT_RANKS = [["synthetic_basin", "9", "3", "{}", json.dumps(dict(n=60, mm=90, nlay=4)), "1"], ["sill_exchange3D", "12", "2", "{}", "null", "1"],
+                    ["conservation", "12", "3", "{}", "null", "1"],                     # ring-closed y-periodic slabs
+                    ["wave_sponge", "12", "4", json.dumps({"mcbc": "0."}), "null", "1"]]  # open-boundary segments spread over the ranks
+early(_GRID_INIT_CMD, {"BEOM_TEST_EMU": "@EMU@"})
+for _spec in _GRID_INIT_RANKS:
+    early([sys.executable, os.path.join(ROOT, "tests", "emu_ranks_worker.py"), "@EMU@"] + _spec, {"BEOM_GRID_INIT": "1"})
+
+
 def test_device_side_initialisation_on_the_emulation(emu_so):
     """beom_gpu_init_grids (gridinit.cuh: index_grid_points as a prefix sum, the rest thickness incl. the Newton solve, the forcing
     files) against the host's read_input_data on every case it covers, and the refusals (tests/test_grid_init.py re-run with the
     emulated library); then every rank of a y-slab run initialised that way."""
-    env = dict(os.environ, BEOM_TEST_EMU=emu_so)
-    cmd = [sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_grid_init.py"), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider"]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=1200, cwd=ROOT, env=env)
+    r = _sp_run(_GRID_INIT_CMD, {"BEOM_TEST_EMU": emu_so}, timeout=1200)
     assert r.returncode == 0 and " passed" in r.stdout and "failed" not in r.stdout, r.stdout[-3000:] + r.stderr[-2000:]
-    for spec in (["synthetic_basin", "9", "3", "{}", json.dumps(dict(n=60, mm=90, nlay=4)), "1"], ["sill_exchange3D", "12", "2", "{}", "null", "1"],
-                 ["conservation", "12", "3", "{}", "null", "1"],                     # ring-closed y-periodic slabs
-                 ["wave_sponge", "12", "4", json.dumps({"mcbc": "0."}), "null", "1"]):  # open-boundary segments spread over the ranks
-        cmd = [sys.executable, os.path.join(ROOT, "tests", "emu_ranks_worker.py"), emu_so] + spec
-        r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=dict(os.environ, BEOM_GRID_INIT="1"))
+    for spec in _GRID_INIT_RANKS:
+        r = _sp_run([sys.executable, os.path.join(ROOT, "tests", "emu_ranks_worker.py"), emu_so] + spec, {"BEOM_GRID_INIT": "1"})
         res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
         assert r.returncode == 0 and all(not k["bad"] and k["path"] == "fused" for k in res["ranks"]), res
+
+
+for _o in ("1", "0"):
+    early(_ranks_cmd("@EMU@", "synthetic_basin", 9, 2, {}, dict(n=60, mm=90, nlay=2), 1), {"BEOM_OVERLAP": _o})
 
 
 @pytest.mark.parametrize("overlap", ["1", "0"])
 def test_halo_overlap_variant_on_emulated_ranks(emu_so, overlap):
     """The default on several ranks: the G rows next to each neighbour first, their exchange while the rows
     in between are computed -- three launches per step instead of one; BEOM_OVERLAP=0 is the plain sequence.  Same result."""
-    cmd = [sys.executable, os.path.join(ROOT, "tests", "emu_ranks_worker.py"), emu_so, "synthetic_basin", "9", "2", "{}",
-           json.dumps(dict(n=60, mm=90, nlay=2)), "1"]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=dict(os.environ, BEOM_OVERLAP=overlap))
+    r = _sp_run(_ranks_cmd(emu_so, "synthetic_basin", 9, 2, {}, dict(n=60, mm=90, nlay=2), 1), {"BEOM_OVERLAP": overlap})
     res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
     assert r.returncode == 0 and all(not k["bad"] and k["path"] == "fused" for k in res["ranks"]), res
 
