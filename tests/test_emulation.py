@@ -64,7 +64,7 @@ def early(argv, env=None):
 def _sp_run(cmd, env=None, timeout=900):
     """subprocess.run of a command of this module: the result of its early start if it had one (same argv, same environment)."""
     fut = _early_futs.pop(_ekey(cmd, env), None)
-    if fut is not None:
+    if fut is not None and not fut.cancel():  # (still queued: run it here, now, instead of waiting for its turn)
         return fut.result()
     return subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT, env=dict(os.environ, **(env or {})))
 
@@ -628,3 +628,20 @@ def test_step_graphs_fall_back_to_direct_launches(emu_so, env):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env=dict(os.environ, **env))
     res = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
     assert r.returncode == 0 and not res["bad"] and res["worst"] == 0.0 and res["graph_steps"] == 0, res
+
+
+for _env in ({}, {"BEOM_GRAPH": "0"}):
+    early([sys.executable, os.path.join(ROOT, "tests", "emu_reupload_worker.py"), "@EMU@", "sill_exchange3D", "24"], _env)
+
+
+def test_a_second_upload_drops_the_step_graphs(emu_so):
+    """beom_gpu_upload_state in the middle of a run (a restart from the downloaded state): the graphs of the first leg are dropped,
+    the second leg captures its own -- same final state as with the graphs switched off."""
+    cmd = [sys.executable, os.path.join(ROOT, "tests", "emu_reupload_worker.py"), emu_so, "sill_exchange3D", "24"]
+    res = []
+    for env in ({}, {"BEOM_GRAPH": "0"}):
+        r = _sp_run(cmd, env)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        res.append(json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1]))
+    assert res[0]["graph_steps"] == [19, 19] and res[1]["graph_steps"] == [0, 0], res
+    assert res[0]["sha256"] == res[1]["sha256"], res
