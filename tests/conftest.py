@@ -12,6 +12,16 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """A kernel that wedges must end the run, not hang it: with pytest-timeout installed every GPU test gets 15 minutes (the
+    longest takes seconds); method "thread" because a test stuck inside a CUDA call never returns to the interpreter."""
+    if not config.pluginmanager.hasplugin("timeout"):
+        return
+    for item in items:
+        if item.get_closest_marker("gpu") and not item.get_closest_marker("timeout"):
+            item.add_marker(pytest.mark.timeout(900, method="thread"))
+
+
 @pytest.fixture(scope="session", autouse=True)
 def _built():
     """The native libraries are built in-tree once per session (CPU-only cross compile works)."""
